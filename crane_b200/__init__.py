@@ -1,0 +1,294 @@
+"""crane_b200 -- Python (ctypes) mirror of the reference's model interface over the C ABI.
+
+The host language of the reference is Rust, which this image cannot build; this module is the
+host-side mirror used by the tests and bench (INTEGRATION.md shows the Rust `impl ModelBackend`
+a Crane maintainer would add over the same C ABI).  Names follow the reference:
+
+    Qwen3Model            crane-core/src/models/qwen3/model.rs:34-349   (`Model`)
+    Qwen3VLModel          crane-core/src/models/qwen3_5/vlm.rs:78-415   (`Qwen3_5VLModel`)
+
+There is no CPU fallback: importing works anywhere, but constructing a model without the in-tree
+CUDA library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrane_b200.so")
+
+F32, BF16, F16 = 0, 1, 2
+OK, INVALID_ARG, OOM, CUDA_ERROR, UNSUPPORTED, NOT_LOADED = 0, -1, -2, -3, -4, -5
+
+# cb::GemmEpiMode (crane_b200/csrc/gemm.cuh)
+EPI_STORE_F32, EPI_STORE_BF16, EPI_RESID_F32, EPI_SILU_MUL_BF16, EPI_GELU_ERF_BF16, EPI_GELU_TANH_BF16 = range(6)
+
+
+class CraneB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"crane_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Logits(C.Structure):
+    _fields_ = [("device_ptr", C.c_void_p), ("rows", C.c_size_t), ("vocab", C.c_size_t), ("stream", C.c_void_p)]
+
+
+_lib = None
+
+# name -> (restype, argtypes): must list every symbol include/crane_b200.h declares
+_SIGNATURES = {
+    "crane_b200_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "crane_b200_destroy": (None, [C.c_void_p]),
+    "crane_b200_last_error": (C.c_char_p, [C.c_void_p]),
+    "crane_b200_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "crane_b200_finalize": (C.c_int, [C.c_void_p]),
+    "crane_b200_forward_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(Logits)]),
+    "crane_b200_forward_step_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "crane_b200_clear_kv_cache": (C.c_int, [C.c_void_p]),
+    "crane_b200_num_layers": (C.c_int, [C.c_void_p]),
+    "crane_b200_warmup": (C.c_int, [C.c_void_p]),
+    "crane_b200_active_kv_cache_bytes": (C.c_uint64, [C.c_void_p]),
+    "crane_b200_kv_len": (C.c_size_t, [C.c_void_p]),
+    "crane_b200_vocab_size": (C.c_int, [C.c_void_p]),
+    "crane_b200_hidden_size": (C.c_int, [C.c_void_p]),
+    "crane_b200_copy_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "crane_b200_forward_embeds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(Logits)]),
+    "crane_b200_decode_greedy": (C.c_int, [C.c_void_p, C.c_uint32, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                           C.c_void_p, C.POINTER(C.c_size_t)]),
+    "crane_b200_generate_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                             C.c_void_p, C.POINTER(C.c_size_t)]),
+    "crane_b200_encode_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "crane_b200_vl_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                        C.POINTER(Logits)]),
+    "crane_b200_vl_decode_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_size_t, C.POINTER(Logits)]),
+    "crane_b200_next_mrope_pos": (C.c_uint32, [C.c_void_p]),
+    "crane_b200_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_size_t)]),
+    "crane_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "crane_b200_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_int]),
+}
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(crane_b200 has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """Thin owner of one `crane_b200_model*`."""
+
+    def __init__(self, config: dict, device: int = 0, **engine_opts):
+        self.lib = load_library()
+        cfg = dict(config)
+        if engine_opts:
+            cfg["engine"] = dict(cfg.get("engine", {}), **engine_opts)
+        self.config = cfg
+        h = C.c_void_p()
+        rc = self.lib.crane_b200_create(json.dumps(cfg).encode(), device, C.byref(h))
+        if rc != OK:
+            raise CraneB200Error(rc, (self.lib.crane_b200_last_error(None) or b"").decode())
+        self.h = h
+        self.vocab = self.lib.crane_b200_vocab_size(h)
+        self.hidden = self.lib.crane_b200_hidden_size(h)
+
+    def _ck(self, rc: int):
+        if rc != OK:
+            raise CraneB200Error(rc, (self.lib.crane_b200_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.crane_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ----
+    def load_tensor(self, name: str, arr: np.ndarray):
+        """f32 arrays are rounded to bf16 for the matrices; uint16 arrays are taken as bf16 bit patterns."""
+        a = np.ascontiguousarray(arr)
+        if a.dtype == np.float32:
+            dt = F32
+        elif a.dtype == np.uint16:
+            dt = BF16
+        elif a.dtype == np.float16:
+            dt = F16
+        else:
+            raise TypeError(f"{name}: unsupported dtype {a.dtype}")
+        shape = (C.c_int64 * a.ndim)(*a.shape)
+        self._ck(self.lib.crane_b200_load_tensor(self.h, name.encode(), dt, shape, a.ndim, _ptr(a)))
+
+    def load_checkpoint(self, tensors):
+        for name, arr in tensors:
+            self.load_tensor(name, arr)
+        self.finalize()
+
+    def finalize(self):
+        self._ck(self.lib.crane_b200_finalize(self.h))
+
+    # ---- ModelBackend surface ----
+    def forward_step(self, ids, start_pos: int) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        lg = Logits()
+        self._ck(self.lib.crane_b200_forward_step(self.h, _ptr(ids), ids.size, start_pos, C.byref(lg)))
+        return self.copy_logits()
+
+    def forward_step_argmax(self, ids, start_pos: int) -> int:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        tok = C.c_uint32()
+        self._ck(self.lib.crane_b200_forward_step_argmax(self.h, _ptr(ids), ids.size, start_pos, C.byref(tok)))
+        return int(tok.value)
+
+    def copy_logits(self) -> np.ndarray:
+        out = np.empty(self.vocab, dtype=np.float32)
+        self._ck(self.lib.crane_b200_copy_logits(self.h, _ptr(out), out.size))
+        return out
+
+    def clear_kv_cache(self):
+        self._ck(self.lib.crane_b200_clear_kv_cache(self.h))
+
+    def num_layers(self) -> int:
+        return self.lib.crane_b200_num_layers(self.h)
+
+    def kv_len(self) -> int:
+        return int(self.lib.crane_b200_kv_len(self.h))
+
+    def warmup(self):
+        self._ck(self.lib.crane_b200_warmup(self.h))
+
+    def forward_embeds(self, embeds, start_pos: int, position_ids=None) -> np.ndarray:
+        e = np.ascontiguousarray(embeds, dtype=np.float32)
+        p = None if position_ids is None else np.ascontiguousarray(position_ids, dtype=np.uint32)
+        lg = Logits()
+        self._ck(self.lib.crane_b200_forward_embeds(self.h, _ptr(e), e.shape[0], None if p is None else _ptr(p), start_pos,
+                                                    C.byref(lg)))
+        return self.copy_logits()
+
+    def decode_greedy(self, first_token: int, start_pos: int, n_steps: int, eos=()):
+        out = np.empty(n_steps, dtype=np.uint32)
+        eos_a = np.ascontiguousarray(list(eos), dtype=np.uint32)
+        n = C.c_size_t()
+        self._ck(self.lib.crane_b200_decode_greedy(self.h, first_token, start_pos, n_steps,
+                                                   _ptr(eos_a) if eos_a.size else None, eos_a.size, _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def generate_greedy(self, prompt, max_new_tokens: int, eos=()):
+        p = np.ascontiguousarray(prompt, dtype=np.uint32)
+        out = np.empty(max_new_tokens, dtype=np.uint32)
+        eos_a = np.ascontiguousarray(list(eos), dtype=np.uint32)
+        n = C.c_size_t()
+        self._ck(self.lib.crane_b200_generate_greedy(self.h, _ptr(p), p.size, max_new_tokens,
+                                                     _ptr(eos_a) if eos_a.size else None, eos_a.size, _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    # ---- vision-language surface ----
+    def encode_images(self, pixel_values, grid_thw, want_deepstack: int = 0):
+        pv = np.ascontiguousarray(pixel_values, dtype=np.float32)
+        g = np.ascontiguousarray(grid_thw, dtype=np.uint32).reshape(-1, 3)
+        merge = self.config["vision_config"]["spatial_merge_size"]
+        n_tok = int(sum(int(t) * int(h) * int(w) for t, h, w in g) // (merge * merge))
+        out = np.empty((n_tok, self.hidden), dtype=np.float32)
+        ds = np.empty((want_deepstack, n_tok, self.hidden), dtype=np.float32) if want_deepstack else None
+        self._ck(self.lib.crane_b200_encode_images(self.h, _ptr(pv), _ptr(g), g.shape[0], _ptr(out), None if ds is None else _ptr(ds)))
+        return out, ds
+
+    def vl_forward(self, ids, pixel_values=None, grid_thw=None, start_pos: int = 0) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        lg = Logits()
+        if pixel_values is None:
+            self._ck(self.lib.crane_b200_vl_forward(self.h, _ptr(ids), ids.size, None, None, 0, start_pos, C.byref(lg)))
+        else:
+            pv = np.ascontiguousarray(pixel_values, dtype=np.float32)
+            g = np.ascontiguousarray(grid_thw, dtype=np.uint32).reshape(-1, 3)
+            self._ck(self.lib.crane_b200_vl_forward(self.h, _ptr(ids), ids.size, _ptr(pv), _ptr(g), g.shape[0], start_pos, C.byref(lg)))
+        return self.copy_logits()
+
+    def vl_decode_step(self, token: int, start_pos: int) -> np.ndarray:
+        lg = Logits()
+        self._ck(self.lib.crane_b200_vl_decode_step(self.h, token, start_pos, C.byref(lg)))
+        return self.copy_logits()
+
+    def next_mrope_pos(self) -> int:
+        return int(self.lib.crane_b200_next_mrope_pos(self.h))
+
+    def last_timing(self):
+        p, d, n = C.c_float(), C.c_float(), C.c_size_t()
+        self._ck(self.lib.crane_b200_last_timing(self.h, C.byref(p), C.byref(d), C.byref(n)))
+        return {"prefill_ms": p.value, "decode_ms": d.value, "decode_steps": int(n.value)}
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.crane_b200_kernel_launches(self.h))
+
+
+class Qwen3Model(Engine):
+    """`crane_core::models::qwen3::Model` (qwen3/model.rs:34-349) without the tokenizer."""
+
+    def generate(self, input_ids, max_new_tokens: int = 128, eos_token_id=(), temperature=None):
+        """`ModelForCausalLM::generate` (generation/based.rs:5-34); greedy only (temperature None => ArgMax,
+        qwen3/model.rs:281-284).  Sampling stays on the caller's side of the boundary."""
+        if temperature not in (None, 0, 0.0):
+            raise CraneB200Error(UNSUPPORTED, "sampled decoding is host-side in the reference (LogitsProcessor); only greedy here")
+        eos = (eos_token_id,) if isinstance(eos_token_id, int) else tuple(eos_token_id)
+        return self.generate_greedy(input_ids, max_new_tokens, eos)
+
+
+class Qwen3VLModel(Engine):
+    """`Qwen3_5VLModel` (qwen3_5/vlm.rs:78-415) over the Qwen3-VL geometry: `forward` = ViT + splice + prefill,
+    `decode_step` = one token with the scalar MRoPE counter."""
+
+    def forward(self, input_ids, pixel_values=None, image_grid_thw=None, start_pos: int = 0):
+        return self.vl_forward(input_ids, pixel_values, image_grid_thw, start_pos)
+
+    def decode_step(self, token: int, start_pos: int):
+        return self.vl_decode_step(token, start_pos)
+
+    def generate(self, input_ids, pixel_values, image_grid_thw, max_new_tokens: int, eos_token_id=()):
+        """vlm.rs:355-414: prefill (argmax on device), then greedy decode on the device."""
+        eos = (eos_token_id,) if isinstance(eos_token_id, int) else tuple(eos_token_id)
+        self.clear_kv_cache()
+        logits = self.forward(input_ids, pixel_values, image_grid_thw, 0)
+        first = int(np.argmax(logits))
+        out = [first]
+        if first in eos or max_new_tokens == 1:
+            return np.array(out, np.uint32)
+        rest = self.decode_greedy(first, len(input_ids), max_new_tokens - 1, eos)
+        return np.concatenate([np.array(out, np.uint32), rest])
+
+
+def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_init=None, use_simt=False, device=0):
+    """Kernel-level test hook: epilogue(A[M,K] x W[N,K]^T) with bf16 bit-pattern inputs."""
+    lib = load_library()
+    M, K = a_bits.shape
+    N = w_bits.shape[0]
+    half = mode in (EPI_STORE_BF16, EPI_SILU_MUL_BF16, EPI_GELU_ERF_BF16, EPI_GELU_TANH_BF16)
+    cols = N // 2 if mode == EPI_SILU_MUL_BF16 else N
+    out = np.zeros((M, cols), dtype=np.uint16 if half else np.float32) if out_init is None else np.ascontiguousarray(out_init).copy()
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    rc = lib.crane_b200_op_gemm(device, _ptr(np.ascontiguousarray(a_bits)), _ptr(np.ascontiguousarray(w_bits)), M, N, K, mode,
+                                None if b is None else _ptr(b), _ptr(out), 1 if use_simt else 0)
+    if rc != OK:
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+    return out

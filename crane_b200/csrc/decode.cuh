@@ -1,0 +1,82 @@
+// Decode-path kernels (S = 1 per sequence): bandwidth-bound weight streaming + paged-KV GQA attention.
+//
+// Replaces, per decoded token, what the reference runs as ~10 Candle ops + cuBLAS gemv calls per layer
+// (crane-core/src/models/qwen3/modeling.rs:698-716 -> :307-533, :608-642, :1024-1035) and the two-phase
+// `gpu_argmax` (crane-core/kernels/cuda/fused_ops.cu:251-382) with 4 fused kernels per layer:
+//   gemv<NORM, STORE>      input RMSNorm + merged QKV projection
+//   attn_decode            QK-norm + RoPE/MRoPE + KV-page append + split-KV GQA attention + split merge
+//   gemv<RESID>            O-projection + residual add
+//   gemv<NORM, SILU_MUL>   post-attention RMSNorm + merged gate/up projection + SiLU*up
+//   gemv<RESID>            down projection + residual add
+// and  gemv<NORM, LOGITS_ARGMAX>  final RMSNorm + lm_head + greedy argmax + next-token embedding gather.
+// All kernels are chained with programmatic dependent launch: each one starts streaming its (immutable)
+// weights before `griddepcontrol.wait`, so the HBM pipe stays busy across kernel boundaries.
+#pragma once
+
+#include "common.cuh"
+
+namespace cb {
+
+constexpr int KV_PAGE = 64;        // tokens per KV page
+constexpr int ATTN_NSPLIT = 16;    // fixed split-KV factor (grid is static so the step can live in a CUDA graph)
+constexpr int MAX_BATCH = 8;
+
+// Device-resident per-sequence decode state (lets a whole decode step replay as a CUDA graph).
+struct SeqState {
+    int kv_len;        // tokens already in the cache (the step appends position kv_len)
+    int pos[3];        // MRoPE (t, h, w) position of the token being decoded
+    uint32_t token;    // input token of the step
+    int step;          // decode steps taken since the state was armed
+    int pad[2];
+};
+
+enum GemvEpi : int { GEMV_STORE = 0, GEMV_RESID = 1, GEMV_SILU_MUL = 2, GEMV_LOGITS_ARGMAX = 3 };
+
+struct GemvArgs {
+    const bf16* W;          // [N, K] row-major (gate/up rows interleaved for GEMV_SILU_MUL)
+    int N, K;
+    const float* x;         // [B, ldx] f32
+    int ldx;
+    const float* norm_w;    // [K] RMSNorm weight (NORM) else nullptr
+    float eps;
+    float* y;               // [B, ldy] f32 (STORE: = ; RESID: += ; SILU_MUL: [B, N/2]; LOGITS_ARGMAX: logits)
+    int ldy;
+    // --- GEMV_LOGITS_ARGMAX only ---
+    float* part_val;        // [B, gridDim.x]
+    int* part_idx;          // [B, gridDim.x]
+    unsigned int* ticket;   // 1 counter
+    SeqState* state;        // [B]
+    uint32_t* out_tokens;   // [B, out_stride] greedy tokens, index state.step
+    int out_stride;
+    const bf16* embed;      // [V, H] embedding table for the next-step gather
+    float* x_next;          // [B, H] residual-stream input of the next step
+    int H;
+    int advance;            // 1: write token / embedding / advance state (on-device greedy loop)
+};
+
+struct AttnDecArgs {
+    const float* qkv;        // [B, q_dim + 2*kv_dim] f32 (pre-norm, pre-rope)
+    const float* q_norm_w;   // [D]
+    const float* k_norm_w;   // [D]
+    float eps;
+    const float* cos_tab;    // [max_pos, D/2]
+    const float* sin_tab;
+    const unsigned char* axis_of;  // [D/2] MRoPE axis per rotary column (all 0 for 1-D RoPE)
+    const SeqState* state;   // [B]
+    const int* block_table;  // [B, max_pages]
+    int max_pages;
+    bf16* k_pool;            // this layer's pages: [n_pages, nkv, KV_PAGE, D]
+    bf16* v_pool;
+    int nh, nkv;
+    float scale;
+    float* part_o;           // [B, nh, NSPLIT, D]
+    float* part_ml;          // [B, nh, NSPLIT, 2]
+    unsigned int* counters;  // [B, nkv]
+    float* out;              // [B, nh*D] f32
+};
+
+int gemv_launch(cudaStream_t st, int B, int epi, bool norm, const GemvArgs& a, int num_sms, bool pdl);
+int attn_decode_launch(cudaStream_t st, int B, int D, const AttnDecArgs& a, bool pdl);
+int embed_decode_launch(cudaStream_t st, int B, const bf16* embed, int H, const SeqState* state, float* x, bool pdl);
+
+}  // namespace cb

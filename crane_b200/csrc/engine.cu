@@ -1,0 +1,1245 @@
+// crane_b200 engine: owns weights / KV pages / workspaces for one model on one GPU and orchestrates the
+// kernels of gemm.cu, decode.cu and prefill.cu behind the C ABI of include/crane_b200.h.
+//
+// Host-side structure mirrors the reference (crane-core/src/models/):
+//   Qwen3Model::{forward, forward_embeds, decode}      qwen3/modeling.rs:942-1036
+//   Model::{forward_step, generate, clear_kv_cache}    qwen3/model.rs:34-349
+//   Qwen3_5VLModel::{encode_images, forward, decode_step, build_position_ids}   qwen3_5/vlm.rs:150-301
+//   Qwen3_5VisionModel::forward                         qwen3_5/vision.rs:558-584
+#include "../../include/crane_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "decode.cuh"
+#include "gemm.cuh"
+#include "json_min.h"
+#include "prefill.cuh"
+
+using namespace cb;
+
+namespace {
+
+struct EngineError {
+    int code;
+    std::string msg;
+};
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw EngineError{code, buf};
+}
+#define CUDA_OK(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            fail(e__ == cudaErrorMemoryAllocation ? CRANE_B200_OOM : CRANE_B200_CUDA_ERROR, "%s: %s (%s:%d)", \
+                 #expr, cudaGetErrorString(e__), __FILE__, __LINE__);                                         \
+    } while (0)
+#define LAUNCH_OK(expr)                                                                                       \
+    do {                                                                                                      \
+        int r__ = (expr);                                                                                     \
+        if (r__ == -1000) fail(CRANE_B200_UNSUPPORTED, "unsupported shape in %s (%s:%d)", #expr, __FILE__, __LINE__); \
+        if (r__ != 0) fail(CRANE_B200_CUDA_ERROR, "%s failed: %d %s (%s:%d)", #expr, r__,                     \
+                           r__ > 0 ? cudaGetErrorString((cudaError_t)r__) : "", __FILE__, __LINE__);          \
+    } while (0)
+
+std::string g_create_error;
+
+// ---- host dtype conversion ---------------------------------------------------------------------
+inline uint16_t f32_to_bf16_bits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+inline float bf16_bits_to_f32(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+inline float f16_bits_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ffu, u;
+    if (exp == 0) {
+        if (man == 0) u = sign;
+        else {
+            exp = 127 - 15 + 1;
+            while (!(man & 0x400u)) { man <<= 1; --exp; }
+            u = sign | (exp << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) u = sign | 0x7f800000u | (man << 13);
+    else u = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+void to_bf16(const void* src, int dt, size_t n, std::vector<uint16_t>& out) {
+    out.resize(n);
+    if (dt == CRANE_B200_BF16) std::memcpy(out.data(), src, n * 2);
+    else if (dt == CRANE_B200_F32) { const float* s = (const float*)src; for (size_t i = 0; i < n; ++i) out[i] = f32_to_bf16_bits(s[i]); }
+    else { const uint16_t* s = (const uint16_t*)src; for (size_t i = 0; i < n; ++i) out[i] = f32_to_bf16_bits(f16_bits_to_f32(s[i])); }
+}
+void to_f32(const void* src, int dt, size_t n, std::vector<float>& out) {
+    out.resize(n);
+    if (dt == CRANE_B200_F32) std::memcpy(out.data(), src, n * 4);
+    else if (dt == CRANE_B200_BF16) { const uint16_t* s = (const uint16_t*)src; for (size_t i = 0; i < n; ++i) out[i] = bf16_bits_to_f32(s[i]); }
+    else { const uint16_t* s = (const uint16_t*)src; for (size_t i = 0; i < n; ++i) out[i] = f16_bits_to_f32(s[i]); }
+}
+
+struct LayerW {
+    bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr;
+    float *ln1 = nullptr, *ln2 = nullptr, *qn = nullptr, *kn = nullptr;
+    bf16 *k_pool = nullptr, *v_pool = nullptr;
+    int loaded = 0;   // bit per tensor
+};
+struct VitBlockW {
+    float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
+    bf16* wqkv = nullptr; float* bqkv = nullptr;
+    bf16* wproj = nullptr; float* bproj = nullptr;
+    bf16* wfc1 = nullptr; float* bfc1 = nullptr;
+    bf16* wfc2 = nullptr; float* bfc2 = nullptr;
+    int loaded = 0;
+};
+struct MergerW {
+    float *nw = nullptr, *nb = nullptr;
+    bf16* w1 = nullptr; float* b1 = nullptr;
+    bf16* w2 = nullptr; float* b2 = nullptr;
+    bool post = false;
+    int loaded = 0;
+};
+
+}  // namespace
+
+struct crane_b200_model {
+    // ---- configuration ----
+    int device = 0, num_sms = 148;
+    bool is_vl = false;
+    int V = 0, H = 0, I = 0, L = 0, nh = 0, nkv = 0, D = 0;
+    float eps = 1e-6f;
+    double theta = 1e6;
+    bool tied = true;
+    std::vector<int> mrope_section;
+    int max_seq = 4096, max_batch = 1, max_pages = 0;
+    bool use_simt = false, use_graphs = true, use_pdl = true;
+    // vision
+    int v_depth = 0, v_H = 0, v_I = 0, v_nh = 0, v_hd = 0, v_patch = 16, v_merge = 2, v_tpatch = 2, v_in = 3, v_out = 0,
+        v_npos = 0, v_side = 0;
+    std::vector<int> v_deepstack;
+    int vit_gelu_mode = EPI_GELU_ERF_BF16, merger_gelu_mode = EPI_GELU_TANH_BF16;
+    uint32_t image_token_id = 0;
+
+    // ---- device state ----
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    bf16 *embed = nullptr, *lm_head = nullptr;
+    float* final_norm = nullptr;
+    std::vector<LayerW> layers;
+    bool got_embed = false, got_lm_head = false, got_final_norm = false, finalized = false;
+    float *cos_tab = nullptr, *sin_tab = nullptr;
+    unsigned char* axis_of = nullptr;
+    // vision weights
+    bf16* v_wpatch = nullptr; float* v_bpatch = nullptr; float* v_pos = nullptr;
+    std::vector<VitBlockW> vblocks;
+    MergerW v_merger;
+    std::vector<MergerW> v_ds_mergers;
+    int v_loaded = 0;
+
+    // decode buffers
+    float *x_dec = nullptr, *qkv_dec = nullptr, *attn_dec = nullptr, *act_dec = nullptr, *logits = nullptr;
+    float *part_o = nullptr, *part_ml = nullptr, *part_val = nullptr;
+    int* part_idx = nullptr;
+    unsigned int *counters = nullptr, *ticket = nullptr;
+    SeqState* state = nullptr;
+    uint32_t* out_tokens = nullptr;
+    int out_cap = 8192;
+    int* block_table = nullptr;
+    SeqState* h_state = nullptr;      // pinned
+    uint32_t* h_tokens = nullptr;     // pinned
+    // prefill workspaces (grown on demand)
+    int ws_S = 0;
+    float *x = nullptr, *qkv = nullptr;
+    bf16 *xn = nullptr, *q_bf = nullptr, *attn_bf = nullptr, *act_bf = nullptr;
+    uint32_t* ids_dev = nullptr;
+    int* pos3_dev = nullptr;
+    int* rows_dev = nullptr;
+    float* embeds_in = nullptr;
+    // vision workspaces
+    int vws_N = 0;
+    float *v_x = nullptr, *v_qkv = nullptr, *v_pv = nullptr, *v_cos = nullptr, *v_sin = nullptr, *v_w4 = nullptr;
+    bf16 *v_pvb = nullptr, *v_xn = nullptr, *v_qkvb = nullptr, *v_attn = nullptr, *v_act = nullptr, *v_m1 = nullptr;
+    int *v_idx4 = nullptr, *v_seq_start = nullptr, *v_seq_len = nullptr;
+    float* img_embeds = nullptr;      // [n_img_tok, v_out]
+    float* ds_embeds = nullptr;       // [n_ds, n_img_tok, v_out]
+    int img_tokens = 0;
+
+    // host state
+    size_t kv_len = 0;
+    uint32_t next_mrope_pos = 0;
+    cudaGraphExec_t graph_step[2] = {nullptr, nullptr};   // [advance]
+    bool graph_failed = false;
+    cudaEvent_t pev0 = nullptr, pev1 = nullptr, dev0 = nullptr, dev1 = nullptr;
+    bool pev0_armed = false;
+    float last_prefill_ms = 0.f, last_decode_ms = 0.f;
+    size_t last_decode_steps = 0;
+    uint64_t launches = 0;
+    std::string last_error;
+
+    // ---------------------------------------------------------------------------------------------
+    template <typename T>
+    T* dalloc(size_t n) {
+        void* p = nullptr;
+        CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        allocs.push_back(p);
+        return (T*)p;
+    }
+    void dfree(void* p) {
+        if (!p) return;
+        auto it = std::find(allocs.begin(), allocs.end(), p);
+        if (it != allocs.end()) allocs.erase(it);
+        cudaFree(p);
+    }
+    int qkv_dim() const { return (nh + 2 * nkv) * D; }
+    int q_dim() const { return nh * D; }
+
+    void parse_config(const char* json);
+    void alloc_weights();
+    void load_tensor(const std::string& name, int dt, const int64_t* shape, int ndim, const void* data);
+    bool load_text_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
+    bool load_vision_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
+    void finalize();
+    void ensure_prefill_ws(int S);
+    void ensure_vision_ws(int N);
+
+    void up_bf16(bf16* dst, const void* data, int dt, size_t n) {
+        std::vector<uint16_t> tmp;
+        to_bf16(data, dt, n, tmp);
+        CUDA_OK(cudaMemcpy(dst, tmp.data(), n * 2, cudaMemcpyHostToDevice));
+    }
+    void up_f32(float* dst, const void* data, int dt, size_t n) {
+        std::vector<float> tmp;
+        to_f32(data, dt, n, tmp);
+        CUDA_OK(cudaMemcpy(dst, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+
+    // forward paths
+    void arm_state(uint32_t token, size_t start_pos, int p0, int p1, int p2);
+    void enqueue_decode_step(int advance, bool with_embed);
+    void decode_step_graphed(int advance);
+    void prefill(const uint32_t* ids, const float* embeds, size_t S, const uint32_t* pos3_host, size_t start_pos,
+                 const int* vis_rows, int n_vis, int advance);
+    void lm_head_last_row(const float* xrow, int advance);
+    void encode_images(const float* pv, const uint32_t* grid, size_t n_images);
+    void gemm(const bf16* A, int lda, const bf16* W, int M, int N, int K, int mode, void* out, int ldo, const float* bias) {
+        GemmEpi ep{out, ldo, bias, mode};
+        LAUNCH_OK(gemm_bf16_launch(stream, A, lda, W, M, N, K, ep, use_simt));
+        ++launches;
+    }
+};
+
+// =================================================================================================
+// configuration
+// =================================================================================================
+void crane_b200_model::parse_config(const char* json) {
+    cbjson::Value root = cbjson::Parser(json).parse();
+    if (root.type != cbjson::Value::OBJ) fail(CRANE_B200_INVALID_ARG, "config must be a JSON object");
+    const cbjson::Value& tc = root.has("text_config") ? root.at("text_config") : root;
+    is_vl = root.has("vision_config");
+    V = (int)tc.integer("vocab_size");
+    H = (int)tc.integer("hidden_size");
+    I = (int)tc.integer("intermediate_size");
+    L = (int)tc.integer("num_hidden_layers");
+    nh = (int)tc.integer("num_attention_heads");
+    nkv = (int)tc.integer("num_key_value_heads");
+    D = (int)tc.integer("head_dim", H / nh);
+    eps = (float)tc.number("rms_norm_eps", 1e-6);
+    theta = tc.number("rope_theta", 1000000.0);
+    if (tc.has("rope_parameters") && tc.at("rope_parameters").has("rope_theta")) theta = tc.at("rope_parameters").number("rope_theta", theta);
+    tied = root.boolean("tie_word_embeddings", tc.boolean("tie_word_embeddings", true));
+    const cbjson::Value* rs = tc.has("rope_scaling") ? &tc.at("rope_scaling") : (tc.has("rope_parameters") ? &tc.at("rope_parameters") : nullptr);
+    if (rs && rs->has("mrope_section"))
+        for (const auto& v : rs->at("mrope_section").arr) mrope_section.push_back((int)v.num);
+    if (tc.boolean("attention_bias", false)) fail(CRANE_B200_UNSUPPORTED, "attention_bias=true is not supported");
+    if (!tc.boolean("use_qk_norm", true)) fail(CRANE_B200_UNSUPPORTED, "use_qk_norm=false is not supported");
+    if (D != 128 && D != 256) fail(CRANE_B200_UNSUPPORTED, "head_dim %d (supported: 128, 256)", D);
+    if (nh % nkv) fail(CRANE_B200_INVALID_ARG, "num_attention_heads %% num_key_value_heads != 0");
+    if (H % 256 || I % 256) fail(CRANE_B200_UNSUPPORTED, "hidden/intermediate sizes must be multiples of 256");
+    if (root.has("engine")) {
+        const cbjson::Value& e = root.at("engine");
+        max_seq = (int)e.integer("max_seq_len", max_seq);
+        max_batch = (int)e.integer("max_batch", max_batch);
+        use_simt = e.string("gemm", "tcgen05") == "simt";
+        use_graphs = e.boolean("graphs", true);
+        use_pdl = e.boolean("pdl", true);
+        if (e.string("vit_act", "erf") == "tanh") vit_gelu_mode = EPI_GELU_TANH_BF16;
+        if (e.string("merger_act", "tanh") == "erf") merger_gelu_mode = EPI_GELU_ERF_BF16;
+    }
+    if (const char* g = getenv("CRANE_B200_GEMM")) use_simt = std::string(g) == "simt";
+    if (const char* g = getenv("CRANE_B200_GRAPHS")) use_graphs = std::string(g) != "0";
+    if (const char* g = getenv("CRANE_B200_PDL")) use_pdl = std::string(g) != "0";
+    if (max_batch != 1) fail(CRANE_B200_UNSUPPORTED, "max_batch %d: only 1 sequence per handle in this build", max_batch);
+    max_seq = (max_seq + KV_PAGE - 1) / KV_PAGE * KV_PAGE;
+    max_pages = max_seq / KV_PAGE;
+    if (is_vl) {
+        const cbjson::Value& vc = root.at("vision_config");
+        v_depth = (int)vc.integer("depth");
+        v_H = (int)vc.integer("hidden_size");
+        v_I = (int)vc.integer("intermediate_size");
+        v_nh = (int)vc.integer("num_heads");
+        v_hd = v_H / v_nh;
+        v_patch = (int)vc.integer("patch_size", 16);
+        v_merge = (int)vc.integer("spatial_merge_size", 2);
+        v_tpatch = (int)vc.integer("temporal_patch_size", 2);
+        v_in = (int)vc.integer("in_channels", 3);
+        v_out = (int)vc.integer("out_hidden_size");
+        v_npos = (int)vc.integer("num_position_embeddings", 2304);
+        v_side = (int)std::lround(std::sqrt((double)v_npos));
+        if (v_side * v_side != v_npos) fail(CRANE_B200_INVALID_ARG, "num_position_embeddings %d is not a perfect square", v_npos);
+        if (vc.has("deepstack_visual_indexes"))
+            for (const auto& v : vc.at("deepstack_visual_indexes").arr) v_deepstack.push_back((int)v.num);
+        if (v_out != H) fail(CRANE_B200_INVALID_ARG, "vision out_hidden_size %d != text hidden_size %d", v_out, H);
+        if (v_hd != 64 && v_hd != 128) fail(CRANE_B200_UNSUPPORTED, "vision head_dim %d", v_hd);
+        image_token_id = (uint32_t)root.integer("image_token_id", 151655);
+        if ((int)v_deepstack.size() > L) fail(CRANE_B200_INVALID_ARG, "more deepstack levels than decoder layers");
+    }
+}
+
+void crane_b200_model::alloc_weights() {
+    embed = dalloc<bf16>((size_t)V * H);
+    lm_head = tied ? embed : dalloc<bf16>((size_t)V * H);
+    final_norm = dalloc<float>(H);
+    layers.resize(L);
+    for (auto& l : layers) {
+        l.wqkv = dalloc<bf16>((size_t)qkv_dim() * H);
+        l.wo = dalloc<bf16>((size_t)H * q_dim());
+        l.wgu = dalloc<bf16>((size_t)2 * I * H);
+        l.wdown = dalloc<bf16>((size_t)H * I);
+        l.ln1 = dalloc<float>(H); l.ln2 = dalloc<float>(H);
+        l.qn = dalloc<float>(D); l.kn = dalloc<float>(D);
+    }
+    if (is_vl) {
+        const int pk = v_in * v_tpatch * v_patch * v_patch, mh = v_H * v_merge * v_merge;
+        v_wpatch = dalloc<bf16>((size_t)v_H * pk);
+        v_bpatch = dalloc<float>(v_H);
+        v_pos = dalloc<float>((size_t)v_npos * v_H);
+        vblocks.resize(v_depth);
+        for (auto& b : vblocks) {
+            b.n1w = dalloc<float>(v_H); b.n1b = dalloc<float>(v_H); b.n2w = dalloc<float>(v_H); b.n2b = dalloc<float>(v_H);
+            b.wqkv = dalloc<bf16>((size_t)3 * v_H * v_H); b.bqkv = dalloc<float>(3 * v_H);
+            b.wproj = dalloc<bf16>((size_t)v_H * v_H); b.bproj = dalloc<float>(v_H);
+            b.wfc1 = dalloc<bf16>((size_t)v_I * v_H); b.bfc1 = dalloc<float>(v_I);
+            b.wfc2 = dalloc<bf16>((size_t)v_H * v_I); b.bfc2 = dalloc<float>(v_H);
+        }
+        auto mk = [&](MergerW& m, bool post) {
+            m.post = post;
+            const int nd = post ? mh : v_H;
+            m.nw = dalloc<float>(nd); m.nb = dalloc<float>(nd);
+            m.w1 = dalloc<bf16>((size_t)mh * mh); m.b1 = dalloc<float>(mh);
+            m.w2 = dalloc<bf16>((size_t)v_out * mh); m.b2 = dalloc<float>(v_out);
+        };
+        mk(v_merger, false);
+        v_ds_mergers.resize(v_deepstack.size());
+        for (auto& m : v_ds_mergers) mk(m, true);
+    }
+}
+
+// =================================================================================================
+// weight registration
+// =================================================================================================
+static void want_shape(const std::string& name, const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
+    size_t n = 1, w = 1;
+    for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+    for (auto v : want) w *= (size_t)v;
+    bool ok = (n == w);
+    if (ok && ndim == (int)want.size()) {
+        int i = 0;
+        for (auto v : want) ok = ok && (shape[i++] == v);
+    }
+    if (!ok) {
+        std::string got;
+        for (int i = 0; i < ndim; ++i) got += (i ? "x" : "") + std::to_string(shape[i]);
+        std::string exp;
+        for (auto v : want) exp += (exp.empty() ? "" : "x") + std::to_string(v);
+        fail(CRANE_B200_INVALID_ARG, "tensor %s: shape %s, expected %s", name.c_str(), got.c_str(), exp.c_str());
+    }
+}
+
+bool crane_b200_model::load_text_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data) {
+    if (n == "embed_tokens.weight") {
+        want_shape(n, shape, ndim, {V, H});
+        up_bf16(embed, data, dt, (size_t)V * H);
+        got_embed = true;
+        return true;
+    }
+    if (n == "norm.weight") {
+        want_shape(n, shape, ndim, {H});
+        up_f32(final_norm, data, dt, H);
+        got_final_norm = true;
+        return true;
+    }
+    if (n.rfind("layers.", 0) != 0) return false;
+    const size_t dot = n.find('.', 7);
+    if (dot == std::string::npos) return false;
+    const int li = std::atoi(n.substr(7, dot - 7).c_str());
+    if (li < 0 || li >= L) fail(CRANE_B200_INVALID_ARG, "tensor %s: layer index out of range", n.c_str());
+    const std::string t = n.substr(dot + 1);
+    LayerW& l = layers[li];
+    const int qd = q_dim(), kvd = nkv * D;
+    auto rows_bf16 = [&](bf16* dst, int rows, int cols) { up_bf16(dst, data, dt, (size_t)rows * cols); };
+    if (t == "self_attn.q_proj.weight") { want_shape(n, shape, ndim, {qd, H}); rows_bf16(l.wqkv, qd, H); l.loaded |= 1; }
+    else if (t == "self_attn.k_proj.weight") { want_shape(n, shape, ndim, {kvd, H}); rows_bf16(l.wqkv + (size_t)qd * H, kvd, H); l.loaded |= 2; }
+    else if (t == "self_attn.v_proj.weight") { want_shape(n, shape, ndim, {kvd, H}); rows_bf16(l.wqkv + (size_t)(qd + kvd) * H, kvd, H); l.loaded |= 4; }
+    else if (t == "self_attn.o_proj.weight") { want_shape(n, shape, ndim, {H, qd}); rows_bf16(l.wo, H, qd); l.loaded |= 8; }
+    else if (t == "mlp.gate_proj.weight" || t == "mlp.up_proj.weight") {
+        // merged gate/up with rows interleaved (gate_j, up_j) so SiLU(gate)*up fuses into the GEMV/GEMM epilogue
+        want_shape(n, shape, ndim, {I, H});
+        std::vector<uint16_t> tmp;
+        to_bf16(data, dt, (size_t)I * H, tmp);
+        const bool up = (t == "mlp.up_proj.weight");
+        CUDA_OK(cudaMemcpy2D(l.wgu + (up ? H : 0), (size_t)2 * H * 2, tmp.data(), (size_t)H * 2, (size_t)H * 2, I, cudaMemcpyHostToDevice));
+        l.loaded |= up ? 32 : 16;
+    }
+    else if (t == "mlp.down_proj.weight") { want_shape(n, shape, ndim, {H, I}); rows_bf16(l.wdown, H, I); l.loaded |= 64; }
+    else if (t == "input_layernorm.weight") { want_shape(n, shape, ndim, {H}); up_f32(l.ln1, data, dt, H); l.loaded |= 128; }
+    else if (t == "post_attention_layernorm.weight") { want_shape(n, shape, ndim, {H}); up_f32(l.ln2, data, dt, H); l.loaded |= 256; }
+    else if (t == "self_attn.q_norm.weight") { want_shape(n, shape, ndim, {D}); up_f32(l.qn, data, dt, D); l.loaded |= 512; }
+    else if (t == "self_attn.k_norm.weight") { want_shape(n, shape, ndim, {D}); up_f32(l.kn, data, dt, D); l.loaded |= 1024; }
+    else return false;
+    return true;
+}
+
+bool crane_b200_model::load_vision_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data) {
+    if (!is_vl) fail(CRANE_B200_INVALID_ARG, "vision tensor %s for a text-only config", n.c_str());
+    const int pk = v_in * v_tpatch * v_patch * v_patch, mh = v_H * v_merge * v_merge;
+    size_t numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= (size_t)shape[i];
+    if (n == "patch_embed.proj.weight") { want_shape(n, shape, ndim, {v_H, v_in, v_tpatch, v_patch, v_patch}); up_bf16(v_wpatch, data, dt, (size_t)v_H * pk); v_loaded |= 1; return true; }
+    if (n == "patch_embed.proj.bias") { want_shape(n, shape, ndim, {v_H}); up_f32(v_bpatch, data, dt, v_H); v_loaded |= 2; return true; }
+    if (n == "pos_embed.weight") { want_shape(n, shape, ndim, {v_npos, v_H}); up_f32(v_pos, data, dt, (size_t)v_npos * v_H); v_loaded |= 4; return true; }
+    auto merger_tensor = [&](MergerW& m, const std::string& t) -> bool {
+        const int nd = m.post ? mh : v_H;
+        if (t == "norm.weight") { want_shape(n, shape, ndim, {nd}); up_f32(m.nw, data, dt, nd); m.loaded |= 1; }
+        else if (t == "norm.bias") { want_shape(n, shape, ndim, {nd}); up_f32(m.nb, data, dt, nd); m.loaded |= 2; }
+        else if (t == "linear_fc1.weight") { want_shape(n, shape, ndim, {mh, mh}); up_bf16(m.w1, data, dt, (size_t)mh * mh); m.loaded |= 4; }
+        else if (t == "linear_fc1.bias") { want_shape(n, shape, ndim, {mh}); up_f32(m.b1, data, dt, mh); m.loaded |= 8; }
+        else if (t == "linear_fc2.weight") { want_shape(n, shape, ndim, {v_out, mh}); up_bf16(m.w2, data, dt, (size_t)v_out * mh); m.loaded |= 16; }
+        else if (t == "linear_fc2.bias") { want_shape(n, shape, ndim, {v_out}); up_f32(m.b2, data, dt, v_out); m.loaded |= 32; }
+        else return false;
+        return true;
+    };
+    if (n.rfind("merger.", 0) == 0) return merger_tensor(v_merger, n.substr(7));
+    if (n.rfind("deepstack_merger_list.", 0) == 0) {
+        const size_t dot = n.find('.', 22);
+        const int j = std::atoi(n.substr(22, dot - 22).c_str());
+        if (j < 0 || j >= (int)v_ds_mergers.size()) fail(CRANE_B200_INVALID_ARG, "tensor %s: merger index out of range", n.c_str());
+        return merger_tensor(v_ds_mergers[j], n.substr(dot + 1));
+    }
+    if (n.rfind("blocks.", 0) != 0) return false;
+    const size_t dot = n.find('.', 7);
+    const int bi = std::atoi(n.substr(7, dot - 7).c_str());
+    if (bi < 0 || bi >= v_depth) fail(CRANE_B200_INVALID_ARG, "tensor %s: block index out of range", n.c_str());
+    const std::string t = n.substr(dot + 1);
+    VitBlockW& b = vblocks[bi];
+    if (t == "norm1.weight") { want_shape(n, shape, ndim, {v_H}); up_f32(b.n1w, data, dt, v_H); b.loaded |= 1; }
+    else if (t == "norm1.bias") { want_shape(n, shape, ndim, {v_H}); up_f32(b.n1b, data, dt, v_H); b.loaded |= 2; }
+    else if (t == "norm2.weight") { want_shape(n, shape, ndim, {v_H}); up_f32(b.n2w, data, dt, v_H); b.loaded |= 4; }
+    else if (t == "norm2.bias") { want_shape(n, shape, ndim, {v_H}); up_f32(b.n2b, data, dt, v_H); b.loaded |= 8; }
+    else if (t == "attn.qkv.weight") { want_shape(n, shape, ndim, {3 * v_H, v_H}); up_bf16(b.wqkv, data, dt, (size_t)3 * v_H * v_H); b.loaded |= 16; }
+    else if (t == "attn.qkv.bias") { want_shape(n, shape, ndim, {3 * v_H}); up_f32(b.bqkv, data, dt, 3 * v_H); b.loaded |= 32; }
+    else if (t == "attn.proj.weight") { want_shape(n, shape, ndim, {v_H, v_H}); up_bf16(b.wproj, data, dt, (size_t)v_H * v_H); b.loaded |= 64; }
+    else if (t == "attn.proj.bias") { want_shape(n, shape, ndim, {v_H}); up_f32(b.bproj, data, dt, v_H); b.loaded |= 128; }
+    else if (t == "mlp.linear_fc1.weight") { want_shape(n, shape, ndim, {v_I, v_H}); up_bf16(b.wfc1, data, dt, (size_t)v_I * v_H); b.loaded |= 256; }
+    else if (t == "mlp.linear_fc1.bias") { want_shape(n, shape, ndim, {v_I}); up_f32(b.bfc1, data, dt, v_I); b.loaded |= 512; }
+    else if (t == "mlp.linear_fc2.weight") { want_shape(n, shape, ndim, {v_H, v_I}); up_bf16(b.wfc2, data, dt, (size_t)v_H * v_I); b.loaded |= 1024; }
+    else if (t == "mlp.linear_fc2.bias") { want_shape(n, shape, ndim, {v_H}); up_f32(b.bfc2, data, dt, v_H); b.loaded |= 2048; }
+    else return false;
+    (void)numel;
+    return true;
+}
+
+void crane_b200_model::load_tensor(const std::string& name, int dt, const int64_t* shape, int ndim, const void* data) {
+    if (finalized) fail(CRANE_B200_INVALID_ARG, "load_tensor after finalize");
+    if (dt < 0 || dt > 2) fail(CRANE_B200_INVALID_ARG, "tensor %s: unknown dtype %d", name.c_str(), dt);
+    CUDA_OK(cudaSetDevice(device));
+    static const char* vis_prefix[] = {"model.visual.", "visual."};
+    for (const char* p : vis_prefix)
+        if (name.rfind(p, 0) == 0) {
+            if (!load_vision_tensor(name.substr(std::strlen(p)), dt, shape, ndim, data))
+                fail(CRANE_B200_INVALID_ARG, "unknown vision tensor %s", name.c_str());
+            return;
+        }
+    if (name == "lm_head.weight") {
+        want_shape(name, shape, ndim, {V, H});
+        if (!tied) { up_bf16(lm_head, data, dt, (size_t)V * H); got_lm_head = true; }
+        return;   // tied checkpoints may still carry a copy: ignored, as the reference does (qwen3/modeling.rs:786-794)
+    }
+    static const char* txt_prefix[] = {"model.language_model.", "language_model.model.", "language_model.", "model."};
+    for (const char* p : txt_prefix)
+        if (name.rfind(p, 0) == 0) {
+            if (!load_text_tensor(name.substr(std::strlen(p)), dt, shape, ndim, data))
+                fail(CRANE_B200_INVALID_ARG, "unknown tensor %s", name.c_str());
+            return;
+        }
+    fail(CRANE_B200_INVALID_ARG, "unknown tensor %s", name.c_str());
+}
+
+// =================================================================================================
+// finalize: tables, KV pages, decode buffers
+// =================================================================================================
+void crane_b200_model::finalize() {
+    if (finalized) return;
+    CUDA_OK(cudaSetDevice(device));
+    if (!got_embed) fail(CRANE_B200_NOT_LOADED, "missing tensor embed_tokens.weight");
+    if (!got_final_norm) fail(CRANE_B200_NOT_LOADED, "missing tensor norm.weight");
+    if (!tied && !got_lm_head) fail(CRANE_B200_NOT_LOADED, "missing tensor lm_head.weight");
+    for (int i = 0; i < L; ++i)
+        if (layers[i].loaded != 2047) fail(CRANE_B200_NOT_LOADED, "layer %d: missing tensors (mask 0x%x)", i, layers[i].loaded);
+    if (is_vl) {
+        if (v_loaded != 7) fail(CRANE_B200_NOT_LOADED, "vision stem: missing tensors (mask 0x%x)", v_loaded);
+        for (int i = 0; i < v_depth; ++i)
+            if (vblocks[i].loaded != 4095) fail(CRANE_B200_NOT_LOADED, "vision block %d: missing tensors (mask 0x%x)", i, vblocks[i].loaded);
+        if (v_merger.loaded != 63) fail(CRANE_B200_NOT_LOADED, "vision merger: missing tensors");
+        for (auto& m : v_ds_mergers)
+            if (m.loaded != 63) fail(CRANE_B200_NOT_LOADED, "deepstack merger: missing tensors");
+    }
+    // RotaryEmbedding::new (modules/rotary.rs:29-46): inv_freq f64 -> f32, freqs = pos_f32 * inv_freq (f32), cos/sin f32
+    const int half = D / 2, rows = max_seq + 1;
+    std::vector<float> inv(half), ct((size_t)rows * half), st((size_t)rows * half);
+    for (int i = 0; i < half; ++i) inv[i] = (float)(1.0 / std::pow(theta, (double)(2 * i) / (double)D));
+    for (int p = 0; p < rows; ++p)
+        for (int i = 0; i < half; ++i) {
+            const float f = (float)p * inv[i];
+            ct[(size_t)p * half + i] = cosf(f);
+            st[(size_t)p * half + i] = sinf(f);
+        }
+    cos_tab = dalloc<float>(ct.size());
+    sin_tab = dalloc<float>(st.size());
+    CUDA_OK(cudaMemcpy(cos_tab, ct.data(), ct.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(sin_tab, st.data(), st.size() * 4, cudaMemcpyHostToDevice));
+    // interleaved-MRoPE column ownership (qwen3_5/modeling.rs:203-233)
+    std::vector<unsigned char> ax(half, 0);
+    for (int dim = 1; dim <= 2; ++dim) {
+        const int sec = dim < (int)mrope_section.size() ? mrope_section[dim] : 0;
+        for (int i = dim; i < std::min(sec * 3, half); i += 3) ax[i] = (unsigned char)dim;
+    }
+    axis_of = dalloc<unsigned char>(half);
+    CUDA_OK(cudaMemcpy(axis_of, ax.data(), half, cudaMemcpyHostToDevice));
+
+    const size_t page_elems = (size_t)nkv * KV_PAGE * D;
+    for (auto& l : layers) {
+        l.k_pool = dalloc<bf16>((size_t)max_pages * page_elems);
+        l.v_pool = dalloc<bf16>((size_t)max_pages * page_elems);
+    }
+    std::vector<int> bt(max_pages);
+    for (int i = 0; i < max_pages; ++i) bt[i] = i;   // one sequence per handle: identity page table
+    block_table = dalloc<int>(max_pages);
+    CUDA_OK(cudaMemcpy(block_table, bt.data(), max_pages * sizeof(int), cudaMemcpyHostToDevice));
+
+    const int B = max_batch;
+    x_dec = dalloc<float>((size_t)B * H);
+    qkv_dec = dalloc<float>((size_t)B * qkv_dim());
+    attn_dec = dalloc<float>((size_t)B * q_dim());
+    act_dec = dalloc<float>((size_t)B * I);
+    logits = dalloc<float>((size_t)B * V);
+    part_o = dalloc<float>((size_t)B * nh * ATTN_NSPLIT * D);
+    part_ml = dalloc<float>((size_t)B * nh * ATTN_NSPLIT * 2);
+    part_val = dalloc<float>((size_t)B * num_sms);
+    part_idx = dalloc<int>((size_t)B * num_sms);
+    counters = dalloc<unsigned int>((size_t)B * nkv);
+    ticket = dalloc<unsigned int>(1);
+    state = dalloc<SeqState>(B);
+    out_tokens = dalloc<uint32_t>((size_t)B * out_cap);
+    CUDA_OK(cudaMemset(counters, 0, (size_t)B * nkv * sizeof(unsigned int)));
+    CUDA_OK(cudaMemset(ticket, 0, sizeof(unsigned int)));
+    CUDA_OK(cudaMemset(state, 0, B * sizeof(SeqState)));
+    CUDA_OK(cudaMallocHost((void**)&h_state, sizeof(SeqState) * B));
+    CUDA_OK(cudaMallocHost((void**)&h_tokens, sizeof(uint32_t) * out_cap));
+    CUDA_OK(cudaEventCreate(&pev0));
+    CUDA_OK(cudaEventCreate(&pev1));
+    CUDA_OK(cudaEventCreate(&dev0));
+    CUDA_OK(cudaEventCreate(&dev1));
+    CUDA_OK(cudaDeviceSynchronize());
+    finalized = true;
+}
+
+void crane_b200_model::ensure_prefill_ws(int S) {
+    if (S <= ws_S) return;
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (void* p : {(void*)x, (void*)qkv, (void*)xn, (void*)q_bf, (void*)attn_bf, (void*)act_bf, (void*)ids_dev, (void*)pos3_dev,
+                    (void*)rows_dev, (void*)embeds_in})
+        dfree(p);
+    const int cap = (S + 127) / 128 * 128;
+    x = dalloc<float>((size_t)cap * H);
+    qkv = dalloc<float>((size_t)cap * qkv_dim());
+    xn = dalloc<bf16>((size_t)cap * H);
+    q_bf = dalloc<bf16>((size_t)cap * q_dim());
+    attn_bf = dalloc<bf16>((size_t)cap * q_dim());
+    act_bf = dalloc<bf16>((size_t)cap * I);
+    ids_dev = dalloc<uint32_t>(cap);
+    pos3_dev = dalloc<int>((size_t)3 * cap);
+    rows_dev = dalloc<int>(cap);
+    embeds_in = dalloc<float>((size_t)cap * H);
+    ws_S = cap;
+}
+
+// =================================================================================================
+// decode step
+// =================================================================================================
+void crane_b200_model::arm_state(uint32_t token, size_t start_pos, int p0, int p1, int p2) {
+    h_state[0].kv_len = (int)start_pos;
+    h_state[0].pos[0] = p0; h_state[0].pos[1] = p1; h_state[0].pos[2] = p2;
+    h_state[0].token = token;
+    h_state[0].step = 0;
+    CUDA_OK(cudaMemcpyAsync(state, h_state, sizeof(SeqState), cudaMemcpyHostToDevice, stream));
+}
+
+void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
+    const int B = 1;
+    const bool pdl = use_pdl;
+    if (with_embed) { LAUNCH_OK(embed_decode_launch(stream, B, embed, H, state, x_dec, false)); ++launches; }
+    for (int li = 0; li < L; ++li) {
+        LayerW& l = layers[li];
+        GemvArgs g = {};
+        g.W = l.wqkv; g.N = qkv_dim(); g.K = H; g.x = x_dec; g.ldx = H; g.norm_w = l.ln1; g.eps = eps; g.y = qkv_dec; g.ldy = qkv_dim();
+        LAUNCH_OK(gemv_launch(stream, B, GEMV_STORE, true, g, num_sms, pdl));
+        AttnDecArgs a = {};
+        a.qkv = qkv_dec; a.q_norm_w = l.qn; a.k_norm_w = l.kn; a.eps = eps; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.axis_of = axis_of;
+        a.state = state; a.block_table = block_table; a.max_pages = max_pages; a.k_pool = l.k_pool; a.v_pool = l.v_pool;
+        a.nh = nh; a.nkv = nkv; a.scale = 1.0f / std::sqrt((float)D);
+        a.part_o = part_o; a.part_ml = part_ml; a.counters = counters; a.out = attn_dec;
+        LAUNCH_OK(attn_decode_launch(stream, B, D, a, pdl));
+        GemvArgs o = {};
+        o.W = l.wo; o.N = H; o.K = q_dim(); o.x = attn_dec; o.ldx = q_dim(); o.y = x_dec; o.ldy = H;
+        LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
+        GemvArgs gu = {};
+        gu.W = l.wgu; gu.N = 2 * I; gu.K = H; gu.x = x_dec; gu.ldx = H; gu.norm_w = l.ln2; gu.eps = eps; gu.y = act_dec; gu.ldy = I;
+        LAUNCH_OK(gemv_launch(stream, B, GEMV_SILU_MUL, true, gu, num_sms, pdl));
+        GemvArgs dn = {};
+        dn.W = l.wdown; dn.N = H; dn.K = I; dn.x = act_dec; dn.ldx = I; dn.y = x_dec; dn.ldy = H;
+        LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, dn, num_sms, pdl));
+        launches += 5;
+    }
+    lm_head_last_row(x_dec, advance);
+}
+
+void crane_b200_model::lm_head_last_row(const float* xrow, int advance) {
+    GemvArgs h = {};
+    h.W = lm_head; h.N = V; h.K = H; h.x = xrow; h.ldx = H; h.norm_w = final_norm; h.eps = eps; h.y = logits; h.ldy = V;
+    h.part_val = part_val; h.part_idx = part_idx; h.ticket = ticket; h.state = state; h.out_tokens = out_tokens; h.out_stride = out_cap;
+    h.embed = embed; h.x_next = x_dec; h.H = H; h.advance = advance;
+    LAUNCH_OK(gemv_launch(stream, 1, GEMV_LOGITS_ARGMAX, true, h, num_sms, use_pdl));
+    ++launches;
+}
+
+// One decode step (layers + lm_head), replayed from a CUDA graph when capture is available.
+void crane_b200_model::decode_step_graphed(int advance) {
+    if (use_graphs && !graph_failed && graph_step[advance] == nullptr) {
+        cudaGraph_t g = nullptr;
+        const uint64_t before = launches;
+        cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
+        bool ok = (e == cudaSuccess);
+        if (ok) {
+            try { enqueue_decode_step(advance, false); } catch (const EngineError&) { ok = false; }
+            e = cudaStreamEndCapture(stream, &g);
+            ok = ok && e == cudaSuccess && g != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&graph_step[advance], g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        launches = before;
+        if (!ok) { graph_failed = true; graph_step[advance] = nullptr; cudaGetLastError(); }
+    }
+    if (graph_step[advance]) {
+        CUDA_OK(cudaGraphLaunch(graph_step[advance], stream));
+        launches += (uint64_t)5 * L + 1;
+    } else {
+        enqueue_decode_step(advance, false);
+    }
+}
+
+// =================================================================================================
+// prefill (S > 1) -- `Qwen3Model::decode` body for a chunk of S tokens
+// =================================================================================================
+void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t S_, const uint32_t* pos3_host, size_t start_pos,
+                               const int* vis_rows, int n_vis, int advance) {
+    const int S = (int)S_;
+    ensure_prefill_ws(S);
+    if (!pev0_armed) CUDA_OK(cudaEventRecord(pev0, stream));
+    pev0_armed = false;
+    // positions [3, S]
+    std::vector<int> p3((size_t)3 * S);
+    for (int a = 0; a < 3; ++a)
+        for (int s = 0; s < S; ++s) p3[(size_t)a * S + s] = pos3_host ? (int)pos3_host[(size_t)a * S + s] : (int)(start_pos + s);
+    for (int v : p3)
+        if (v < 0 || v > max_seq) fail(CRANE_B200_INVALID_ARG, "rotary position %d outside the table (max_seq_len %d)", v, max_seq);
+    CUDA_OK(cudaMemcpyAsync(pos3_dev, p3.data(), p3.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (ids) {
+        CUDA_OK(cudaMemcpyAsync(ids_dev, ids, S * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        LAUNCH_OK(embed_rows_launch(stream, ids_dev, S, embed, H, x));
+        ++launches;
+    } else {
+        CUDA_OK(cudaMemcpyAsync(x, embeds, (size_t)S * H * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    if (n_vis > 0) {   // splice the image features over the placeholder rows (qwen3_5/vlm.rs:433-468)
+        CUDA_OK(cudaMemcpyAsync(rows_dev, vis_rows, n_vis * sizeof(int), cudaMemcpyHostToDevice, stream));
+        LAUNCH_OK(set_rows_launch(stream, x, H, rows_dev, n_vis, img_embeds, false));
+        ++launches;
+    }
+    CUDA_OK(cudaStreamSynchronize(stream));   // p3 / ids staging buffers are host stack/heap memory
+
+    const int qd = q_dim();
+    for (int li = 0; li < L; ++li) {
+        LayerW& l = layers[li];
+        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln1, eps, xn));
+        gemm(xn, H, l.wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
+        RopeAppendArgs ra = {};
+        ra.qkv = qkv; ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
+        ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = block_table; ra.k_pool = l.k_pool; ra.v_pool = l.v_pool;
+        ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf;
+        LAUNCH_OK(rope_append_launch(stream, D, ra));
+        FlashArgs fa = {};
+        fa.q = q_bf; fa.q_stride = qd; fa.k_pool = l.k_pool; fa.v_pool = l.v_pool; fa.block_table = block_table; fa.nh = nh; fa.nkv = nkv;
+        fa.out = attn_bf; fa.o_stride = qd; fa.S = S; fa.kv_offset = (int)start_pos; fa.scale = 1.0f / std::sqrt((float)D); fa.nseq = 1;
+        LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
+        gemm(attn_bf, qd, l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
+        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln2, eps, xn));
+        gemm(xn, H, l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr);
+        gemm(act_bf, I, l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
+        launches += 4;
+        if (n_vis > 0 && li < (int)v_deepstack.size()) {   // DeepStack (qwen3_vl/text.rs:262-268)
+            LAUNCH_OK(set_rows_launch(stream, x, H, rows_dev, n_vis, ds_embeds + (size_t)li * n_vis * H, true));
+            ++launches;
+        }
+    }
+    // state for the last-row lm_head / a following on-device decode loop
+    const int last_p[3] = {p3[(size_t)0 * S + S - 1], p3[(size_t)1 * S + S - 1], p3[(size_t)2 * S + S - 1]};
+    (void)last_p;
+    h_state[0].kv_len = (int)(start_pos + S - 1);   // lm_head(advance) bumps it to start_pos + S
+    h_state[0].pos[0] = h_state[0].pos[1] = h_state[0].pos[2] = (int)next_mrope_pos - 1;
+    h_state[0].token = 0;
+    h_state[0].step = 0;
+    CUDA_OK(cudaMemcpyAsync(state, h_state, sizeof(SeqState), cudaMemcpyHostToDevice, stream));
+    lm_head_last_row(x + (size_t)(S - 1) * H, advance);
+    CUDA_OK(cudaEventRecord(pev1, stream));
+    kv_len = start_pos + S;
+}
+
+// =================================================================================================
+// vision tower
+// =================================================================================================
+void crane_b200_model::ensure_vision_ws(int N) {
+    if (N <= vws_N) return;
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (void* p : {(void*)v_x, (void*)v_qkv, (void*)v_pv, (void*)v_cos, (void*)v_sin, (void*)v_w4, (void*)v_pvb, (void*)v_xn, (void*)v_qkvb,
+                    (void*)v_attn, (void*)v_act, (void*)v_m1, (void*)v_idx4, (void*)v_seq_start, (void*)v_seq_len, (void*)img_embeds,
+                    (void*)ds_embeds})
+        dfree(p);
+    const int cap = (N + 127) / 128 * 128;
+    const int pk = v_in * v_tpatch * v_patch * v_patch, mh = v_H * v_merge * v_merge, m2 = v_merge * v_merge;
+    v_x = dalloc<float>((size_t)cap * v_H);
+    v_qkv = dalloc<float>((size_t)cap * 3 * v_H);
+    v_pv = dalloc<float>((size_t)cap * pk);
+    v_cos = dalloc<float>((size_t)cap * (v_hd / 2));
+    v_sin = dalloc<float>((size_t)cap * (v_hd / 2));
+    v_w4 = dalloc<float>((size_t)4 * cap);
+    v_pvb = dalloc<bf16>((size_t)cap * pk);
+    v_xn = dalloc<bf16>((size_t)cap * v_H);
+    v_qkvb = dalloc<bf16>((size_t)cap * 3 * v_H);
+    v_attn = dalloc<bf16>((size_t)cap * v_H);
+    v_act = dalloc<bf16>((size_t)cap * v_I);
+    v_m1 = dalloc<bf16>((size_t)(cap / m2) * mh);
+    v_idx4 = dalloc<int>((size_t)4 * cap);
+    v_seq_start = dalloc<int>(cap);
+    v_seq_len = dalloc<int>(cap);
+    img_embeds = dalloc<float>((size_t)(cap / m2) * v_out);
+    ds_embeds = dalloc<float>((size_t)std::max<size_t>(v_deepstack.size(), 1) * (cap / m2) * v_out);
+    vws_N = cap;
+}
+
+void crane_b200_model::encode_images(const float* pv, const uint32_t* grid, size_t n_images) {
+    if (!is_vl) fail(CRANE_B200_UNSUPPORTED, "encode_images on a text-only model");
+    const int pk = v_in * v_tpatch * v_patch * v_patch, mh = v_H * v_merge * v_merge, m2 = v_merge * v_merge, half = v_hd / 2;
+    int N = 0;
+    for (size_t i = 0; i < n_images; ++i) {
+        const int t = grid[3 * i], h = grid[3 * i + 1], w = grid[3 * i + 2];
+        if (t < 1 || h < 1 || w < 1 || h % v_merge || w % v_merge) fail(CRANE_B200_INVALID_ARG, "bad grid_thw for image %zu", i);
+        N += t * h * w;
+    }
+    if (N == 0) fail(CRANE_B200_INVALID_ARG, "no patches");
+    ensure_vision_ws(N);
+    // ---- host index arithmetic: bilinear pos-embed corners (vision.rs:382-489), 2-D rotary table (:491-541),
+    //      per-frame sequence bounds (:543-556) ----
+    std::vector<int> idx4((size_t)4 * N), sstart, slen;
+    std::vector<float> w4((size_t)4 * N), cs((size_t)N * half), sn((size_t)N * half);
+    const int qdim = half / 2;   // rotary_pos_emb dim = head_dim/2 -> head_dim/4 frequencies per axis
+    std::vector<float> inv(qdim);
+    for (int i = 0; i < qdim; ++i) inv[i] = 1.0f / powf(10000.0f, (float)(2 * i) / (float)half);
+    int base = 0;
+    for (size_t im = 0; im < n_images; ++im) {
+        const int t = grid[3 * im], h = grid[3 * im + 1], w = grid[3 * im + 2];
+        auto lin = [&](int steps, std::vector<float>& out) {
+            out.resize(steps);
+            if (steps == 1) { out[0] = 0.f; return; }
+            const float step = (float)(v_side - 1) / (float)(steps - 1);
+            for (int i = 0; i < steps; ++i) out[i] = (float)i * step;
+        };
+        std::vector<float> hv, wv;
+        lin(h, hv); lin(w, wv);
+        int p = base;
+        for (int f = 0; f < t; ++f) {
+            sstart.push_back(base + f * h * w);
+            slen.push_back(h * w);
+            for (int br = 0; br < h / v_merge; ++br)
+                for (int bc = 0; bc < w / v_merge; ++bc)
+                    for (int ir = 0; ir < v_merge; ++ir)
+                        for (int ic = 0; ic < v_merge; ++ic, ++p) {
+                            const int r = br * v_merge + ir, c = bc * v_merge + ic;
+                            const int hf = (int)floorf(hv[r]), wf = (int)floorf(wv[c]);
+                            const int hc = std::min((int)ceilf(hv[r]), v_side - 1), wc = std::min((int)ceilf(wv[c]), v_side - 1);
+                            const float dh = hv[r] - (float)hf, dw = wv[c] - (float)wf;
+                            idx4[(size_t)0 * N + p] = hf * v_side + wf; w4[(size_t)0 * N + p] = (1.f - dh) * (1.f - dw);
+                            idx4[(size_t)1 * N + p] = hf * v_side + wc; w4[(size_t)1 * N + p] = (1.f - dh) * dw;
+                            idx4[(size_t)2 * N + p] = hc * v_side + wf; w4[(size_t)2 * N + p] = dh * (1.f - dw);
+                            idx4[(size_t)3 * N + p] = hc * v_side + wc; w4[(size_t)3 * N + p] = dh * dw;
+                            for (int i = 0; i < qdim; ++i) {
+                                const float fr = (float)r * inv[i], fc = (float)c * inv[i];
+                                cs[(size_t)p * half + i] = cosf(fr); sn[(size_t)p * half + i] = sinf(fr);
+                                cs[(size_t)p * half + qdim + i] = cosf(fc); sn[(size_t)p * half + qdim + i] = sinf(fc);
+                            }
+                        }
+        }
+        base += t * h * w;
+    }
+    const int nseq = (int)sstart.size();
+    int max_len = 0;
+    for (int v : slen) max_len = std::max(max_len, v);
+    CUDA_OK(cudaMemcpyAsync(v_pv, pv, (size_t)N * pk * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(v_idx4, idx4.data(), idx4.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(v_w4, w4.data(), w4.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(v_cos, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(v_sin, sn.data(), sn.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(v_seq_start, sstart.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(v_seq_len, slen.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream));
+    LAUNCH_OK(cast_f32_bf16_launch(stream, v_pv, v_pvb, (size_t)N * pk));
+    CUDA_OK(cudaStreamSynchronize(stream));   // host staging vectors go out of scope below
+
+    // patch embed: Conv3d(kernel == stride) == GEMM [N, C*T*P*P] x [Hv, C*T*P*P]^T + bias (vision.rs:46-58)
+    gemm(v_pvb, pk, v_wpatch, N, v_H, pk, EPI_STORE_F32, v_x, v_H, v_bpatch);
+    LAUNCH_OK(vit_pos_embed_add_launch(stream, v_x, N, v_H, v_pos, v_idx4, v_w4));
+    launches += 2;
+    const int Ng = N / m2;
+    auto run_merger = [&](MergerW& m, float* out) {
+        if (m.post) LAUNCH_OK(layernorm_rows_launch(stream, v_x, Ng, mh, m.nw, m.nb, 1e-6f, v_xn));
+        else LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, m.nw, m.nb, 1e-6f, v_xn));
+        gemm(v_xn, mh, m.w1, Ng, mh, mh, merger_gelu_mode, v_m1, mh, m.b1);
+        gemm(v_m1, mh, m.w2, Ng, v_out, mh, EPI_STORE_F32, out, v_out, m.b2);
+        ++launches;
+    };
+    for (int bi = 0; bi < v_depth; ++bi) {
+        VitBlockW& b = vblocks[bi];
+        LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, b.n1w, b.n1b, 1e-6f, v_xn));
+        gemm(v_xn, v_H, b.wqkv, N, 3 * v_H, v_H, EPI_STORE_F32, v_qkv, 3 * v_H, b.bqkv);
+        LAUNCH_OK(vit_rope_launch(stream, v_qkv, N, v_nh, v_hd, v_cos, v_sin, v_qkvb));
+        FlashArgs fa = {};
+        fa.q = v_qkvb; fa.q_stride = 3 * v_H; fa.k = v_qkvb + v_H; fa.v = v_qkvb + 2 * v_H; fa.kv_stride = 3 * v_H;
+        fa.nh = v_nh; fa.nkv = v_nh; fa.out = v_attn; fa.o_stride = v_H; fa.seq_start = v_seq_start; fa.seq_len = v_seq_len;
+        fa.scale = 1.0f / std::sqrt((float)v_hd); fa.nseq = nseq; fa.max_len = max_len;
+        LAUNCH_OK(flash_prefill_launch(stream, v_hd, false, false, fa));
+        gemm(v_attn, v_H, b.wproj, N, v_H, v_H, EPI_RESID_F32, v_x, v_H, b.bproj);
+        LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, b.n2w, b.n2b, 1e-6f, v_xn));
+        gemm(v_xn, v_H, b.wfc1, N, v_I, v_H, vit_gelu_mode, v_act, v_I, b.bfc1);
+        gemm(v_act, v_I, b.wfc2, N, v_H, v_I, EPI_RESID_F32, v_x, v_H, b.bfc2);
+        launches += 4;
+        for (size_t j = 0; j < v_deepstack.size(); ++j)
+            if (v_deepstack[j] == bi) run_merger(v_ds_mergers[j], ds_embeds + j * (size_t)Ng * v_out);
+    }
+    run_merger(v_merger, img_embeds);
+    img_tokens = Ng;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define API_BEGIN(m)                                   \
+    if (!(m)) return CRANE_B200_INVALID_ARG;           \
+    try {                                              \
+        cudaSetDevice((m)->device);
+#define API_END(m)                                     \
+    }                                                  \
+    catch (const EngineError& e) {                     \
+        (m)->last_error = e.msg;                       \
+        return e.code;                                 \
+    }                                                  \
+    catch (const std::exception& e) {                  \
+        (m)->last_error = e.what();                    \
+        return CRANE_B200_INVALID_ARG;                 \
+    }                                                  \
+    return CRANE_B200_OK;
+
+static void need_ready(crane_b200_model* m) {
+    if (!m->finalized) fail(CRANE_B200_NOT_LOADED, "model is not finalized");
+}
+static void fill_logits(crane_b200_model* m, crane_b200_logits* out) {
+    if (out) { out->device_ptr = m->logits; out->rows = 1; out->vocab = (size_t)m->V; out->stream = (void*)m->stream; }
+}
+static void check_room(crane_b200_model* m, size_t start_pos, size_t n) {
+    if (start_pos != m->kv_len) fail(CRANE_B200_INVALID_ARG, "start_pos %zu != cached length %zu", start_pos, m->kv_len);
+    if (start_pos + n > (size_t)m->max_seq) fail(CRANE_B200_OOM, "sequence length %zu exceeds max_seq_len %d", start_pos + n, m->max_seq);
+}
+
+extern "C" {
+
+int crane_b200_create(const char* config_json, int device_ordinal, crane_b200_model** out) {
+    if (!config_json || !out) { g_create_error = "null argument"; return CRANE_B200_INVALID_ARG; }
+    *out = nullptr;
+    std::unique_ptr<crane_b200_model> m(new crane_b200_model());
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            fail(CRANE_B200_CUDA_ERROR, "no CUDA device: %s (crane_b200 has no CPU fallback)", cudaGetErrorString(e));
+        if (device_ordinal < 0 || device_ordinal >= ndev) fail(CRANE_B200_INVALID_ARG, "device ordinal %d of %d", device_ordinal, ndev);
+        m->device = device_ordinal;
+        CUDA_OK(cudaSetDevice(device_ordinal));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device_ordinal));
+        if (prop.major != 10) fail(CRANE_B200_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+        m->num_sms = prop.multiProcessorCount;
+        m->parse_config(config_json);
+        CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->alloc_weights();
+    } catch (const EngineError& e) {
+        g_create_error = e.msg;
+        for (void* p : m->allocs) cudaFree(p);
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        for (void* p : m->allocs) cudaFree(p);
+        return CRANE_B200_INVALID_ARG;
+    }
+    *out = m.release();
+    return CRANE_B200_OK;
+}
+
+void crane_b200_destroy(crane_b200_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (auto& g : m->graph_step) if (g) cudaGraphExecDestroy(g);
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->h_state) cudaFreeHost(m->h_state);
+    if (m->h_tokens) cudaFreeHost(m->h_tokens);
+    for (cudaEvent_t e : {m->pev0, m->pev1, m->dev0, m->dev1}) if (e) cudaEventDestroy(e);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+const char* crane_b200_last_error(const crane_b200_model* m) { return m ? m->last_error.c_str() : g_create_error.c_str(); }
+
+int crane_b200_load_tensor(crane_b200_model* m, const char* name, int dtype, const int64_t* shape, int ndim, const void* data) {
+    API_BEGIN(m)
+    if (!name || !shape || !data || ndim < 1 || ndim > 8) fail(CRANE_B200_INVALID_ARG, "load_tensor: bad arguments");
+    m->load_tensor(name, dtype, shape, ndim, data);
+    API_END(m)
+}
+
+int crane_b200_finalize(crane_b200_model* m) {
+    API_BEGIN(m)
+    m->finalize();
+    API_END(m)
+}
+
+int crane_b200_forward_step(crane_b200_model* m, const uint32_t* ids, size_t n, size_t start_pos, crane_b200_logits* out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!ids || n == 0) fail(CRANE_B200_INVALID_ARG, "forward_step: empty input");
+    check_room(m, start_pos, n);
+    for (size_t i = 0; i < n; ++i)
+        if (ids[i] >= (uint32_t)m->V) fail(CRANE_B200_INVALID_ARG, "token id %u >= vocab %d", ids[i], m->V);
+    if (n == 1) {
+        CUDA_OK(cudaEventRecord(m->dev0, m->stream));
+        m->arm_state(ids[0], start_pos, (int)start_pos, (int)start_pos, (int)start_pos);
+        LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
+        ++m->launches;
+        m->decode_step_graphed(0);
+        CUDA_OK(cudaEventRecord(m->dev1, m->stream));
+        m->last_decode_steps = 1;
+        m->kv_len = start_pos + 1;
+        m->next_mrope_pos = (uint32_t)(start_pos + 1);
+    } else {
+        m->next_mrope_pos = (uint32_t)(start_pos + n);
+        m->prefill(ids, nullptr, n, nullptr, start_pos, nullptr, 0, 0);
+    }
+    fill_logits(m, out);
+    API_END(m)
+}
+
+int crane_b200_forward_step_argmax(crane_b200_model* m, const uint32_t* ids, size_t n, size_t start_pos, uint32_t* token_out) {
+    if (!token_out) return CRANE_B200_INVALID_ARG;
+    int r = crane_b200_forward_step(m, ids, n, start_pos, nullptr);
+    if (r != CRANE_B200_OK) return r;
+    API_BEGIN(m)
+    CUDA_OK(cudaMemcpyAsync(m->h_tokens, m->out_tokens, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    *token_out = m->h_tokens[0];
+    API_END(m)
+}
+
+int crane_b200_clear_kv_cache(crane_b200_model* m) {
+    API_BEGIN(m)
+    m->kv_len = 0;
+    m->next_mrope_pos = 0;
+    API_END(m)
+}
+
+int crane_b200_num_layers(const crane_b200_model* m) { return m ? m->L : 0; }
+int crane_b200_vocab_size(const crane_b200_model* m) { return m ? m->V : 0; }
+int crane_b200_hidden_size(const crane_b200_model* m) { return m ? m->H : 0; }
+size_t crane_b200_kv_len(const crane_b200_model* m) { return m ? m->kv_len : 0; }
+uint32_t crane_b200_next_mrope_pos(const crane_b200_model* m) { return m ? m->next_mrope_pos : 0; }
+uint64_t crane_b200_active_kv_cache_bytes(const crane_b200_model* m) {
+    return m ? (uint64_t)m->kv_len * m->nkv * m->D * 2 /*K,V*/ * 2 /*bf16*/ * m->L : 0;
+}
+uint64_t crane_b200_kernel_launches(const crane_b200_model* m) { return m ? m->launches : 0; }
+
+int crane_b200_warmup(crane_b200_model* m) {
+    API_BEGIN(m)
+    need_ready(m);
+    const size_t saved = m->kv_len;
+    const uint32_t saved_pos = m->next_mrope_pos;
+    if (saved != 0) fail(CRANE_B200_INVALID_ARG, "warmup requires an empty KV cache");
+    uint32_t ids[4] = {0, 1 % (uint32_t)m->V, 2 % (uint32_t)m->V, 3 % (uint32_t)m->V};
+    m->prefill(ids, nullptr, 4, nullptr, 0, nullptr, 0, 1);
+    m->decode_step_graphed(1);
+    m->decode_step_graphed(0);
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->kv_len = 0;
+    m->next_mrope_pos = saved_pos;
+    API_END(m)
+}
+
+int crane_b200_copy_logits(crane_b200_model* m, float* host_out, size_t n_floats) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!host_out || n_floats > (size_t)m->V) fail(CRANE_B200_INVALID_ARG, "copy_logits: bad arguments");
+    CUDA_OK(cudaMemcpyAsync(host_out, m->logits, n_floats * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    API_END(m)
+}
+
+int crane_b200_forward_embeds(crane_b200_model* m, const float* embeds, size_t s, const uint32_t* pos3, size_t start_pos,
+                              crane_b200_logits* out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!embeds || s == 0) fail(CRANE_B200_INVALID_ARG, "forward_embeds: empty input");
+    check_room(m, start_pos, s);
+    uint32_t nxt = (uint32_t)(start_pos + s);
+    if (pos3) {
+        nxt = 0;
+        for (size_t i = 0; i < 3 * s; ++i) nxt = std::max(nxt, pos3[i] + 1);
+    }
+    m->next_mrope_pos = nxt;
+    // the single-row case also goes through the prefill kernels: embeddings come from the caller, not the table
+    m->prefill(nullptr, embeds, s, pos3, start_pos, nullptr, 0, 0);
+    fill_logits(m, out);
+    API_END(m)
+}
+
+int crane_b200_decode_greedy(crane_b200_model* m, uint32_t first_token, size_t start_pos, size_t n_steps, const uint32_t* eos_ids,
+                             size_t n_eos, uint32_t* tokens_out, size_t* n_out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!tokens_out || !n_out || n_steps == 0) fail(CRANE_B200_INVALID_ARG, "decode_greedy: bad arguments");
+    if (n_steps > (size_t)m->out_cap) fail(CRANE_B200_INVALID_ARG, "decode_greedy: n_steps %zu > %d", n_steps, m->out_cap);
+    if (first_token >= (uint32_t)m->V) fail(CRANE_B200_INVALID_ARG, "token id %u >= vocab %d", first_token, m->V);
+    check_room(m, start_pos, n_steps);
+    CUDA_OK(cudaEventRecord(m->dev0, m->stream));
+    const int p = (int)m->next_mrope_pos;
+    m->arm_state(first_token, start_pos, p, p, p);
+    LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
+    ++m->launches;
+    for (size_t i = 0; i < n_steps; ++i) m->decode_step_graphed(1);
+    CUDA_OK(cudaEventRecord(m->dev1, m->stream));
+    CUDA_OK(cudaMemcpyAsync(m->h_tokens, m->out_tokens, n_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->last_decode_steps = n_steps;
+    m->kv_len = start_pos + n_steps;
+    m->next_mrope_pos += (uint32_t)n_steps;
+    size_t cnt = 0;
+    for (size_t i = 0; i < n_steps; ++i) {
+        tokens_out[cnt++] = m->h_tokens[i];
+        bool stop = false;
+        for (size_t e = 0; e < n_eos; ++e) stop = stop || (eos_ids && m->h_tokens[i] == eos_ids[e]);
+        if (stop) break;
+    }
+    *n_out = cnt;
+    API_END(m)
+}
+
+int crane_b200_generate_greedy(crane_b200_model* m, const uint32_t* prompt, size_t n_prompt, size_t max_new_tokens, const uint32_t* eos_ids,
+                               size_t n_eos, uint32_t* tokens_out, size_t* n_out) {
+    if (!m || !prompt || n_prompt == 0 || !tokens_out || !n_out || max_new_tokens == 0) return CRANE_B200_INVALID_ARG;
+    int r = crane_b200_clear_kv_cache(m);
+    if (r) return r;
+    uint32_t tok = 0;
+    r = crane_b200_forward_step_argmax(m, prompt, n_prompt, 0, &tok);
+    if (r) return r;
+    tokens_out[0] = tok;
+    *n_out = 1;
+    for (size_t e = 0; e < n_eos; ++e)
+        if (eos_ids && tok == eos_ids[e]) return CRANE_B200_OK;
+    if (max_new_tokens == 1) return CRANE_B200_OK;
+    size_t got = 0;
+    r = crane_b200_decode_greedy(m, tok, n_prompt, max_new_tokens - 1, eos_ids, n_eos, tokens_out + 1, &got);
+    if (r) return r;
+    *n_out = 1 + got;
+    return CRANE_B200_OK;
+}
+
+int crane_b200_encode_images(crane_b200_model* m, const float* pixel_values, const uint32_t* grid_thw, size_t n_images, float* image_embeds_out,
+                             float* deepstack_out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!pixel_values || !grid_thw || n_images == 0) fail(CRANE_B200_INVALID_ARG, "encode_images: bad arguments");
+    m->encode_images(pixel_values, grid_thw, n_images);
+    const size_t n = (size_t)m->img_tokens * m->v_out;
+    if (image_embeds_out) CUDA_OK(cudaMemcpyAsync(image_embeds_out, m->img_embeds, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    if (deepstack_out && !m->v_deepstack.empty())
+        CUDA_OK(cudaMemcpyAsync(deepstack_out, m->ds_embeds, m->v_deepstack.size() * n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    API_END(m)
+}
+
+int crane_b200_vl_forward(crane_b200_model* m, const uint32_t* ids, size_t n, const float* pixel_values, const uint32_t* grid_thw,
+                          size_t n_images, size_t start_pos, crane_b200_logits* out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!m->is_vl) fail(CRANE_B200_UNSUPPORTED, "vl_forward on a text-only model");
+    if (!ids || n == 0) fail(CRANE_B200_INVALID_ARG, "vl_forward: empty input");
+    check_room(m, start_pos, n);
+    for (size_t i = 0; i < n; ++i)
+        if (ids[i] >= (uint32_t)m->V) fail(CRANE_B200_INVALID_ARG, "token id %u >= vocab %d", ids[i], m->V);
+    std::vector<int> vis_rows;
+    std::vector<uint32_t> pos3((size_t)3 * n);
+    uint32_t next_pos = (uint32_t)start_pos;
+    if (pixel_values && grid_thw && n_images > 0) {
+        CUDA_OK(cudaEventRecord(m->pev0, m->stream));   // the prefill span of a VL request includes the ViT
+        m->pev0_armed = true;
+        m->encode_images(pixel_values, grid_thw, n_images);
+        // build_position_ids (qwen3_5/vlm.rs:190-241)
+        size_t i = 0, img = 0;
+        while (i < n) {
+            if (ids[i] != m->image_token_id) {
+                pos3[0 * n + i] = pos3[1 * n + i] = pos3[2 * n + i] = next_pos++;
+                ++i;
+                continue;
+            }
+            if (img >= n_images) fail(CRANE_B200_INVALID_ARG, "image span %zu has no image_grid_thw entry", img);
+            const uint32_t gt = grid_thw[3 * img], gh = grid_thw[3 * img + 1] / m->v_merge, gw = grid_thw[3 * img + 2] / m->v_merge;
+            const size_t span = (size_t)gt * gh * gw;
+            if (i + span > n) fail(CRANE_B200_INVALID_ARG, "image %zu needs %zu placeholder tokens but only %zu remain", img, span, n - i);
+            const uint32_t base = next_pos, hw = gh * gw;
+            for (size_t k = 0; k < span; ++k) {
+                if (ids[i + k] != m->image_token_id) fail(CRANE_B200_INVALID_ARG, "image span %zu interrupted at token %zu", img, i + k);
+                pos3[0 * n + i + k] = base + (uint32_t)k / hw;
+                pos3[1 * n + i + k] = base + ((uint32_t)k % hw) / gw;
+                pos3[2 * n + i + k] = base + ((uint32_t)k % hw) % gw;
+                vis_rows.push_back((int)(i + k));
+            }
+            next_pos = base + std::max(gt, std::max(gh, gw));
+            i += span;
+            ++img;
+        }
+        if ((int)vis_rows.size() != m->img_tokens)
+            fail(CRANE_B200_INVALID_ARG, "placeholder positions (%zu) != image embeddings (%d)", vis_rows.size(), m->img_tokens);
+    } else {
+        for (size_t i = 0; i < n; ++i) pos3[0 * n + i] = pos3[1 * n + i] = pos3[2 * n + i] = (uint32_t)(start_pos + i);
+        next_pos = (uint32_t)(start_pos + n);
+    }
+    m->next_mrope_pos = next_pos;
+    if (n == 1 && vis_rows.empty()) {
+        m->arm_state(ids[0], start_pos, (int)pos3[0], (int)pos3[1], (int)pos3[2]);
+        LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
+        ++m->launches;
+        m->decode_step_graphed(0);
+        m->kv_len = start_pos + 1;
+    } else {
+        m->prefill(ids, nullptr, n, pos3.data(), start_pos, vis_rows.data(), (int)vis_rows.size(), 0);
+    }
+    fill_logits(m, out);
+    API_END(m)
+}
+
+int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token, size_t start_pos, crane_b200_logits* out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (token >= (uint32_t)m->V) fail(CRANE_B200_INVALID_ARG, "token id %u >= vocab %d", token, m->V);
+    check_room(m, start_pos, 1);
+    const int p = (int)m->next_mrope_pos;
+    if (p > m->max_seq) fail(CRANE_B200_OOM, "rotary position exceeds max_seq_len");
+    m->arm_state(token, start_pos, p, p, p);
+    LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
+    ++m->launches;
+    m->decode_step_graphed(0);
+    m->next_mrope_pos = (uint32_t)(p + 1);
+    m->kv_len = start_pos + 1;
+    fill_logits(m, out);
+    API_END(m)
+}
+
+int crane_b200_last_timing(const crane_b200_model* m, float* prefill_ms, float* decode_ms, size_t* decode_steps) {
+    if (!m || !m->finalized) return CRANE_B200_INVALID_ARG;
+    cudaSetDevice(m->device);
+    float ms = 0.f;
+    crane_b200_model* mm = const_cast<crane_b200_model*>(m);
+    if (cudaEventSynchronize(m->pev1) == cudaSuccess && cudaEventElapsedTime(&ms, m->pev0, m->pev1) == cudaSuccess) mm->last_prefill_ms = ms;
+    if (cudaEventSynchronize(m->dev1) == cudaSuccess && cudaEventElapsedTime(&ms, m->dev0, m->dev1) == cudaSuccess) mm->last_decode_ms = ms;
+    cudaGetLastError();
+    if (prefill_ms) *prefill_ms = m->last_prefill_ms;
+    if (decode_ms) *decode_ms = m->last_decode_ms;
+    if (decode_steps) *decode_steps = m->last_decode_steps;
+    return CRANE_B200_OK;
+}
+
+int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* w, int M, int N, int K, int mode, const float* bias, void* out_inout,
+                       int use_simt) {
+    if (!a || !w || !out_inout) return CRANE_B200_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return CRANE_B200_CUDA_ERROR;
+    const bool half_out = (mode == EPI_STORE_BF16 || mode == EPI_SILU_MUL_BF16 || mode == EPI_GELU_ERF_BF16 || mode == EPI_GELU_TANH_BF16);
+    const int out_cols = (mode == EPI_SILU_MUL_BF16) ? N / 2 : N;
+    const size_t out_bytes = (size_t)M * out_cols * (half_out ? 2 : 4);
+    bf16 *da = nullptr, *dw = nullptr;
+    float* db = nullptr;
+    void* dout = nullptr;
+    int rc = CRANE_B200_CUDA_ERROR;
+    if (cudaMalloc(&da, (size_t)M * K * 2) == cudaSuccess && cudaMalloc(&dw, (size_t)N * K * 2) == cudaSuccess &&
+        cudaMalloc(&dout, out_bytes) == cudaSuccess && (!bias || cudaMalloc(&db, (size_t)N * 4) == cudaSuccess)) {
+        cudaMemcpy(da, a, (size_t)M * K * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dw, w, (size_t)N * K * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dout, out_inout, out_bytes, cudaMemcpyHostToDevice);
+        if (bias) cudaMemcpy(db, bias, (size_t)N * 4, cudaMemcpyHostToDevice);
+        GemmEpi ep{dout, out_cols, db, mode};
+        const int r = gemm_bf16_launch(nullptr, da, K, dw, M, N, K, ep, use_simt != 0);
+        if (r == -1000) rc = CRANE_B200_UNSUPPORTED;
+        else if (r == 0 && cudaDeviceSynchronize() == cudaSuccess) {
+            cudaMemcpy(out_inout, dout, out_bytes, cudaMemcpyDeviceToHost);
+            rc = CRANE_B200_OK;
+        } else {
+            g_create_error = std::string("op_gemm: ") + cudaGetErrorString(cudaGetLastError()) + " rc=" + std::to_string(r);
+        }
+    }
+    cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dout);
+    return rc;
+}
+
+}  // extern "C"

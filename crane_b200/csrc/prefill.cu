@@ -1,0 +1,449 @@
+// Prefill / ViT kernels around the tcgen05 GEMMs.
+//
+// Reference arithmetic being replaced (crane-core/src/models/):
+//   embedding gather ................ qwen3/modeling.rs:951
+//   RMSNorm rows .................... qwen3/modeling.rs:706,713,1024 (candle_nn::rms_norm, f32 accumulate)
+//   QK-norm + rope_thd + KV append .. qwen3/modeling.rs:335-366, modules/kv_cache.rs:38-101
+//   causal attention (flash, f32) ... qwen3/modeling.rs:422-456 ; ViT non-causal: qwen3_5/vision.rs:144-172
+//   LayerNorm / ViT RoPE / pos-embed  qwen3_5/vision.rs:90-102,215-218,382-489
+//   splice / DeepStack .............. qwen3_5/vlm.rs:433-468 ; qwen3_vl/text.rs:280-333
+#include "prefill.cuh"
+
+namespace cb {
+
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_rows_kernel(const uint32_t* __restrict__ ids, const bf16* __restrict__ embed, int H, float* __restrict__ x) {
+    const int s = blockIdx.x;
+    const bf16* row = embed + (size_t)ids[s] * H;
+    for (int i = threadIdx.x * 2; i < H; i += 512) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(row + i);
+        *reinterpret_cast<float2*>(x + (size_t)s * H + i) = make_float2(bf16lo(u), bf16hi(u));
+    }
+}
+int embed_rows_launch(cudaStream_t st, const uint32_t* ids, int S, const bf16* embed, int H, float* x) {
+    embed_rows_kernel<<<S, 256, 0, st>>>(ids, embed, H, x);
+    return (int)cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_kernel(const float* __restrict__ x, int H, const float* __restrict__ w, float eps, bf16* __restrict__ out) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * H;
+    float ssq = 0.f;
+    for (int i = threadIdx.x * 4; i < H; i += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        ssq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    const float rstd = rsqrtf(block_sum(ssq, red) / (float)H + eps);
+    bf16* o = out + (size_t)blockIdx.x * H;
+    for (int i = threadIdx.x * 4; i < H; i += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        const float4 g = *reinterpret_cast<const float4*>(w + i);
+        *reinterpret_cast<uint2*>(o + i) = make_uint2(pack_bf16(v.x * rstd * g.x, v.y * rstd * g.y),
+                                                      pack_bf16(v.z * rstd * g.z, v.w * rstd * g.w));
+    }
+}
+int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out) {
+    if (H % 4) return -1000;
+    rmsnorm_rows_kernel<<<S, 256, 0, st>>>(x, H, w, eps, out);
+    return (int)cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, int W, const float* __restrict__ w, const float* __restrict__ b,
+                      float eps, bf16* __restrict__ out) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * W;
+    float s = 0.f;
+    for (int i = threadIdx.x * 4; i < W; i += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        s += v.x + v.y + v.z + v.w;
+    }
+    const float mean = block_sum(s, red) / (float)W;
+    float ss = 0.f;
+    for (int i = threadIdx.x * 4; i < W; i += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        const float a = v.x - mean, c = v.y - mean, d = v.z - mean, e = v.w - mean;
+        ss += a * a + c * c + d * d + e * e;
+    }
+    const float rstd = rsqrtf(block_sum(ss, red) / (float)W + eps);
+    bf16* o = out + (size_t)blockIdx.x * W;
+    for (int i = threadIdx.x * 4; i < W; i += 1024) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        const float4 g = *reinterpret_cast<const float4*>(w + i);
+        const float4 bb = *reinterpret_cast<const float4*>(b + i);
+        *reinterpret_cast<uint2*>(o + i) =
+            make_uint2(pack_bf16((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y),
+                       pack_bf16((v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w));
+    }
+}
+int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out) {
+    if (W % 4) return -1000;
+    layernorm_rows_kernel<<<rows, 256, 0, st>>>(x, W, w, b, eps, out);
+    return (int)cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------
+// One warp per (token, vector): nh query heads, nkv key heads, nkv value heads.
+template <int D>
+__global__ void __launch_bounds__(128)
+rope_append_kernel(RopeAppendArgs a) {
+    constexpr int NE = D / 32, HALF = D / 2;
+    const int lane = threadIdx.x & 31;
+    const int nvec = a.nh + 2 * a.nkv;
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (gw >= a.S * nvec) return;
+    const int s = gw / nvec, vec = gw % nvec;
+    const int q_dim = a.nh * D, kv_dim = a.nkv * D;
+    const float* row = a.qkv + (size_t)s * (q_dim + 2 * kv_dim);
+    const int t = a.start_pos + s;
+    const int page = a.block_table[t / KV_PAGE];
+    if (vec >= a.nh + a.nkv) {   // value: cast + append
+        const int kvh = vec - a.nh - a.nkv;
+        const float* src = row + q_dim + kv_dim + kvh * D;
+        bf16* dst = a.v_pool + (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
+#pragma unroll
+        for (int j = 0; j < NE; ++j) dst[lane + 32 * j] = __float2bfloat16_rn(src[lane + 32 * j]);
+        return;
+    }
+    const bool is_k = vec >= a.nh;
+    const int head = is_k ? vec - a.nh : vec;
+    const float* src = row + (is_k ? q_dim : 0) + head * D;
+    const float* nw = is_k ? a.k_norm_w : a.q_norm_w;
+    float e[NE];
+    float ssq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) { e[j] = src[lane + 32 * j]; ssq += e[j] * e[j]; }
+    if (nw != nullptr) {
+        ssq = warp_sum(ssq);
+        const float rstd = rsqrtf(ssq / (float)D + a.eps);
+#pragma unroll
+        for (int j = 0; j < NE; ++j) e[j] = e[j] * rstd * nw[lane + 32 * j];
+    }
+    bf16* dst = is_k ? a.k_pool + (((size_t)page * a.nkv + head) * KV_PAGE + (t % KV_PAGE)) * D
+                     : a.q_out + (size_t)s * q_dim + head * D;
+#pragma unroll
+    for (int j = 0; j < NE / 2; ++j) {
+        const int i = lane + 32 * j;
+        const int p = a.pos3[a.axis_of[i] * a.S + s];
+        const float c = a.cos_tab[(size_t)p * HALF + i], sn = a.sin_tab[(size_t)p * HALF + i];
+        const float x1 = e[j], x2 = e[j + NE / 2];
+        dst[i] = __float2bfloat16_rn(x1 * c - x2 * sn);
+        dst[i + HALF] = __float2bfloat16_rn(x1 * sn + x2 * c);
+    }
+}
+int rope_append_launch(cudaStream_t st, int D, const RopeAppendArgs& a) {
+    const int nwarps = a.S * (a.nh + 2 * a.nkv);
+    const int grid = (nwarps + 3) / 4;
+    if (D == 128) rope_append_kernel<128><<<grid, 128, 0, st>>>(a);
+    else if (D == 256) rope_append_kernel<256><<<grid, 128, 0, st>>>(a);
+    else if (D == 64) rope_append_kernel<64><<<grid, 128, 0, st>>>(a);
+    else return -1000;
+    return (int)cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------
+// Flash attention forward (prefill + ViT): 64 query rows x one head per CTA, 64-key tiles,
+// bf16 mma.sync m16n8k16 with f32 accumulation and an online (base-2) softmax.
+// Keys/values come either from KV pages (one tile == one page) or from a strided buffer.
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D, bool CAUSAL, bool PAGED>
+__global__ void __launch_bounds__(128)
+flash_prefill_kernel(FlashArgs a) {
+    constexpr int BM = 64, BN = 64;
+    constexpr int LDS = D + 8;                 // padded row (elements): conflict-free ldmatrix
+    constexpr int TILE = BN * LDS;             // elements per K or V tile
+    constexpr int CPR = D / 8;                 // 16-byte chunks per row
+    extern __shared__ __align__(16) unsigned char fsm[];
+    bf16* q_s = reinterpret_cast<bf16*>(fsm);
+    bf16* kv_s = q_s + BM * LDS;               // [2 stages][K tile | V tile]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int head = blockIdx.y, z = blockIdx.z;
+    const int row0 = a.seq_start ? a.seq_start[z] : 0;
+    const int S = a.seq_len ? a.seq_len[z] : a.S;
+    const int q0 = blockIdx.x * BM;
+    if (q0 >= S) return;
+    const int kv_off = CAUSAL ? a.kv_offset : 0;
+    const int T = CAUSAL ? (kv_off + S) : S;   // keys available
+    const int kvh = head / (a.nh / a.nkv);
+    const int n_tiles = CAUSAL ? min((T + BN - 1) / BN, (kv_off + q0 + BM - 1) / BN + 1) : (T + BN - 1) / BN;
+
+    // ---- Q tile -> smem (zero-fill rows past S) ----
+    for (int c = tid; c < BM * CPR; c += 128) {
+        const int r = c / CPR, ch = c % CPR;
+        const int qr = q0 + r;
+        const bf16* src = a.q + (size_t)(row0 + min(qr, S - 1)) * a.q_stride + head * D + ch * 8;
+        cp_async16(smem_u32(q_s + r * LDS + ch * 8), src, qr < S ? 16 : 0);
+    }
+    auto load_kv = [&](int tile, int stage) {
+        bf16* ks = kv_s + stage * 2 * TILE;
+        bf16* vs = ks + TILE;
+        const int kv0 = tile * BN;
+        for (int c = tid; c < BN * CPR; c += 128) {
+            const int r = c / CPR, ch = c % CPR;
+            const int t = kv0 + r;
+            const bool ok = t < T;
+            const bf16 *ksrc, *vsrc;
+            if (PAGED) {
+                const int page = a.block_table[tile];     // BN == KV_PAGE
+                const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + r) * D + ch * 8;
+                ksrc = a.k_pool + off; vsrc = a.v_pool + off;
+            } else {
+                const size_t off = (size_t)(row0 + (ok ? t : 0)) * a.kv_stride + kvh * D + ch * 8;
+                ksrc = a.k + off; vsrc = a.v + off;
+            }
+            cp_async16(smem_u32(ks + r * LDS + ch * 8), ksrc, ok ? 16 : 0);
+            cp_async16(smem_u32(vs + r * LDS + ch * 8), vsrc, ok ? 16 : 0);
+        }
+    };
+    load_kv(0, 0);
+    cp_async_commit();
+
+    float o_acc[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+    float m_row[2] = {-INFINITY, -INFINITY}, l_row[2] = {0.f, 0.f};
+    const float sl2 = a.scale * 1.4426950408889634f;
+    uint32_t qf[D / 16][4];
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int stage = tile & 1;
+        if (tile + 1 < n_tiles) load_kv(tile + 1, stage ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (tile == 0) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = kk * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(q_s + r * LDS + c));
+            }
+        }
+        const bf16* ks = kv_s + stage * 2 * TILE;
+        const bf16* vs = ks + TILE;
+        // ---- S = Q K^T ----
+        float s_acc[BN / 8][4];
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) { s_acc[j][0] = s_acc[j][1] = s_acc[j][2] = s_acc[j][3] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; kk += 2) {
+                uint32_t b0, b1, b2, b3;
+                const int r = j * 8 + (lane & 7);
+                const int c = kk * 16 + (lane >> 3) * 8;
+                ldmatrix_x4(b0, b1, b2, b3, smem_u32(ks + r * LDS + c));
+                mma_bf16_16816(s_acc[j], qf[kk], b0, b1);
+                mma_bf16_16816(s_acc[j], qf[kk + 1], b2, b3);
+            }
+        }
+        // ---- mask + online softmax (rows g and g+8 of this warp's 16) ----
+        const int kv0 = tile * BN;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = kv0 + j * 8 + tq * 2 + (e & 1);
+                const int qrow = q0 + warp * 16 + g + (e >> 1) * 8;
+                const bool vis = (col < T) && (!CAUSAL || col <= kv_off + qrow);
+                const float v = vis ? s_acc[j][e] * sl2 : -INFINITY;
+                s_acc[j][e] = v;
+                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            }
+        }
+        float corr[2], muse[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float mn = fmaxf(m_row[r], mx[r]);
+            muse[r] = (mn == -INFINITY) ? 0.f : mn;
+            corr[r] = exp2f(m_row[r] - muse[r]);      // m_row = -inf -> 0
+            m_row[r] = mn;
+            l_row[r] *= corr[r];
+        }
+        float ps[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float p = exp2f(s_acc[j][e] - muse[e >> 1]);
+                s_acc[j][e] = p;
+                ps[e >> 1] += p;
+            }
+        }
+        l_row[0] += ps[0];
+        l_row[1] += ps[1];
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+            o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+        }
+        // ---- O += P V ----
+#pragma unroll
+        for (int kt = 0; kt < BN / 16; ++kt) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16(s_acc[2 * kt][0], s_acc[2 * kt][1]);
+            pa[1] = pack_bf16(s_acc[2 * kt][2], s_acc[2 * kt][3]);
+            pa[2] = pack_bf16(s_acc[2 * kt + 1][0], s_acc[2 * kt + 1][1]);
+            pa[3] = pack_bf16(s_acc[2 * kt + 1][2], s_acc[2 * kt + 1][3]);
+#pragma unroll
+            for (int dj = 0; dj < D / 8; dj += 2) {
+                uint32_t b0, b1, b2, b3;
+                const int r = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = dj * 8 + (lane >> 4) * 8;
+                ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(vs + r * LDS + c));
+                mma_bf16_16816(o_acc[dj], pa, b0, b1);
+                mma_bf16_16816(o_acc[dj + 1], pa, b2, b3);
+            }
+        }
+        __syncthreads();   // everyone done with this stage before it is refilled
+    }
+    cp_async_wait<0>();
+    // ---- normalise and store ----
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_row[r] += __shfl_xor_sync(0xffffffffu, l_row[r], 1);
+        l_row[r] += __shfl_xor_sync(0xffffffffu, l_row[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int qrow = q0 + warp * 16 + g + r * 8;
+        if (qrow < S) {
+            const float inv = 1.f / l_row[r];
+            bf16* o = a.out + (size_t)(row0 + qrow) * a.o_stride + head * D;
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i)
+                *reinterpret_cast<uint32_t*>(o + i * 8 + tq * 2) = pack_bf16(o_acc[i][2 * r] * inv, o_acc[i][2 * r + 1] * inv);
+        }
+    }
+}
+
+template <int D, bool CAUSAL, bool PAGED>
+static int flash_launch_t(cudaStream_t st, const FlashArgs& a) {
+    constexpr int SMEM = (64 * (D + 8) + 4 * 64 * (D + 8)) * 2;
+    static bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(flash_prefill_kernel<D, CAUSAL, PAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return (int)e;
+        set = true;
+    }
+    const int max_len = a.seq_len ? a.max_len : a.S;
+    dim3 grid((max_len + 63) / 64, a.nh, a.seq_len ? a.nseq : 1);
+    flash_prefill_kernel<D, CAUSAL, PAGED><<<grid, 128, SMEM, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const FlashArgs& a) {
+    if (D == 128 && causal && paged) return flash_launch_t<128, true, true>(st, a);
+    if (D == 256 && causal && paged) return flash_launch_t<256, true, true>(st, a);
+    if (D == 64 && !causal && !paged) return flash_launch_t<64, false, false>(st, a);
+    if (D == 128 && !causal && !paged) return flash_launch_t<128, false, false>(st, a);
+    return -1000;
+}
+
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+set_rows_kernel(float* __restrict__ x, int H, const int* __restrict__ rows, const float* __restrict__ src, int add) {
+    float* dst = x + (size_t)rows[blockIdx.x] * H;
+    const float* s = src + (size_t)blockIdx.x * H;
+    for (int i = threadIdx.x * 4; i < H; i += 1024) {
+        float4 v = *reinterpret_cast<const float4*>(s + i);
+        if (add) {
+            const float4 d = *reinterpret_cast<const float4*>(dst + i);
+            v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+        }
+        *reinterpret_cast<float4*>(dst + i) = v;
+    }
+}
+int set_rows_launch(cudaStream_t st, float* x, int H, const int* rows, int n, const float* src, bool add) {
+    if (n <= 0) return 0;
+    set_rows_kernel<<<n, 256, 0, st>>>(x, H, rows, src, add ? 1 : 0);
+    return (int)cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n) {
+    if (n % 4) return -1000;
+    const size_t n4 = n / 4;
+    const int grid = (int)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+    cast_f32_bf16_kernel<<<grid, 256, 0, st>>>(src, dst, n4);
+    return (int)cudaGetLastError();
+}
+
+// x[p] += sum_c w4[c][p] * table[idx4[c][p]]      (bilinear pos-embed, qwen3_5/vision.rs:445-459)
+__global__ void __launch_bounds__(256)
+vit_pos_embed_add_kernel(float* __restrict__ x, int N, int Hv, const float* __restrict__ table,
+                         const int* __restrict__ idx4, const float* __restrict__ w4) {
+    const int p = blockIdx.x;
+    int id[4]; float w[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { id[c] = idx4[c * N + p]; w[c] = w4[c * N + p]; }
+    for (int i = threadIdx.x; i < Hv; i += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc += table[(size_t)id[c] * Hv + i] * w[c];
+        x[(size_t)p * Hv + i] += acc;
+    }
+}
+int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const float* table, const int* idx4, const float* w4) {
+    vit_pos_embed_add_kernel<<<N, 256, 0, st>>>(x, N, Hv, table, idx4, w4);
+    return (int)cudaGetLastError();
+}
+
+// qkv f32 [N, 3, nh, hd] -> bf16 same layout; q and k rotated in f32 with the 2-D (row, col) table
+// cos/sin [N, hd/2] (full-width cat(emb, emb) of the reference collapses to a half-split rotation).
+__global__ void __launch_bounds__(256)
+vit_rope_kernel(const float* __restrict__ qkv, int nh, int hd, const float* __restrict__ cs, const float* __restrict__ sn,
+                bf16* __restrict__ out) {
+    const int p = blockIdx.x;
+    const int half = hd / 2;
+    const int Hv = nh * hd;
+    const float* row = qkv + (size_t)p * 3 * Hv;
+    bf16* orow = out + (size_t)p * 3 * Hv;
+    for (int i = threadIdx.x; i < 2 * nh * half; i += blockDim.x) {   // q and k pairs
+        const int which = i / (nh * half), rem = i % (nh * half);
+        const int h = rem / half, j = rem % half;
+        const float c = cs[(size_t)p * half + j], s = sn[(size_t)p * half + j];
+        const float* v = row + which * Hv + h * hd;
+        const float x1 = v[j], x2 = v[j + half];
+        bf16* o = orow + which * Hv + h * hd;
+        o[j] = __float2bfloat16_rn(x1 * c - x2 * s);
+        o[j + half] = __float2bfloat16_rn(x2 * c + x1 * s);
+    }
+    for (int i = threadIdx.x; i < Hv; i += blockDim.x) orow[2 * Hv + i] = __float2bfloat16_rn(row[2 * Hv + i]);
+}
+int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out) {
+    vit_rope_kernel<<<N, 256, 0, st>>>(qkv, nh, hd, cos, sin, out);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace cb

@@ -1,0 +1,54 @@
+// Prefill / ViT kernels around the tcgen05 GEMMs: row norms, RoPE + KV-page append, flash attention,
+// image-feature splice / DeepStack adds.  See prefill.cu.
+#pragma once
+
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace cb {
+
+struct RopeAppendArgs {
+    const float* qkv;        // [S, q_dim + 2 kv_dim] f32
+    const float* q_norm_w;   // [D] (nullptr: no QK-norm)
+    const float* k_norm_w;
+    float eps;
+    const float* cos_tab;    // [max_pos, D/2]
+    const float* sin_tab;
+    const unsigned char* axis_of;   // [D/2]
+    const int* pos3;         // [3, S] rotary positions per token
+    int S, start_pos;        // cache positions start_pos .. start_pos + S - 1
+    const int* block_table;  // [max_pages] of this sequence
+    bf16* k_pool;
+    bf16* v_pool;
+    int nh, nkv;
+    bf16* q_out;             // [S, nh * D]
+};
+
+struct FlashArgs {
+    const bf16* q;   int q_stride;      // q[(row) * q_stride + head * D + d]
+    const bf16* k;   const bf16* v;     // contiguous mode: k[(row) * kv_stride + kv_head * D + d]
+    int kv_stride;
+    const bf16* k_pool; const bf16* v_pool;   // paged mode: [n_pages, nkv, KV_PAGE, D]
+    const int* block_table;
+    int nh, nkv;
+    bf16* out;       int o_stride;      // out[(row) * o_stride + head * D + d]
+    const int* seq_start;               // [nseq] first row of each sequence (nullptr: single sequence at row 0)
+    const int* seq_len;                 // [nseq] query rows per sequence
+    int S;                              // single-sequence mode: query rows
+    int kv_offset;                      // causal: query row i sees keys j <= kv_offset + i; keys total = kv_offset + S
+    float scale;
+    int nseq;
+    int max_len;                        // max query rows over sequences (grid sizing)
+};
+
+int embed_rows_launch(cudaStream_t st, const uint32_t* ids, int S, const bf16* embed, int H, float* x);
+int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out);
+int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out);
+int rope_append_launch(cudaStream_t st, int D, const RopeAppendArgs& a);
+int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const FlashArgs& a);
+int set_rows_launch(cudaStream_t st, float* x, int H, const int* rows, int n, const float* src, bool add);
+int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n);
+int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const float* table, const int* idx4, const float* w4);
+int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out);
+
+}  // namespace cb

@@ -1,0 +1,161 @@
+/*
+ * crane_b200 -- C ABI of the B200-native forward-pass engine that sits behind crane-core's model API.
+ *
+ * Every entry point below is what the reference's Rust side would bind through `extern "C"` for this
+ * path; the reference interface each one replaces is cited as file:line under /root/reference.
+ * The Rust-side binding a Crane maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *   - every function returns 0 on success or a negative crane_b200_status; it never throws/aborts;
+ *     `crane_b200_last_error()` gives the message (per handle; handle NULL = last create() failure);
+ *   - a handle is externally synchronised (one caller at a time, the engine thread of
+ *     crane-serve/src/engine/mod.rs:169-271) but may migrate between threads;
+ *   - the library owns weights, KV pages, workspaces and the logits buffer (valid until the next call
+ *     on the same handle); the caller owns every input array (consumed before return);
+ *   - there is no CPU fallback: without a CUDA device create() fails with CRANE_B200_CUDA_ERROR.
+ */
+#ifndef CRANE_B200_H
+#define CRANE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CRANE_B200_API __attribute__((visibility("default")))
+#else
+#define CRANE_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crane_b200_model crane_b200_model;
+
+typedef enum {
+    CRANE_B200_OK = 0,
+    CRANE_B200_INVALID_ARG = -1,
+    CRANE_B200_OOM = -2,
+    CRANE_B200_CUDA_ERROR = -3,
+    CRANE_B200_UNSUPPORTED = -4,
+    CRANE_B200_NOT_LOADED = -5
+} crane_b200_status;
+
+typedef enum {
+    CRANE_B200_F32 = 0,
+    CRANE_B200_BF16 = 1,
+    CRANE_B200_F16 = 2
+} crane_b200_dtype;
+
+/* Logits of the LAST position of the most recent forward call (f32, device memory, `stream` ordered).
+ * Shape [rows, vocab]; rows == 1 for the single-sequence calls.
+ * Mirrors the `Tensor` returned by `Model::forward_step` (crane-core/src/models/qwen3/model.rs:34-268;
+ * logits [1,1,V], qwen3/modeling.rs:1032-1035). */
+typedef struct {
+    const float* device_ptr;
+    size_t rows;
+    size_t vocab;
+    void* stream; /* cudaStream_t the result is ordered on */
+} crane_b200_logits;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+
+/* Create an engine for one model on one GPU.  `config_json` is the checkpoint's HF config.json text
+ * (qwen3: crane-core/src/models/qwen3/modeling.rs:94-130 `Config`; qwen3_vl: text_config + vision_config
+ * as crane-core/src/models/qwen3_5/config.rs:112-137) optionally extended with an "engine" object:
+ *   {"max_seq_len": 4096, "max_batch": 1, "gemm": "tcgen05"|"simt", "graphs": true,
+ *    "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf"}
+ * Replaces `model_factory::create_backend` / `Qwen3Backend::new`
+ * (crane-serve/src/engine/model_factory.rs:471-560, backend.rs:615-625). */
+CRANE_B200_API int crane_b200_create(const char* config_json, int device_ordinal, crane_b200_model** out);
+CRANE_B200_API void crane_b200_destroy(crane_b200_model* m);
+CRANE_B200_API const char* crane_b200_last_error(const crane_b200_model* m);
+
+/* Register one checkpoint tensor by its safetensors name (`model.layers.{i}.self_attn.q_proj.weight`,
+ * `model.language_model...`, `model.visual.blocks.{i}.attn.qkv.weight`, `lm_head.weight`, ... exactly
+ * the names read at crane-core/src/models/qwen3/modeling.rs:160-282,598-606,771-813 and
+ * qwen3_5/vision.rs:23-35,70-71,114-115,245-250,321-339).  `data` is host memory. */
+CRANE_B200_API int crane_b200_load_tensor(crane_b200_model* m, const char* name, int dtype, const int64_t* shape, int ndim,
+                           const void* data);
+/* All tensors registered: merge QKV / gate-up, build rotary tables, allocate KV pages + workspaces. */
+CRANE_B200_API int crane_b200_finalize(crane_b200_model* m);
+
+/* ---- ModelBackend surface (crane-serve/src/engine/backend.rs:30-151) ---------------------------- */
+
+/* `forward_step(&mut self, input_ids: &[u32], start_pos: usize) -> Result<Tensor>` (backend.rs:42). */
+CRANE_B200_API int crane_b200_forward_step(crane_b200_model* m, const uint32_t* input_ids, size_t n, size_t start_pos,
+                            crane_b200_logits* out);
+/* Same pass + device-side greedy argmax; only 4 bytes return to the host.  The server's greedy fast
+ * path: `gpu_argmax` (crane-serve/src/engine/sampling.rs:189-218,
+ * crane-core/src/ops/fused_ops/cuda_impl.rs:204-282).  Ties resolve to the LOWEST index. */
+CRANE_B200_API int crane_b200_forward_step_argmax(crane_b200_model* m, const uint32_t* input_ids, size_t n, size_t start_pos,
+                                   uint32_t* token_out);
+/* `clear_kv_cache` (backend.rs:45), `num_layers` (:48), `warmup` (:61). */
+CRANE_B200_API int crane_b200_clear_kv_cache(crane_b200_model* m);
+CRANE_B200_API int crane_b200_num_layers(const crane_b200_model* m);
+CRANE_B200_API int crane_b200_warmup(crane_b200_model* m);
+/* `active_kv_cache_bytes` (backend.rs:82-84) and the cached length (`Qwen3Model::kv_cache_len`,
+ * qwen3/modeling.rs:1068). */
+CRANE_B200_API uint64_t crane_b200_active_kv_cache_bytes(const crane_b200_model* m);
+CRANE_B200_API size_t crane_b200_kv_len(const crane_b200_model* m);
+CRANE_B200_API int crane_b200_vocab_size(const crane_b200_model* m);
+CRANE_B200_API int crane_b200_hidden_size(const crane_b200_model* m);
+
+/* Copy the logits of the last call to host memory (`logits.to_dtype(F32)?.to_vec1()`, model.rs:305). */
+CRANE_B200_API int crane_b200_copy_logits(crane_b200_model* m, float* host_out, size_t n_floats);
+
+/* ---- library surface (crane-core/src/models/qwen3/model.rs) ------------------------------------- */
+
+/* `Qwen3Model::forward_embeds` (qwen3/modeling.rs:964-978): caller-supplied embeddings [s, hidden] f32
+ * (host).  `position_ids_3xs` is NULL for 1-D positions start_pos..start_pos+s-1, else the [3, s] MRoPE
+ * ids of `MRotaryEmbedding::cos_sin_with_position_ids` (qwen3_5/modeling.rs:172-245). */
+CRANE_B200_API int crane_b200_forward_embeds(crane_b200_model* m, const float* embeds, size_t s, const uint32_t* position_ids_3xs,
+                              size_t start_pos, crane_b200_logits* out);
+
+/* On-device greedy decode loop: `n_steps` dependent single-token passes without returning to the host
+ * (the inner loop of `Model::generate`, qwen3/model.rs:298-331 with temperature None, and of
+ * `step_decode_batch`'s `decode_tokens_per_seq` rounds, crane-serve/src/engine/mod.rs:898-1008).
+ * `first_token` is consumed at cache position `start_pos` (== kv_len).  Writes min(n_steps, up to and
+ * including the first EOS) tokens to `tokens_out`, the count to `n_out`.  The KV cache afterwards holds
+ * start_pos + n_steps positions. */
+CRANE_B200_API int crane_b200_decode_greedy(crane_b200_model* m, uint32_t first_token, size_t start_pos, size_t n_steps,
+                             const uint32_t* eos_ids, size_t n_eos, uint32_t* tokens_out, size_t* n_out);
+
+/* `ModelForCausalLM::generate` greedy branch (crane-core/src/generation/based.rs:5-34,
+ * qwen3/model.rs:275-349): clear cache, prefill `prompt`, then decode until EOS / max_new_tokens. */
+CRANE_B200_API int crane_b200_generate_greedy(crane_b200_model* m, const uint32_t* prompt, size_t n_prompt, size_t max_new_tokens,
+                               const uint32_t* eos_ids, size_t n_eos, uint32_t* tokens_out, size_t* n_out);
+
+/* ---- vision-language surface (crane-core/src/models/qwen3_5/vlm.rs) ------------------------------ */
+
+/* `Qwen3_5VLModel::encode_images` -> `Qwen3_5VisionModel::forward` (vlm.rs:150-170, vision.rs:558-584).
+ * pixel_values [sum(t*h*w), C*T*P*P] f32 host, grid_thw [n_images, 3].  Optional host outputs:
+ * image_embeds_out [sum(t*h*w)/merge^2, out_hidden], deepstack_out [n_deepstack, same rows, out_hidden]. */
+CRANE_B200_API int crane_b200_encode_images(crane_b200_model* m, const float* pixel_values, const uint32_t* grid_thw, size_t n_images,
+                             float* image_embeds_out, float* deepstack_out);
+/* `Qwen3_5VLModel::forward` (vlm.rs:250-285): ViT + embed + splice + 3-axis position ids + decoder
+ * (+ DeepStack, qwen3_vl/text.rs:252-270).  `pixel_values` may be NULL (text-only prefill). */
+CRANE_B200_API int crane_b200_vl_forward(crane_b200_model* m, const uint32_t* input_ids, size_t n, const float* pixel_values,
+                          const uint32_t* grid_thw, size_t n_images, size_t start_pos, crane_b200_logits* out);
+/* `Qwen3_5VLModel::decode_step` (vlm.rs:294-301): one token at cache position start_pos with the scalar
+ * MRoPE counter seeded by vl_forward. */
+CRANE_B200_API int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token, size_t start_pos, crane_b200_logits* out);
+/* The MRoPE counter (`next_mrope_pos`, vlm.rs:272-282). */
+CRANE_B200_API uint32_t crane_b200_next_mrope_pos(const crane_b200_model* m);
+
+/* ---- profiling (crane-core/src/ops/prof.rs:37-243 `CRANE_PROF`) ----------------------------------- */
+/* Device time (ms, CUDA events on the engine stream) of the last prefill pass and last decode run. */
+CRANE_B200_API int crane_b200_last_timing(const crane_b200_model* m, float* prefill_ms, float* decode_ms, size_t* decode_steps);
+/* Kernels launched by this handle since creation (graph replays count their nodes). */
+CRANE_B200_API uint64_t crane_b200_kernel_launches(const crane_b200_model* m);
+
+/* ---- kernel-level test hooks (used by tests/ only; host buffers in, host buffers out) ------------ */
+/* C[M,N] = epilogue(A[M,K] bf16 x W[N,K]^T bf16); mode = cb::GemmEpiMode; out dtype follows the mode. */
+CRANE_B200_API int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* w, int M, int N, int K, int mode,
+                       const float* bias, void* out_inout, int use_simt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRANE_B200_H */

@@ -1,0 +1,147 @@
+"""CPU: the oracle against (a) the committed HF-generated fixtures and (b) every literal known answer /
+property the reference's own tests hold for this path."""
+import math
+
+import numpy as np
+import torch
+
+from conftest import golden, rel_err
+from crane_b200 import synth
+from oracle import qwen3 as oq
+from oracle import qwen3_vl as ov
+
+
+def _weights(cfg):
+    return dict(synth.synth_checkpoint(cfg))
+
+
+def test_tiny_qwen3_matches_hf_fixture():
+    for name, cfg in (("tiny_qwen3", synth.TINY_QWEN3), ("tiny_qwen3_untied", synth.TINY_QWEN3_UNTIED)):
+        g = golden(name)
+        orc = oq.Qwen3Oracle(cfg, _weights(cfg))
+        toks = [int(t) for t in g["prompt"]]
+        for step in range(g["logits"].shape[0]):
+            ctx = toks if step == 0 else toks[-1:]
+            lo = orc.forward(ctx, len(toks) - len(ctx)).numpy()
+            assert rel_err(lo, g["logits"][step]) < 2e-5
+            assert oq.argmax_first(torch.from_numpy(lo)) == int(g["tokens"][step])
+            toks.append(int(g["tokens"][step]))
+
+
+def test_tiny_qwen3_vl_matches_hf_fixture():
+    cfg = synth.TINY_QWEN3_VL
+    g = golden("tiny_qwen3_vl")
+    w = _weights(cfg)
+    pv, grid = synth.patchify(g["image"])
+    assert tuple(grid) == tuple(int(x) for x in g["grid"])
+    hf = ov.Qwen3VLOracle(cfg, w, vit_act="tanh", merger_act="erf")      # HF's activation choice
+    img, _ = hf.vision.forward(pv, [grid])
+    assert rel_err(img.numpy(), g["hf_image_embeds"]) < 2e-5
+    lo = hf.prefill(g["prompt"], pv, [grid]).numpy()
+    assert rel_err(lo, g["hf_logits"][0]) < 2e-5
+    S = len(g["prompt"])
+    tok = int(g["hf_tokens"][0])
+    for step in range(1, g["hf_logits"].shape[0]):
+        lo = hf.decode_step(tok, S + step - 1).numpy()
+        assert rel_err(lo, g["hf_logits"][step]) < 2e-5
+        tok = int(g["hf_tokens"][step])
+    ref = ov.Qwen3VLOracle(cfg, w)                                          # the reference's activation choice
+    img, deep = ref.vision.forward(pv, [grid])
+    assert rel_err(img.numpy(), g["ref_image_embeds"]) < 1e-6
+    assert rel_err(torch.stack(deep).numpy(), g["ref_deepstack"]) < 1e-6
+    assert rel_err(ref.prefill(g["prompt"], pv, [grid]).numpy(), g["ref_logits"][0]) < 1e-6
+
+
+# ---- literal known answers from the reference's tests ------------------------------------------------
+
+def test_rope_inv_freq_literals():
+    # crane-core/src/models/modules/rotary.rs:166-189: dim=8, theta=1e4 => inv_freq [1, .1, .01, .001]
+    cos, sin = oq.rope_tables(8, 2, 10000.0)
+    for i, f in enumerate([1.0, 0.1, 0.01, 0.001]):
+        assert abs(float(cos[1, i]) - math.cos(f)) < 1e-5 and abs(float(sin[1, i]) - math.sin(f)) < 1e-5
+    # rotary.rs:214-235: dim=4, theta=100 => inv_freq [1, .1] at several positions
+    cos, sin = oq.rope_tables(4, 16, 100.0)
+    for pos in (0, 1, 5, 10):
+        for i, f in enumerate([pos * 1.0, pos * 0.1]):
+            assert abs(float(cos[pos, i]) - math.cos(f)) < 1e-5 and abs(float(sin[pos, i]) - math.sin(f)) < 1e-5
+
+
+def test_topk_order_literals():
+    # crane-core/tests/rocm_kernels.rs:169-172 and the tie rule :141-160 (value desc, index asc)
+    assert list(oq.topk_order(np.array([0.5, -3, 7.25, 1, 7.5], np.float32), 5)) == [4, 2, 3, 0, 1]
+    v = np.zeros(64, np.float32)
+    v[3::4] = 1.0
+    assert list(oq.topk_order(v, 5)) == [3, 7, 11, 15, 19]
+
+
+def test_causal_mask_rows():
+    # crane-core/src/models/qwen3_5/prefill.rs:283-296 and qwen3/modeling.rs:1000-1014
+    assert oq.build_causal_mask_rows(3, 0) == [[1, 0, 0], [1, 1, 0], [1, 1, 1]]
+    assert oq.build_causal_mask_rows(2, 3) == [[1, 1, 1, 1, 0], [1, 1, 1, 1, 1]]
+
+
+def test_repeat_penalty_rule():
+    # crane-core/src/models/utils.rs:25-44
+    out = oq.apply_repeat_penalty(np.array([2.0, -2.0, 1.0], np.float32), 2.0, [0, 1, 1, 0])
+    assert list(out) == [1.0, -4.0, 1.0]
+
+
+def test_patch_order_literal():
+    # crane-core/src/models/qwen3_5/processor.rs:306-314: a 4x2-patch image emits patches in order [0,1,4,5,2,3,6,7]
+    img = np.zeros((32, 64, 3), np.uint8)
+    for py in range(2):
+        for px in range(4):
+            img[py * 16:(py + 1) * 16, px * 16:(px + 1) * 16, :] = py * 4 + px
+    pv, grid = synth.patchify(img, mean=(0, 0, 0), std=(1, 1, 1))
+    assert grid == (1, 2, 4)
+    order = [int(round(float(r[0]) * 255)) for r in pv]
+    assert order == [0, 1, 4, 5, 2, 3, 6, 7]
+    assert pv.shape == (8, 3 * 2 * 16 * 16)
+
+
+def test_position_ids_and_mrope_ownership():
+    # crane-core/src/models/qwen3_5/vlm.rs:190-241
+    ids = [5, 6, 9, 9, 9, 9, 9, 9, 7]
+    pos, nxt = ov.build_position_ids(ids, [(1, 4, 6)], 2, 9, 0)
+    assert pos[:, :2].tolist() == [[0, 1]] * 3
+    assert pos[:, 2:8].tolist() == [[2] * 6, [2, 2, 2, 3, 3, 3], [2, 3, 4, 2, 3, 4]]
+    assert nxt == 2 + 3 + 1 and pos[:, 8].tolist() == [5, 5, 5]
+    # qwen3_5/modeling.rs:203-233 for mrope_section [11,11,10], half_rot 32
+    ax = ov.mrope_axis_of(32, [11, 11, 10])
+    assert [i for i, a in enumerate(ax) if a == 1] == list(range(1, 32, 3))
+    assert [i for i, a in enumerate(ax) if a == 2] == list(range(2, 30, 3))
+
+
+# ---- properties the reference's unit tests assert --------------------------------------------------
+
+def test_chunked_prefill_equals_single_and_incremental_decode():
+    # qwen3/modeling.rs:1763-1801 (chunked == single, 1e-4); modules/attention.rs:1125-1232 (incremental == prefill, 1e-5)
+    cfg = synth.TINY_QWEN3
+    w = _weights(cfg)
+    ids = synth.synth_token_ids(20, cfg["vocab_size"], "chunk")
+    a = oq.Qwen3Oracle(cfg, w)
+    full = a.forward(ids, 0).numpy()
+    b = oq.Qwen3Oracle(cfg, w)
+    b.forward(ids[:7], 0)
+    b.forward(ids[7:15], 7)
+    part = b.forward(ids[15:], 15).numpy()
+    assert rel_err(part, full) < 1e-4
+    c = oq.Qwen3Oracle(cfg, w)
+    for i, t in enumerate(ids):
+        inc = c.forward([t], i).numpy()
+    assert rel_err(inc, full) < 1e-4
+
+
+def test_forward_embeds_equals_forward():
+    # qwen3/modeling.rs:1440-1462
+    cfg = synth.TINY_QWEN3
+    w = _weights(cfg)
+    ids = synth.synth_token_ids(9, cfg["vocab_size"], "emb")
+    a, b = oq.Qwen3Oracle(cfg, w), oq.Qwen3Oracle(cfg, w)
+    assert rel_err(b.forward_embeds(b.embed(ids), 0).numpy(), a.forward(ids, 0).numpy()) < 1e-6
+
+
+def test_bf16_helpers_roundtrip():
+    x = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
+    bits = synth.f32_to_bf16_bits(x)
+    assert np.array_equal(synth.bf16_bits_to_f32(bits), torch.from_numpy(x).to(torch.bfloat16).float().numpy())
