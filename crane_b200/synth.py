@@ -93,6 +93,31 @@ TINY_QWEN3_VL = {
 }
 
 
+QWEN3_5_0_8B = {
+    "model_type": "qwen3_5_text",
+    "vocab_size": 248320, "hidden_size": 1024, "intermediate_size": 3584,
+    "num_hidden_layers": 24, "num_attention_heads": 8, "num_key_value_heads": 2, "head_dim": 256,
+    "max_position_embeddings": 262144, "rms_norm_eps": 1e-6, "tie_word_embeddings": True,
+    "full_attention_interval": 4, "partial_rotary_factor": 0.25,
+    "linear_conv_kernel_dim": 4, "linear_key_head_dim": 128, "linear_value_head_dim": 128,
+    "linear_num_key_heads": 16, "linear_num_value_heads": 16,
+    "rope_parameters": {"rope_type": "default", "rope_theta": 10000000.0, "partial_rotary_factor": 0.25,
+                        "mrope_section": [11, 11, 10], "mrope_interleaved": True},
+}
+
+TINY_QWEN3_5 = {
+    "model_type": "qwen3_5_text",
+    "vocab_size": 1024, "hidden_size": 256, "intermediate_size": 512,
+    "num_hidden_layers": 4, "num_attention_heads": 4, "num_key_value_heads": 2, "head_dim": 256,
+    "max_position_embeddings": 4096, "rms_norm_eps": 1e-6, "tie_word_embeddings": True,
+    "full_attention_interval": 4, "partial_rotary_factor": 0.25,
+    "linear_conv_kernel_dim": 4, "linear_key_head_dim": 128, "linear_value_head_dim": 128,
+    "linear_num_key_heads": 2, "linear_num_value_heads": 4,
+    "rope_parameters": {"rope_type": "default", "rope_theta": 10000000.0, "partial_rotary_factor": 0.25,
+                        "mrope_section": [11, 11, 10], "mrope_interleaved": True},
+}
+
+
 def text_config(cfg: dict) -> dict:
     return cfg.get("text_config", cfg)
 
@@ -162,6 +187,53 @@ def text_tensor_specs(tc: dict, prefix: str = "model.", tie: bool | None = None)
         yield "lm_head.weight", (V, H), "linear"
 
 
+def is_full_attention_layer(tc: dict, i: int) -> bool:
+    """Layer i is softmax attention iff (i + 1) % full_attention_interval == 0 (qwen3_5/config.rs, HF layer_types)."""
+    lt = tc.get("layer_types")
+    if lt:
+        return lt[i] == "full_attention"
+    return (i + 1) % tc.get("full_attention_interval", 4) == 0
+
+
+def qwen3_5_tensor_specs(tc: dict, prefix: str = "model."):
+    """Hybrid Qwen3.5 text decoder: GDN (`linear_attn.*`) on 3 of 4 layers, gated softmax attention on the 4th.
+    Names as read at crane-core/src/ops/gdn/layer.rs:55-67, projection.rs:75-83, models/qwen3_5/modeling.rs:337-358,587-669."""
+    H, I, V = tc["hidden_size"], tc["intermediate_size"], tc["vocab_size"]
+    nh, nkv, d = tc["num_attention_heads"], tc["num_key_value_heads"], head_dim(tc)
+    nk, nv = tc["linear_num_key_heads"], tc["linear_num_value_heads"]
+    dk, dv, ck = tc["linear_key_head_dim"], tc["linear_value_head_dim"], tc["linear_conv_kernel_dim"]
+    key_dim, value_dim = nk * dk, nv * dv
+    yield prefix + "embed_tokens.weight", (V, H), "embed"
+    for i in range(tc["num_hidden_layers"]):
+        p = f"{prefix}layers.{i}."
+        yield p + "input_layernorm.weight", (H,), "norm0"
+        if is_full_attention_layer(tc, i):
+            yield p + "self_attn.q_proj.weight", (nh * d * 2, H), "linear"
+            yield p + "self_attn.k_proj.weight", (nkv * d, H), "linear"
+            yield p + "self_attn.v_proj.weight", (nkv * d, H), "linear"
+            yield p + "self_attn.q_norm.weight", (d,), "norm0"
+            yield p + "self_attn.k_norm.weight", (d,), "norm0"
+            yield p + "self_attn.o_proj.weight", (H, nh * d), "linear"
+        else:
+            q = p + "linear_attn."
+            yield q + "in_proj_qkv.weight", (2 * key_dim + value_dim, H), "linear"
+            yield q + "in_proj_z.weight", (value_dim, H), "linear"
+            yield q + "in_proj_b.weight", (nv, H), "linear"
+            yield q + "in_proj_a.weight", (nv, H), "linear"
+            yield q + "conv1d.weight", (2 * key_dim + value_dim, 1, ck), "linear"
+            yield q + "dt_bias", (nv,), "dt_bias"
+            yield q + "A_log", (nv,), "a_log"
+            yield q + "norm.weight", (dv,), "norm"
+            yield q + "out_proj.weight", (H, value_dim), "linear"
+        yield p + "post_attention_layernorm.weight", (H,), "norm0"
+        yield p + "mlp.gate_proj.weight", (I, H), "linear"
+        yield p + "mlp.up_proj.weight", (I, H), "linear"
+        yield p + "mlp.down_proj.weight", (H, I), "linear"
+    yield prefix + "norm.weight", (H,), "norm0"
+    if not tc.get("tie_word_embeddings", True):
+        yield "lm_head.weight", (V, H), "linear"
+
+
 def vision_tensor_specs(vc: dict, prefix: str = "model.visual."):
     Hv, Iv = vc["hidden_size"], vc["intermediate_size"]
     m2 = vc["spatial_merge_size"] ** 2
@@ -197,7 +269,9 @@ def vision_tensor_specs(vc: dict, prefix: str = "model.visual."):
 
 
 def tensor_specs(cfg: dict):
-    if cfg.get("model_type") == "qwen3_vl":
+    if cfg.get("model_type", "").startswith("qwen3_5"):
+        yield from qwen3_5_tensor_specs(cfg)
+    elif cfg.get("model_type") == "qwen3_vl":
         yield from text_tensor_specs(cfg["text_config"], "model.language_model.",
                                      tie=cfg.get("tie_word_embeddings", True))
         yield from vision_tensor_specs(cfg["vision_config"])
@@ -215,6 +289,12 @@ def make_tensor(name: str, shape, kind: str) -> np.ndarray:
         x = _normal(name, shape, shape[1] ** -0.5)
     elif kind == "norm":
         x = _normal(name, shape, 0.02, 1.0)
+    elif kind == "norm0":      # Qwen3.5 stores w with (1 + w) applied at run time; real checkpoints sit near 0.24
+        x = _normal(name, shape, 0.05, 0.24)
+    elif kind == "a_log":      # keep the decay near 1 so state survives (qwen3_5/prefill.rs:164-171)
+        x = _normal(name, shape, 0.1, -2.0)
+    elif kind == "dt_bias":
+        x = _normal(name, shape, 1.0)
     elif kind == "bias":
         x = _normal(name, shape, 0.02)
     else:

@@ -125,6 +125,36 @@ def golden_qwen3_vl(name, cfg, img_hw=(64, 96), n_text=20, n_new=6):
     print(f"{name}: ok, hf tokens {tokens}, ref-act tokens {ref_tokens}")
 
 
+def golden_qwen3_5(name, cfg, n_prompt=21, n_new=6):
+    from transformers.models.qwen3_5 import Qwen3_5ForCausalLM, Qwen3_5TextConfig
+    from oracle.qwen3_5 import Qwen3_5Oracle
+    w = dict(synth.synth_checkpoint(cfg))
+    hf_cfg = Qwen3_5TextConfig(**{k: v for k, v in cfg.items() if k != "model_type"})
+    hf_cfg._attn_implementation = "eager"
+    hf = _load_hf(Qwen3_5ForCausalLM(hf_cfg), w)
+    ids = synth.synth_token_ids(n_prompt, cfg["vocab_size"], tag=name)
+    orc = Qwen3_5Oracle(cfg, w)
+    with torch.no_grad():
+        toks = [int(t) for t in ids]
+        hf_logits, tokens = [], []
+        past = None
+        for step in range(n_new):
+            ctx = toks if step == 0 else toks[-1:]
+            out = hf(input_ids=torch.tensor([ctx]), past_key_values=past, use_cache=True)
+            past = out.past_key_values
+            lg = out.logits[0, -1].float()
+            lo = orc.forward(ctx, len(toks) - len(ctx))
+            err = float((lg - lo).abs().max() / lg.abs().max())
+            assert err < 5e-5, f"{name}: oracle vs HF step {step}: {err}"
+            nxt = int(lg.argmax())
+            hf_logits.append(lg.numpy())
+            tokens.append(nxt)
+            toks.append(nxt)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), prompt=ids, logits=np.stack(hf_logits),
+                        tokens=np.array(tokens, np.uint32))
+    print(f"{name}: ok, tokens {tokens}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -132,6 +162,7 @@ def main():
     golden_qwen3("tiny_qwen3", synth.TINY_QWEN3)
     golden_qwen3("tiny_qwen3_untied", synth.TINY_QWEN3_UNTIED)
     golden_qwen3_vl("tiny_qwen3_vl", synth.TINY_QWEN3_VL)
+    golden_qwen3_5("tiny_qwen3_5", synth.TINY_QWEN3_5)
 
 
 if __name__ == "__main__":

@@ -145,3 +145,50 @@ def test_bf16_helpers_roundtrip():
     x = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
     bits = synth.f32_to_bf16_bits(x)
     assert np.array_equal(synth.bf16_bits_to_f32(bits), torch.from_numpy(x).to(torch.bfloat16).float().numpy())
+
+
+# ---- Qwen3.5 hybrid (GDN + gated attention) ---------------------------------------------------------
+
+def test_tiny_qwen3_5_matches_hf_fixture():
+    from oracle.qwen3_5 import Qwen3_5Oracle
+    cfg = synth.TINY_QWEN3_5
+    g = golden("tiny_qwen3_5")
+    orc = Qwen3_5Oracle(cfg, _weights(cfg))
+    toks = [int(t) for t in g["prompt"]]
+    for step in range(g["logits"].shape[0]):
+        ctx = toks if step == 0 else toks[-1:]
+        lo = orc.forward(ctx, len(toks) - len(ctx)).numpy()
+        assert rel_err(lo, g["logits"][step]) < 5e-5
+        toks.append(int(g["tokens"][step]))
+
+
+def test_qwen3_5_chunked_prefill_equals_single_pass():
+    # crane-core/src/models/qwen3_5/prefill.rs:146-278 (RandWeights backend, 1e-4): KV + conv + recurrent state hand-off
+    from oracle.qwen3_5 import Qwen3_5Oracle
+    cfg = synth.TINY_QWEN3_5
+    w = _weights(cfg)
+    ids = synth.synth_token_ids(23, cfg["vocab_size"], "q35chunk")
+    a, b, c = (Qwen3_5Oracle(cfg, w) for _ in range(3))
+    full = a.forward(ids, 0).numpy()
+    b.forward(ids[:9], 0)
+    b.forward(ids[9:10], 9)          # a one-token chunk takes decode_conv1d's path (ops/gdn/conv.rs:82-101)
+    part = b.forward(ids[10:], 10).numpy()
+    assert rel_err(part, full) < 1e-4
+    for i, t in enumerate(ids):
+        inc = c.forward([t], i).numpy()
+    assert rel_err(inc, full) < 1e-4
+
+
+def test_gdn_v_head_expansion_order():
+    # crane-core/src/ops/gdn/layer.rs:281-293: Interleaved (HF) puts a key head's replicas next to each other
+    k = torch.tensor([10.0, 20.0]).view(1, 2, 1)
+    assert k.repeat_interleave(2, dim=1).flatten().tolist() == [10, 10, 20, 20]
+
+
+def test_gdn_recurrence_definition():
+    # kernels/cuda/gdn.cu:29-34 / ops/gdn/backend.rs:121-148, one step by hand: S=0, k=e0, v, beta -> S=k (x) beta v ; y = S^T q
+    from oracle.qwen3_5 import gated_delta_rule
+    K, V = 4, 3
+    q = torch.tensor([[[2.0, 0, 0, 0]]]); k = torch.tensor([[[1.0, 0, 0, 0]]]); v = torch.tensor([[[1.0, 2, 3]]])
+    y, s = gated_delta_rule(q, k, v, torch.zeros(1, 1), torch.tensor([[0.5]]), torch.zeros(1, K, V))
+    assert torch.allclose(s[0, 0], torch.tensor([0.5, 1.0, 1.5])) and torch.allclose(y[0, 0], s[0, 0] * 2.0 / 2.0)
