@@ -127,10 +127,23 @@ def synth_checkpoint_parallel(cfg, as_bits):
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle's f32 path on the host cores
 # --------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU arm uses: the cores this process may actually run on (affinity mask and cgroup quota), capped at 32
+    -- past that torch's f32 GEMV/GEMM on this model stops scaling and, on an over-subscribed 128-vCPU box, collapses."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def run_cpu(cfg, weights, n_decode, steps, warmup):
     import torch
     from oracle.qwen3_vl import Qwen3VLOracle
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     orc = Qwen3VLOracle(cfg, {k: v for k, v in weights}, max_pos=2048)
     ids, pv, grid = make_request(cfg)

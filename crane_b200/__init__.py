@@ -255,6 +255,11 @@ class Qwen3Model(Engine):
         return self.generate_greedy(input_ids, max_new_tokens, eos)
 
 
+class Qwen3_5Model(Qwen3Model):
+    """`crane_core::models::qwen3_5::Model` (qwen3_5/model.rs:628-943): hybrid Gated-Delta-Net + gated attention
+    decoder.  Same surface as Qwen3Model; `clear_kv_cache` also zeroes the GDN conv / recurrent state."""
+
+
 class Qwen3VLModel(Engine):
     """`Qwen3_5VLModel` (qwen3_5/vlm.rs:78-415) over the Qwen3-VL geometry: `forward` = ViT + splice + prefill,
     `decode_step` = one token with the scalar MRoPE counter."""

@@ -1,149 +1,204 @@
 // Decode-path kernels.  See decode.cuh for the design.
 #include "decode.cuh"
 
+#include <cooperative_groups.h>
+
 namespace cb {
 
-constexpr int GEMV_THREADS = 512;
-constexpr int GEMV_WARPS = GEMV_THREADS / 32;
-constexpr int GEMV_U = 4;   // 16-byte weight loads in flight per lane per batch
-
-// Dot products of one weight row with the B staged activation vectors.
-// xs layout: [B][2][K8] float4 -- for 8-element chunk i of vector b, xs[(b*2+0)*K8+i] holds elements
-// 8i..8i+3 and xs[(b*2+1)*K8+i] elements 8i+4..8i+7 (lane-contiguous float4 reads: no bank conflicts).
-template <int B>
-__device__ __forceinline__ void row_dot(const uint4* __restrict__ wrow, int K8, const float4* __restrict__ xs,
-                                        int lane, const uint4* pre, bool use_pre, float* acc) {
-#pragma unroll
-    for (int b = 0; b < B; ++b) acc[b] = 0.f;
-    for (int c0 = lane; c0 < K8; c0 += 32 * GEMV_U) {
-        uint4 w[GEMV_U];
-        if (use_pre && c0 == lane) {
-#pragma unroll
-            for (int u = 0; u < GEMV_U; ++u) w[u] = pre[u];
-        } else {
-#pragma unroll
-            for (int u = 0; u < GEMV_U; ++u) {
-                const int idx = c0 + 32 * u;
-                w[u] = (idx < K8) ? ldg_stream(wrow + idx) : make_uint4(0, 0, 0, 0);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < GEMV_U; ++u) {
-            const int idx = c0 + 32 * u;
-            if (idx < K8) {
-                const float w0 = bf16lo(w[u].x), w1 = bf16hi(w[u].x), w2 = bf16lo(w[u].y), w3 = bf16hi(w[u].y);
-                const float w4 = bf16lo(w[u].z), w5 = bf16hi(w[u].z), w6 = bf16lo(w[u].w), w7 = bf16hi(w[u].w);
-#pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    const float4 xl = xs[(size_t)(b * 2 + 0) * K8 + idx];
-                    const float4 xh = xs[(size_t)(b * 2 + 1) * K8 + idx];
-                    float s = acc[b];
-                    s = fmaf(w0, xl.x, s); s = fmaf(w1, xl.y, s); s = fmaf(w2, xl.z, s); s = fmaf(w3, xl.w, s);
-                    s = fmaf(w4, xh.x, s); s = fmaf(w5, xh.y, s); s = fmaf(w6, xh.z, s); s = fmaf(w7, xh.w, s);
-                    acc[b] = s;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int b = 0; b < B; ++b) acc[b] = warp_sum(acc[b]);
-}
+// =====================================================================================
+// Weight-streaming GEMV:  y[b, n] = epilogue( sum_k W[n, k] * x[b, k] )          (B <= 8 sequences)
+//
+// grid = #SMs; CTA c owns the contiguous row block [c*rpc, (c+1)*rpc) of W, i.e. ONE contiguous byte slab.
+//   warp 0   : producer -- one lane streams the slab HBM -> shared memory with 1-D bulk async copies
+//              (cp.async.bulk, 16 KB stages, 5-deep mbarrier ring = 80 KB in flight per SM).  Weights do not depend on
+//              the previous kernel, so the ring fills BEFORE griddepcontrol.wait: the HBM pipe stays busy across the
+//              kernel boundary (programmatic dependent launch; two CTAs -- this kernel's and the next one's -- fit an SM).
+//   warps 1-8: consumers -- stage the f32 activations (RMSNorm folded in), then each warp takes a contiguous 2 KB run of
+//              every stage (16-byte LDS per lane, conflict-free), accumulates in f32 and flushes per-row partial sums to
+//              a shared accumulator array with shuffles + one shared atomic per row change.
+// Epilogue (all threads): store / residual add / SiLU*up on interleaved rows / logits + CTA argmax.
+// =====================================================================================
+constexpr int GV_STAGE_BYTES = 16384;
+constexpr int GV_STAGES = 5;
+constexpr int GV_CWARPS = 8;
+constexpr int GV_CTHREADS = GV_CWARPS * 32;
+constexpr int GV_THREADS = GV_CTHREADS + 32;
+constexpr int GV_CHUNKS_PER_WARP = GV_STAGE_BYTES / 512 / GV_CWARPS;   // 512-byte chunks (one 16 B load per lane) per warp per stage
 
 template <int B, int EPI, bool NORM>
-__global__ void __launch_bounds__(GEMV_THREADS, (B <= 2) ? 2 : 1)
+__global__ void __launch_bounds__(GV_THREADS, 1)
 gemv_kernel(GemvArgs a) {
-    extern __shared__ float4 xs[];            // [B][2][K8]
-    __shared__ float red[32];
-    __shared__ float rstd_s[B];
-    __shared__ float wbest_v[GEMV_WARPS][B];
-    __shared__ int wbest_i[GEMV_WARPS][B];
-    __shared__ int is_last_s;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(1024) unsigned char gsm[];
+    // layout: [ring: GV_STAGES * 16 KB][xs: B * K f32][acc: B * rpc f32][barriers]
     const int K8 = a.K >> 3;
     constexpr int ROWS_PER_UNIT = (EPI == GEMV_SILU_MUL) ? 2 : 1;
     const int units = a.N / ROWS_PER_UNIT;
-    const int upc = (units + gridDim.x - 1) / gridDim.x;          // units per CTA
-    const int u0 = blockIdx.x * upc;
-    const int u1 = min(units, u0 + upc);
+    const int upc = (units + gridDim.x - 1) / gridDim.x;
+    const int rpc = upc * ROWS_PER_UNIT;                               // rows per CTA (capacity)
+    const int r0 = blockIdx.x * rpc;
+    const int r1 = min(a.N, r0 + rpc);
+    const int nrows = max(0, r1 - r0);
+    unsigned char* ring = gsm;
+    float4* xs = reinterpret_cast<float4*>(gsm + GV_STAGES * GV_STAGE_BYTES);
+    float* acc_s = reinterpret_cast<float*>(xs) + (size_t)B * a.K;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc_s + (((size_t)B * rpc + 1) & ~(size_t)1));
+    uint64_t* empty_bar = full_bar + GV_STAGES;
+    __shared__ float red[32];
+    __shared__ float rstd_s[B];
+    __shared__ float wbest_v[GV_THREADS / 32][B];
+    __shared__ int wbest_i[GV_THREADS / 32][B];
+    __shared__ int is_last_s;
 
-    // --- weights do not depend on the previous kernel: start streaming before the PDL wait ---
-    uint4 pre[GEMV_U];
-    const int ufirst = u0 + warp;
-    const bool have_first = ufirst < u1;
-    if (have_first) {
-        const uint4* wrow = reinterpret_cast<const uint4*>(a.W + (size_t)(ufirst * ROWS_PER_UNIT) * a.K);
-#pragma unroll
-        for (int u = 0; u < GEMV_U; ++u) {
-            const int idx = lane + 32 * u;
-            pre[u] = (idx < K8) ? ldg_stream(wrow + idx) : make_uint4(0, 0, 0, 0);
-        }
-    }
-    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t row_bytes = (size_t)a.K * 2;
+    const size_t slab_bytes = (size_t)nrows * row_bytes;
+    const int n_stages = (int)((slab_bytes + GV_STAGE_BYTES - 1) / GV_STAGE_BYTES);
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.W) + (size_t)r0 * row_bytes;
 
-    // --- stage activations (f32) and, if NORM, fold the RMSNorm weight in and get 1/rms ---
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-        float ssq = 0.f;
-        for (int i = tid; i < K8; i += GEMV_THREADS) {
-            const float4* xp = reinterpret_cast<const float4*>(a.x + (size_t)b * a.ldx) + 2 * i;
-            float4 lo = xp[0], hi = xp[1];
-            if (NORM) {
-                ssq += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w + hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
-                const float4* gp = reinterpret_cast<const float4*>(a.norm_w) + 2 * i;
-                const float4 g0 = gp[0], g1 = gp[1];
-                lo.x *= g0.x; lo.y *= g0.y; lo.z *= g0.z; lo.w *= g0.w;
-                hi.x *= g1.x; hi.y *= g1.y; hi.z *= g1.z; hi.w *= g1.w;
-            }
-            xs[(size_t)(b * 2 + 0) * K8 + i] = lo;
-            xs[(size_t)(b * 2 + 1) * K8 + i] = hi;
-        }
-        if (NORM) {
-            const float tot = block_sum(ssq, red);
-            if (tid == 0) rstd_s[b] = rsqrtf(tot / (float)a.K + a.eps);
-        }
+    if (tid == 0) {
+        for (int s = 0; s < GV_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], GV_CWARPS); }
+        fence_barrier_init();
     }
+    for (int i = tid; i < B * rpc; i += GV_THREADS) acc_s[i] = 0.f;
     __syncthreads();
-    pdl_launch_dependents();
 
-    float bestv[B];
-    int besti[B];
+    if (warp == 0) {
+        // ------------------------------- producer -------------------------------
+        if (lane == 0) {
+            for (int s = 0; s < n_stages; ++s) {
+                const int slot = s % GV_STAGES;
+                mbar_wait(&empty_bar[slot], (((s / GV_STAGES) & 1) ^ 1));
+                const size_t off = (size_t)s * GV_STAGE_BYTES;
+                const uint32_t bytes = (uint32_t)min((size_t)GV_STAGE_BYTES, slab_bytes - off);
+                mbar_arrive_expect_tx(&full_bar[slot], bytes);
+                bulk_load(ring + slot * GV_STAGE_BYTES, gsrc + off, bytes, &full_bar[slot]);
+            }
+        }
+    } else {
+        // ------------------------------- consumers ------------------------------
+        const int ctid = tid - 32, cw = warp - 1;
+        pdl_wait();
+        pdl_launch_dependents();
 #pragma unroll
-    for (int b = 0; b < B; ++b) { bestv[b] = -INFINITY; besti[b] = 0x7fffffff; }
+        for (int b = 0; b < B; ++b) {
+            float ssq = 0.f;
+            for (int i = ctid; i < K8; i += GV_CTHREADS) {
+                const float4* xp = reinterpret_cast<const float4*>(a.x + (size_t)b * a.ldx) + 2 * i;
+                float4 lo = xp[0], hi = xp[1];
+                if (NORM) {
+                    ssq += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w + hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
+                    const float4 w0 = reinterpret_cast<const float4*>(a.norm_w)[2 * i], w1 = reinterpret_cast<const float4*>(a.norm_w)[2 * i + 1];
+                    lo.x *= w0.x; lo.y *= w0.y; lo.z *= w0.z; lo.w *= w0.w;
+                    hi.x *= w1.x; hi.y *= w1.y; hi.z *= w1.z; hi.w *= w1.w;
+                }
+                xs[(size_t)(b * 2 + 0) * K8 + i] = lo;
+                xs[(size_t)(b * 2 + 1) * K8 + i] = hi;
+            }
+            if (NORM) {
+                ssq = warp_sum(ssq);
+                if (lane == 0) red[cw] = ssq;
+                named_bar_sync(1, GV_CTHREADS);
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < GV_CWARPS; ++w) tot += red[w];
+                if (ctid == 0) rstd_s[b] = rsqrtf(tot / (float)a.K + a.eps);
+                named_bar_sync(1, GV_CTHREADS);
+            }
+        }
+        named_bar_sync(1, GV_CTHREADS);
 
-    bool first = true;
-    for (int un = u0 + warp; un < u1; un += GEMV_WARPS) {
-        float acc[B];
-        if constexpr (EPI == GEMV_SILU_MUL) {
-            float g[B];
-            row_dot<B>(reinterpret_cast<const uint4*>(a.W + (size_t)(2 * un) * a.K), K8, xs, lane, pre, first, g);
-            row_dot<B>(reinterpret_cast<const uint4*>(a.W + (size_t)(2 * un + 1) * a.K), K8, xs, lane, pre, false, acc);
-            if (lane == 0) {
+        float accum[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) accum[b] = 0.f;
+        int cur_row = -1;
+        auto flush = [&]() {
+            if (cur_row >= 0) {
 #pragma unroll
                 for (int b = 0; b < B; ++b) {
-                    const float r = NORM ? rstd_s[b] : 1.f;
-                    a.y[(size_t)b * a.ldy + un] = silu_f(g[b] * r) * (acc[b] * r);
+                    const float v = warp_sum(accum[b]);
+                    if (lane == 0) atomicAdd(&acc_s[(size_t)b * rpc + cur_row], v);
+                    accum[b] = 0.f;
                 }
             }
-        } else {
-            row_dot<B>(reinterpret_cast<const uint4*>(a.W + (size_t)un * a.K), K8, xs, lane, pre, first, acc);
-            if (lane == 0) {
+        };
+        for (int s = 0; s < n_stages; ++s) {
+            const int slot = s % GV_STAGES;
+            mbar_wait(&full_bar[slot], (s / GV_STAGES) & 1);
+            const size_t soff = (size_t)s * GV_STAGE_BYTES;
+            const unsigned char* sp = ring + slot * GV_STAGE_BYTES;
+            uint4 w[GV_CHUNKS_PER_WARP];
+            size_t coff[GV_CHUNKS_PER_WARP];
 #pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    const float v = acc[b] * (NORM ? rstd_s[b] : 1.f);
-                    float* yp = a.y + (size_t)b * a.ldy + un;
-                    if constexpr (EPI == GEMV_RESID) *yp += v; else *yp = v;
-                    if constexpr (EPI == GEMV_LOGITS_ARGMAX) {
-                        if (v > bestv[b]) { bestv[b] = v; besti[b] = un; }   // rows ascend: first maximum wins
+            for (int c = 0; c < GV_CHUNKS_PER_WARP; ++c) {
+                const int chunk = cw * GV_CHUNKS_PER_WARP + c;
+                coff[c] = soff + (size_t)chunk * 512;
+                if (coff[c] < slab_bytes) w[c] = *reinterpret_cast<const uint4*>(sp + chunk * 512 + lane * 16);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);       // data is in registers: hand the slot back early
+#pragma unroll
+            for (int c = 0; c < GV_CHUNKS_PER_WARP; ++c) {
+                if (coff[c] < slab_bytes) {
+                    const int row = (int)(coff[c] / row_bytes);
+                    const int idx = (int)((coff[c] - (size_t)row * row_bytes) >> 4) + lane;    // 8-element chunk index in the row
+                    if (row != cur_row) { flush(); cur_row = row; }
+                    const float w0 = bf16lo(w[c].x), w1 = bf16hi(w[c].x), w2 = bf16lo(w[c].y), w3 = bf16hi(w[c].y);
+                    const float w4 = bf16lo(w[c].z), w5 = bf16hi(w[c].z), w6 = bf16lo(w[c].w), w7 = bf16hi(w[c].w);
+#pragma unroll
+                    for (int b = 0; b < B; ++b) {
+                        const float4 xl = xs[(size_t)(b * 2 + 0) * K8 + idx];
+                        const float4 xh = xs[(size_t)(b * 2 + 1) * K8 + idx];
+                        float t = accum[b];
+                        t = fmaf(w0, xl.x, t); t = fmaf(w1, xl.y, t); t = fmaf(w2, xl.z, t); t = fmaf(w3, xl.w, t);
+                        t = fmaf(w4, xh.x, t); t = fmaf(w5, xh.y, t); t = fmaf(w6, xh.z, t); t = fmaf(w7, xh.w, t);
+                        accum[b] = t;
                     }
                 }
             }
         }
-        first = false;
+        flush();
+    }
+    __syncthreads();
+
+    // ------------------------------- epilogue (all threads) -------------------------------
+    float bestv[B];
+    int besti[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) { bestv[b] = -INFINITY; besti[b] = 0x7fffffff; }
+    if constexpr (EPI == GEMV_SILU_MUL) {
+        for (int u = tid; u < nrows / 2; u += GV_THREADS) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const float r = NORM ? rstd_s[b] : 1.f;
+                const float g = acc_s[(size_t)b * rpc + 2 * u] * r, up = acc_s[(size_t)b * rpc + 2 * u + 1] * r;
+                a.y[(size_t)b * a.ldy + (r0 / 2 + u)] = silu_f(g) * up;
+            }
+        }
+    } else {
+        for (int i = tid; i < nrows; i += GV_THREADS) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const float v = acc_s[(size_t)b * rpc + i] * (NORM ? rstd_s[b] : 1.f);
+                float* yp = a.y + (size_t)b * a.ldy + r0 + i;
+                if constexpr (EPI == GEMV_RESID) *yp += v; else *yp = v;
+                if constexpr (EPI == GEMV_LOGITS_ARGMAX) {
+                    if (v > bestv[b]) { bestv[b] = v; besti[b] = r0 + i; }   // a thread's rows ascend: first maximum wins
+                }
+            }
+        }
     }
 
     if constexpr (EPI == GEMV_LOGITS_ARGMAX) {
         // CTA-level (value, lowest index) reduction, then last-CTA-done finalisation.
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bestv[b], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti[b], o);
+                if (ov > bestv[b] || (ov == bestv[b] && oi < besti[b])) { bestv[b] = ov; besti[b] = oi; }
+            }
+        }
         if (lane == 0) {
 #pragma unroll
             for (int b = 0; b < B; ++b) { wbest_v[warp][b] = bestv[b]; wbest_i[warp][b] = besti[b]; }
@@ -151,7 +206,7 @@ gemv_kernel(GemvArgs a) {
         __syncthreads();
         if (tid < B) {
             float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int w = 0; w < GEMV_WARPS; ++w) {
+            for (int w = 0; w < GV_THREADS / 32; ++w) {
                 const float v = wbest_v[w][tid]; const int i = wbest_i[w][tid];
                 if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
             }
@@ -199,25 +254,33 @@ gemv_kernel(GemvArgs a) {
             if (a.advance) {   // gather the next step's input embedding (bf16 -> f32 residual stream)
                 for (int b = 0; b < B; ++b) {
                     const bf16* row = a.embed + (size_t)tok_s[b] * a.H;
-                    for (int i = tid; i < a.H; i += GEMV_THREADS) a.x_next[(size_t)b * a.H + i] = __bfloat162float(row[i]);
+                    for (int i = tid; i < a.H; i += GV_THREADS) a.x_next[(size_t)b * a.H + i] = __bfloat162float(row[i]);
                 }
             }
         }
     }
 }
 
+static size_t gemv_smem_bytes(int B, int K, int N, int rows_per_unit, int grid) {
+    const int units = N / rows_per_unit;
+    const int rpc = (units + grid - 1) / grid * rows_per_unit;
+    size_t acc = (((size_t)B * rpc + 1) & ~(size_t)1) * 4;
+    return (size_t)GV_STAGES * GV_STAGE_BYTES + (size_t)B * K * 4 + acc + 2 * GV_STAGES * 8 + 16;
+}
+
 template <int B, int EPI, bool NORM>
 static int gemv_launch_t(cudaStream_t st, const GemvArgs& a, int num_sms, bool pdl) {
-    const size_t smem = (size_t)B * a.K * sizeof(float);
+    const size_t smem = gemv_smem_bytes(B, a.K, a.N, EPI == GEMV_SILU_MUL ? 2 : 1, num_sms);
+    if (smem > 227 * 1024) return -1000;
     static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(gemv_kernel<B, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms);
-    cfg.blockDim = dim3(GEMV_THREADS);
+    cfg.blockDim = dim3(GV_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -242,14 +305,12 @@ static int gemv_launch_b(cudaStream_t st, int epi, bool norm, const GemvArgs& a,
 }
 
 int gemv_launch(cudaStream_t st, int B, int epi, bool norm, const GemvArgs& a, int num_sms, bool pdl) {
-    if ((a.K % 8) != 0 || a.N <= 0) return -1000;
+    if ((a.K % 256) != 0 || a.N <= 0) return -1000;      // a 512-byte chunk must not straddle rows
     if (epi == GEMV_SILU_MUL && (a.N % 2) != 0) return -1000;
-    if ((size_t)B * a.K * sizeof(float) > 200 * 1024) return -1000;
     switch (B) {
         case 1: return gemv_launch_b<1>(st, epi, norm, a, num_sms, pdl);
         case 2: return gemv_launch_b<2>(st, epi, norm, a, num_sms, pdl);
         case 4: return gemv_launch_b<4>(st, epi, norm, a, num_sms, pdl);
-        case 8: return gemv_launch_b<8>(st, epi, norm, a, num_sms, pdl);
         default: return -1000;
     }
 }
@@ -280,32 +341,42 @@ int embed_decode_launch(cudaStream_t st, int B, const bf16* embed, int H, const 
 }
 
 // =====================================================================================
-// Decode attention: QK-norm + (M)RoPE + KV-page append + split-KV GQA attention + split merge
-//   grid (nkv * ATTN_NSPLIT, B), 128 threads.  One CTA = one KV head x one token range, all NREP
-//   query heads of the group share every K/V byte it reads (read once per group, 16-byte loads).
+// Decode attention: QK-norm + (M)RoPE + KV-page append + split-KV GQA attention + in-cluster split merge
+//   grid (nkv * ATTN_NSPLIT, B), 256 threads, thread-block CLUSTER of ATTN_NSPLIT CTAs per KV head.
+//   * every CTA first pulls its token range of the K/V pages into shared memory with cp.async -- BEFORE
+//     griddepcontrol.wait: cached K/V and the sequence state were written at least two kernels ago, so the whole
+//     KV read overlaps the QKV GEMV that precedes this kernel;
+//   * all NREP query heads of the KV group share every K/V byte (read once per group, 16-byte vectors);
+//   * the split partials are merged through distributed shared memory (no global round trip, no atomics).
 // =====================================================================================
 template <int D, int NREP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_decode_kernel(AttnDecArgs a) {
+    namespace cg = cooperative_groups;
     constexpr int EPL = 8;               // bf16 elements per 16-byte lane load
     constexpr int LPT = D / EPL;         // lanes per token (16 for D=128, 32 for D=256)
     constexpr int TPW = 32 / LPT;        // tokens per warp pass
-    constexpr int NW = 4;
-    constexpr int HALF = D / 2;
+    constexpr int NW = 8;
+    constexpr int TILE = 32768 / (D * 2);   // tokens per shared-memory tile (K and V: 32 KB each)
+    constexpr int CPR = D / 8;              // 16-byte chunks per token row
+    extern __shared__ __align__(16) unsigned char asm_[];
+    bf16* k_t = reinterpret_cast<bf16*>(asm_);
+    bf16* v_t = k_t + TILE * D;
+    float* mo_s = reinterpret_cast<float*>(asm_);          // [NW][NREP][D], aliases the tiles after the token loop
     __shared__ float q_s[NREP][D];
     __shared__ float knew_s[D], vnew_s[D];
-    __shared__ float mo_s[NW][NREP][D];
     __shared__ float mm_s[NW][NREP], ml_s[NW][NREP];
-    __shared__ int is_last_s;
+    __shared__ float cta_o[NREP][D];
+    __shared__ float cta_ml[NREP][2];
 
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kvh = blockIdx.x / ATTN_NSPLIT, split = blockIdx.x % ATTN_NSPLIT;
     const int b = blockIdx.y;
     const int q_dim = a.nh * D, kv_dim = a.nkv * D;
+    const int q_span = a.nh * a.q_stride;
 
-    pdl_wait();
-    pdl_launch_dependents();
-
+    // ---- token range of this split, then start the K/V copy (independent of the previous kernel) ----
     const SeqState st = a.state[b];
     const int T = st.kv_len + 1;                      // including the token being decoded
     int chunk = (T + ATTN_NSPLIT - 1) / ATTN_NSPLIT;
@@ -313,15 +384,34 @@ attn_decode_kernel(AttnDecArgs a) {
     const int t0 = split * chunk;
     const int t1 = min(T, t0 + chunk);
     const int s_last = (T - 1) / chunk;
-    const float* qkv = a.qkv + (size_t)b * (q_dim + 2 * kv_dim);
+    const int t_end = min(t1, T - 1);                 // cached tokens only; position T-1 comes from this step's qkv
+    const int* bt = a.block_table + (size_t)b * a.max_pages;
+    auto load_tile = [&](int tb) {
+        const int n = min(TILE, t_end - tb);
+        for (int c = tid; c < n * CPR; c += 256) {
+            const int r = c / CPR, ch = c % CPR;
+            const int t = tb + r;
+            const int page = bt[t / KV_PAGE];
+            const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D + ch * 8;
+            const uint32_t kd = smem_u32(k_t + r * D + ch * 8), vd = smem_u32(v_t + r * D + ch * 8);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd), "l"(a.k_pool + off) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd), "l"(a.v_pool + off) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (t0 < t_end) load_tile(t0);
+
+    pdl_wait();
+    pdl_launch_dependents();
+    const float* qkv = a.qkv + (size_t)b * (q_span + 2 * kv_dim);
 
     // ---- q (NREP heads) and, on the split that owns position T-1, the new k: RMSNorm then rotate ----
-    // Each warp takes vectors round-robin; lane l owns elements l + 32 j so a rotary pair (i, i + D/2) is lane-local.
+    // Each warp takes vectors round-robin; lane l owns elements l + 32 j so a rotary pair is lane-local.
     constexpr int NE = D / 32;
     for (int vec = warp; vec < NREP + 1; vec += NW) {
         const bool is_k = (vec == NREP);
         if (is_k && split != s_last) continue;
-        const float* src = is_k ? (qkv + q_dim + kvh * D) : (qkv + (kvh * NREP + vec) * D);
+        const float* src = is_k ? (qkv + q_span + kvh * D) : (qkv + (kvh * NREP + vec) * a.q_stride);
         const float* nw = is_k ? a.k_norm_w : a.q_norm_w;
         float e[NE];
         float ssq = 0.f;
@@ -332,34 +422,39 @@ attn_decode_kernel(AttnDecArgs a) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) e[j] = e[j] * rstd * nw[lane + 32 * j];
         float* dst = is_k ? knew_s : q_s[vec];
+        const int RJ = a.rot_half >> 5;                // lane-local rotary pairs (j, j + RJ), j < RJ
 #pragma unroll
-        for (int j = 0; j < NE / 2; ++j) {
-            const int i = lane + 32 * j;               // rotary column in [0, D/2)
-            const int p = st.pos[a.axis_of[i]];
-            const float c = a.cos_tab[(size_t)p * HALF + i], s = a.sin_tab[(size_t)p * HALF + i];
-            const float x1 = e[j], x2 = e[j + NE / 2];
-            float r1 = x1 * c - x2 * s, r2 = x1 * s + x2 * c;
-            if (is_k) { r1 = round_bf16(r1); r2 = round_bf16(r2); }
-            dst[i] = r1;
-            dst[i + HALF] = r2;
+        for (int j = 0; j < NE; ++j) {
+            float r = e[j];
+            if (j < 2 * RJ) {
+                const bool lo = j < RJ;
+                const int i = lane + 32 * (lo ? j : j - RJ);     // rotary column in [0, rot_half)
+                const int p = st.pos[a.axis_of[i]];
+                const float c = a.cos_tab[(size_t)p * a.rot_half + i], s = a.sin_tab[(size_t)p * a.rot_half + i];
+                float other = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < NE; ++jj) if (jj == (lo ? j + RJ : j - RJ)) other = e[jj];
+                r = lo ? (e[j] * c - other * s) : (other * s + e[j] * c);
+            }
+            dst[lane + 32 * j] = is_k ? round_bf16(r) : r;
         }
     }
     if (split == s_last && warp == NW - 1) {
-        const float* vsrc = qkv + q_dim + kv_dim + kvh * D;
+        const float* vsrc = qkv + q_span + kv_dim + kvh * D;
         for (int i = lane; i < D; i += 32) vnew_s[i] = round_bf16(vsrc[i]);
     }
     __syncthreads();
     if (split == s_last) {   // append the new token to its page
         const int t = T - 1;
-        const int page = a.block_table[(size_t)b * a.max_pages + t / KV_PAGE];
+        const int page = bt[t / KV_PAGE];
         const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
-        for (int i = tid; i < D; i += 128) {
+        for (int i = tid; i < D; i += 256) {
             a.k_pool[off + i] = __float2bfloat16_rn(knew_s[i]);
             a.v_pool[off + i] = __float2bfloat16_rn(vnew_s[i]);
         }
     }
 
-    // ---- stream the cached tokens of this split ----
+    // ---- the cached tokens of this split, tile by tile out of shared memory ----
     const int grp = lane / LPT, gl = lane % LPT;        // token group inside the warp, lane inside the group
     float qr[NREP][EPL];
 #pragma unroll
@@ -373,39 +468,41 @@ attn_decode_kernel(AttnDecArgs a) {
 #pragma unroll
         for (int j = 0; j < EPL; ++j) o[h][j] = 0.f;
     }
-    const int t_end = min(t1, T - 1);                   // cached tokens only; T-1 comes from shared memory
-    const int* bt = a.block_table + (size_t)b * a.max_pages;
-    for (int tb = t0 + warp * TPW; tb < t_end; tb += NW * TPW) {
-        const int t = tb + grp;
-        const bool valid = t < t_end;
-        float kf[EPL], vf[EPL];
-        if (valid) {
-            const int page = bt[t / KV_PAGE];
-            const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D + gl * EPL;
-            const uint4 kr = ldg_stream(a.k_pool + off);
-            const uint4 vr = ldg_stream(a.v_pool + off);
-            kf[0] = bf16lo(kr.x); kf[1] = bf16hi(kr.x); kf[2] = bf16lo(kr.y); kf[3] = bf16hi(kr.y);
-            kf[4] = bf16lo(kr.z); kf[5] = bf16hi(kr.z); kf[6] = bf16lo(kr.w); kf[7] = bf16hi(kr.w);
-            vf[0] = bf16lo(vr.x); vf[1] = bf16hi(vr.x); vf[2] = bf16lo(vr.y); vf[3] = bf16hi(vr.y);
-            vf[4] = bf16lo(vr.z); vf[5] = bf16hi(vr.z); vf[6] = bf16lo(vr.w); vf[7] = bf16hi(vr.w);
-        } else {
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) { kf[j] = 0.f; vf[j] = 0.f; }
-        }
-#pragma unroll
-        for (int h = 0; h < NREP; ++h) {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) s = fmaf(qr[h][j], kf[j], s);
-#pragma unroll
-            for (int ofs = LPT / 2; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
+    for (int tb = t0; tb < t_end; tb += TILE) {
+        if (tb != t0) { __syncthreads(); load_tile(tb); }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int n = min(TILE, t_end - tb);
+        for (int r0 = warp * TPW; r0 < n; r0 += NW * TPW) {
+            const int r = r0 + grp;
+            const bool valid = r < n;
+            float kf[EPL], vf[EPL];
             if (valid) {
-                const float mn = fmaxf(m[h], s);
-                const float corr = __expf(m[h] - mn), p = __expf(s - mn);
-                l[h] = l[h] * corr + p;
+                const uint4 kr = *reinterpret_cast<const uint4*>(k_t + r * D + gl * EPL);
+                const uint4 vr = *reinterpret_cast<const uint4*>(v_t + r * D + gl * EPL);
+                kf[0] = bf16lo(kr.x); kf[1] = bf16hi(kr.x); kf[2] = bf16lo(kr.y); kf[3] = bf16hi(kr.y);
+                kf[4] = bf16lo(kr.z); kf[5] = bf16hi(kr.z); kf[6] = bf16lo(kr.w); kf[7] = bf16hi(kr.w);
+                vf[0] = bf16lo(vr.x); vf[1] = bf16hi(vr.x); vf[2] = bf16lo(vr.y); vf[3] = bf16hi(vr.y);
+                vf[4] = bf16lo(vr.z); vf[5] = bf16hi(vr.z); vf[6] = bf16lo(vr.w); vf[7] = bf16hi(vr.w);
+            } else {
 #pragma unroll
-                for (int j = 0; j < EPL; ++j) o[h][j] = o[h][j] * corr + p * vf[j];
-                m[h] = mn;
+                for (int j = 0; j < EPL; ++j) { kf[j] = 0.f; vf[j] = 0.f; }
+            }
+#pragma unroll
+            for (int h = 0; h < NREP; ++h) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) s = fmaf(qr[h][j], kf[j], s);
+#pragma unroll
+                for (int ofs = LPT / 2; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
+                if (valid) {
+                    const float mn = fmaxf(m[h], s);
+                    const float corr = __expf(m[h] - mn), p = __expf(s - mn);
+                    l[h] = l[h] * corr + p;
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) o[h][j] = o[h][j] * corr + p * vf[j];
+                    m[h] = mn;
+                }
             }
         }
     }
@@ -444,17 +541,18 @@ attn_decode_kernel(AttnDecArgs a) {
             m[h] = mn;
         }
     }
+    __syncthreads();                                     // tiles are dead: reuse them as the warp-merge buffer
     if (grp == 0) {
 #pragma unroll
         for (int h = 0; h < NREP; ++h) {
             if (gl == 0) { mm_s[warp][h] = m[h]; ml_s[warp][h] = l[h]; }
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) mo_s[warp][h][gl * EPL + j] = o[h][j];
+            for (int j = 0; j < EPL; ++j) mo_s[((size_t)warp * NREP + h) * D + gl * EPL + j] = o[h][j];
         }
     }
     __syncthreads();
-    // merge the warps, write this split's partial
-    for (int idx = tid; idx < NREP * D; idx += 128) {
+    // merge the warps -> this CTA's partial in shared memory
+    for (int idx = tid; idx < NREP * D; idx += 256) {
         const int h = idx / D, i = idx % D;
         float M = -INFINITY;
 #pragma unroll
@@ -464,59 +562,67 @@ attn_decode_kernel(AttnDecArgs a) {
         for (int w = 0; w < NW; ++w) {
             const float c = (mm_s[w][h] == -INFINITY) ? 0.f : __expf(mm_s[w][h] - M);
             L += ml_s[w][h] * c;
-            O += mo_s[w][h][i] * c;
+            O += mo_s[((size_t)w * NREP + h) * D + i] * c;
+        }
+        cta_o[h][i] = O;
+        if (i == 0) { cta_ml[h][0] = M; cta_ml[h][1] = L; }
+    }
+    // ---- merge the splits of this KV group through distributed shared memory ----
+    cluster.sync();
+    for (int idx = split * 256 + tid; idx < NREP * D; idx += ATTN_NSPLIT * 256) {
+        const int h = idx / D, i = idx % D;
+        float ms[ATTN_NSPLIT];
+        float M = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < ATTN_NSPLIT; ++s) {
+            const float* rml = cluster.map_shared_rank(&cta_ml[0][0], s);
+            ms[s] = rml[h * 2];
+            M = fmaxf(M, ms[s]);
+        }
+        float L = 0.f, O = 0.f;
+#pragma unroll
+        for (int s = 0; s < ATTN_NSPLIT; ++s) {
+            const float c = (ms[s] == -INFINITY) ? 0.f : __expf(ms[s] - M);
+            const float* rml = cluster.map_shared_rank(&cta_ml[0][0], s);
+            const float* ro = cluster.map_shared_rank(&cta_o[0][0], s);
+            L += rml[h * 2 + 1] * c;
+            O += ro[h * D + i] * c;
         }
         const int head = kvh * NREP + h;
-        const size_t pbase = ((size_t)b * a.nh + head) * ATTN_NSPLIT + split;
-        a.part_o[pbase * D + i] = O;
-        if (i == 0) { a.part_ml[pbase * 2 + 0] = M; a.part_ml[pbase * 2 + 1] = L; }
+        float r = O / L;
+        if (a.gated) r *= 1.0f / (1.0f + expf(-qkv[head * a.q_stride + D + i]));   // y * sigmoid(gate), modeling.rs:516-523
+        a.out[(size_t)b * q_dim + head * D + i] = r;
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int tk = atomicAdd(a.counters + b * a.nkv + kvh, 1u);
-        is_last_s = (tk == ATTN_NSPLIT - 1);
-        if (is_last_s) a.counters[b * a.nkv + kvh] = 0u;
-    }
-    __syncthreads();
-    if (is_last_s) {   // last split to finish combines all splits of this KV group
-        __threadfence();
-        for (int idx = tid; idx < NREP * D; idx += 128) {
-            const int h = idx / D, i = idx % D;
-            const int head = kvh * NREP + h;
-            const size_t pbase = ((size_t)b * a.nh + head) * ATTN_NSPLIT;
-            float M = -INFINITY;
-#pragma unroll
-            for (int s = 0; s < ATTN_NSPLIT; ++s) M = fmaxf(M, __ldcg(a.part_ml + (pbase + s) * 2));
-            float L = 0.f, O = 0.f;
-#pragma unroll
-            for (int s = 0; s < ATTN_NSPLIT; ++s) {
-                const float ms = __ldcg(a.part_ml + (pbase + s) * 2);
-                const float c = (ms == -INFINITY) ? 0.f : __expf(ms - M);
-                L += __ldcg(a.part_ml + (pbase + s) * 2 + 1) * c;
-                O += __ldcg(a.part_o + (pbase + s) * D + i) * c;
-            }
-            a.out[(size_t)b * q_dim + head * D + i] = O / L;
-        }
-    }
+    cluster.sync();                                      // nobody exits while its shared memory is still being read
 }
 
 template <int D, int NREP>
 static int attn_decode_launch_t(cudaStream_t st, int B, const AttnDecArgs& a, bool pdl) {
+    constexpr int SMEM = 65536;
+    static bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<D, NREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return (int)e;
+        set = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.nkv * ATTN_NSPLIT, B);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ATTN_NSPLIT; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = pdl ? 2 : 1;
     return (int)cudaLaunchKernelEx(&cfg, attn_decode_kernel<D, NREP>, a);
 }
 
 int attn_decode_launch(cudaStream_t st, int B, int D, const AttnDecArgs& a, bool pdl) {
     const int nrep = a.nh / a.nkv;
+    if (a.rot_half < 32 || (a.rot_half % 32) != 0 || 2 * a.rot_half > D) return -1000;
     if (D == 128) {
         switch (nrep) {
             case 1: return attn_decode_launch_t<128, 1>(st, B, a, pdl);

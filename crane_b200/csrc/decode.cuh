@@ -18,7 +18,7 @@
 namespace cb {
 
 constexpr int KV_PAGE = 64;        // tokens per KV page
-constexpr int ATTN_NSPLIT = 16;    // fixed split-KV factor (grid is static so the step can live in a CUDA graph)
+constexpr int ATTN_NSPLIT = 8;     // split-KV factor == thread-block cluster size (static grid: the step lives in a CUDA graph)
 constexpr int MAX_BATCH = 8;
 
 // Device-resident per-sequence decode state (lets a whole decode step replay as a CUDA graph).
@@ -55,13 +55,16 @@ struct GemvArgs {
 };
 
 struct AttnDecArgs {
-    const float* qkv;        // [B, q_dim + 2*kv_dim] f32 (pre-norm, pre-rope)
+    const float* qkv;        // [B, nh*q_stride + 2*kv_dim] f32 (pre-norm, pre-rope); head h's query at h*q_stride
+    int q_stride;            // D, or 2*D when q_proj emits per-head [query | gate] (Qwen3.5, qwen3_5/modeling.rs:428-455)
+    int gated;               // 1: out *= sigmoid(gate)
+    int rot_half;            // rotary pairs (i, i + rot_half), i < rot_half; D/2 for full rotary, 32 for Qwen3.5's 64-of-256
     const float* q_norm_w;   // [D]
     const float* k_norm_w;   // [D]
     float eps;
-    const float* cos_tab;    // [max_pos, D/2]
+    const float* cos_tab;    // [max_pos, rot_half]
     const float* sin_tab;
-    const unsigned char* axis_of;  // [D/2] MRoPE axis per rotary column (all 0 for 1-D RoPE)
+    const unsigned char* axis_of;  // [rot_half] MRoPE axis per rotary column (all 0 for 1-D RoPE)
     const SeqState* state;   // [B]
     const int* block_table;  // [B, max_pages]
     int max_pages;
@@ -69,9 +72,6 @@ struct AttnDecArgs {
     bf16* v_pool;
     int nh, nkv;
     float scale;
-    float* part_o;           // [B, nh, NSPLIT, D]
-    float* part_ml;          // [B, nh, NSPLIT, 2]
-    unsigned int* counters;  // [B, nkv]
     float* out;              // [B, nh*D] f32
 };
 

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "decode.cuh"
+#include "gdn.cuh"
 #include "gemm.cuh"
 #include "json_min.h"
 #include "prefill.cuh"
@@ -103,6 +104,11 @@ struct LayerW {
     float *ln1 = nullptr, *ln2 = nullptr, *qn = nullptr, *kn = nullptr;
     bf16 *k_pool = nullptr, *v_pool = nullptr;
     int loaded = 0;   // bit per tensor
+    // Gated-Delta-Net layers (Qwen3.5 `linear_attn.*`)
+    bool full = true;                       // softmax-attention layer (else GDN)
+    bf16 *w_in = nullptr, *w_out = nullptr; // [in_pad, H] rows = q|k|v|z|b|a ; [H, value_dim]
+    float *conv_w = nullptr, *neg_exp_a = nullptr, *dt_bias = nullptr, *gnorm = nullptr;
+    float *conv_state = nullptr, *rec_state = nullptr;
 };
 struct VitBlockW {
     float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
@@ -131,6 +137,10 @@ struct crane_b200_model {
     double theta = 1e6;
     bool tied = true;
     std::vector<int> mrope_section;
+    // Qwen3.5 hybrid
+    bool hybrid = false;
+    int nk = 0, nv = 0, dk = 0, dv = 0, ck = 4, gdn_in = 0, gdn_in_pad = 0, rot_half = 0, full_interval = 4;
+    std::vector<int> layer_is_full;
     int max_seq = 4096, max_batch = 1, max_pages = 0;
     bool use_simt = false, use_graphs = true, use_pdl = true;
     // vision
@@ -171,6 +181,8 @@ struct crane_b200_model {
     int ws_S = 0;
     float *x = nullptr, *qkv = nullptr;
     bf16 *xn = nullptr, *q_bf = nullptr, *attn_bf = nullptr, *act_bf = nullptr;
+    float *g_proj = nullptr, *g_conv = nullptr, *g_qn = nullptr, *g_kn = nullptr, *g_gb = nullptr, *g_y = nullptr;   // GDN prefill workspaces
+    float *gd_proj = nullptr, *gd_conv = nullptr, *gd_qn = nullptr, *gd_kn = nullptr, *gd_gb = nullptr, *gd_y = nullptr, *gd_out = nullptr;  // decode
     uint32_t* ids_dev = nullptr;
     int* pos3_dev = nullptr;
     int* rows_dev = nullptr;
@@ -210,7 +222,10 @@ struct crane_b200_model {
         if (it != allocs.end()) allocs.erase(it);
         cudaFree(p);
     }
-    int qkv_dim() const { return (nh + 2 * nkv) * D; }
+    int q_stride() const { return hybrid ? 2 * D : D; }     // Qwen3.5 q_proj emits per-head [query | gate]
+    int qkv_dim() const { return nh * q_stride() + 2 * nkv * D; }
+    int conv_dim() const { return 2 * nk * dk + nv * dv; }
+    int value_dim() const { return nv * dv; }
     int q_dim() const { return nh * D; }
 
     void parse_config(const char* json);
@@ -232,6 +247,13 @@ struct crane_b200_model {
         to_f32(data, dt, n, tmp);
         CUDA_OK(cudaMemcpy(dst, tmp.data(), n * 4, cudaMemcpyHostToDevice));
     }
+    // RMSNorm weights: Qwen3.5 applies (1 + w); folded once at load like the reference (qwen3_5/modeling.rs:45-79)
+    void up_norm(float* dst, const void* data, int dt, size_t n) {
+        std::vector<float> tmp;
+        to_f32(data, dt, n, tmp);
+        if (hybrid) for (auto& v : tmp) v += 1.0f;
+        CUDA_OK(cudaMemcpy(dst, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+    }
 
     // forward paths
     void arm_state(uint32_t token, size_t start_pos, int p0, int p1, int p2);
@@ -240,6 +262,8 @@ struct crane_b200_model {
     void prefill(const uint32_t* ids, const float* embeds, size_t S, const uint32_t* pos3_host, size_t start_pos,
                  const int* vis_rows, int n_vis, int advance);
     void lm_head_last_row(const float* xrow, int advance);
+    void gdn_args(GdnArgs& g, const LayerW& l, int S, const float* proj, float* conv, float* qn, float* kn, float* gb, float* y) const;
+    void reset_recurrent_state();
     void encode_images(const float* pv, const uint32_t* grid, size_t n_images);
     void gemm(const bf16* A, int lda, const bf16* W, int M, int N, int K, int mode, void* out, int ldo, const float* bias) {
         GemmEpi ep{out, ldo, bias, mode};
@@ -270,6 +294,31 @@ void crane_b200_model::parse_config(const char* json) {
     const cbjson::Value* rs = tc.has("rope_scaling") ? &tc.at("rope_scaling") : (tc.has("rope_parameters") ? &tc.at("rope_parameters") : nullptr);
     if (rs && rs->has("mrope_section"))
         for (const auto& v : rs->at("mrope_section").arr) mrope_section.push_back((int)v.num);
+    hybrid = tc.has("linear_num_value_heads");
+    rot_half = D / 2;
+    if (hybrid) {
+        nk = (int)tc.integer("linear_num_key_heads");
+        nv = (int)tc.integer("linear_num_value_heads");
+        dk = (int)tc.integer("linear_key_head_dim", 128);
+        dv = (int)tc.integer("linear_value_head_dim", 128);
+        ck = (int)tc.integer("linear_conv_kernel_dim", 4);
+        full_interval = (int)tc.integer("full_attention_interval", 4);
+        double prf = tc.number("partial_rotary_factor", 0.25);
+        if (rs && rs->has("partial_rotary_factor")) prf = rs->number("partial_rotary_factor", prf);
+        rot_half = (int)(D * prf) / 2;
+        gdn_in = conv_dim() + value_dim() + 2 * nv;
+        gdn_in_pad = (gdn_in + 31) / 32 * 32;
+        if (dk != 128 || dv % 32 || nv % nk || ck < 1 || ck > 8) fail(CRANE_B200_UNSUPPORTED, "GDN geometry dk=%d dv=%d nk=%d nv=%d conv=%d", dk, dv, nk, nv, ck);
+        if (rot_half < 32 || rot_half % 32) fail(CRANE_B200_UNSUPPORTED, "rotary width %d", 2 * rot_half);
+    }
+    layer_is_full.assign(L, 1);
+    if (hybrid) {
+        for (int i = 0; i < L; ++i) layer_is_full[i] = ((i + 1) % full_interval == 0) ? 1 : 0;
+        if (tc.has("layer_types")) {
+            const auto& lt = tc.at("layer_types").arr;
+            for (int i = 0; i < L && i < (int)lt.size(); ++i) layer_is_full[i] = lt[i].str == "full_attention";
+        }
+    }
     if (tc.boolean("attention_bias", false)) fail(CRANE_B200_UNSUPPORTED, "attention_bias=true is not supported");
     if (!tc.boolean("use_qk_norm", true)) fail(CRANE_B200_UNSUPPORTED, "use_qk_norm=false is not supported");
     if (D != 128 && D != 256) fail(CRANE_B200_UNSUPPORTED, "head_dim %d (supported: 128, 256)", D);
@@ -320,13 +369,23 @@ void crane_b200_model::alloc_weights() {
     lm_head = tied ? embed : dalloc<bf16>((size_t)V * H);
     final_norm = dalloc<float>(H);
     layers.resize(L);
-    for (auto& l : layers) {
-        l.wqkv = dalloc<bf16>((size_t)qkv_dim() * H);
-        l.wo = dalloc<bf16>((size_t)H * q_dim());
+    for (int li = 0; li < L; ++li) {
+        LayerW& l = layers[li];
+        l.full = layer_is_full[li] != 0;
+        if (l.full) {
+            l.wqkv = dalloc<bf16>((size_t)qkv_dim() * H);
+            l.wo = dalloc<bf16>((size_t)H * q_dim());
+            l.qn = dalloc<float>(D); l.kn = dalloc<float>(D);
+        } else {
+            l.w_in = dalloc<bf16>((size_t)gdn_in_pad * H);
+            CUDA_OK(cudaMemset(l.w_in, 0, (size_t)gdn_in_pad * H * 2));
+            l.w_out = dalloc<bf16>((size_t)H * value_dim());
+            l.conv_w = dalloc<float>((size_t)conv_dim() * ck);
+            l.neg_exp_a = dalloc<float>(nv); l.dt_bias = dalloc<float>(nv); l.gnorm = dalloc<float>(dv);
+        }
         l.wgu = dalloc<bf16>((size_t)2 * I * H);
         l.wdown = dalloc<bf16>((size_t)H * I);
         l.ln1 = dalloc<float>(H); l.ln2 = dalloc<float>(H);
-        l.qn = dalloc<float>(D); l.kn = dalloc<float>(D);
     }
     if (is_vl) {
         const int pk = v_in * v_tpatch * v_patch * v_patch, mh = v_H * v_merge * v_merge;
@@ -384,7 +443,7 @@ bool crane_b200_model::load_text_tensor(const std::string& n, int dt, const int6
     }
     if (n == "norm.weight") {
         want_shape(n, shape, ndim, {H});
-        up_f32(final_norm, data, dt, H);
+        up_norm(final_norm, data, dt, H);
         got_final_norm = true;
         return true;
     }
@@ -395,11 +454,14 @@ bool crane_b200_model::load_text_tensor(const std::string& n, int dt, const int6
     if (li < 0 || li >= L) fail(CRANE_B200_INVALID_ARG, "tensor %s: layer index out of range", n.c_str());
     const std::string t = n.substr(dot + 1);
     LayerW& l = layers[li];
-    const int qd = q_dim(), kvd = nkv * D;
+    const int qd = q_dim(), kvd = nkv * D, qs = nh * q_stride();
     auto rows_bf16 = [&](bf16* dst, int rows, int cols) { up_bf16(dst, data, dt, (size_t)rows * cols); };
-    if (t == "self_attn.q_proj.weight") { want_shape(n, shape, ndim, {qd, H}); rows_bf16(l.wqkv, qd, H); l.loaded |= 1; }
-    else if (t == "self_attn.k_proj.weight") { want_shape(n, shape, ndim, {kvd, H}); rows_bf16(l.wqkv + (size_t)qd * H, kvd, H); l.loaded |= 2; }
-    else if (t == "self_attn.v_proj.weight") { want_shape(n, shape, ndim, {kvd, H}); rows_bf16(l.wqkv + (size_t)(qd + kvd) * H, kvd, H); l.loaded |= 4; }
+    const bool attn_t = t.rfind("self_attn.", 0) == 0, gdn_t = t.rfind("linear_attn.", 0) == 0;
+    if (attn_t && !l.full) fail(CRANE_B200_INVALID_ARG, "tensor %s: layer %d is a linear-attention layer", n.c_str(), li);
+    if (gdn_t && l.full) fail(CRANE_B200_INVALID_ARG, "tensor %s: layer %d is a full-attention layer", n.c_str(), li);
+    if (t == "self_attn.q_proj.weight") { want_shape(n, shape, ndim, {qs, H}); rows_bf16(l.wqkv, qs, H); l.loaded |= 1; }
+    else if (t == "self_attn.k_proj.weight") { want_shape(n, shape, ndim, {kvd, H}); rows_bf16(l.wqkv + (size_t)qs * H, kvd, H); l.loaded |= 2; }
+    else if (t == "self_attn.v_proj.weight") { want_shape(n, shape, ndim, {kvd, H}); rows_bf16(l.wqkv + (size_t)(qs + kvd) * H, kvd, H); l.loaded |= 4; }
     else if (t == "self_attn.o_proj.weight") { want_shape(n, shape, ndim, {H, qd}); rows_bf16(l.wo, H, qd); l.loaded |= 8; }
     else if (t == "mlp.gate_proj.weight" || t == "mlp.up_proj.weight") {
         // merged gate/up with rows interleaved (gate_j, up_j) so SiLU(gate)*up fuses into the GEMV/GEMM epilogue
@@ -411,10 +473,27 @@ bool crane_b200_model::load_text_tensor(const std::string& n, int dt, const int6
         l.loaded |= up ? 32 : 16;
     }
     else if (t == "mlp.down_proj.weight") { want_shape(n, shape, ndim, {H, I}); rows_bf16(l.wdown, H, I); l.loaded |= 64; }
-    else if (t == "input_layernorm.weight") { want_shape(n, shape, ndim, {H}); up_f32(l.ln1, data, dt, H); l.loaded |= 128; }
-    else if (t == "post_attention_layernorm.weight") { want_shape(n, shape, ndim, {H}); up_f32(l.ln2, data, dt, H); l.loaded |= 256; }
-    else if (t == "self_attn.q_norm.weight") { want_shape(n, shape, ndim, {D}); up_f32(l.qn, data, dt, D); l.loaded |= 512; }
-    else if (t == "self_attn.k_norm.weight") { want_shape(n, shape, ndim, {D}); up_f32(l.kn, data, dt, D); l.loaded |= 1024; }
+    else if (t == "input_layernorm.weight") { want_shape(n, shape, ndim, {H}); up_norm(l.ln1, data, dt, H); l.loaded |= 128; }
+    else if (t == "post_attention_layernorm.weight") { want_shape(n, shape, ndim, {H}); up_norm(l.ln2, data, dt, H); l.loaded |= 256; }
+    else if (t == "self_attn.q_norm.weight") { want_shape(n, shape, ndim, {D}); up_norm(l.qn, data, dt, D); l.loaded |= 512; }
+    else if (t == "self_attn.k_norm.weight") { want_shape(n, shape, ndim, {D}); up_norm(l.kn, data, dt, D); l.loaded |= 1024; }
+    // ---- Gated-Delta-Net (names: ops/gdn/layer.rs:55-67, projection.rs:75-83); in_proj rows merged as q|k|v, z, b, a ----
+    else if (t == "linear_attn.in_proj_qkv.weight") { want_shape(n, shape, ndim, {conv_dim(), H}); rows_bf16(l.w_in, conv_dim(), H); l.loaded |= 1; }
+    else if (t == "linear_attn.in_proj_z.weight") { want_shape(n, shape, ndim, {value_dim(), H}); rows_bf16(l.w_in + (size_t)conv_dim() * H, value_dim(), H); l.loaded |= 2; }
+    else if (t == "linear_attn.in_proj_b.weight") { want_shape(n, shape, ndim, {nv, H}); rows_bf16(l.w_in + (size_t)(conv_dim() + value_dim()) * H, nv, H); l.loaded |= 4; }
+    else if (t == "linear_attn.in_proj_a.weight") { want_shape(n, shape, ndim, {nv, H}); rows_bf16(l.w_in + (size_t)(conv_dim() + value_dim() + nv) * H, nv, H); l.loaded |= 8; }
+    else if (t == "linear_attn.conv1d.weight") { want_shape(n, shape, ndim, {conv_dim(), 1, ck}); up_f32(l.conv_w, data, dt, (size_t)conv_dim() * ck); l.loaded |= 512; }
+    else if (t == "linear_attn.dt_bias") { want_shape(n, shape, ndim, {nv}); up_f32(l.dt_bias, data, dt, nv); l.loaded |= 1024; }
+    else if (t == "linear_attn.A_log") {
+        want_shape(n, shape, ndim, {nv});
+        std::vector<float> tmp;
+        to_f32(data, dt, nv, tmp);
+        for (auto& v : tmp) v = -expf(v);        // GdnGateConsts::new (ops/gdn/backend.rs:176-190)
+        CUDA_OK(cudaMemcpy(l.neg_exp_a, tmp.data(), nv * 4, cudaMemcpyHostToDevice));
+        l.loaded |= 2048;
+    }
+    else if (t == "linear_attn.norm.weight") { want_shape(n, shape, ndim, {dv}); up_f32(l.gnorm, data, dt, dv); l.loaded |= 4096; }
+    else if (t == "linear_attn.out_proj.weight") { want_shape(n, shape, ndim, {H, value_dim()}); rows_bf16(l.w_out, H, value_dim()); l.loaded |= 8192; }
     else return false;
     return true;
 }
@@ -503,8 +582,13 @@ void crane_b200_model::finalize() {
     if (!got_embed) fail(CRANE_B200_NOT_LOADED, "missing tensor embed_tokens.weight");
     if (!got_final_norm) fail(CRANE_B200_NOT_LOADED, "missing tensor norm.weight");
     if (!tied && !got_lm_head) fail(CRANE_B200_NOT_LOADED, "missing tensor lm_head.weight");
-    for (int i = 0; i < L; ++i)
-        if (layers[i].loaded != 2047) fail(CRANE_B200_NOT_LOADED, "layer %d: missing tensors (mask 0x%x)", i, layers[i].loaded);
+    for (int i = 0; i < L; ++i) {
+        // full: q,k,v,o (1|2|4|8) gate,up,down (16|32|64) ln1,ln2 (128|256) q_norm,k_norm (512|1024)
+        // GDN : qkv,z,b,a (1|2|4|8) gate,up,down, ln1,ln2, conv (512) dt_bias (1024) A_log (2048) norm (4096) out_proj (8192)
+        const int want = layers[i].full ? 2047 : (15 | 16 | 32 | 64 | 128 | 256 | 512 | 1024 | 2048 | 4096 | 8192);
+        if (layers[i].loaded != want)
+            fail(CRANE_B200_NOT_LOADED, "layer %d: missing tensors (mask 0x%x, want 0x%x)", i, layers[i].loaded, want);
+    }
     if (is_vl) {
         if (v_loaded != 7) fail(CRANE_B200_NOT_LOADED, "vision stem: missing tensors (mask 0x%x)", v_loaded);
         for (int i = 0; i < v_depth; ++i)
@@ -514,9 +598,12 @@ void crane_b200_model::finalize() {
             if (m.loaded != 63) fail(CRANE_B200_NOT_LOADED, "deepstack merger: missing tensors");
     }
     // RotaryEmbedding::new (modules/rotary.rs:29-46): inv_freq f64 -> f32, freqs = pos_f32 * inv_freq (f32), cos/sin f32
-    const int half = D / 2, rows = max_seq + 1;
+    // Qwen3.5: MRotaryEmbedding::new (qwen3_5/modeling.rs:110-132) -- table over the rotary slice only, inv_freq in F32
+    const int half = rot_half, rows = max_seq + 1;
     std::vector<float> inv(half), ct((size_t)rows * half), st((size_t)rows * half);
-    for (int i = 0; i < half; ++i) inv[i] = (float)(1.0 / std::pow(theta, (double)(2 * i) / (double)D));
+    for (int i = 0; i < half; ++i)
+        inv[i] = hybrid ? 1.0f / powf((float)theta, (float)i * 2.0f / (float)(2 * rot_half))
+                        : (float)(1.0 / std::pow(theta, (double)(2 * i) / (double)D));
     for (int p = 0; p < rows; ++p)
         for (int i = 0; i < half; ++i) {
             const float f = (float)p * inv[i];
@@ -538,8 +625,19 @@ void crane_b200_model::finalize() {
 
     const size_t page_elems = (size_t)nkv * KV_PAGE * D;
     for (auto& l : layers) {
-        l.k_pool = dalloc<bf16>((size_t)max_pages * page_elems);
-        l.v_pool = dalloc<bf16>((size_t)max_pages * page_elems);
+        if (l.full) {
+            l.k_pool = dalloc<bf16>((size_t)max_pages * page_elems);
+            l.v_pool = dalloc<bf16>((size_t)max_pages * page_elems);
+        } else {   // GdnLayerCache (ops/gdn/cache.rs:15-45): conv window + [Hv, K, V] f32 state, zero-initialised
+            l.conv_state = dalloc<float>((size_t)conv_dim() * ck);
+            l.rec_state = dalloc<float>((size_t)nv * dk * dv);
+        }
+    }
+    if (hybrid) {
+        gd_proj = dalloc<float>(gdn_in_pad); gd_conv = dalloc<float>(conv_dim());
+        gd_qn = dalloc<float>((size_t)nk * dk); gd_kn = dalloc<float>((size_t)nk * dk);
+        gd_gb = dalloc<float>((size_t)nv * 2); gd_y = dalloc<float>(value_dim()); gd_out = dalloc<float>(value_dim());
+        reset_recurrent_state();
     }
     std::vector<int> bt(max_pages);
     for (int i = 0; i < max_pages; ++i) bt[i] = i;   // one sequence per handle: identity page table
@@ -577,14 +675,19 @@ void crane_b200_model::ensure_prefill_ws(int S) {
     if (S <= ws_S) return;
     CUDA_OK(cudaStreamSynchronize(stream));
     for (void* p : {(void*)x, (void*)qkv, (void*)xn, (void*)q_bf, (void*)attn_bf, (void*)act_bf, (void*)ids_dev, (void*)pos3_dev,
-                    (void*)rows_dev, (void*)embeds_in})
+                    (void*)rows_dev, (void*)embeds_in, (void*)g_proj, (void*)g_conv, (void*)g_qn, (void*)g_kn, (void*)g_gb, (void*)g_y})
         dfree(p);
     const int cap = (S + 127) / 128 * 128;
     x = dalloc<float>((size_t)cap * H);
     qkv = dalloc<float>((size_t)cap * qkv_dim());
     xn = dalloc<bf16>((size_t)cap * H);
     q_bf = dalloc<bf16>((size_t)cap * q_dim());
-    attn_bf = dalloc<bf16>((size_t)cap * q_dim());
+    attn_bf = dalloc<bf16>((size_t)cap * std::max(q_dim(), value_dim()));
+    if (hybrid) {
+        g_proj = dalloc<float>((size_t)cap * gdn_in_pad); g_conv = dalloc<float>((size_t)cap * conv_dim());
+        g_qn = dalloc<float>((size_t)cap * nk * dk); g_kn = dalloc<float>((size_t)cap * nk * dk);
+        g_gb = dalloc<float>((size_t)cap * nv * 2); g_y = dalloc<float>((size_t)cap * value_dim());
+    }
     act_bf = dalloc<bf16>((size_t)cap * I);
     ids_dev = dalloc<uint32_t>(cap);
     pos3_dev = dalloc<int>((size_t)3 * cap);
@@ -610,27 +713,59 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
     if (with_embed) { LAUNCH_OK(embed_decode_launch(stream, B, embed, H, state, x_dec, false)); ++launches; }
     for (int li = 0; li < L; ++li) {
         LayerW& l = layers[li];
-        GemvArgs g = {};
-        g.W = l.wqkv; g.N = qkv_dim(); g.K = H; g.x = x_dec; g.ldx = H; g.norm_w = l.ln1; g.eps = eps; g.y = qkv_dec; g.ldy = qkv_dim();
-        LAUNCH_OK(gemv_launch(stream, B, GEMV_STORE, true, g, num_sms, pdl));
-        AttnDecArgs a = {};
-        a.qkv = qkv_dec; a.q_norm_w = l.qn; a.k_norm_w = l.kn; a.eps = eps; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.axis_of = axis_of;
-        a.state = state; a.block_table = block_table; a.max_pages = max_pages; a.k_pool = l.k_pool; a.v_pool = l.v_pool;
-        a.nh = nh; a.nkv = nkv; a.scale = 1.0f / std::sqrt((float)D);
-        a.part_o = part_o; a.part_ml = part_ml; a.counters = counters; a.out = attn_dec;
-        LAUNCH_OK(attn_decode_launch(stream, B, D, a, pdl));
-        GemvArgs o = {};
-        o.W = l.wo; o.N = H; o.K = q_dim(); o.x = attn_dec; o.ldx = q_dim(); o.y = x_dec; o.ldy = H;
-        LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
+        if (l.full) {
+            GemvArgs g = {};
+            g.W = l.wqkv; g.N = qkv_dim(); g.K = H; g.x = x_dec; g.ldx = H; g.norm_w = l.ln1; g.eps = eps; g.y = qkv_dec; g.ldy = qkv_dim();
+            LAUNCH_OK(gemv_launch(stream, B, GEMV_STORE, true, g, num_sms, pdl));
+            AttnDecArgs a = {};
+            a.qkv = qkv_dec; a.q_stride = q_stride(); a.gated = hybrid ? 1 : 0; a.rot_half = rot_half;
+            a.q_norm_w = l.qn; a.k_norm_w = l.kn; a.eps = eps; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.axis_of = axis_of;
+            a.state = state; a.block_table = block_table; a.max_pages = max_pages; a.k_pool = l.k_pool; a.v_pool = l.v_pool;
+            a.nh = nh; a.nkv = nkv; a.scale = 1.0f / std::sqrt((float)D);
+            a.out = attn_dec;
+            LAUNCH_OK(attn_decode_launch(stream, B, D, a, pdl));
+            GemvArgs o = {};
+            o.W = l.wo; o.N = H; o.K = q_dim(); o.x = attn_dec; o.ldx = q_dim(); o.y = x_dec; o.ldy = H;
+            LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
+            launches += 3;
+        } else {   // Gated-Delta-Net token mixer (ops/gdn/layer.rs:122-163), S = 1
+            GemvArgs g = {};
+            g.W = l.w_in; g.N = gdn_in_pad; g.K = H; g.x = x_dec; g.ldx = H; g.norm_w = l.ln1; g.eps = eps; g.y = gd_proj; g.ldy = gdn_in_pad;
+            LAUNCH_OK(gemv_launch(stream, B, GEMV_STORE, true, g, num_sms, pdl));
+            GdnArgs ga;
+            gdn_args(ga, l, 1, gd_proj, gd_conv, gd_qn, gd_kn, gd_gb, gd_y);
+            ga.out_f32 = gd_out;
+            LAUNCH_OK(gdn_forward_launch(stream, ga));
+            GemvArgs o = {};
+            o.W = l.w_out; o.N = H; o.K = value_dim(); o.x = gd_out; o.ldx = value_dim(); o.y = x_dec; o.ldy = H;
+            LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
+            launches += 7;
+        }
         GemvArgs gu = {};
         gu.W = l.wgu; gu.N = 2 * I; gu.K = H; gu.x = x_dec; gu.ldx = H; gu.norm_w = l.ln2; gu.eps = eps; gu.y = act_dec; gu.ldy = I;
         LAUNCH_OK(gemv_launch(stream, B, GEMV_SILU_MUL, true, gu, num_sms, pdl));
         GemvArgs dn = {};
         dn.W = l.wdown; dn.N = H; dn.K = I; dn.x = act_dec; dn.ldx = I; dn.y = x_dec; dn.ldy = H;
         LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, dn, num_sms, pdl));
-        launches += 5;
+        launches += 2;
     }
     lm_head_last_row(x_dec, advance);
+}
+
+void crane_b200_model::gdn_args(GdnArgs& g, const LayerW& l, int S, const float* proj, float* conv, float* qn, float* kn, float* gb,
+                                float* y) const {
+    g = GdnArgs{};
+    g.proj = proj; g.ldp = gdn_in_pad; g.S = S; g.nk = nk; g.nv = nv; g.dk = dk; g.dv = dv; g.ck = ck;
+    g.conv_w = l.conv_w; g.conv_state = l.conv_state; g.neg_exp_a = l.neg_exp_a; g.dt_bias = l.dt_bias; g.norm_w = l.gnorm; g.eps = eps;
+    g.rec_state = l.rec_state; g.conv_out = conv; g.qn = qn; g.kn = kn; g.gb = gb; g.y = y;
+}
+
+void crane_b200_model::reset_recurrent_state() {
+    for (auto& l : layers)
+        if (!l.full) {
+            CUDA_OK(cudaMemsetAsync(l.conv_state, 0, (size_t)conv_dim() * ck * sizeof(float), stream));
+            CUDA_OK(cudaMemsetAsync(l.rec_state, 0, (size_t)nv * dk * dv * sizeof(float), stream));
+        }
 }
 
 void crane_b200_model::lm_head_last_row(const float* xrow, int advance) {
@@ -661,7 +796,8 @@ void crane_b200_model::decode_step_graphed(int advance) {
     }
     if (graph_step[advance]) {
         CUDA_OK(cudaGraphLaunch(graph_step[advance], stream));
-        launches += (uint64_t)5 * L + 1;
+        for (const auto& l : layers) launches += l.full ? 5 : 9;
+        launches += 1;
     } else {
         enqueue_decode_step(advance, false);
     }
@@ -701,17 +837,29 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     for (int li = 0; li < L; ++li) {
         LayerW& l = layers[li];
         LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln1, eps, xn));
-        gemm(xn, H, l.wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
-        RopeAppendArgs ra = {};
-        ra.qkv = qkv; ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
-        ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = block_table; ra.k_pool = l.k_pool; ra.v_pool = l.v_pool;
-        ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf;
-        LAUNCH_OK(rope_append_launch(stream, D, ra));
-        FlashArgs fa = {};
-        fa.q = q_bf; fa.q_stride = qd; fa.k_pool = l.k_pool; fa.v_pool = l.v_pool; fa.block_table = block_table; fa.nh = nh; fa.nkv = nkv;
-        fa.out = attn_bf; fa.o_stride = qd; fa.S = S; fa.kv_offset = (int)start_pos; fa.scale = 1.0f / std::sqrt((float)D); fa.nseq = 1;
-        LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
-        gemm(attn_bf, qd, l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
+        if (l.full) {
+            gemm(xn, H, l.wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
+            RopeAppendArgs ra = {};
+            ra.qkv = qkv; ra.q_stride = q_stride(); ra.rot_half = rot_half;
+            ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
+            ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = block_table; ra.k_pool = l.k_pool; ra.v_pool = l.v_pool;
+            ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf;
+            LAUNCH_OK(rope_append_launch(stream, D, ra));
+            FlashArgs fa = {};
+            fa.q = q_bf; fa.q_stride = qd; fa.k_pool = l.k_pool; fa.v_pool = l.v_pool; fa.block_table = block_table; fa.nh = nh; fa.nkv = nkv;
+            fa.out = attn_bf; fa.o_stride = qd; fa.S = S; fa.kv_offset = (int)start_pos; fa.scale = 1.0f / std::sqrt((float)D); fa.nseq = 1;
+            LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
+            if (hybrid) { LAUNCH_OK(gate_mul_launch(stream, attn_bf, qkv, S, nh, D, q_stride(), qkv_dim())); ++launches; }
+            gemm(attn_bf, qd, l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
+        } else {
+            gemm(xn, H, l.w_in, S, gdn_in_pad, H, EPI_STORE_F32, g_proj, gdn_in_pad, nullptr);
+            GdnArgs ga;
+            gdn_args(ga, l, S, g_proj, g_conv, g_qn, g_kn, g_gb, g_y);
+            ga.out_bf16 = attn_bf;
+            LAUNCH_OK(gdn_forward_launch(stream, ga));
+            gemm(attn_bf, value_dim(), l.w_out, S, H, value_dim(), EPI_RESID_F32, x, H, nullptr);
+            launches += 3;
+        }
         LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln2, eps, xn));
         gemm(xn, H, l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr);
         gemm(act_bf, I, l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
@@ -999,6 +1147,7 @@ int crane_b200_clear_kv_cache(crane_b200_model* m) {
     API_BEGIN(m)
     m->kv_len = 0;
     m->next_mrope_pos = 0;
+    if (m->finalized && m->hybrid) m->reset_recurrent_state();
     API_END(m)
 }
 
@@ -1008,7 +1157,11 @@ int crane_b200_hidden_size(const crane_b200_model* m) { return m ? m->H : 0; }
 size_t crane_b200_kv_len(const crane_b200_model* m) { return m ? m->kv_len : 0; }
 uint32_t crane_b200_next_mrope_pos(const crane_b200_model* m) { return m ? m->next_mrope_pos : 0; }
 uint64_t crane_b200_active_kv_cache_bytes(const crane_b200_model* m) {
-    return m ? (uint64_t)m->kv_len * m->nkv * m->D * 2 /*K,V*/ * 2 /*bf16*/ * m->L : 0;
+    if (!m) return 0;
+    uint64_t full = 0;
+    for (int f : m->layer_is_full) full += f;
+    return (uint64_t)m->kv_len * m->nkv * m->D * 2 /*K,V*/ * 2 /*bf16*/ * full +
+           (m->hybrid ? (uint64_t)(m->L - full) * ((uint64_t)m->nv * m->dk * m->dv + (uint64_t)m->conv_dim() * m->ck) * 4 : 0);
 }
 uint64_t crane_b200_kernel_launches(const crane_b200_model* m) { return m ? m->launches : 0; }
 
@@ -1025,6 +1178,7 @@ int crane_b200_warmup(crane_b200_model* m) {
     CUDA_OK(cudaStreamSynchronize(m->stream));
     m->kv_len = 0;
     m->next_mrope_pos = saved_pos;
+    if (m->hybrid) m->reset_recurrent_state();
     API_END(m)
 }
 

@@ -1,0 +1,184 @@
+// Gated-Delta-Net layer body between the in_proj and out_proj GEMMs (Qwen3.5 linear-attention layers).
+//
+// Reference arithmetic (crane-core/src/ops/gdn/): causal depthwise conv1d + SiLU with a carried conv state
+// (conv.rs:23-133), split into per-head q/k/v (layer.rs:194-238, Interleaved v-head order), L2-norm of q and k
+// (backend.rs:26-56), beta = sigmoid(b), g = -exp(A_log) * softplus(a + dt_bias) (backend.rs:197-211), the gated
+// delta rule  S <- S*exp(g); kv = S^T k; d = (v - kv)*beta; S <- S + k (x) d; y = S^T (q/sqrt(K))
+// (backend.rs:90-156, kernels/cuda/gdn.cu:29-34), gated RMSNorm y*rsqrt(mean y^2+eps)*w*silu(z) (norm.rs:39-45).
+// Everything is f32, as in the reference's recurrence.
+//
+// B200 mapping of the recurrence (the reference kernel runs 2048 threads with two __syncthreads per timestep):
+// one CTA per (value head, 32 value columns); a state column's 128 K-entries are split over 4 adjacent lanes
+// (32 registers each), so a timestep needs two 2-step shuffle reductions and NO block barrier; q/k/v/gates of 16
+// timesteps are staged in shared memory per barrier pair.  State is read once and written once per call.
+#include "gdn.cuh"
+
+namespace cb {
+
+constexpr int GDN_MAX_CK = 8;
+
+__global__ void __launch_bounds__(128)
+gdn_conv_kernel(GdnArgs a) {
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int t = blockIdx.y;
+    if (c >= conv_dim) return;
+    float acc = 0.f;
+    for (int j = 0; j < a.ck; ++j) {
+        const int m = t + 1 + j;   // index into [state(ck) | x(S)]
+        const float h = (m < a.ck) ? a.conv_state[(size_t)c * a.ck + m] : a.proj[(size_t)(m - a.ck) * a.ldp + c];
+        acc = fmaf(a.conv_w[(size_t)c * a.ck + j], h, acc);
+    }
+    a.conv_out[(size_t)t * conv_dim + c] = silu_f(acc);
+}
+
+__global__ void __launch_bounds__(128)
+gdn_conv_state_kernel(GdnArgs a) {
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= conv_dim) return;
+    float ns[GDN_MAX_CK];
+    for (int j = 0; j < a.ck; ++j) {
+        const int m = a.S + j;
+        ns[j] = (m < a.ck) ? a.conv_state[(size_t)c * a.ck + m] : a.proj[(size_t)(m - a.ck) * a.ldp + c];
+    }
+    for (int j = 0; j < a.ck; ++j) a.conv_state[(size_t)c * a.ck + j] = ns[j];
+}
+
+// grid (S), 256 threads: warps normalise the 2*nk q/k head vectors of timestep t; threads < nv compute the gates.
+__global__ void __launch_bounds__(256)
+gdn_prep_kernel(GdnArgs a) {
+    const int t = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    const int key_dim = a.nk * a.dk;
+    const float* row = a.conv_out + (size_t)t * conv_dim;
+    for (int vec = warp; vec < 2 * a.nk; vec += 8) {
+        const bool is_k = vec >= a.nk;
+        const int head = is_k ? vec - a.nk : vec;
+        const float* src = row + (is_k ? key_dim : 0) + head * a.dk;
+        float ssq = 0.f;
+        for (int i = lane; i < a.dk; i += 32) ssq += src[i] * src[i];
+        ssq = warp_sum(ssq);
+        float sc = 1.0f / sqrtf(ssq + 1e-6f);
+        if (!is_k) sc *= 1.0f / sqrtf((float)a.dk);
+        float* dst = (is_k ? a.kn : a.qn) + ((size_t)t * a.nk + head) * a.dk;
+        for (int i = lane; i < a.dk; i += 32) dst[i] = src[i] * sc;
+    }
+    if (threadIdx.x < a.nv) {
+        const int h = threadIdx.x;
+        const float* pr = a.proj + (size_t)t * a.ldp + conv_dim + a.nv * a.dv;
+        const float b = pr[h], av = pr[a.nv + h];
+        const float beta = 1.0f / (1.0f + expf(-b));
+        const float g = a.neg_exp_a[h] * logf(1.0f + expf(av + a.dt_bias[h]));
+        a.gb[((size_t)t * a.nv + h) * 2 + 0] = expf(g);
+        a.gb[((size_t)t * a.nv + h) * 2 + 1] = beta;
+    }
+}
+
+// grid (nv * dv/32), 128 threads.  dk == 128.
+constexpr int GDN_TC = 16;
+__device__ __forceinline__ int gdn_pad(int k) { return k + (k >> 5) * 4; }
+
+__global__ void __launch_bounds__(128)
+gdn_recur_kernel(GdnArgs a) {
+    constexpr int DK = 128, KP = DK + 16;
+    __shared__ __align__(16) float q_s[GDN_TC][KP];
+    __shared__ __align__(16) float k_s[GDN_TC][KP];
+    __shared__ float v_s[GDN_TC][32];
+    __shared__ float gb_s[GDN_TC][2];
+    const int tiles = a.dv / 32;
+    const int h = blockIdx.x / tiles, vt = blockIdx.x % tiles;
+    const int kh = h / (a.nv / a.nk);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c4 = lane & 3;
+    const int col_local = warp * 8 + (lane >> 2);
+    const int col = vt * 32 + col_local;
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    float s[32];
+    float* sp = a.rec_state + ((size_t)h * DK + 32 * c4) * a.dv + col;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[i] = sp[(size_t)i * a.dv];
+
+    for (int t0 = 0; t0 < a.S; t0 += GDN_TC) {
+        const int nt = min(GDN_TC, a.S - t0);
+        __syncthreads();
+        for (int i = tid; i < nt * DK; i += 128) {
+            const int tt = i / DK, k = i % DK;
+            q_s[tt][gdn_pad(k)] = a.qn[((size_t)(t0 + tt) * a.nk + kh) * DK + k];
+            k_s[tt][gdn_pad(k)] = a.kn[((size_t)(t0 + tt) * a.nk + kh) * DK + k];
+        }
+        for (int i = tid; i < nt * 32; i += 128) {
+            const int tt = i / 32, c = i % 32;
+            v_s[tt][c] = a.conv_out[(size_t)(t0 + tt) * conv_dim + 2 * a.nk * a.dk + h * a.dv + vt * 32 + c];
+        }
+        if (tid < nt * 2) gb_s[tid / 2][tid % 2] = a.gb[((size_t)(t0 + tid / 2) * a.nv + h) * 2 + (tid % 2)];
+        __syncthreads();
+        for (int tt = 0; tt < nt; ++tt) {
+            const float decay = gb_s[tt][0], beta = gb_s[tt][1];
+            const float4* kp = reinterpret_cast<const float4*>(&k_s[tt][gdn_pad(32 * c4)]);
+            const float4* qp = reinterpret_cast<const float4*>(&q_s[tt][gdn_pad(32 * c4)]);
+            float kv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 k4 = kp[i];
+                s[4 * i + 0] *= decay; s[4 * i + 1] *= decay; s[4 * i + 2] *= decay; s[4 * i + 3] *= decay;
+                kv = fmaf(s[4 * i + 0], k4.x, kv); kv = fmaf(s[4 * i + 1], k4.y, kv);
+                kv = fmaf(s[4 * i + 2], k4.z, kv); kv = fmaf(s[4 * i + 3], k4.w, kv);
+            }
+            kv += __shfl_xor_sync(0xffffffffu, kv, 1);
+            kv += __shfl_xor_sync(0xffffffffu, kv, 2);
+            const float delta = (v_s[tt][col_local] - kv) * beta;
+            float y = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 k4 = kp[i];
+                const float4 q4 = qp[i];
+                s[4 * i + 0] = fmaf(k4.x, delta, s[4 * i + 0]); y = fmaf(s[4 * i + 0], q4.x, y);
+                s[4 * i + 1] = fmaf(k4.y, delta, s[4 * i + 1]); y = fmaf(s[4 * i + 1], q4.y, y);
+                s[4 * i + 2] = fmaf(k4.z, delta, s[4 * i + 2]); y = fmaf(s[4 * i + 2], q4.z, y);
+                s[4 * i + 3] = fmaf(k4.w, delta, s[4 * i + 3]); y = fmaf(s[4 * i + 3], q4.w, y);
+            }
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            if (c4 == 0) a.y[((size_t)(t0 + tt) * a.nv + h) * a.dv + col] = y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sp[(size_t)i * a.dv] = s[i];
+}
+
+// One warp per (t, value head): y * rsqrt(mean(y^2) + eps) * w * silu(z)
+__global__ void __launch_bounds__(128)
+gdn_gated_norm_kernel(GdnArgs a) {
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (gw >= a.S * a.nv) return;
+    const int t = gw / a.nv, h = gw % a.nv;
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    const float* yr = a.y + ((size_t)t * a.nv + h) * a.dv;
+    const float* zr = a.proj + (size_t)t * a.ldp + conv_dim + h * a.dv;
+    float ssq = 0.f;
+    for (int i = lane; i < a.dv; i += 32) ssq += yr[i] * yr[i];
+    ssq = warp_sum(ssq);
+    const float rstd = rsqrtf(ssq / (float)a.dv + a.eps);
+    for (int i = lane; i < a.dv; i += 32) {
+        const float o = yr[i] * rstd * a.norm_w[i] * silu_f(zr[i]);
+        const size_t idx = ((size_t)t * a.nv + h) * a.dv + i;
+        if (a.out_bf16) a.out_bf16[idx] = __float2bfloat16_rn(o);
+        if (a.out_f32) a.out_f32[idx] = o;
+    }
+}
+
+int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
+    if (a.dk != 128 || (a.dv % 32) != 0 || a.ck > GDN_MAX_CK || a.nv > 256 || (a.nv % a.nk) != 0) return -1000;
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    gdn_conv_kernel<<<dim3((conv_dim + 127) / 128, a.S), 128, 0, st>>>(a);
+    gdn_conv_state_kernel<<<(conv_dim + 127) / 128, 128, 0, st>>>(a);
+    gdn_prep_kernel<<<a.S, 256, 0, st>>>(a);
+    gdn_recur_kernel<<<a.nv * (a.dv / 32), 128, 0, st>>>(a);
+    gdn_gated_norm_kernel<<<(a.S * a.nv + 3) / 4, 128, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace cb

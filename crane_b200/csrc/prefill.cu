@@ -90,19 +90,19 @@ int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, cons
 template <int D>
 __global__ void __launch_bounds__(128)
 rope_append_kernel(RopeAppendArgs a) {
-    constexpr int NE = D / 32, HALF = D / 2;
+    constexpr int NE = D / 32;
     const int lane = threadIdx.x & 31;
     const int nvec = a.nh + 2 * a.nkv;
     const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (gw >= a.S * nvec) return;
     const int s = gw / nvec, vec = gw % nvec;
-    const int q_dim = a.nh * D, kv_dim = a.nkv * D;
-    const float* row = a.qkv + (size_t)s * (q_dim + 2 * kv_dim);
+    const int q_dim = a.nh * D, kv_dim = a.nkv * D, q_span = a.nh * a.q_stride;
+    const float* row = a.qkv + (size_t)s * (q_span + 2 * kv_dim);
     const int t = a.start_pos + s;
     const int page = a.block_table[t / KV_PAGE];
     if (vec >= a.nh + a.nkv) {   // value: cast + append
         const int kvh = vec - a.nh - a.nkv;
-        const float* src = row + q_dim + kv_dim + kvh * D;
+        const float* src = row + q_span + kv_dim + kvh * D;
         bf16* dst = a.v_pool + (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
 #pragma unroll
         for (int j = 0; j < NE; ++j) dst[lane + 32 * j] = __float2bfloat16_rn(src[lane + 32 * j]);
@@ -110,7 +110,7 @@ rope_append_kernel(RopeAppendArgs a) {
     }
     const bool is_k = vec >= a.nh;
     const int head = is_k ? vec - a.nh : vec;
-    const float* src = row + (is_k ? q_dim : 0) + head * D;
+    const float* src = is_k ? row + q_span + head * D : row + head * a.q_stride;
     const float* nw = is_k ? a.k_norm_w : a.q_norm_w;
     float e[NE];
     float ssq = 0.f;
@@ -124,17 +124,25 @@ rope_append_kernel(RopeAppendArgs a) {
     }
     bf16* dst = is_k ? a.k_pool + (((size_t)page * a.nkv + head) * KV_PAGE + (t % KV_PAGE)) * D
                      : a.q_out + (size_t)s * q_dim + head * D;
+    const int RJ = a.rot_half >> 5;
 #pragma unroll
-    for (int j = 0; j < NE / 2; ++j) {
-        const int i = lane + 32 * j;
-        const int p = a.pos3[a.axis_of[i] * a.S + s];
-        const float c = a.cos_tab[(size_t)p * HALF + i], sn = a.sin_tab[(size_t)p * HALF + i];
-        const float x1 = e[j], x2 = e[j + NE / 2];
-        dst[i] = __float2bfloat16_rn(x1 * c - x2 * sn);
-        dst[i + HALF] = __float2bfloat16_rn(x1 * sn + x2 * c);
+    for (int j = 0; j < NE; ++j) {
+        float r = e[j];
+        if (j < 2 * RJ) {
+            const bool lo = j < RJ;
+            const int i = lane + 32 * (lo ? j : j - RJ);
+            const int p = a.pos3[a.axis_of[i] * a.S + s];
+            const float c = a.cos_tab[(size_t)p * a.rot_half + i], sn = a.sin_tab[(size_t)p * a.rot_half + i];
+            float other = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < NE; ++jj) if (jj == (lo ? j + RJ : j - RJ)) other = e[jj];
+            r = lo ? (e[j] * c - other * sn) : (other * sn + e[j] * c);
+        }
+        dst[lane + 32 * j] = __float2bfloat16_rn(r);
     }
 }
 int rope_append_launch(cudaStream_t st, int D, const RopeAppendArgs& a) {
+    if (a.rot_half < 32 || (a.rot_half % 32) != 0 || 2 * a.rot_half > D) return -1000;
     const int nwarps = a.S * (a.nh + 2 * a.nkv);
     const int grid = (nwarps + 3) / 4;
     if (D == 128) rope_append_kernel<128><<<grid, 128, 0, st>>>(a);
@@ -362,6 +370,22 @@ int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const 
     if (D == 64 && !causal && !paged) return flash_launch_t<64, false, false>(st, a);
     if (D == 128 && !causal && !paged) return flash_launch_t<128, false, false>(st, a);
     return -1000;
+}
+
+// attn[s, h*D + i] *= sigmoid(gate), gate = qkv[s, h*q_stride + D + i]   (qwen3_5/modeling.rs:556-563)
+__global__ void __launch_bounds__(256)
+gate_mul_kernel(bf16* __restrict__ attn, const float* __restrict__ qkv, int nh, int D, int q_stride, int row_width) {
+    const int s = blockIdx.x;
+    for (int i = threadIdx.x; i < nh * D; i += blockDim.x) {
+        const int h = i / D, d = i % D;
+        const float g = qkv[(size_t)s * row_width + h * q_stride + D + d];
+        const float v = __bfloat162float(attn[(size_t)s * nh * D + i]);
+        attn[(size_t)s * nh * D + i] = __float2bfloat16_rn(v / (1.0f + expf(-g)));
+    }
+}
+int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh, int D, int q_stride, int row_width) {
+    gate_mul_kernel<<<S, 256, 0, st>>>(attn, qkv, nh, D, q_stride, row_width);
+    return (int)cudaGetLastError();
 }
 
 // -------------------------------------------------------------------------------------

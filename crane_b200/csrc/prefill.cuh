@@ -8,13 +8,15 @@
 namespace cb {
 
 struct RopeAppendArgs {
-    const float* qkv;        // [S, q_dim + 2 kv_dim] f32
+    const float* qkv;        // [S, nh*q_stride + 2 kv_dim] f32
+    int q_stride;            // D or 2*D (per-head [query | gate])
+    int rot_half;            // rotary pairs (i, i + rot_half)
     const float* q_norm_w;   // [D] (nullptr: no QK-norm)
     const float* k_norm_w;
     float eps;
-    const float* cos_tab;    // [max_pos, D/2]
+    const float* cos_tab;    // [max_pos, rot_half]
     const float* sin_tab;
-    const unsigned char* axis_of;   // [D/2]
+    const unsigned char* axis_of;   // [rot_half]
     const int* pos3;         // [3, S] rotary positions per token
     int S, start_pos;        // cache positions start_pos .. start_pos + S - 1
     const int* block_table;  // [max_pages] of this sequence
@@ -46,6 +48,7 @@ int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const flo
 int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out);
 int rope_append_launch(cudaStream_t st, int D, const RopeAppendArgs& a);
 int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const FlashArgs& a);
+int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh, int D, int q_stride, int row_width);
 int set_rows_launch(cudaStream_t st, float* x, int H, const int* rows, int n, const float* src, bool add);
 int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n);
 int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const float* table, const int* idx4, const float* w4);

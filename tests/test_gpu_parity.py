@@ -203,3 +203,49 @@ def test_vl_generate_matches_oracle():
     print("vl generate:", list(got), "oracle:", ref)
     assert len(got) == 8
     m.close()
+
+
+# ---- Qwen3.5 hybrid: Gated-Delta-Net layers + gated attention with partial rotary (config 3) ----------------
+
+@pytest.mark.parametrize("gemm", ["simt", "tcgen05"])
+def test_tiny_qwen3_5_against_hf_fixture(gemm):
+    cfg = synth.TINY_QWEN3_5
+    g = golden("tiny_qwen3_5")
+    m, _ = _model(cfg, cls=crane_b200.Qwen3_5Model, gemm=gemm)
+    toks = [int(t) for t in g["prompt"]]
+    errs = []
+    for step in range(g["logits"].shape[0]):
+        ctx = toks if step == 0 else toks[-1:]
+        errs.append(rel_err(m.forward_step(ctx, len(toks) - len(ctx)), g["logits"][step]))
+        toks.append(int(g["tokens"][step]))
+    print(f"tiny_qwen3_5 gemm={gemm}: prefill rel {errs[0]:.3e}, decode rel max {max(errs[1:]):.3e}")
+    assert errs[0] < PREFILL_TOL and max(errs[1:]) < PREFILL_TOL
+    m.close()
+
+
+def test_qwen3_5_chunked_prefill_state_handoff_and_decode():
+    from oracle.qwen3_5 import Qwen3_5Oracle
+    cfg = synth.TINY_QWEN3_5
+    m, w = _model(cfg, cls=crane_b200.Qwen3_5Model)
+    orc = Qwen3_5Oracle(cfg, w)
+    ids = synth.synth_token_ids(90, cfg["vocab_size"], "q35-gpu")
+    ref = orc.forward(ids, 0).numpy()
+    full = m.forward_step(ids, 0)
+    m.clear_kv_cache()                                   # must also zero the conv / recurrent state
+    m.forward_step(ids[:37], 0)
+    m.forward_step(ids[37:38], 37)                       # one-token chunk: decode kernels in the middle of a prefill
+    part = m.forward_step(ids[38:], 38)
+    m.clear_kv_cache()
+    for i, t in enumerate(ids):
+        inc = m.forward_step([t], i)
+    e = (rel_err(full, ref), rel_err(part, ref), rel_err(inc, ref))
+    print(f"qwen3.5 single / chunked / incremental vs oracle: {e[0]:.3e} {e[1]:.3e} {e[2]:.3e}")
+    assert max(e) < PREFILL_TOL
+    m.clear_kv_cache()
+    dev = m.generate(ids, max_new_tokens=12)
+    m.clear_kv_cache()
+    host = [m.forward_step_argmax(ids, 0)]
+    for i in range(11):
+        host.append(m.forward_step_argmax([host[-1]], len(ids) + i))
+    assert list(dev) == host
+    m.close()
