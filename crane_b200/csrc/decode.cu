@@ -6,30 +6,39 @@
 namespace cb {
 
 // =====================================================================================
-// Weight-streaming GEMV:  y[b, n] = epilogue( sum_k W[n, k] * x[b, k] )          (B <= 8 sequences)
+// Weight-streaming GEMV:  y[b, n] = epilogue( sum_k W[n, k] * x[b, k] )          (B <= 4 sequences)
 //
-// grid = #SMs; CTA c owns the contiguous row block [c*rpc, (c+1)*rpc) of W, i.e. ONE contiguous byte slab.
-//   warp 0   : producer -- one lane streams the slab HBM -> shared memory with 1-D bulk async copies
-//              (cp.async.bulk, 16 KB stages, 5-deep mbarrier ring = 80 KB in flight per SM).  Weights do not depend on
-//              the previous kernel, so the ring fills BEFORE griddepcontrol.wait: the HBM pipe stays busy across the
-//              kernel boundary (programmatic dependent launch; two CTAs -- this kernel's and the next one's -- fit an SM).
-//   warps 1-8: consumers -- stage the f32 activations (RMSNorm folded in), then each warp takes a contiguous 2 KB run of
-//              every stage (16-byte LDS per lane, conflict-free), accumulates in f32 and flushes per-row partial sums to
-//              a shared accumulator array with shuffles + one shared atomic per row change.
+// grid = #SMs; CTA c owns the contiguous row block [c*rpc, (c+1)*rpc) of W -- one contiguous byte slab -- and splits it
+// into GV_WARPS contiguous sub-slabs, one per warp.  Every warp runs its own private, barrier-free pipeline:
+// GV_DEPTH x 2 KB shared-memory slots filled by cp.async (LDGSTS, 16 B per lane, L1-bypassing) and drained with 16-byte
+// LDS (conflict-free) into f32 FMAs -- 80 KB of weight bytes in flight per SM, no cross-warp synchronisation in the
+// streaming loop.  Weights do not depend on the previous kernel, so the pipelines are primed BEFORE griddepcontrol.wait:
+// with programmatic dependent launch the next kernel's CTAs sit next to this kernel's on the SM (2 x 104 KB shared
+// memory) and the HBM pipe stays busy across the kernel boundary.  Activations are staged once per CTA as f32 (RMSNorm
+// folded in).  Rows are flushed to a shared accumulator (shuffle reduce + one shared atomic per row change per warp).
 // Epilogue (all threads): store / residual add / SiLU*up on interleaved rows / logits + CTA argmax.
 // =====================================================================================
-constexpr int GV_STAGE_BYTES = 16384;
-constexpr int GV_STAGES = 5;
-constexpr int GV_CWARPS = 8;
-constexpr int GV_CTHREADS = GV_CWARPS * 32;
-constexpr int GV_THREADS = GV_CTHREADS + 32;
-constexpr int GV_CHUNKS_PER_WARP = GV_STAGE_BYTES / 512 / GV_CWARPS;   // 512-byte chunks (one 16 B load per lane) per warp per stage
+#ifndef GV_WARPS
+#define GV_WARPS 32
+#endif
+#ifndef GV_DEPTH
+#define GV_DEPTH 2
+#endif
+constexpr int GV_SEG_CHUNKS = 4;                       // 512-byte chunks per pipeline slot (2 KB)
+constexpr int GV_SEG_BYTES = GV_SEG_CHUNKS * 512;
+constexpr int GV_THREADS = GV_WARPS * 32;
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_g() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int B, int EPI, bool NORM>
 __global__ void __launch_bounds__(GV_THREADS, 1)
 gemv_kernel(GemvArgs a) {
     extern __shared__ __align__(1024) unsigned char gsm[];
-    // layout: [ring: GV_STAGES * 16 KB][xs: B * K f32][acc: B * rpc f32][barriers]
+    // layout: [rings: GV_WARPS * GV_DEPTH * 2 KB][xs: B * K f32][acc: B * rpc f32]
     const int K8 = a.K >> 3;
     constexpr int ROWS_PER_UNIT = (EPI == GEMV_SILU_MUL) ? 2 : 1;
     const int units = a.N / ROWS_PER_UNIT;
@@ -38,123 +47,117 @@ gemv_kernel(GemvArgs a) {
     const int r0 = blockIdx.x * rpc;
     const int r1 = min(a.N, r0 + rpc);
     const int nrows = max(0, r1 - r0);
-    unsigned char* ring = gsm;
-    float4* xs = reinterpret_cast<float4*>(gsm + GV_STAGES * GV_STAGE_BYTES);
+    float4* xs = reinterpret_cast<float4*>(gsm + GV_WARPS * GV_DEPTH * GV_SEG_BYTES);
     float* acc_s = reinterpret_cast<float*>(xs) + (size_t)B * a.K;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(acc_s + (((size_t)B * rpc + 1) & ~(size_t)1));
-    uint64_t* empty_bar = full_bar + GV_STAGES;
     __shared__ float red[32];
     __shared__ float rstd_s[B];
-    __shared__ float wbest_v[GV_THREADS / 32][B];
-    __shared__ int wbest_i[GV_THREADS / 32][B];
+    __shared__ float wbest_v[GV_WARPS][B];
+    __shared__ int wbest_i[GV_WARPS][B];
     __shared__ int is_last_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t row_bytes = (size_t)a.K * 2;
-    const size_t slab_bytes = (size_t)nrows * row_bytes;
-    const int n_stages = (int)((slab_bytes + GV_STAGE_BYTES - 1) / GV_STAGE_BYTES);
-    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.W) + (size_t)r0 * row_bytes;
+    // 32-bit chunk bookkeeping (chunk = 512 B = 256 elements; never straddles a row since K % 256 == 0)
+    const uint32_t cpr = (uint32_t)(a.K >> 8);                                     // chunks per row
+    const uint32_t total_chunks = (uint32_t)nrows * cpr;
+    const uint32_t total_segs = (total_chunks + GV_SEG_CHUNKS - 1) / GV_SEG_CHUNKS;
+    const uint32_t spw = (total_segs + GV_WARPS - 1) / GV_WARPS;                   // segments per warp
+    const uint32_t c_begin = min(total_chunks, (uint32_t)warp * spw * GV_SEG_CHUNKS);
+    const uint32_t c_end = min(total_chunks, ((uint32_t)warp + 1) * spw * GV_SEG_CHUNKS);
+    const uint32_t nseg = (c_end - c_begin + GV_SEG_CHUNKS - 1) / GV_SEG_CHUNKS;
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.W) + (size_t)r0 * a.K * 2 + (size_t)c_begin * 512 + lane * 16;
+    unsigned char* ring = gsm + (size_t)warp * GV_DEPTH * GV_SEG_BYTES + lane * 16;
+    const uint32_t ring_u32 = smem_u32(ring);
 
-    if (tid == 0) {
-        for (int s = 0; s < GV_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], GV_CWARPS); }
-        fence_barrier_init();
-    }
+    auto issue = [&](uint32_t g) {                      // segment g of this warp -> slot g % GV_DEPTH
+        if (g < nseg) {
+            const uint32_t cb = g * GV_SEG_CHUNKS;
+            const uint32_t slot = g % GV_DEPTH;
+#pragma unroll
+            for (int c = 0; c < GV_SEG_CHUNKS; ++c)
+                if (c_begin + cb + c < c_end)
+                    cp_async16_cg(ring_u32 + slot * GV_SEG_BYTES + c * 512, gsrc + (size_t)(cb + c) * 512);
+        }
+        cp_async_commit_g();
+    };
+    // prime the pipeline: weights do not depend on the previous kernel
+#pragma unroll
+    for (int g = 0; g < GV_DEPTH; ++g) issue((uint32_t)g);
     for (int i = tid; i < B * rpc; i += GV_THREADS) acc_s[i] = 0.f;
+
+    pdl_wait();
+    pdl_launch_dependents();
+
+    // --- stage activations (f32) and, if NORM, fold the RMSNorm weight in and get 1/rms ---
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        float ssq = 0.f;
+        for (int i = tid; i < K8; i += GV_THREADS) {
+            const float4* xp = reinterpret_cast<const float4*>(a.x + (size_t)b * a.ldx) + 2 * i;
+            float4 lo = xp[0], hi = xp[1];
+            if (NORM) {
+                ssq += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w + hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
+                const float4 w0 = reinterpret_cast<const float4*>(a.norm_w)[2 * i], w1 = reinterpret_cast<const float4*>(a.norm_w)[2 * i + 1];
+                lo.x *= w0.x; lo.y *= w0.y; lo.z *= w0.z; lo.w *= w0.w;
+                hi.x *= w1.x; hi.y *= w1.y; hi.z *= w1.z; hi.w *= w1.w;
+            }
+            xs[(size_t)(b * 2 + 0) * K8 + i] = lo;
+            xs[(size_t)(b * 2 + 1) * K8 + i] = hi;
+        }
+        if (NORM) {
+            const float tot = block_sum(ssq, red);
+            if (tid == 0) rstd_s[b] = rsqrtf(tot / (float)a.K + a.eps);
+        }
+    }
     __syncthreads();
 
-    if (warp == 0) {
-        // ------------------------------- producer -------------------------------
-        if (lane == 0) {
-            for (int s = 0; s < n_stages; ++s) {
-                const int slot = s % GV_STAGES;
-                mbar_wait(&empty_bar[slot], (((s / GV_STAGES) & 1) ^ 1));
-                const size_t off = (size_t)s * GV_STAGE_BYTES;
-                const uint32_t bytes = (uint32_t)min((size_t)GV_STAGE_BYTES, slab_bytes - off);
-                mbar_arrive_expect_tx(&full_bar[slot], bytes);
-                bulk_load(ring + slot * GV_STAGE_BYTES, gsrc + off, bytes, &full_bar[slot]);
-            }
-        }
-    } else {
-        // ------------------------------- consumers ------------------------------
-        const int ctid = tid - 32, cw = warp - 1;
-        pdl_wait();
-        pdl_launch_dependents();
+    {
+        float accum[B], accum2[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-            float ssq = 0.f;
-            for (int i = ctid; i < K8; i += GV_CTHREADS) {
-                const float4* xp = reinterpret_cast<const float4*>(a.x + (size_t)b * a.ldx) + 2 * i;
-                float4 lo = xp[0], hi = xp[1];
-                if (NORM) {
-                    ssq += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w + hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
-                    const float4 w0 = reinterpret_cast<const float4*>(a.norm_w)[2 * i], w1 = reinterpret_cast<const float4*>(a.norm_w)[2 * i + 1];
-                    lo.x *= w0.x; lo.y *= w0.y; lo.z *= w0.z; lo.w *= w0.w;
-                    hi.x *= w1.x; hi.y *= w1.y; hi.z *= w1.z; hi.w *= w1.w;
-                }
-                xs[(size_t)(b * 2 + 0) * K8 + i] = lo;
-                xs[(size_t)(b * 2 + 1) * K8 + i] = hi;
-            }
-            if (NORM) {
-                ssq = warp_sum(ssq);
-                if (lane == 0) red[cw] = ssq;
-                named_bar_sync(1, GV_CTHREADS);
-                float tot = 0.f;
-#pragma unroll
-                for (int w = 0; w < GV_CWARPS; ++w) tot += red[w];
-                if (ctid == 0) rstd_s[b] = rsqrtf(tot / (float)a.K + a.eps);
-                named_bar_sync(1, GV_CTHREADS);
-            }
-        }
-        named_bar_sync(1, GV_CTHREADS);
-
-        float accum[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) accum[b] = 0.f;
+        for (int b = 0; b < B; ++b) { accum[b] = 0.f; accum2[b] = 0.f; }
         int cur_row = -1;
         auto flush = [&]() {
             if (cur_row >= 0) {
 #pragma unroll
                 for (int b = 0; b < B; ++b) {
-                    const float v = warp_sum(accum[b]);
+                    const float v = warp_sum(accum[b] + accum2[b]);
                     if (lane == 0) atomicAdd(&acc_s[(size_t)b * rpc + cur_row], v);
-                    accum[b] = 0.f;
+                    accum[b] = 0.f; accum2[b] = 0.f;
                 }
             }
         };
-        for (int s = 0; s < n_stages; ++s) {
-            const int slot = s % GV_STAGES;
-            mbar_wait(&full_bar[slot], (s / GV_STAGES) & 1);
-            const size_t soff = (size_t)s * GV_STAGE_BYTES;
-            const unsigned char* sp = ring + slot * GV_STAGE_BYTES;
-            uint4 w[GV_CHUNKS_PER_WARP];
-            size_t coff[GV_CHUNKS_PER_WARP];
-#pragma unroll
-            for (int c = 0; c < GV_CHUNKS_PER_WARP; ++c) {
-                const int chunk = cw * GV_CHUNKS_PER_WARP + c;
-                coff[c] = soff + (size_t)chunk * 512;
-                if (coff[c] < slab_bytes) w[c] = *reinterpret_cast<const uint4*>(sp + chunk * 512 + lane * 16);
-            }
+        uint32_t row = c_begin / cpr, rem = c_begin - row * cpr;
+        for (uint32_t g = 0; g < nseg; ++g) {
+            cp_async_wait_g<GV_DEPTH - 1>();            // segment g has landed (groups complete in order)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);       // data is in registers: hand the slot back early
+            const unsigned char* sp = ring + (g % GV_DEPTH) * GV_SEG_BYTES;
+            const uint32_t cb = c_begin + g * GV_SEG_CHUNKS;
+            uint4 w[GV_SEG_CHUNKS];
 #pragma unroll
-            for (int c = 0; c < GV_CHUNKS_PER_WARP; ++c) {
-                if (coff[c] < slab_bytes) {
-                    const int row = (int)(coff[c] / row_bytes);
-                    const int idx = (int)((coff[c] - (size_t)row * row_bytes) >> 4) + lane;    // 8-element chunk index in the row
-                    if (row != cur_row) { flush(); cur_row = row; }
+            for (int c = 0; c < GV_SEG_CHUNKS; ++c)
+                if (cb + c < c_end) w[c] = *reinterpret_cast<const uint4*>(sp + c * 512);
+#pragma unroll
+            for (int c = 0; c < GV_SEG_CHUNKS; ++c) {
+                if (cb + c < c_end) {
+                    const int idx = (int)(rem << 5) + lane;                     // 8-element chunk index in the row
+                    if ((int)row != cur_row) { flush(); cur_row = (int)row; }
                     const float w0 = bf16lo(w[c].x), w1 = bf16hi(w[c].x), w2 = bf16lo(w[c].y), w3 = bf16hi(w[c].y);
                     const float w4 = bf16lo(w[c].z), w5 = bf16hi(w[c].z), w6 = bf16lo(w[c].w), w7 = bf16hi(w[c].w);
 #pragma unroll
                     for (int b = 0; b < B; ++b) {
                         const float4 xl = xs[(size_t)(b * 2 + 0) * K8 + idx];
                         const float4 xh = xs[(size_t)(b * 2 + 1) * K8 + idx];
-                        float t = accum[b];
-                        t = fmaf(w0, xl.x, t); t = fmaf(w1, xl.y, t); t = fmaf(w2, xl.z, t); t = fmaf(w3, xl.w, t);
-                        t = fmaf(w4, xh.x, t); t = fmaf(w5, xh.y, t); t = fmaf(w6, xh.z, t); t = fmaf(w7, xh.w, t);
-                        accum[b] = t;
+                        float t = accum[b], u = accum2[b];
+                        t = fmaf(w0, xl.x, t); u = fmaf(w4, xh.x, u);
+                        t = fmaf(w1, xl.y, t); u = fmaf(w5, xh.y, u);
+                        t = fmaf(w2, xl.z, t); u = fmaf(w6, xh.z, u);
+                        t = fmaf(w3, xl.w, t); u = fmaf(w7, xh.w, u);
+                        accum[b] = t; accum2[b] = u;
                     }
                 }
+                if (++rem == cpr) { rem = 0; ++row; }
             }
+            __syncwarp();                               // every lane has its slot data in registers
+            issue(g + GV_DEPTH);                        // refill the slot just drained
         }
         flush();
     }
@@ -206,7 +209,7 @@ gemv_kernel(GemvArgs a) {
         __syncthreads();
         if (tid < B) {
             float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int w = 0; w < GV_THREADS / 32; ++w) {
+            for (int w = 0; w < GV_WARPS; ++w) {
                 const float v = wbest_v[w][tid]; const int i = wbest_i[w][tid];
                 if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
             }
@@ -264,8 +267,7 @@ gemv_kernel(GemvArgs a) {
 static size_t gemv_smem_bytes(int B, int K, int N, int rows_per_unit, int grid) {
     const int units = N / rows_per_unit;
     const int rpc = (units + grid - 1) / grid * rows_per_unit;
-    size_t acc = (((size_t)B * rpc + 1) & ~(size_t)1) * 4;
-    return (size_t)GV_STAGES * GV_STAGE_BYTES + (size_t)B * K * 4 + acc + 2 * GV_STAGES * 8 + 16;
+    return (size_t)GV_WARPS * GV_DEPTH * GV_SEG_BYTES + (size_t)B * K * 4 + (size_t)B * rpc * 4 + 16;
 }
 
 template <int B, int EPI, bool NORM>
