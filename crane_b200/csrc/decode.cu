@@ -83,6 +83,9 @@ gemv_kernel(GemvArgs a) {
 #pragma unroll
     for (int g = 0; g < GV_DEPTH; ++g) issue((uint32_t)g);
     for (int i = tid; i < B * rpc; i += GV_THREADS) acc_s[i] = 0.f;
+    // RMSNorm weights are immutable (and cold in every cache): fetch this thread's first chunk before the dependency wait
+    float4 nw0 = make_float4(0.f, 0.f, 0.f, 0.f), nw1 = nw0;
+    if (NORM && tid < K8) { nw0 = reinterpret_cast<const float4*>(a.norm_w)[2 * tid]; nw1 = reinterpret_cast<const float4*>(a.norm_w)[2 * tid + 1]; }
 
     pdl_wait();
     pdl_launch_dependents();
@@ -96,7 +99,8 @@ gemv_kernel(GemvArgs a) {
             float4 lo = xp[0], hi = xp[1];
             if (NORM) {
                 ssq += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w + hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
-                const float4 w0 = reinterpret_cast<const float4*>(a.norm_w)[2 * i], w1 = reinterpret_cast<const float4*>(a.norm_w)[2 * i + 1];
+                const float4 w0 = (i == tid) ? nw0 : reinterpret_cast<const float4*>(a.norm_w)[2 * i];
+                const float4 w1 = (i == tid) ? nw1 : reinterpret_cast<const float4*>(a.norm_w)[2 * i + 1];
                 lo.x *= w0.x; lo.y *= w0.y; lo.z *= w0.z; lo.w *= w0.w;
                 hi.x *= w1.x; hi.y *= w1.y; hi.z *= w1.z; hi.w *= w1.w;
             }
@@ -359,6 +363,7 @@ attn_decode_kernel(AttnDecArgs a) {
     constexpr int LPT = D / EPL;         // lanes per token (16 for D=128, 32 for D=256)
     constexpr int TPW = 32 / LPT;        // tokens per warp pass
     constexpr int NW = 8;
+    static_assert(NREP < NW, "one q/k vector per warp");
     constexpr int TILE = 32768 / (D * 2);   // tokens per shared-memory tile (K and V: 32 KB each)
     constexpr int CPR = D / 8;              // 16-byte chunks per token row
     extern __shared__ __align__(16) unsigned char asm_[];
@@ -403,18 +408,36 @@ attn_decode_kernel(AttnDecArgs a) {
     };
     if (t0 < t_end) load_tile(t0);
 
+    // norm weights and this position's cos/sin depend only on immutable data and the sequence state: fetch them before
+    // the dependency wait too (lane l owns elements l + 32 j, so a rotary pair is lane-local)
+    constexpr int NE = D / 32;
+    const int RJ = a.rot_half >> 5;                    // lane-local rotary pairs (j, j + RJ), j < RJ
+    const bool vec_is_k = (warp == NREP);
+    float nwv[NE], cs_c[NE], cs_s[NE];
+    if (warp <= NREP) {
+        const float* nw = vec_is_k ? a.k_norm_w : a.q_norm_w;
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+            nwv[j] = nw[lane + 32 * j];
+            cs_c[j] = 1.f; cs_s[j] = 0.f;
+            if (j < 2 * RJ) {
+                const int i = lane + 32 * (j < RJ ? j : j - RJ);
+                const int p = st.pos[a.axis_of[i]];
+                cs_c[j] = a.cos_tab[(size_t)p * a.rot_half + i];
+                cs_s[j] = a.sin_tab[(size_t)p * a.rot_half + i];
+            }
+        }
+    }
+
     pdl_wait();
     pdl_launch_dependents();
     const float* qkv = a.qkv + (size_t)b * (q_span + 2 * kv_dim);
 
     // ---- q (NREP heads) and, on the split that owns position T-1, the new k: RMSNorm then rotate ----
-    // Each warp takes vectors round-robin; lane l owns elements l + 32 j so a rotary pair is lane-local.
-    constexpr int NE = D / 32;
-    for (int vec = warp; vec < NREP + 1; vec += NW) {
+    for (int vec = warp; vec < NREP + 1; vec += NW) {      // NW > NREP: one vector per warp, vec == warp
         const bool is_k = (vec == NREP);
         if (is_k && split != s_last) continue;
         const float* src = is_k ? (qkv + q_span + kvh * D) : (qkv + (kvh * NREP + vec) * a.q_stride);
-        const float* nw = is_k ? a.k_norm_w : a.q_norm_w;
         float e[NE];
         float ssq = 0.f;
 #pragma unroll
@@ -422,17 +445,14 @@ attn_decode_kernel(AttnDecArgs a) {
         ssq = warp_sum(ssq);
         const float rstd = rsqrtf(ssq / (float)D + a.eps);
 #pragma unroll
-        for (int j = 0; j < NE; ++j) e[j] = e[j] * rstd * nw[lane + 32 * j];
+        for (int j = 0; j < NE; ++j) e[j] = e[j] * rstd * nwv[j];
         float* dst = is_k ? knew_s : q_s[vec];
-        const int RJ = a.rot_half >> 5;                // lane-local rotary pairs (j, j + RJ), j < RJ
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
             float r = e[j];
             if (j < 2 * RJ) {
                 const bool lo = j < RJ;
-                const int i = lane + 32 * (lo ? j : j - RJ);     // rotary column in [0, rot_half)
-                const int p = st.pos[a.axis_of[i]];
-                const float c = a.cos_tab[(size_t)p * a.rot_half + i], s = a.sin_tab[(size_t)p * a.rot_half + i];
+                const float c = cs_c[j], s = cs_s[j];
                 float other = 0.f;
 #pragma unroll
                 for (int jj = 0; jj < NE; ++jj) if (jj == (lo ? j + RJ : j - RJ)) other = e[jj];
@@ -630,7 +650,6 @@ int attn_decode_launch(cudaStream_t st, int B, int D, const AttnDecArgs& a, bool
             case 1: return attn_decode_launch_t<128, 1>(st, B, a, pdl);
             case 2: return attn_decode_launch_t<128, 2>(st, B, a, pdl);
             case 4: return attn_decode_launch_t<128, 4>(st, B, a, pdl);
-            case 8: return attn_decode_launch_t<128, 8>(st, B, a, pdl);
         }
     } else if (D == 256) {
         switch (nrep) {

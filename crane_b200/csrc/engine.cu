@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "decode.cuh"
+#include "decode_persistent.cuh"
 #include "gdn.cuh"
 #include "gemm.cuh"
 #include "json_min.h"
@@ -142,7 +143,10 @@ struct crane_b200_model {
     int nk = 0, nv = 0, dk = 0, dv = 0, ck = 4, gdn_in = 0, gdn_in_pad = 0, rot_half = 0, full_interval = 4;
     std::vector<int> layer_is_full;
     int max_seq = 4096, max_batch = 1, max_pages = 0;
-    bool use_simt = false, use_graphs = true, use_pdl = true;
+    bool use_simt = false, use_graphs = true, use_pdl = true, use_persistent = false;
+    PLayer* players = nullptr;
+    unsigned int* grid_bar = nullptr;
+    unsigned long long* pk_prof = nullptr;
     // vision
     int v_depth = 0, v_H = 0, v_I = 0, v_nh = 0, v_hd = 0, v_patch = 16, v_merge = 2, v_tpatch = 2, v_in = 3, v_out = 0,
         v_npos = 0, v_side = 0;
@@ -259,6 +263,7 @@ struct crane_b200_model {
     void arm_state(uint32_t token, size_t start_pos, int p0, int p1, int p2);
     void enqueue_decode_step(int advance, bool with_embed);
     void decode_step_graphed(int advance);
+    void decode_steps(int n_steps, int advance);
     void prefill(const uint32_t* ids, const float* embeds, size_t S, const uint32_t* pos3_host, size_t start_pos,
                  const int* vis_rows, int n_vis, int advance);
     void lm_head_last_row(const float* xrow, int advance);
@@ -337,6 +342,8 @@ void crane_b200_model::parse_config(const char* json) {
     if (const char* g = getenv("CRANE_B200_GEMM")) use_simt = std::string(g) == "simt";
     if (const char* g = getenv("CRANE_B200_GRAPHS")) use_graphs = std::string(g) != "0";
     if (const char* g = getenv("CRANE_B200_PDL")) use_pdl = std::string(g) != "0";
+    if (root.has("engine")) use_persistent = root.at("engine").boolean("persistent", false);
+    if (const char* g = getenv("CRANE_B200_PERSISTENT")) use_persistent = std::string(g) != "0";
     if (max_batch != 1) fail(CRANE_B200_UNSUPPORTED, "max_batch %d: only 1 sequence per handle in this build", max_batch);
     max_seq = (max_seq + KV_PAGE - 1) / KV_PAGE * KV_PAGE;
     max_pages = max_seq / KV_PAGE;
@@ -661,6 +668,18 @@ void crane_b200_model::finalize() {
     CUDA_OK(cudaMemset(counters, 0, (size_t)B * nkv * sizeof(unsigned int)));
     CUDA_OK(cudaMemset(ticket, 0, sizeof(unsigned int)));
     CUDA_OK(cudaMemset(state, 0, B * sizeof(SeqState)));
+    use_persistent = use_persistent && !hybrid && decode_persistent_supported(D, nh / nkv, H, I, q_dim(), nkv, num_sms);
+    if (use_persistent) {
+        std::vector<PLayer> pl(L);
+        for (int i = 0; i < L; ++i) {
+            const LayerW& l = layers[i];
+            pl[i] = PLayer{l.wqkv, l.wo, l.wgu, l.wdown, l.ln1, l.ln2, l.qn, l.kn, l.k_pool, l.v_pool};
+        }
+        players = dalloc<PLayer>(L);
+        CUDA_OK(cudaMemcpy(players, pl.data(), L * sizeof(PLayer), cudaMemcpyHostToDevice));
+        grid_bar = dalloc<unsigned int>(64);
+        if (getenv("CRANE_B200_PROF")) { pk_prof = dalloc<unsigned long long>(8); CUDA_OK(cudaMemset(pk_prof, 0, 64)); }
+    }
     CUDA_OK(cudaMallocHost((void**)&h_state, sizeof(SeqState) * B));
     CUDA_OK(cudaMallocHost((void**)&h_tokens, sizeof(uint32_t) * out_cap));
     CUDA_OK(cudaEventCreate(&pev0));
@@ -801,6 +820,36 @@ void crane_b200_model::decode_step_graphed(int advance) {
     } else {
         enqueue_decode_step(advance, false);
     }
+}
+
+// n dependent decode steps: one persistent launch when available, else n graph replays / kernel chains.
+void crane_b200_model::decode_steps(int n_steps, int advance) {
+    if (use_persistent) {
+        PersistArgs p = {};
+        p.L = L; p.H = H; p.I = I; p.V = V; p.nh = nh; p.nkv = nkv; p.qkv_dim = qkv_dim(); p.q_dim = q_dim();
+        p.eps = eps; p.scale = 1.0f / std::sqrt((float)D);
+        p.layers = players; p.lm_head = lm_head; p.final_norm = final_norm; p.embed = embed;
+        p.cos_tab = cos_tab; p.sin_tab = sin_tab; p.axis_of = axis_of; p.state = state; p.block_table = block_table;
+        p.x = x_dec; p.qkv = qkv_dec; p.act = act_dec; p.logits = logits; p.part_o = part_o; p.part_ml = part_ml;
+        p.part_val = part_val; p.part_idx = part_idx; p.out_tokens = out_tokens; p.barrier = grid_bar;
+        p.n_steps = n_steps; p.advance = advance; p.prof = pk_prof;
+        p.xs_floats = std::max(std::max(H, I), std::max(q_dim(), PK_WARPS_C * (nh / nkv) * 128));
+        CUDA_OK(cudaMemsetAsync(grid_bar, 0, 64 * sizeof(unsigned int), stream));
+        LAUNCH_OK(decode_persistent_launch(stream, p, num_sms));
+        ++launches;
+        if (pk_prof && n_steps > 8) {   // CRANE_B200_PROF=1: per-phase device time of CTA 0 (the CRANE_PROF spans of ops/prof.rs:37-61)
+            unsigned long long h[8];
+            CUDA_OK(cudaStreamSynchronize(stream));
+            CUDA_OK(cudaMemcpy(h, pk_prof, 64, cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemset(pk_prof, 0, 64));
+            const char* names[7] = {"attention", "attn_barrier", "staging", "stream", "epilogue", "barrier", "token"};
+            fprintf(stderr, "[crane_b200 prof] per step (us):");
+            for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f", names[i], (double)h[i] / 1e3 / n_steps);
+            fprintf(stderr, "\n");
+        }
+        return;
+    }
+    for (int i = 0; i < n_steps; ++i) decode_step_graphed(advance);
 }
 
 // =================================================================================================
@@ -1119,7 +1168,7 @@ int crane_b200_forward_step(crane_b200_model* m, const uint32_t* ids, size_t n, 
         m->arm_state(ids[0], start_pos, (int)start_pos, (int)start_pos, (int)start_pos);
         LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
         ++m->launches;
-        m->decode_step_graphed(0);
+        m->decode_steps(1, 0);
         CUDA_OK(cudaEventRecord(m->dev1, m->stream));
         m->last_decode_steps = 1;
         m->kv_len = start_pos + 1;
@@ -1173,8 +1222,8 @@ int crane_b200_warmup(crane_b200_model* m) {
     if (saved != 0) fail(CRANE_B200_INVALID_ARG, "warmup requires an empty KV cache");
     uint32_t ids[4] = {0, 1 % (uint32_t)m->V, 2 % (uint32_t)m->V, 3 % (uint32_t)m->V};
     m->prefill(ids, nullptr, 4, nullptr, 0, nullptr, 0, 1);
-    m->decode_step_graphed(1);
-    m->decode_step_graphed(0);
+    m->decode_steps(2, 1);
+    m->decode_steps(1, 0);
     CUDA_OK(cudaStreamSynchronize(m->stream));
     m->kv_len = 0;
     m->next_mrope_pos = saved_pos;
@@ -1222,7 +1271,7 @@ int crane_b200_decode_greedy(crane_b200_model* m, uint32_t first_token, size_t s
     m->arm_state(first_token, start_pos, p, p, p);
     LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
     ++m->launches;
-    for (size_t i = 0; i < n_steps; ++i) m->decode_step_graphed(1);
+    m->decode_steps((int)n_steps, 1);
     CUDA_OK(cudaEventRecord(m->dev1, m->stream));
     CUDA_OK(cudaMemcpyAsync(m->h_tokens, m->out_tokens, n_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
     CUDA_OK(cudaStreamSynchronize(m->stream));
@@ -1325,7 +1374,7 @@ int crane_b200_vl_forward(crane_b200_model* m, const uint32_t* ids, size_t n, co
         m->arm_state(ids[0], start_pos, (int)pos3[0], (int)pos3[1], (int)pos3[2]);
         LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
         ++m->launches;
-        m->decode_step_graphed(0);
+        m->decode_steps(1, 0);
         m->kv_len = start_pos + 1;
     } else {
         m->prefill(ids, nullptr, n, pos3.data(), start_pos, vis_rows.data(), (int)vis_rows.size(), 0);
@@ -1344,7 +1393,7 @@ int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token, size_t start_
     m->arm_state(token, start_pos, p, p, p);
     LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
     ++m->launches;
-    m->decode_step_graphed(0);
+    m->decode_steps(1, 0);
     m->next_mrope_pos = (uint32_t)(p + 1);
     m->kv_len = start_pos + 1;
     fill_logits(m, out);
