@@ -46,6 +46,7 @@ _SIGNATURES = {
     "crane_b200_destroy": (None, [C.c_void_p]),
     "crane_b200_last_error": (C.c_char_p, [C.c_void_p]),
     "crane_b200_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "crane_b200_load_tensor_ggml": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_size_t]),
     "crane_b200_finalize": (C.c_int, [C.c_void_p]),
     "crane_b200_forward_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(Logits)]),
     "crane_b200_forward_step_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]),
@@ -140,6 +141,12 @@ class Engine:
             raise TypeError(f"{name}: unsupported dtype {a.dtype}")
         shape = (C.c_int64 * a.ndim)(*a.shape)
         self._ck(self.lib.crane_b200_load_tensor(self.h, name.encode(), dt, shape, a.ndim, _ptr(a)))
+
+    def load_tensor_ggml(self, name: str, ggml_type: int, shape, raw: np.ndarray):
+        """Raw ggml blocks (uint8) of a [rows, cols] tensor; ggml_type 8 = Q8_0, 12 = Q4_K, 14 = Q6_K."""
+        a = np.ascontiguousarray(raw, dtype=np.uint8)
+        shp = (C.c_int64 * len(shape))(*shape)
+        self._ck(self.lib.crane_b200_load_tensor_ggml(self.h, name.encode(), ggml_type, shp, len(shape), _ptr(a), a.size))
 
     def load_checkpoint(self, tensors):
         for name, arr in tensors:

@@ -22,6 +22,7 @@
 #include "gemm.cuh"
 #include "json_min.h"
 #include "prefill.cuh"
+#include "quant.cuh"
 
 using namespace cb;
 
@@ -105,6 +106,9 @@ struct LayerW {
     float *ln1 = nullptr, *ln2 = nullptr, *qn = nullptr, *kn = nullptr;
     bf16 *k_pool = nullptr, *v_pool = nullptr;
     int loaded = 0;   // bit per tensor
+    // GGUF-quantised linears (ggml bytes repacked by q_repack_rows): qt_* == 0 means the bf16 buffer above is used
+    unsigned char *q_wq = nullptr, *q_wk = nullptr, *q_wv = nullptr, *q_wo = nullptr, *q_wgu = nullptr, *q_wdown = nullptr;
+    int qt_q = 0, qt_k = 0, qt_v = 0, qt_o = 0, qt_gu = 0, qt_down = 0, qt_gate_seen = 0, qt_up_seen = 0;
     // Gated-Delta-Net layers (Qwen3.5 `linear_attn.*`)
     bool full = true;                       // softmax-attention layer (else GDN)
     bf16 *w_in = nullptr, *w_out = nullptr; // [in_pad, H] rows = q|k|v|z|b|a ; [H, value_dim]
@@ -158,6 +162,11 @@ struct crane_b200_model {
     cudaStream_t stream = nullptr;
     std::vector<void*> allocs;
     bf16 *embed = nullptr, *lm_head = nullptr;
+    unsigned char* q_lm_head = nullptr;   // quantised output head (GGUF `output.weight`, or the tied quantised `token_embd.weight`)
+    int qt_lm = 0;
+    bool any_quant = false;
+    bf16* dq_scratch = nullptr;           // one dequantised weight matrix at a time for the prefill GEMMs
+    size_t dq_scratch_elems = 0;
     float* final_norm = nullptr;
     std::vector<LayerW> layers;
     bool got_embed = false, got_lm_head = false, got_final_norm = false, finalized = false;
@@ -235,6 +244,11 @@ struct crane_b200_model {
     void parse_config(const char* json);
     void alloc_weights();
     void load_tensor(const std::string& name, int dt, const int64_t* shape, int ndim, const void* data);
+    void load_tensor_ggml(const std::string& name, int qt, const int64_t* shape, int ndim, const void* data, size_t nbytes);
+    unsigned char* up_quant(int qt, const void* data, size_t rows, int K, unsigned char* dst = nullptr, size_t dst_row_pitch = 0);
+    void linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
+                       const float* norm_w, float* y, int ldy, const GemvArgs* extra = nullptr);
+    const bf16* dequant_for_gemm(const unsigned char* qw, int qt, size_t rows, int K, size_t row_offset = 0);
     bool load_text_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
     bool load_vision_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
     void finalize();
@@ -373,16 +387,14 @@ void crane_b200_model::parse_config(const char* json) {
 
 void crane_b200_model::alloc_weights() {
     embed = dalloc<bf16>((size_t)V * H);
-    lm_head = tied ? embed : dalloc<bf16>((size_t)V * H);
+    lm_head = tied ? embed : nullptr;      // untied head: allocated when `lm_head.weight` arrives (bf16 or quantised)
     final_norm = dalloc<float>(H);
     layers.resize(L);
     for (int li = 0; li < L; ++li) {
         LayerW& l = layers[li];
         l.full = layer_is_full[li] != 0;
         if (l.full) {
-            l.wqkv = dalloc<bf16>((size_t)qkv_dim() * H);
-            l.wo = dalloc<bf16>((size_t)H * q_dim());
-            l.qn = dalloc<float>(D); l.kn = dalloc<float>(D);
+            l.qn = dalloc<float>(D); l.kn = dalloc<float>(D);   // big matrices are allocated when their tensors arrive (bf16 or quantised)
         } else {
             l.w_in = dalloc<bf16>((size_t)gdn_in_pad * H);
             CUDA_OK(cudaMemset(l.w_in, 0, (size_t)gdn_in_pad * H * 2));
@@ -390,8 +402,6 @@ void crane_b200_model::alloc_weights() {
             l.conv_w = dalloc<float>((size_t)conv_dim() * ck);
             l.neg_exp_a = dalloc<float>(nv); l.dt_bias = dalloc<float>(nv); l.gnorm = dalloc<float>(dv);
         }
-        l.wgu = dalloc<bf16>((size_t)2 * I * H);
-        l.wdown = dalloc<bf16>((size_t)H * I);
         l.ln1 = dalloc<float>(H); l.ln2 = dalloc<float>(H);
     }
     if (is_vl) {
@@ -423,6 +433,7 @@ void crane_b200_model::alloc_weights() {
 // =================================================================================================
 // weight registration
 // =================================================================================================
+static std::string gguf_to_hf(const std::string& n);
 static void want_shape(const std::string& name, const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
     size_t n = 1, w = 1;
     for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
@@ -463,6 +474,11 @@ bool crane_b200_model::load_text_tensor(const std::string& n, int dt, const int6
     LayerW& l = layers[li];
     const int qd = q_dim(), kvd = nkv * D, qs = nh * q_stride();
     auto rows_bf16 = [&](bf16* dst, int rows, int cols) { up_bf16(dst, data, dt, (size_t)rows * cols); };
+    if (l.full && !l.wqkv && (t == "self_attn.q_proj.weight" || t == "self_attn.k_proj.weight" || t == "self_attn.v_proj.weight"))
+        l.wqkv = dalloc<bf16>((size_t)qkv_dim() * H);
+    if (!l.wo && t == "self_attn.o_proj.weight") l.wo = dalloc<bf16>((size_t)H * q_dim());
+    if (!l.wgu && (t == "mlp.gate_proj.weight" || t == "mlp.up_proj.weight")) l.wgu = dalloc<bf16>((size_t)2 * I * H);
+    if (!l.wdown && t == "mlp.down_proj.weight") l.wdown = dalloc<bf16>((size_t)H * I);
     const bool attn_t = t.rfind("self_attn.", 0) == 0, gdn_t = t.rfind("linear_attn.", 0) == 0;
     if (attn_t && !l.full) fail(CRANE_B200_INVALID_ARG, "tensor %s: layer %d is a linear-attention layer", n.c_str(), li);
     if (gdn_t && l.full) fail(CRANE_B200_INVALID_ARG, "tensor %s: layer %d is a full-attention layer", n.c_str(), li);
@@ -554,7 +570,8 @@ bool crane_b200_model::load_vision_tensor(const std::string& n, int dt, const in
     return true;
 }
 
-void crane_b200_model::load_tensor(const std::string& name, int dt, const int64_t* shape, int ndim, const void* data) {
+void crane_b200_model::load_tensor(const std::string& name_in, int dt, const int64_t* shape, int ndim, const void* data) {
+    const std::string name = gguf_to_hf(name_in);
     if (finalized) fail(CRANE_B200_INVALID_ARG, "load_tensor after finalize");
     if (dt < 0 || dt > 2) fail(CRANE_B200_INVALID_ARG, "tensor %s: unknown dtype %d", name.c_str(), dt);
     CUDA_OK(cudaSetDevice(device));
@@ -567,7 +584,11 @@ void crane_b200_model::load_tensor(const std::string& name, int dt, const int64_
         }
     if (name == "lm_head.weight") {
         want_shape(name, shape, ndim, {V, H});
-        if (!tied) { up_bf16(lm_head, data, dt, (size_t)V * H); got_lm_head = true; }
+        if (!tied) {
+            if (!lm_head) lm_head = dalloc<bf16>((size_t)V * H);
+            up_bf16(lm_head, data, dt, (size_t)V * H);
+            got_lm_head = true;
+        }
         return;   // tied checkpoints may still carry a copy: ignored, as the reference does (qwen3/modeling.rs:786-794)
     }
     static const char* txt_prefix[] = {"model.language_model.", "language_model.model.", "language_model.", "model."};
@@ -580,6 +601,120 @@ void crane_b200_model::load_tensor(const std::string& name, int dt, const int64_
     fail(CRANE_B200_INVALID_ARG, "unknown tensor %s", name.c_str());
 }
 
+// GGUF tensor names as read by the reference's GGUF loaders (qwen3/modeling.rs:252-282,598-606,686-689,898-916)
+static std::string gguf_to_hf(const std::string& n) {
+    if (n == "token_embd.weight") return "model.embed_tokens.weight";
+    if (n == "output_norm.weight") return "model.norm.weight";
+    if (n == "output.weight") return "lm_head.weight";
+    if (n.rfind("blk.", 0) != 0) return n;
+    const size_t dot = n.find('.', 4);
+    if (dot == std::string::npos) return n;
+    const std::string idx = n.substr(4, dot - 4), t = n.substr(dot + 1);
+    static const char* map[][2] = {
+        {"attn_norm.weight", "input_layernorm.weight"}, {"ffn_norm.weight", "post_attention_layernorm.weight"},
+        {"attn_q.weight", "self_attn.q_proj.weight"}, {"attn_k.weight", "self_attn.k_proj.weight"}, {"attn_v.weight", "self_attn.v_proj.weight"},
+        {"attn_output.weight", "self_attn.o_proj.weight"}, {"attn_q_norm.weight", "self_attn.q_norm.weight"},
+        {"attn_k_norm.weight", "self_attn.k_norm.weight"}, {"ffn_gate.weight", "mlp.gate_proj.weight"}, {"ffn_up.weight", "mlp.up_proj.weight"},
+        {"ffn_down.weight", "mlp.down_proj.weight"}};
+    for (auto& m : map)
+        if (t == m[0]) return "model.layers." + idx + "." + m[1];
+    return n;
+}
+
+// Upload `rows` x K quantised weights: repack on the host, copy row-wise (dst_row_pitch lets gate/up rows interleave).
+unsigned char* crane_b200_model::up_quant(int qt, const void* data, size_t rows, int K, unsigned char* dst, size_t dst_row_pitch) {
+    const size_t rb = (size_t)(K / 256) * q_sb_bytes(qt);
+    std::vector<unsigned char> tmp(rows * rb);
+    q_repack_rows(qt, (const unsigned char*)data, tmp.data(), rows, K);
+    if (!dst) { dst = dalloc<unsigned char>(rows * rb); dst_row_pitch = rb; }
+    CUDA_OK(cudaMemcpy2D(dst, dst_row_pitch, tmp.data(), rb, rb, rows, cudaMemcpyHostToDevice));
+    return dst;
+}
+
+void crane_b200_model::load_tensor_ggml(const std::string& name_in, int qt, const int64_t* shape, int ndim, const void* data, size_t nbytes) {
+    if (finalized) fail(CRANE_B200_INVALID_ARG, "load_tensor after finalize");
+    if (qt != QT_Q4_K && qt != QT_Q6_K && qt != QT_Q8_0) fail(CRANE_B200_UNSUPPORTED, "ggml type %d (supported: Q8_0=8, Q4_K=12, Q6_K=14)", qt);
+    if (hybrid || is_vl) fail(CRANE_B200_UNSUPPORTED, "quantised tensors are supported for the dense Qwen3 decoder only");
+    if (ndim != 2) fail(CRANE_B200_INVALID_ARG, "tensor %s: quantised tensors are 2-D [rows, cols]", name_in.c_str());
+    CUDA_OK(cudaSetDevice(device));
+    std::string name = gguf_to_hf(name_in);
+    const int64_t rows = shape[0], K = shape[1];
+    if (K % 256) fail(CRANE_B200_UNSUPPORTED, "tensor %s: in_dim %lld is not a multiple of 256 (ops/linear.rs:86-94 falls back to Q8_0 there)", name.c_str(), (long long)K);
+    const size_t want = (size_t)rows * (K / q_src_block_elems(qt)) * q_src_block_bytes(qt);
+    if (nbytes != want) fail(CRANE_B200_INVALID_ARG, "tensor %s: %zu bytes, expected %zu", name.c_str(), nbytes, want);
+    any_quant = true;
+    auto dequant_to = [&](bf16* dst) {      // device-side dequantisation into a bf16 matrix
+        unsigned char* tmpq = up_quant(qt, data, (size_t)rows, (int)K);
+        LAUNCH_OK(q_dequant_bf16_launch(stream, qt, tmpq, (size_t)rows, (int)K, dst));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        return tmpq;
+    };
+    if (name == "model.embed_tokens.weight") {
+        // rows are gathered as bf16 (whole table dequantised at load); a tied head streams the quantised bytes
+        want_shape(name, shape, ndim, {V, H});
+        unsigned char* qb = dequant_to(embed);
+        got_embed = true;
+        if (tied) { q_lm_head = qb; qt_lm = qt; } else dfree(qb);
+        return;
+    }
+    if (name == "lm_head.weight") {
+        want_shape(name, shape, ndim, {V, H});
+        if (!tied) { q_lm_head = up_quant(qt, data, (size_t)V, H); qt_lm = qt; got_lm_head = true; }
+        return;
+    }
+    static const char* txt_prefix[] = {"model.language_model.", "model."};
+    std::string n;
+    for (const char* p : txt_prefix)
+        if (name.rfind(p, 0) == 0) { n = name.substr(std::strlen(p)); break; }
+    if (n.rfind("layers.", 0) != 0) fail(CRANE_B200_INVALID_ARG, "unknown quantised tensor %s", name_in.c_str());
+    const size_t dot = n.find('.', 7);
+    const int li = std::atoi(n.substr(7, dot - 7).c_str());
+    if (li < 0 || li >= L) fail(CRANE_B200_INVALID_ARG, "tensor %s: layer index out of range", name.c_str());
+    const std::string t = n.substr(dot + 1);
+    LayerW& l = layers[li];
+    const int qd = q_dim(), kvd = nkv * D;
+    if (t == "self_attn.q_proj.weight") { want_shape(name, shape, ndim, {qd, H}); l.q_wq = up_quant(qt, data, qd, H); l.qt_q = qt; l.loaded |= 1; }
+    else if (t == "self_attn.k_proj.weight") { want_shape(name, shape, ndim, {kvd, H}); l.q_wk = up_quant(qt, data, kvd, H); l.qt_k = qt; l.loaded |= 2; }
+    else if (t == "self_attn.v_proj.weight") { want_shape(name, shape, ndim, {kvd, H}); l.q_wv = up_quant(qt, data, kvd, H); l.qt_v = qt; l.loaded |= 4; }
+    else if (t == "self_attn.o_proj.weight") { want_shape(name, shape, ndim, {H, qd}); l.q_wo = up_quant(qt, data, H, qd); l.qt_o = qt; l.loaded |= 8; }
+    else if (t == "mlp.gate_proj.weight" || t == "mlp.up_proj.weight") {
+        want_shape(name, shape, ndim, {I, H});
+        const bool up = (t == "mlp.up_proj.weight");
+        if (l.qt_gu && l.qt_gu != qt) fail(CRANE_B200_UNSUPPORTED, "layer %d: gate_proj and up_proj use different ggml types (%d vs %d)", li, l.qt_gu, qt);
+        const size_t rb = (size_t)(H / 256) * q_sb_bytes(qt);
+        if (!l.q_wgu) l.q_wgu = dalloc<unsigned char>((size_t)2 * I * rb);
+        l.qt_gu = qt;
+        up_quant(qt, data, I, H, l.q_wgu + (up ? rb : 0), 2 * rb);     // rows interleaved (gate_j, up_j)
+        l.loaded |= up ? 32 : 16;
+    }
+    else if (t == "mlp.down_proj.weight") { want_shape(name, shape, ndim, {H, I}); l.q_wdown = up_quant(qt, data, H, I); l.qt_down = qt; l.loaded |= 64; }
+    else fail(CRANE_B200_INVALID_ARG, "tensor %s cannot be quantised here", name.c_str());
+}
+
+// One decode-path linear: bf16 GEMV or quantised GEMV with the same fused epilogue.
+void crane_b200_model::linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
+                                     const float* norm_w, float* y, int ldy, const GemvArgs* extra) {
+    GemvArgs g = extra ? *extra : GemvArgs{};
+    g.N = N; g.K = K; g.x = xin; g.ldx = ldx; g.norm_w = norm_w; g.eps = eps; g.y = y; g.ldy = ldy;
+    if (qt) {
+        QGemvArgs qa;
+        g.W = reinterpret_cast<const bf16*>(qw);
+        qa.g = g; qa.qtype = qt; qa.epi = epi; qa.norm = norm ? 1 : 0;
+        LAUNCH_OK(qgemv_launch(stream, 1, qa, num_sms, use_pdl));
+    } else {
+        g.W = w;
+        LAUNCH_OK(gemv_launch(stream, 1, epi, norm, g, num_sms, use_pdl));
+    }
+    ++launches;
+}
+
+// Prefill: dequantise `rows` x K into the shared bf16 scratch (at `row_offset` rows) and hand back the GEMM operand.
+const bf16* crane_b200_model::dequant_for_gemm(const unsigned char* qw, int qt, size_t rows, int K, size_t row_offset) {
+    LAUNCH_OK(q_dequant_bf16_launch(stream, qt, qw, rows, K, dq_scratch + row_offset * K));
+    ++launches;
+    return dq_scratch;
+}
+
 // =================================================================================================
 // finalize: tables, KV pages, decode buffers
 // =================================================================================================
@@ -589,6 +724,19 @@ void crane_b200_model::finalize() {
     if (!got_embed) fail(CRANE_B200_NOT_LOADED, "missing tensor embed_tokens.weight");
     if (!got_final_norm) fail(CRANE_B200_NOT_LOADED, "missing tensor norm.weight");
     if (!tied && !got_lm_head) fail(CRANE_B200_NOT_LOADED, "missing tensor lm_head.weight");
+    if (any_quant) {
+        size_t mx = 0;
+        for (auto& l : layers) {
+            if (l.qt_q || l.qt_k || l.qt_v) {
+                if (!(l.qt_q && l.qt_k && l.qt_v)) fail(CRANE_B200_UNSUPPORTED, "q/k/v must be all quantised or all bf16 within a layer");
+                mx = std::max(mx, (size_t)qkv_dim() * H);
+            }
+            if (l.qt_o) mx = std::max(mx, (size_t)H * q_dim());
+            if (l.qt_gu) mx = std::max(mx, (size_t)2 * I * H);
+            if (l.qt_down) mx = std::max(mx, (size_t)H * I);
+        }
+        if (mx) { dq_scratch = dalloc<bf16>(mx); dq_scratch_elems = mx; }
+    }
     for (int i = 0; i < L; ++i) {
         // full: q,k,v,o (1|2|4|8) gate,up,down (16|32|64) ln1,ln2 (128|256) q_norm,k_norm (512|1024)
         // GDN : qkv,z,b,a (1|2|4|8) gate,up,down, ln1,ln2, conv (512) dt_bias (1024) A_log (2048) norm (4096) out_proj (8192)
@@ -668,7 +816,7 @@ void crane_b200_model::finalize() {
     CUDA_OK(cudaMemset(counters, 0, (size_t)B * nkv * sizeof(unsigned int)));
     CUDA_OK(cudaMemset(ticket, 0, sizeof(unsigned int)));
     CUDA_OK(cudaMemset(state, 0, B * sizeof(SeqState)));
-    use_persistent = use_persistent && !hybrid && decode_persistent_supported(D, nh / nkv, H, I, q_dim(), nkv, num_sms);
+    use_persistent = use_persistent && !hybrid && !any_quant && decode_persistent_supported(D, nh / nkv, H, I, q_dim(), nkv, num_sms);
     if (use_persistent) {
         std::vector<PLayer> pl(L);
         for (int i = 0; i < L; ++i) {
@@ -733,9 +881,14 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
     for (int li = 0; li < L; ++li) {
         LayerW& l = layers[li];
         if (l.full) {
-            GemvArgs g = {};
-            g.W = l.wqkv; g.N = qkv_dim(); g.K = H; g.x = x_dec; g.ldx = H; g.norm_w = l.ln1; g.eps = eps; g.y = qkv_dec; g.ldy = qkv_dim();
-            LAUNCH_OK(gemv_launch(stream, B, GEMV_STORE, true, g, num_sms, pdl));
+            if (l.qt_q) {   // GGUF keeps q/k/v as separate quantised matrices (qwen3/modeling.rs:252-255): three GEMVs into one qkv row
+                const int qs = nh * q_stride(), kvd = nkv * D;
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wq, l.qt_q, qs, H, x_dec, H, l.ln1, qkv_dec, qkv_dim());
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wk, l.qt_k, kvd, H, x_dec, H, l.ln1, qkv_dec + qs, qkv_dim());
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wv, l.qt_v, kvd, H, x_dec, H, l.ln1, qkv_dec + qs + kvd, qkv_dim());
+            } else {
+                linear_decode(GEMV_STORE, true, l.wqkv, nullptr, 0, qkv_dim(), H, x_dec, H, l.ln1, qkv_dec, qkv_dim());
+            }
             AttnDecArgs a = {};
             a.qkv = qkv_dec; a.q_stride = q_stride(); a.gated = hybrid ? 1 : 0; a.rot_half = rot_half;
             a.q_norm_w = l.qn; a.k_norm_w = l.kn; a.eps = eps; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.axis_of = axis_of;
@@ -743,10 +896,8 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
             a.nh = nh; a.nkv = nkv; a.scale = 1.0f / std::sqrt((float)D);
             a.out = attn_dec;
             LAUNCH_OK(attn_decode_launch(stream, B, D, a, pdl));
-            GemvArgs o = {};
-            o.W = l.wo; o.N = H; o.K = q_dim(); o.x = attn_dec; o.ldx = q_dim(); o.y = x_dec; o.ldy = H;
-            LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
-            launches += 3;
+            ++launches;   // attention
+            linear_decode(GEMV_RESID, false, l.wo, l.q_wo, l.qt_o, H, q_dim(), attn_dec, q_dim(), nullptr, x_dec, H);
         } else {   // Gated-Delta-Net token mixer (ops/gdn/layer.rs:122-163), S = 1
             GemvArgs g = {};
             g.W = l.w_in; g.N = gdn_in_pad; g.K = H; g.x = x_dec; g.ldx = H; g.norm_w = l.ln1; g.eps = eps; g.y = gd_proj; g.ldy = gdn_in_pad;
@@ -760,13 +911,8 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
             LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
             launches += 7;
         }
-        GemvArgs gu = {};
-        gu.W = l.wgu; gu.N = 2 * I; gu.K = H; gu.x = x_dec; gu.ldx = H; gu.norm_w = l.ln2; gu.eps = eps; gu.y = act_dec; gu.ldy = I;
-        LAUNCH_OK(gemv_launch(stream, B, GEMV_SILU_MUL, true, gu, num_sms, pdl));
-        GemvArgs dn = {};
-        dn.W = l.wdown; dn.N = H; dn.K = I; dn.x = act_dec; dn.ldx = I; dn.y = x_dec; dn.ldy = H;
-        LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, dn, num_sms, pdl));
-        launches += 2;
+        linear_decode(GEMV_SILU_MUL, true, l.wgu, l.q_wgu, l.qt_gu, 2 * I, H, x_dec, H, l.ln2, act_dec, I);
+        linear_decode(GEMV_RESID, false, l.wdown, l.q_wdown, l.qt_down, H, I, act_dec, I, nullptr, x_dec, H);
     }
     lm_head_last_row(x_dec, advance);
 }
@@ -789,11 +935,9 @@ void crane_b200_model::reset_recurrent_state() {
 
 void crane_b200_model::lm_head_last_row(const float* xrow, int advance) {
     GemvArgs h = {};
-    h.W = lm_head; h.N = V; h.K = H; h.x = xrow; h.ldx = H; h.norm_w = final_norm; h.eps = eps; h.y = logits; h.ldy = V;
     h.part_val = part_val; h.part_idx = part_idx; h.ticket = ticket; h.state = state; h.out_tokens = out_tokens; h.out_stride = out_cap;
     h.embed = embed; h.x_next = x_dec; h.H = H; h.advance = advance;
-    LAUNCH_OK(gemv_launch(stream, 1, GEMV_LOGITS_ARGMAX, true, h, num_sms, use_pdl));
-    ++launches;
+    linear_decode(GEMV_LOGITS_ARGMAX, true, lm_head, q_lm_head, qt_lm, V, H, xrow, H, final_norm, logits, V, &h);
 }
 
 // One decode step (layers + lm_head), replayed from a CUDA graph when capture is available.
@@ -815,7 +959,7 @@ void crane_b200_model::decode_step_graphed(int advance) {
     }
     if (graph_step[advance]) {
         CUDA_OK(cudaGraphLaunch(graph_step[advance], stream));
-        for (const auto& l : layers) launches += l.full ? 5 : 9;
+        for (const auto& l : layers) launches += l.full ? (l.qt_q ? 7 : 5) : 9;
         launches += 1;
     } else {
         enqueue_decode_step(advance, false);
@@ -887,7 +1031,14 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
         LayerW& l = layers[li];
         LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln1, eps, xn));
         if (l.full) {
-            gemm(xn, H, l.wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
+            const bf16* wqkv = l.wqkv;
+            if (l.qt_q) {   // dequantise q | k | v into consecutive rows of the scratch -> one merged GEMM
+                const size_t qs = (size_t)nh * q_stride(), kvd = (size_t)nkv * D;
+                dequant_for_gemm(l.q_wq, l.qt_q, qs, H, 0);
+                dequant_for_gemm(l.q_wk, l.qt_k, kvd, H, qs);
+                wqkv = dequant_for_gemm(l.q_wv, l.qt_v, kvd, H, qs + kvd);
+            }
+            gemm(xn, H, wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
             RopeAppendArgs ra = {};
             ra.qkv = qkv; ra.q_stride = q_stride(); ra.rot_half = rot_half;
             ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
@@ -899,7 +1050,7 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             fa.out = attn_bf; fa.o_stride = qd; fa.S = S; fa.kv_offset = (int)start_pos; fa.scale = 1.0f / std::sqrt((float)D); fa.nseq = 1;
             LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
             if (hybrid) { LAUNCH_OK(gate_mul_launch(stream, attn_bf, qkv, S, nh, D, q_stride(), qkv_dim())); ++launches; }
-            gemm(attn_bf, qd, l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
+            gemm(attn_bf, qd, l.qt_o ? dequant_for_gemm(l.q_wo, l.qt_o, H, qd) : l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
         } else {
             gemm(xn, H, l.w_in, S, gdn_in_pad, H, EPI_STORE_F32, g_proj, gdn_in_pad, nullptr);
             GdnArgs ga;
@@ -910,8 +1061,8 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             launches += 3;
         }
         LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln2, eps, xn));
-        gemm(xn, H, l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr);
-        gemm(act_bf, I, l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
+        gemm(xn, H, l.qt_gu ? dequant_for_gemm(l.q_wgu, l.qt_gu, (size_t)2 * I, H) : l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr);
+        gemm(act_bf, I, l.qt_down ? dequant_for_gemm(l.q_wdown, l.qt_down, H, I) : l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
         launches += 4;
         if (n_vis > 0 && li < (int)v_deepstack.size()) {   // DeepStack (qwen3_vl/text.rs:262-268)
             LAUNCH_OK(set_rows_launch(stream, x, H, rows_dev, n_vis, ds_embeds + (size_t)li * n_vis * H, true));
@@ -1147,6 +1298,14 @@ int crane_b200_load_tensor(crane_b200_model* m, const char* name, int dtype, con
     API_BEGIN(m)
     if (!name || !shape || !data || ndim < 1 || ndim > 8) fail(CRANE_B200_INVALID_ARG, "load_tensor: bad arguments");
     m->load_tensor(name, dtype, shape, ndim, data);
+    API_END(m)
+}
+
+int crane_b200_load_tensor_ggml(crane_b200_model* m, const char* name, int ggml_type, const int64_t* shape, int ndim, const void* data,
+                                size_t nbytes) {
+    API_BEGIN(m)
+    if (!name || !shape || !data) fail(CRANE_B200_INVALID_ARG, "load_tensor_ggml: bad arguments");
+    m->load_tensor_ggml(name, ggml_type, shape, ndim, data, nbytes);
     API_END(m)
 }
 

@@ -78,6 +78,13 @@ CRANE_B200_API const char* crane_b200_last_error(const crane_b200_model* m);
  * qwen3_5/vision.rs:23-35,70-71,114-115,245-250,321-339).  `data` is host memory. */
 CRANE_B200_API int crane_b200_load_tensor(crane_b200_model* m, const char* name, int dtype, const int64_t* shape, int ndim,
                            const void* data);
+/* Register a GGUF-quantised 2-D tensor as raw ggml blocks (ggml_type: Q8_0 = 8, Q4_K = 12, Q6_K = 14), shape = [rows, cols]
+ * (cols % 256 == 0).  Accepts the HF names above or the GGUF names the reference's GGUF loaders read
+ * (`blk.{i}.attn_q.weight`, `token_embd.weight`, `output.weight`, ...: crane-core/src/models/qwen3/modeling.rs:252-282,598-606,
+ * 898-916).  Replaces `Gguf::linear` -> `LinearLayer::Quantized(QMatMul)` (crane-core/src/models/hunyuan_dense/modeling.rs:37-41,
+ * crane-core/src/ops/linear.rs:23-48): decode streams the quantised bytes, prefill dequantises one matrix at a time. */
+CRANE_B200_API int crane_b200_load_tensor_ggml(crane_b200_model* m, const char* name, int ggml_type, const int64_t* shape, int ndim,
+                                               const void* data, size_t nbytes);
 /* All tensors registered: merge QKV / gate-up, build rotary tables, allocate KV pages + workspaces. */
 CRANE_B200_API int crane_b200_finalize(crane_b200_model* m);
 

@@ -249,3 +249,79 @@ def test_qwen3_5_chunked_prefill_state_handoff_and_decode():
         host.append(m.forward_step_argmax([host[-1]], len(ids) + i))
     assert list(dev) == host
     m.close()
+
+
+# ---- GGUF-quantised linears (config 4 path): Q4_K / Q6_K / Q8_0 bytes streamed by the decode GEMV, dequantised for prefill ----
+
+def _quantised_model(cfg, recipe, gemm="tcgen05"):
+    """recipe: tensor-name suffix -> ggml type name; returns (engine, oracle weights with dequantised values)."""
+    from oracle import ggml_quant as gq
+    w = dict(synth.synth_checkpoint(cfg))
+    m = crane_b200.Qwen3Model(cfg, device=0, max_seq_len=512, gemm=gemm)
+    wq = {}
+    for name, arr in w.items():
+        qt = next((t for suf, t in recipe.items() if name.endswith(suf)), None)
+        if qt is None or arr.ndim != 2:
+            m.load_tensor(name, arr)
+            wq[name] = arr
+        else:
+            raw = gq.quantize(arr, qt)
+            m.load_tensor_ggml(name, gq.GGML_TYPE_ID[qt], arr.shape, raw)
+            wq[name] = gq.dequantize(raw, qt, arr.shape[1])
+    m.finalize()
+    return m, wq
+
+
+Q4_K_M_LIKE = {"q_proj.weight": "Q4_K", "k_proj.weight": "Q4_K", "v_proj.weight": "Q6_K", "o_proj.weight": "Q4_K",
+               "gate_proj.weight": "Q4_K", "up_proj.weight": "Q4_K", "down_proj.weight": "Q6_K", "lm_head.weight": "Q6_K"}
+ALL_Q8_0 = {k: "Q8_0" for k in Q4_K_M_LIKE} | {"embed_tokens.weight": "Q8_0"}
+
+
+@pytest.mark.parametrize("recipe_name", ["q4_k_m_like", "all_q8_0"])
+def test_quantised_linears_against_dequant_oracle(recipe_name):
+    cfg = synth.TINY_QWEN3_UNTIED if recipe_name == "q4_k_m_like" else synth.TINY_QWEN3
+    recipe = Q4_K_M_LIKE if recipe_name == "q4_k_m_like" else ALL_Q8_0
+    m, wq = _quantised_model(cfg, recipe)
+    orc = Qwen3Oracle(cfg, wq)                                    # y = x_f32 . dequant(W)^T  (SURVEY 8c)
+    ids = synth.synth_token_ids(70, cfg["vocab_size"], "quant")
+    ref = orc.forward(ids, 0).numpy()
+    e_pre = rel_err(m.forward_step(ids, 0), ref)                 # prefill: dequantise -> tcgen05 GEMM
+    tok = int(ref.argmax())
+    errs = []
+    for i in range(6):                                            # decode: dp4a on the quantised bytes, int8 activations
+        ref = orc.forward([tok], len(ids) + i).numpy()
+        errs.append(rel_err(m.forward_step([tok], len(ids) + i), ref))
+        tok = int(ref.argmax())
+    print(f"quantised {recipe_name}: prefill rel {e_pre:.3e}, decode rel max {max(errs):.3e}")
+    assert e_pre < 3e-2 and max(errs) < 5e-2
+    m.clear_kv_cache()
+    dev = m.generate(ids, max_new_tokens=8)
+    m.clear_kv_cache()
+    host = [m.forward_step_argmax(ids, 0)]
+    for i in range(7):
+        host.append(m.forward_step_argmax([host[-1]], len(ids) + i))
+    assert list(dev) == host
+    m.close()
+
+
+def test_gguf_tensor_names_are_accepted():
+    from oracle import ggml_quant as gq
+    cfg = synth.TINY_QWEN3_UNTIED
+    w = dict(synth.synth_checkpoint(cfg))
+    ren = {"self_attn.q_proj": "attn_q", "self_attn.k_proj": "attn_k", "self_attn.v_proj": "attn_v", "self_attn.o_proj": "attn_output",
+           "self_attn.q_norm": "attn_q_norm", "self_attn.k_norm": "attn_k_norm", "mlp.gate_proj": "ffn_gate", "mlp.up_proj": "ffn_up",
+           "mlp.down_proj": "ffn_down", "input_layernorm": "attn_norm", "post_attention_layernorm": "ffn_norm"}
+    m = crane_b200.Qwen3Model(cfg, device=0, max_seq_len=256)
+    for name, arr in w.items():
+        g = {"model.embed_tokens.weight": "token_embd.weight", "model.norm.weight": "output_norm.weight", "lm_head.weight": "output.weight"}.get(name)
+        if g is None:
+            parts = name.split(".")                               # model.layers.N.<...>.weight
+            key = ".".join(parts[3:-1])
+            g = f"blk.{parts[2]}.{ren[key]}.weight"
+        if arr.ndim == 2 and "embd" not in g:
+            m.load_tensor_ggml(g, gq.GGML_TYPE_ID["Q8_0"], arr.shape, gq.quantize(arr, "Q8_0"))
+        else:
+            m.load_tensor(g, arr)
+    m.finalize()
+    assert len(m.generate(synth.synth_token_ids(12, cfg["vocab_size"], "gguf"), max_new_tokens=4)) == 4
+    m.close()

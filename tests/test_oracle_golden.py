@@ -192,3 +192,20 @@ def test_gdn_recurrence_definition():
     q = torch.tensor([[[2.0, 0, 0, 0]]]); k = torch.tensor([[[1.0, 0, 0, 0]]]); v = torch.tensor([[[1.0, 2, 3]]])
     y, s = gated_delta_rule(q, k, v, torch.zeros(1, 1), torch.tensor([[0.5]]), torch.zeros(1, K, V))
     assert torch.allclose(s[0, 0], torch.tensor([0.5, 1.0, 1.5])) and torch.allclose(y[0, 0], s[0, 0] * 2.0 / 2.0)
+
+
+# ---- ggml block formats (A14): pinned byte-for-byte to the `gguf` package's definition ----------------------------
+
+def test_ggml_dequant_matches_gguf_package():
+    from gguf import quants, GGMLQuantizationType as T
+    from oracle import ggml_quant as gq
+    x = (np.random.default_rng(5).standard_normal((5, 1024)) * 0.05).astype(np.float32)
+    for name, t, tol in (("Q8_0", T.Q8_0, 0.01), ("Q4_K", T.Q4_K, 0.12), ("Q6_K", T.Q6_K, 0.04)):
+        raw = gq.quantize(x, name)
+        assert raw.shape == (5, gq.row_bytes(name, 1024))
+        mine = gq.dequantize(raw, name, 1024)
+        assert np.array_equal(mine, quants.dequantize(raw, t)), name           # layout == ggml's
+        assert np.abs(mine - x).max() / np.abs(x).max() < tol, name            # and the encoder is a sane quantiser
+    # gguf's own Q8_0 encoder decodes identically through ours
+    raw = quants.quantize(x, T.Q8_0)
+    assert np.array_equal(gq.dequantize(raw, "Q8_0", 1024), quants.dequantize(raw, T.Q8_0))
