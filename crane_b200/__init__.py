@@ -63,6 +63,10 @@ _SIGNATURES = {
                                            C.c_void_p, C.POINTER(C.c_size_t)]),
     "crane_b200_generate_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
                                              C.c_void_p, C.POINTER(C.c_size_t)]),
+    "crane_b200_seq_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "crane_b200_seq_free": (C.c_int, [C.c_void_p, C.c_int]),
+    "crane_b200_seq_select": (C.c_int, [C.c_void_p, C.c_int]),
+    "crane_b200_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
     "crane_b200_encode_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "crane_b200_vl_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                         C.POINTER(Logits)]),
@@ -210,6 +214,27 @@ class Engine:
         self._ck(self.lib.crane_b200_generate_greedy(self.h, _ptr(p), p.size, max_new_tokens,
                                                      _ptr(eos_a) if eos_a.size else None, eos_a.size, _ptr(out), C.byref(n)))
         return out[: n.value].copy()
+
+    # ---- sequence slots + batched decode ----
+    def seq_create(self) -> int:
+        s = C.c_int()
+        self._ck(self.lib.crane_b200_seq_create(self.h, C.byref(s)))
+        return int(s.value)
+
+    def seq_free(self, seq: int):
+        self._ck(self.lib.crane_b200_seq_free(self.h, seq))
+
+    def seq_select(self, seq: int):
+        self._ck(self.lib.crane_b200_seq_select(self.h, seq))
+
+    def decode_batch(self, seqs, tokens, n_steps: int = 1, want_logits: bool = False):
+        """`step_batch_decode` x n_steps for the listed sequences -> (tokens [n, n_steps], logits [n, V] of the last round | None)."""
+        sq = np.ascontiguousarray(seqs, dtype=np.int32)
+        tk = np.ascontiguousarray(tokens, dtype=np.uint32)
+        out = np.empty((sq.size, n_steps), dtype=np.uint32)
+        lg = np.empty((sq.size, self.vocab), dtype=np.float32) if want_logits else None
+        self._ck(self.lib.crane_b200_decode_batch(self.h, _ptr(sq), _ptr(tk), sq.size, n_steps, _ptr(out), None if lg is None else _ptr(lg)))
+        return out, lg
 
     # ---- vision-language surface ----
     def encode_images(self, pixel_values, grid_thw, want_deepstack: int = 0):

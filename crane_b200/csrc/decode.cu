@@ -27,6 +27,7 @@ namespace cb {
 constexpr int GV_SEG_CHUNKS = 4;                       // 512-byte chunks per pipeline slot (2 KB)
 constexpr int GV_SEG_BYTES = GV_SEG_CHUNKS * 512;
 constexpr int GV_THREADS = GV_WARPS * 32;
+__host__ __device__ constexpr int gv_depth(int B) { return B == 1 ? GV_DEPTH : 1; }   // batched activations take the ring's shared memory
 
 __device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -47,7 +48,8 @@ gemv_kernel(GemvArgs a) {
     const int r0 = blockIdx.x * rpc;
     const int r1 = min(a.N, r0 + rpc);
     const int nrows = max(0, r1 - r0);
-    float4* xs = reinterpret_cast<float4*>(gsm + GV_WARPS * GV_DEPTH * GV_SEG_BYTES);
+    constexpr int DEPTH = gv_depth(B);
+    float4* xs = reinterpret_cast<float4*>(gsm + GV_WARPS * DEPTH * GV_SEG_BYTES);
     float* acc_s = reinterpret_cast<float*>(xs) + (size_t)B * a.K;
     __shared__ float red[32];
     __shared__ float rstd_s[B];
@@ -65,13 +67,13 @@ gemv_kernel(GemvArgs a) {
     const uint32_t c_end = min(total_chunks, ((uint32_t)warp + 1) * spw * GV_SEG_CHUNKS);
     const uint32_t nseg = (c_end - c_begin + GV_SEG_CHUNKS - 1) / GV_SEG_CHUNKS;
     const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.W) + (size_t)r0 * a.K * 2 + (size_t)c_begin * 512 + lane * 16;
-    unsigned char* ring = gsm + (size_t)warp * GV_DEPTH * GV_SEG_BYTES + lane * 16;
+    unsigned char* ring = gsm + (size_t)warp * DEPTH * GV_SEG_BYTES + lane * 16;
     const uint32_t ring_u32 = smem_u32(ring);
 
     auto issue = [&](uint32_t g) {                      // segment g of this warp -> slot g % GV_DEPTH
         if (g < nseg) {
             const uint32_t cb = g * GV_SEG_CHUNKS;
-            const uint32_t slot = g % GV_DEPTH;
+            const uint32_t slot = g % DEPTH;
 #pragma unroll
             for (int c = 0; c < GV_SEG_CHUNKS; ++c)
                 if (c_begin + cb + c < c_end)
@@ -81,7 +83,7 @@ gemv_kernel(GemvArgs a) {
     };
     // prime the pipeline: weights do not depend on the previous kernel
 #pragma unroll
-    for (int g = 0; g < GV_DEPTH; ++g) issue((uint32_t)g);
+    for (int g = 0; g < DEPTH; ++g) issue((uint32_t)g);
     for (int i = tid; i < B * rpc; i += GV_THREADS) acc_s[i] = 0.f;
     // RMSNorm weights are immutable (and cold in every cache): fetch this thread's first chunk before the dependency wait
     float4 nw0 = make_float4(0.f, 0.f, 0.f, 0.f), nw1 = nw0;
@@ -131,9 +133,9 @@ gemv_kernel(GemvArgs a) {
         };
         uint32_t row = c_begin / cpr, rem = c_begin - row * cpr;
         for (uint32_t g = 0; g < nseg; ++g) {
-            cp_async_wait_g<GV_DEPTH - 1>();            // segment g has landed (groups complete in order)
+            cp_async_wait_g<DEPTH - 1>();               // segment g has landed (groups complete in order)
             __syncwarp();
-            const unsigned char* sp = ring + (g % GV_DEPTH) * GV_SEG_BYTES;
+            const unsigned char* sp = ring + (g % DEPTH) * GV_SEG_BYTES;
             const uint32_t cb = c_begin + g * GV_SEG_CHUNKS;
             uint4 w[GV_SEG_CHUNKS];
 #pragma unroll
@@ -161,7 +163,7 @@ gemv_kernel(GemvArgs a) {
                 if (++rem == cpr) { rem = 0; ++row; }
             }
             __syncwarp();                               // every lane has its slot data in registers
-            issue(g + GV_DEPTH);                        // refill the slot just drained
+            issue(g + DEPTH);                           // refill the slot just drained
         }
         flush();
     }
@@ -271,7 +273,7 @@ gemv_kernel(GemvArgs a) {
 static size_t gemv_smem_bytes(int B, int K, int N, int rows_per_unit, int grid) {
     const int units = N / rows_per_unit;
     const int rpc = (units + grid - 1) / grid * rows_per_unit;
-    return (size_t)GV_WARPS * GV_DEPTH * GV_SEG_BYTES + (size_t)B * K * 4 + (size_t)B * rpc * 4 + 16;
+    return (size_t)GV_WARPS * gv_depth(B) * GV_SEG_BYTES + (size_t)B * K * 4 + (size_t)B * rpc * 4 + 16;
 }
 
 template <int B, int EPI, bool NORM>
@@ -308,6 +310,13 @@ static int gemv_launch_b(cudaStream_t st, int epi, bool norm, const GemvArgs& a,
         case GEMV_LOGITS_ARGMAX: return gemv_launch_t<B, GEMV_LOGITS_ARGMAX, true>(st, a, num_sms, pdl);
         default: return -1000;
     }
+}
+
+// Largest sequence group (4, 2 or 1) whose f32 activations fit next to the weight rings for an in_dim of K.
+int gemv_max_group(int K, int N, int num_sms) {
+    for (int B : {4, 2})
+        if (gemv_smem_bytes(B, K, N, 1, num_sms) <= 227 * 1024) return B;
+    return 1;
 }
 
 int gemv_launch(cudaStream_t st, int B, int epi, bool norm, const GemvArgs& a, int num_sms, bool pdl) {
@@ -392,7 +401,7 @@ attn_decode_kernel(AttnDecArgs a) {
     const int t1 = min(T, t0 + chunk);
     const int s_last = (T - 1) / chunk;
     const int t_end = min(t1, T - 1);                 // cached tokens only; position T-1 comes from this step's qkv
-    const int* bt = a.block_table + (size_t)b * a.max_pages;
+    const int* bt = a.block_table + (size_t)st.slot * a.max_pages;
     auto load_tile = [&](int tb) {
         const int n = min(TILE, t_end - tb);
         for (int c = tid; c < n * CPR; c += 256) {

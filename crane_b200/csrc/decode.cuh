@@ -27,7 +27,8 @@ struct SeqState {
     int pos[3];        // MRoPE (t, h, w) position of the token being decoded
     uint32_t token;    // input token of the step
     int step;          // decode steps taken since the state was armed
-    int pad[2];
+    int slot;          // sequence slot: its page table is block_table + slot * max_pages
+    int pad;
 };
 
 enum GemvEpi : int { GEMV_STORE = 0, GEMV_RESID = 1, GEMV_SILU_MUL = 2, GEMV_LOGITS_ARGMAX = 3 };
@@ -66,7 +67,7 @@ struct AttnDecArgs {
     const float* sin_tab;
     const unsigned char* axis_of;  // [rot_half] MRoPE axis per rotary column (all 0 for 1-D RoPE)
     const SeqState* state;   // [B]
-    const int* block_table;  // [B, max_pages]
+    const int* block_table;  // [n_slots, max_pages], row = SeqState.slot
     int max_pages;
     bf16* k_pool;            // this layer's pages: [n_pages, nkv, KV_PAGE, D]
     bf16* v_pool;
@@ -75,6 +76,7 @@ struct AttnDecArgs {
     float* out;              // [B, nh*D] f32
 };
 
+int gemv_max_group(int K, int N, int num_sms);
 int gemv_launch(cudaStream_t st, int B, int epi, bool norm, const GemvArgs& a, int num_sms, bool pdl);
 int attn_decode_launch(cudaStream_t st, int B, int D, const AttnDecArgs& a, bool pdl);
 int embed_decode_launch(cudaStream_t st, int B, const bf16* embed, int H, const SeqState* state, float* x, bool pdl);

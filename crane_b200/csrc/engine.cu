@@ -209,9 +209,20 @@ struct crane_b200_model {
     float* ds_embeds = nullptr;       // [n_ds, n_img_tok, v_out]
     int img_tokens = 0;
 
-    // host state
+    // host state: `kv_len` / `next_mrope_pos` are the view of the CURRENT sequence slot (`cur`); the others are parked in seq_*
     size_t kv_len = 0;
     uint32_t next_mrope_pos = 0;
+    int cur = 0;
+    std::vector<size_t> seq_kv;
+    std::vector<uint32_t> seq_pos;
+    std::vector<char> seq_used;
+    void select_seq(int s) {
+        if (s == cur) return;
+        seq_kv[cur] = kv_len; seq_pos[cur] = next_mrope_pos;
+        cur = s;
+        kv_len = seq_kv[s]; next_mrope_pos = seq_pos[s];
+    }
+    const int* bt_cur() const { return block_table + (size_t)cur * max_pages; }
     cudaGraphExec_t graph_step[2] = {nullptr, nullptr};   // [advance]
     bool graph_failed = false;
     cudaEvent_t pev0 = nullptr, pev1 = nullptr, dev0 = nullptr, dev1 = nullptr;
@@ -247,7 +258,7 @@ struct crane_b200_model {
     void load_tensor_ggml(const std::string& name, int qt, const int64_t* shape, int ndim, const void* data, size_t nbytes);
     unsigned char* up_quant(int qt, const void* data, size_t rows, int K, unsigned char* dst = nullptr, size_t dst_row_pitch = 0);
     void linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
-                       const float* norm_w, float* y, int ldy, const GemvArgs* extra = nullptr);
+                       const float* norm_w, float* y, int ldy, const GemvArgs* extra = nullptr, int B = 1);
     const bf16* dequant_for_gemm(const unsigned char* qw, int qt, size_t rows, int K, size_t row_offset = 0);
     bool load_text_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
     bool load_vision_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
@@ -275,12 +286,12 @@ struct crane_b200_model {
 
     // forward paths
     void arm_state(uint32_t token, size_t start_pos, int p0, int p1, int p2);
-    void enqueue_decode_step(int advance, bool with_embed);
+    void enqueue_decode_step(int advance, bool with_embed, int B = 1);
     void decode_step_graphed(int advance);
     void decode_steps(int n_steps, int advance);
     void prefill(const uint32_t* ids, const float* embeds, size_t S, const uint32_t* pos3_host, size_t start_pos,
                  const int* vis_rows, int n_vis, int advance);
-    void lm_head_last_row(const float* xrow, int advance);
+    void lm_head_last_row(const float* xrow, int advance, int B = 1);
     void gdn_args(GdnArgs& g, const LayerW& l, int S, const float* proj, float* conv, float* qn, float* kn, float* gb, float* y) const;
     void reset_recurrent_state();
     void encode_images(const float* pv, const uint32_t* grid, size_t n_images);
@@ -358,9 +369,10 @@ void crane_b200_model::parse_config(const char* json) {
     if (const char* g = getenv("CRANE_B200_PDL")) use_pdl = std::string(g) != "0";
     if (root.has("engine")) use_persistent = root.at("engine").boolean("persistent", false);
     if (const char* g = getenv("CRANE_B200_PERSISTENT")) use_persistent = std::string(g) != "0";
-    if (max_batch != 1) fail(CRANE_B200_UNSUPPORTED, "max_batch %d: only 1 sequence per handle in this build", max_batch);
+    if (max_batch < 1 || max_batch > 64) fail(CRANE_B200_INVALID_ARG, "max_batch %d (1..64 sequence slots)", max_batch);
     max_seq = (max_seq + KV_PAGE - 1) / KV_PAGE * KV_PAGE;
     max_pages = max_seq / KV_PAGE;
+    if (hybrid && max_batch != 1) fail(CRANE_B200_UNSUPPORTED, "the Qwen3.5 hybrid keeps one recurrent state: max_batch must be 1");
     if (is_vl) {
         const cbjson::Value& vc = root.at("vision_config");
         v_depth = (int)vc.integer("depth");
@@ -693,17 +705,17 @@ void crane_b200_model::load_tensor_ggml(const std::string& name_in, int qt, cons
 
 // One decode-path linear: bf16 GEMV or quantised GEMV with the same fused epilogue.
 void crane_b200_model::linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
-                                     const float* norm_w, float* y, int ldy, const GemvArgs* extra) {
+                                     const float* norm_w, float* y, int ldy, const GemvArgs* extra, int B) {
     GemvArgs g = extra ? *extra : GemvArgs{};
     g.N = N; g.K = K; g.x = xin; g.ldx = ldx; g.norm_w = norm_w; g.eps = eps; g.y = y; g.ldy = ldy;
     if (qt) {
         QGemvArgs qa;
         g.W = reinterpret_cast<const bf16*>(qw);
         qa.g = g; qa.qtype = qt; qa.epi = epi; qa.norm = norm ? 1 : 0;
-        LAUNCH_OK(qgemv_launch(stream, 1, qa, num_sms, use_pdl));
+        LAUNCH_OK(qgemv_launch(stream, B, qa, num_sms, use_pdl));
     } else {
         g.W = w;
-        LAUNCH_OK(gemv_launch(stream, 1, epi, norm, g, num_sms, use_pdl));
+        LAUNCH_OK(gemv_launch(stream, B, epi, norm, g, num_sms, use_pdl));
     }
     ++launches;
 }
@@ -781,8 +793,8 @@ void crane_b200_model::finalize() {
     const size_t page_elems = (size_t)nkv * KV_PAGE * D;
     for (auto& l : layers) {
         if (l.full) {
-            l.k_pool = dalloc<bf16>((size_t)max_pages * page_elems);
-            l.v_pool = dalloc<bf16>((size_t)max_pages * page_elems);
+            l.k_pool = dalloc<bf16>((size_t)max_batch * max_pages * page_elems);
+            l.v_pool = dalloc<bf16>((size_t)max_batch * max_pages * page_elems);
         } else {   // GdnLayerCache (ops/gdn/cache.rs:15-45): conv window + [Hv, K, V] f32 state, zero-initialised
             l.conv_state = dalloc<float>((size_t)conv_dim() * ck);
             l.rec_state = dalloc<float>((size_t)nv * dk * dv);
@@ -794,12 +806,15 @@ void crane_b200_model::finalize() {
         gd_gb = dalloc<float>((size_t)nv * 2); gd_y = dalloc<float>(value_dim()); gd_out = dalloc<float>(value_dim());
         reset_recurrent_state();
     }
-    std::vector<int> bt(max_pages);
-    for (int i = 0; i < max_pages; ++i) bt[i] = i;   // one sequence per handle: identity page table
-    block_table = dalloc<int>(max_pages);
-    CUDA_OK(cudaMemcpy(block_table, bt.data(), max_pages * sizeof(int), cudaMemcpyHostToDevice));
+    // page tables: slot s owns pages [s * max_pages, (s+1) * max_pages) -- static assignment, 64-token pages
+    std::vector<int> bt((size_t)max_batch * max_pages);
+    for (size_t i = 0; i < bt.size(); ++i) bt[i] = (int)i;
+    block_table = dalloc<int>(bt.size());
+    CUDA_OK(cudaMemcpy(block_table, bt.data(), bt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    seq_kv.assign(max_batch, 0); seq_pos.assign(max_batch, 0); seq_used.assign(max_batch, 0);
+    seq_used[0] = 1;
 
-    const int B = max_batch;
+    const int B = std::min(max_batch, 4);   // decode batches run in groups of <= 4 sequences per weight pass
     x_dec = dalloc<float>((size_t)B * H);
     qkv_dec = dalloc<float>((size_t)B * qkv_dim());
     attn_dec = dalloc<float>((size_t)B * q_dim());
@@ -871,11 +886,11 @@ void crane_b200_model::arm_state(uint32_t token, size_t start_pos, int p0, int p
     h_state[0].pos[0] = p0; h_state[0].pos[1] = p1; h_state[0].pos[2] = p2;
     h_state[0].token = token;
     h_state[0].step = 0;
+    h_state[0].slot = cur;
     CUDA_OK(cudaMemcpyAsync(state, h_state, sizeof(SeqState), cudaMemcpyHostToDevice, stream));
 }
 
-void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
-    const int B = 1;
+void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) {
     const bool pdl = use_pdl;
     if (with_embed) { LAUNCH_OK(embed_decode_launch(stream, B, embed, H, state, x_dec, false)); ++launches; }
     for (int li = 0; li < L; ++li) {
@@ -883,11 +898,11 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
         if (l.full) {
             if (l.qt_q) {   // GGUF keeps q/k/v as separate quantised matrices (qwen3/modeling.rs:252-255): three GEMVs into one qkv row
                 const int qs = nh * q_stride(), kvd = nkv * D;
-                linear_decode(GEMV_STORE, true, nullptr, l.q_wq, l.qt_q, qs, H, x_dec, H, l.ln1, qkv_dec, qkv_dim());
-                linear_decode(GEMV_STORE, true, nullptr, l.q_wk, l.qt_k, kvd, H, x_dec, H, l.ln1, qkv_dec + qs, qkv_dim());
-                linear_decode(GEMV_STORE, true, nullptr, l.q_wv, l.qt_v, kvd, H, x_dec, H, l.ln1, qkv_dec + qs + kvd, qkv_dim());
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wq, l.qt_q, qs, H, x_dec, H, l.ln1, qkv_dec, qkv_dim(), nullptr, B);
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wk, l.qt_k, kvd, H, x_dec, H, l.ln1, qkv_dec + qs, qkv_dim(), nullptr, B);
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wv, l.qt_v, kvd, H, x_dec, H, l.ln1, qkv_dec + qs + kvd, qkv_dim(), nullptr, B);
             } else {
-                linear_decode(GEMV_STORE, true, l.wqkv, nullptr, 0, qkv_dim(), H, x_dec, H, l.ln1, qkv_dec, qkv_dim());
+                linear_decode(GEMV_STORE, true, l.wqkv, nullptr, 0, qkv_dim(), H, x_dec, H, l.ln1, qkv_dec, qkv_dim(), nullptr, B);
             }
             AttnDecArgs a = {};
             a.qkv = qkv_dec; a.q_stride = q_stride(); a.gated = hybrid ? 1 : 0; a.rot_half = rot_half;
@@ -897,7 +912,7 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
             a.out = attn_dec;
             LAUNCH_OK(attn_decode_launch(stream, B, D, a, pdl));
             ++launches;   // attention
-            linear_decode(GEMV_RESID, false, l.wo, l.q_wo, l.qt_o, H, q_dim(), attn_dec, q_dim(), nullptr, x_dec, H);
+            linear_decode(GEMV_RESID, false, l.wo, l.q_wo, l.qt_o, H, q_dim(), attn_dec, q_dim(), nullptr, x_dec, H, nullptr, B);
         } else {   // Gated-Delta-Net token mixer (ops/gdn/layer.rs:122-163), S = 1
             GemvArgs g = {};
             g.W = l.w_in; g.N = gdn_in_pad; g.K = H; g.x = x_dec; g.ldx = H; g.norm_w = l.ln1; g.eps = eps; g.y = gd_proj; g.ldy = gdn_in_pad;
@@ -911,10 +926,10 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed) {
             LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
             launches += 7;
         }
-        linear_decode(GEMV_SILU_MUL, true, l.wgu, l.q_wgu, l.qt_gu, 2 * I, H, x_dec, H, l.ln2, act_dec, I);
-        linear_decode(GEMV_RESID, false, l.wdown, l.q_wdown, l.qt_down, H, I, act_dec, I, nullptr, x_dec, H);
+        linear_decode(GEMV_SILU_MUL, true, l.wgu, l.q_wgu, l.qt_gu, 2 * I, H, x_dec, H, l.ln2, act_dec, I, nullptr, B);
+        linear_decode(GEMV_RESID, false, l.wdown, l.q_wdown, l.qt_down, H, I, act_dec, I, nullptr, x_dec, H, nullptr, B);
     }
-    lm_head_last_row(x_dec, advance);
+    lm_head_last_row(x_dec, advance, B);
 }
 
 void crane_b200_model::gdn_args(GdnArgs& g, const LayerW& l, int S, const float* proj, float* conv, float* qn, float* kn, float* gb,
@@ -933,11 +948,11 @@ void crane_b200_model::reset_recurrent_state() {
         }
 }
 
-void crane_b200_model::lm_head_last_row(const float* xrow, int advance) {
+void crane_b200_model::lm_head_last_row(const float* xrow, int advance, int B) {
     GemvArgs h = {};
     h.part_val = part_val; h.part_idx = part_idx; h.ticket = ticket; h.state = state; h.out_tokens = out_tokens; h.out_stride = out_cap;
     h.embed = embed; h.x_next = x_dec; h.H = H; h.advance = advance;
-    linear_decode(GEMV_LOGITS_ARGMAX, true, lm_head, q_lm_head, qt_lm, V, H, xrow, H, final_norm, logits, V, &h);
+    linear_decode(GEMV_LOGITS_ARGMAX, true, lm_head, q_lm_head, qt_lm, V, H, xrow, H, final_norm, logits, V, &h, B);
 }
 
 // One decode step (layers + lm_head), replayed from a CUDA graph when capture is available.
@@ -973,7 +988,7 @@ void crane_b200_model::decode_steps(int n_steps, int advance) {
         p.L = L; p.H = H; p.I = I; p.V = V; p.nh = nh; p.nkv = nkv; p.qkv_dim = qkv_dim(); p.q_dim = q_dim();
         p.eps = eps; p.scale = 1.0f / std::sqrt((float)D);
         p.layers = players; p.lm_head = lm_head; p.final_norm = final_norm; p.embed = embed;
-        p.cos_tab = cos_tab; p.sin_tab = sin_tab; p.axis_of = axis_of; p.state = state; p.block_table = block_table;
+        p.cos_tab = cos_tab; p.sin_tab = sin_tab; p.axis_of = axis_of; p.state = state; p.block_table = bt_cur();
         p.x = x_dec; p.qkv = qkv_dec; p.act = act_dec; p.logits = logits; p.part_o = part_o; p.part_ml = part_ml;
         p.part_val = part_val; p.part_idx = part_idx; p.out_tokens = out_tokens; p.barrier = grid_bar;
         p.n_steps = n_steps; p.advance = advance; p.prof = pk_prof;
@@ -1042,11 +1057,11 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             RopeAppendArgs ra = {};
             ra.qkv = qkv; ra.q_stride = q_stride(); ra.rot_half = rot_half;
             ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
-            ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = block_table; ra.k_pool = l.k_pool; ra.v_pool = l.v_pool;
+            ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = bt_cur(); ra.k_pool = l.k_pool; ra.v_pool = l.v_pool;
             ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf;
             LAUNCH_OK(rope_append_launch(stream, D, ra));
             FlashArgs fa = {};
-            fa.q = q_bf; fa.q_stride = qd; fa.k_pool = l.k_pool; fa.v_pool = l.v_pool; fa.block_table = block_table; fa.nh = nh; fa.nkv = nkv;
+            fa.q = q_bf; fa.q_stride = qd; fa.k_pool = l.k_pool; fa.v_pool = l.v_pool; fa.block_table = bt_cur(); fa.nh = nh; fa.nkv = nkv;
             fa.out = attn_bf; fa.o_stride = qd; fa.S = S; fa.kv_offset = (int)start_pos; fa.scale = 1.0f / std::sqrt((float)D); fa.nseq = 1;
             LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
             if (hybrid) { LAUNCH_OK(gate_mul_launch(stream, attn_bf, qkv, S, nh, D, q_stride(), qkv_dim())); ++launches; }
@@ -1076,6 +1091,7 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     h_state[0].pos[0] = h_state[0].pos[1] = h_state[0].pos[2] = (int)next_mrope_pos - 1;
     h_state[0].token = 0;
     h_state[0].step = 0;
+    h_state[0].slot = cur;
     CUDA_OK(cudaMemcpyAsync(state, h_state, sizeof(SeqState), cudaMemcpyHostToDevice, stream));
     lm_head_last_row(x + (size_t)(S - 1) * H, advance);
     CUDA_OK(cudaEventRecord(pev1, stream));
@@ -1556,6 +1572,95 @@ int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token, size_t start_
     m->next_mrope_pos = (uint32_t)(p + 1);
     m->kv_len = start_pos + 1;
     fill_logits(m, out);
+    API_END(m)
+}
+
+// ---- sequence slots + batched decode (ModelBackend::{setup,step}_batch_decode / extract_batch_kv, backend.rs:86-150) ----
+int crane_b200_seq_create(crane_b200_model* m, int* seq_out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!seq_out) fail(CRANE_B200_INVALID_ARG, "seq_create: null output");
+    int s = -1;
+    for (int i = 0; i < m->max_batch; ++i)
+        if (!m->seq_used[i]) { s = i; break; }
+    if (s < 0) fail(CRANE_B200_OOM, "all %d sequence slots are in use (engine.max_batch)", m->max_batch);
+    m->seq_used[s] = 1;
+    m->seq_kv[s] = 0; m->seq_pos[s] = 0;
+    if (s == m->cur) { m->kv_len = 0; m->next_mrope_pos = 0; }
+    *seq_out = s;
+    API_END(m)
+}
+
+int crane_b200_seq_free(crane_b200_model* m, int seq) {
+    API_BEGIN(m)
+    if (seq < 0 || seq >= m->max_batch || !m->seq_used[seq]) fail(CRANE_B200_INVALID_ARG, "seq_free: bad sequence %d", seq);
+    if (seq == 0) fail(CRANE_B200_INVALID_ARG, "sequence 0 is the handle's implicit sequence (use clear_kv_cache)");
+    m->select_seq(0);
+    m->seq_used[seq] = 0;
+    m->seq_kv[seq] = 0; m->seq_pos[seq] = 0;
+    API_END(m)
+}
+
+int crane_b200_seq_select(crane_b200_model* m, int seq) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (seq < 0 || seq >= m->max_batch || !m->seq_used[seq]) fail(CRANE_B200_INVALID_ARG, "seq_select: bad sequence %d", seq);
+    m->select_seq(seq);
+    API_END(m)
+}
+
+int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t* tokens, size_t n, size_t n_steps, uint32_t* tokens_out,
+                            float* logits_host) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!seqs || !tokens || !tokens_out || n == 0 || n_steps == 0) fail(CRANE_B200_INVALID_ARG, "decode_batch: bad arguments");
+    if (m->hybrid) fail(CRANE_B200_UNSUPPORTED, "decode_batch on the hybrid model");
+    if (n_steps > (size_t)m->out_cap) fail(CRANE_B200_INVALID_ARG, "decode_batch: n_steps %zu > %d", n_steps, m->out_cap);
+    m->seq_kv[m->cur] = m->kv_len; m->seq_pos[m->cur] = m->next_mrope_pos;
+    for (size_t i = 0; i < n; ++i) {
+        const int s = seqs[i];
+        if (s < 0 || s >= m->max_batch || !m->seq_used[s]) fail(CRANE_B200_INVALID_ARG, "decode_batch: bad sequence %d", s);
+        for (size_t j = 0; j < i; ++j) if (seqs[j] == s) fail(CRANE_B200_INVALID_ARG, "decode_batch: sequence %d listed twice", s);
+        if (tokens[i] >= (uint32_t)m->V) fail(CRANE_B200_INVALID_ARG, "token id %u >= vocab %d", tokens[i], m->V);
+        if (m->seq_kv[s] + n_steps > (size_t)m->max_seq) fail(CRANE_B200_OOM, "sequence %d would exceed max_seq_len %d", s, m->max_seq);
+    }
+    CUDA_OK(cudaEventRecord(m->dev0, m->stream));
+    // groups of 4 / 2 / 1 sequences share one pass over the weights (cb::gemv_kernel<B>)
+    int maxg = 4;
+    if (!m->any_quant)
+        for (int K : {m->H, m->I, m->q_dim()}) maxg = std::min(maxg, gemv_max_group(K, m->V, m->num_sms));
+    size_t done = 0;
+    while (done < n) {
+        const int B = std::min(maxg, (n - done >= 4) ? 4 : (n - done >= 2) ? 2 : 1);
+        for (int b = 0; b < B; ++b) {
+            const int s = seqs[done + b];
+            SeqState& st = m->h_state[b];
+            st.kv_len = (int)m->seq_kv[s];
+            st.pos[0] = st.pos[1] = st.pos[2] = (int)m->seq_pos[s];
+            st.token = tokens[done + b];
+            st.step = 0;
+            st.slot = s;
+        }
+        CUDA_OK(cudaMemcpyAsync(m->state, m->h_state, B * sizeof(SeqState), cudaMemcpyHostToDevice, m->stream));
+        LAUNCH_OK(embed_decode_launch(m->stream, B, m->embed, m->H, m->state, m->x_dec, false));
+        ++m->launches;
+        for (size_t t = 0; t < n_steps; ++t) m->enqueue_decode_step(1, false, B);
+        for (int b = 0; b < B; ++b)
+            CUDA_OK(cudaMemcpyAsync(tokens_out + (done + b) * n_steps, m->out_tokens + (size_t)b * m->out_cap, n_steps * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, m->stream));
+        if (logits_host)
+            CUDA_OK(cudaMemcpyAsync(logits_host + done * (size_t)m->V, m->logits, (size_t)B * m->V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));     // h_state is reused by the next group
+        for (int b = 0; b < B; ++b) {
+            const int s = seqs[done + b];
+            m->seq_kv[s] += n_steps;
+            m->seq_pos[s] += (uint32_t)n_steps;
+        }
+        done += B;
+    }
+    CUDA_OK(cudaEventRecord(m->dev1, m->stream));
+    m->last_decode_steps = n_steps;
+    m->kv_len = m->seq_kv[m->cur]; m->next_mrope_pos = m->seq_pos[m->cur];
     API_END(m)
 }
 

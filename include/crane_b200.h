@@ -134,6 +134,22 @@ CRANE_B200_API int crane_b200_decode_greedy(crane_b200_model* m, uint32_t first_
 CRANE_B200_API int crane_b200_generate_greedy(crane_b200_model* m, const uint32_t* prompt, size_t n_prompt, size_t max_new_tokens,
                                const uint32_t* eos_ids, size_t n_eos, uint32_t* tokens_out, size_t* n_out);
 
+/* ---- sequence slots + batched decode (crane-serve continuous batching) ------------------------------- */
+
+/* A handle holds `engine.max_batch` sequence slots, each with its own KV pages (slot 0 is the implicit sequence of all the calls
+ * above).  `seq_select` makes a slot current: forward_step / forward_embeds / clear_kv_cache / kv_len then act on it -- the
+ * handle-level counterpart of the engine's per-Sequence swap-in (`set_kv_caches`, crane-serve/src/engine/mod.rs:1172). */
+CRANE_B200_API int crane_b200_seq_create(crane_b200_model* m, int* seq_out);
+CRANE_B200_API int crane_b200_seq_free(crane_b200_model* m, int seq);
+CRANE_B200_API int crane_b200_seq_select(crane_b200_model* m, int seq);
+/* `n_steps` greedy decode rounds for `n` sequences at once: replaces setup_batch_decode + step_batch_decode x rounds +
+ * extract_batch_kv (crane-core/src/models/qwen3/modeling.rs:1141-1277, crane-serve/src/engine/mod.rs:822-1062).  No left-padding,
+ * mask or KV copy: each sequence attends over its own pages with its own length and position; groups of up to 4 sequences share
+ * one pass over the weights.  tokens[i] is consumed by seqs[i] at its cached length; tokens_out is [n, n_steps];
+ * logits_host (optional) receives the [n, vocab] f32 logits of the LAST round. */
+CRANE_B200_API int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t* tokens, size_t n, size_t n_steps,
+                                           uint32_t* tokens_out, float* logits_host);
+
 /* ---- vision-language surface (crane-core/src/models/qwen3_5/vlm.rs) ------------------------------ */
 
 /* `Qwen3_5VLModel::encode_images` -> `Qwen3_5VisionModel::forward` (vlm.rs:150-170, vision.rs:558-584).

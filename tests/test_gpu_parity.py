@@ -325,3 +325,53 @@ def test_gguf_tensor_names_are_accepted():
     m.finalize()
     assert len(m.generate(synth.synth_token_ids(12, cfg["vocab_size"], "gguf"), max_new_tokens=4)) == 4
     m.close()
+
+
+# ---- sequence slots + batched decode (A13: setup/step/extract_batch_decode without padding or KV copies) ------------
+
+@pytest.mark.parametrize("quant", [False, True], ids=["bf16", "q8_0"])
+def test_batched_decode_matches_per_sequence_decode(quant):
+    cfg = synth.TINY_QWEN3
+    if quant:
+        m, w = _quantised_model(cfg, ALL_Q8_0)
+        m.close()
+        from oracle import ggml_quant as gq
+        wsrc = dict(synth.synth_checkpoint(cfg))
+        m = crane_b200.Qwen3Model(cfg, device=0, max_seq_len=256, max_batch=8)
+        for name, arr in wsrc.items():
+            if arr.ndim == 2:
+                m.load_tensor_ggml(name, gq.GGML_TYPE_ID["Q8_0"], arr.shape, gq.quantize(arr, "Q8_0"))
+            else:
+                m.load_tensor(name, arr)
+        m.finalize()
+    else:
+        w = dict(synth.synth_checkpoint(cfg))
+        m = crane_b200.Qwen3Model(cfg, device=0, max_seq_len=256, max_batch=8)
+        m.load_checkpoint(w.items())
+    n, steps = 7, 6                                               # 7 sequences -> groups of 4 + 2 + 1, ragged prompt lengths
+    prompts = [synth.synth_token_ids(5 + 9 * i, cfg["vocab_size"], f"b{i}") for i in range(n)]
+    # reference: each sequence alone through the single-sequence path
+    solo = []
+    for p in prompts:
+        m.clear_kv_cache()
+        solo.append(list(m.generate(p, max_new_tokens=steps + 1)))
+    m.clear_kv_cache()
+    seqs, first = [], []
+    for p in prompts:
+        s = m.seq_create()
+        m.seq_select(s)
+        first.append(m.forward_step_argmax(p, 0))                 # prefill each sequence into its own pages
+        seqs.append(s)
+    toks, logits = m.decode_batch(seqs, first, n_steps=steps, want_logits=True)
+    for i in range(n):
+        assert [first[i]] + list(toks[i]) == solo[i], f"sequence {i}"
+    assert logits.shape == (n, cfg["vocab_size"]) and np.isfinite(logits).all()
+    # a freed slot is reusable and sequence 0 still works
+    m.seq_free(seqs[-1])
+    s = m.seq_create()
+    assert s == seqs[-1]
+    m.seq_select(0)
+    assert m.kv_len() == 0 and len(m.generate(prompts[0], max_new_tokens=3)) == 3
+    with pytest.raises(crane_b200.CraneB200Error):
+        m.decode_batch([seqs[0], seqs[0]], [1, 2])
+    m.close()
