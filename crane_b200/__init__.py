@@ -71,6 +71,10 @@ _SIGNATURES = {
     "crane_b200_vl_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                         C.POINTER(Logits)]),
     "crane_b200_vl_decode_step": (C.c_int, [C.c_void_p, C.c_uint32, C.c_size_t, C.POINTER(Logits)]),
+    "crane_b200_tts_text_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "crane_b200_tts_codec_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "crane_b200_tts_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "crane_b200_tts_generate": (C.c_int, [C.c_void_p, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]),
     "crane_b200_next_mrope_pos": (C.c_uint32, [C.c_void_p]),
     "crane_b200_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_size_t)]),
     "crane_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
@@ -313,6 +317,71 @@ class Qwen3VLModel(Engine):
             return np.array(out, np.uint32)
         rest = self.decode_greedy(first, len(input_ids), max_new_tokens - 1, eos)
         return np.concatenate([np.array(out, np.uint32), rest])
+
+
+class Qwen3TTSModel(Engine):
+    """`Qwen3TTSModel` codec-LM (crane-core/src/models/qwen3_tts/modeling.rs:1347-1760): talker + code predictor.
+    The host glue (`build_prefill_embeds`, :597-726) lives here exactly as it lives in Rust in the reference; the
+    arithmetic (text projection, embedding gathers, every transformer pass, the frame loop) runs behind the C ABI."""
+
+    def __init__(self, config: dict, device: int = 0, **engine_opts):
+        super().__init__(config, device, **engine_opts)
+        self.tk = config["talker_config"]
+        self.groups = self.tk["num_code_groups"]
+        self.cp_vocab = self.tk["code_predictor_config"]["vocab_size"]
+
+    def text_project(self, ids) -> np.ndarray:
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.empty((a.size, self.hidden), np.float32)
+        self._ck(self.lib.crane_b200_tts_text_project(self.h, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def codec_embed(self, ids, group: int = -1) -> np.ndarray:
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.empty((a.size, self.hidden), np.float32)
+        self._ck(self.lib.crane_b200_tts_codec_embed(self.h, group, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def build_prefill_embeds(self, text_ids, language_id=None, speaker_id=None):
+        """TalkerModel::build_prefill_embeds (modeling.rs:597-726) -> (prefill [P, H], trailing_text [n, H], tts_pad [H])."""
+        tk, cfg = self.tk, self.config
+        vt = tk["text_vocab_size"]
+        role = self.text_project([151644 % vt, 77091 % vt, 198])
+        tts = self.text_project([cfg["tts_pad_token_id"], cfg["tts_bos_token_id"], cfg["tts_eos_token_id"]])
+        pad, bos, eos = tts[0], tts[1], tts[2]
+        if language_id is not None:
+            codec = [tk["codec_think_id"], tk["codec_think_bos_id"], language_id, tk["codec_think_eos_id"]]
+        else:
+            codec = [tk["codec_nothink_id"], tk["codec_think_bos_id"], tk["codec_think_eos_id"]]
+        if speaker_id is not None:
+            codec.append(speaker_id)
+        codec += [tk["codec_pad_id"], tk["codec_bos_id"]]
+        ce = self.codec_embed(codec)
+        n_over = len(codec) - 1
+        overlay = np.concatenate([np.repeat(pad[None], n_over - 1, 0), bos[None]], 0)
+        codec_hidden = overlay + ce[:n_over]
+        first = (self.text_project(text_ids[:1])[0] if len(text_ids) else pad) + ce[-1]
+        prefill = np.concatenate([role, codec_hidden, first[None]], 0).astype(np.float32)
+        trailing = np.concatenate([self.text_project(text_ids[1:]), eos[None]], 0) if len(text_ids) > 1 else eos[None]
+        return prefill, trailing.astype(np.float32), pad
+
+    def generate_codes(self, text_ids, max_new_tokens: int, repetition_penalty: float = 1.0, forced_frames=None, want_logits=False):
+        """`generate_speech_codes` (modeling.rs:1429-1596), greedy or teacher-forced -> frames [n, groups] (+ logits)."""
+        self.clear_kv_cache()
+        prefill, trailing, pad = self.build_prefill_embeds(list(text_ids))
+        prefill = np.ascontiguousarray(prefill); trailing = np.ascontiguousarray(trailing); pad = np.ascontiguousarray(pad)
+        self._ck(self.lib.crane_b200_tts_prefill(self.h, _ptr(prefill), prefill.shape[0], _ptr(trailing), trailing.shape[0], _ptr(pad)))
+        frames = np.zeros((max_new_tokens, self.groups), np.uint32)
+        forced = None if forced_frames is None else np.ascontiguousarray(
+            np.concatenate([np.asarray(forced_frames, np.uint32).reshape(-1, self.groups),
+                            np.zeros((max_new_tokens - len(forced_frames), self.groups), np.uint32)], 0))
+        fl = np.zeros((max_new_tokens, self.vocab), np.float32) if want_logits else None
+        gl = np.zeros((max_new_tokens, self.groups - 1, self.cp_vocab), np.float32) if want_logits else None
+        n = C.c_size_t()
+        self._ck(self.lib.crane_b200_tts_generate(self.h, max_new_tokens, repetition_penalty, None if forced is None else _ptr(forced),
+                                                  _ptr(frames), C.byref(n), None if fl is None else _ptr(fl), None if gl is None else _ptr(gl)))
+        k = int(n.value)
+        return (frames[:k], fl[:k], gl[:k]) if want_logits else frames[:k]
 
 
 def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_init=None, use_simt=False, device=0):

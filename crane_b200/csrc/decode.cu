@@ -115,6 +115,17 @@ gemv_kernel(GemvArgs a) {
         }
     }
     __syncthreads();
+    if (NORM && a.norm_out != nullptr && blockIdx.x == 0) {      // post-norm hidden state for callers that need it (TTS code predictor input)
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+            for (int i = tid; i < K8; i += GV_THREADS) {
+                const float r = rstd_s[b];
+                const float4 lo = xs[(size_t)(b * 2 + 0) * K8 + i], hi = xs[(size_t)(b * 2 + 1) * K8 + i];
+                float4* o = reinterpret_cast<float4*>(a.norm_out + (size_t)b * a.K) + 2 * i;
+                o[0] = make_float4(lo.x * r, lo.y * r, lo.z * r, lo.w * r);
+                o[1] = make_float4(hi.x * r, hi.y * r, hi.z * r, hi.w * r);
+            }
+    }
 
     {
         float accum[B], accum2[B];
@@ -247,11 +258,14 @@ gemv_kernel(GemvArgs a) {
                     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
                 if (lane == 0) {
-                    tok_s[b] = (uint32_t)bi;
                     SeqState* s = a.state + b;
                     if (a.out_tokens) a.out_tokens[(size_t)b * a.out_stride + s->step] = (uint32_t)bi;
+                    uint32_t fed = (uint32_t)bi;
+                    if (a.force_tokens) fed = a.force_tokens[s->step];
+                    if (a.advance == 2) fed = s->token;
+                    tok_s[b] = fed;
                     if (a.advance) {
-                        s->token = (uint32_t)bi;
+                        s->token = fed;
                         s->kv_len += 1;
                         s->pos[0] += 1; s->pos[1] += 1; s->pos[2] += 1;
                     }
@@ -260,7 +274,7 @@ gemv_kernel(GemvArgs a) {
             }
             if (tid == 0) *a.ticket = 0u;
             __syncthreads();
-            if (a.advance) {   // gather the next step's input embedding (bf16 -> f32 residual stream)
+            if (a.advance && a.embed != nullptr) {   // gather the next step's input embedding (bf16 -> f32 residual stream)
                 for (int b = 0; b < B; ++b) {
                     const bf16* row = a.embed + (size_t)tok_s[b] * a.H;
                     for (int i = tid; i < a.H; i += GV_THREADS) a.x_next[(size_t)b * a.H + i] = __bfloat162float(row[i]);

@@ -52,7 +52,10 @@ struct GemvArgs {
     const bf16* embed;      // [V, H] embedding table for the next-step gather
     float* x_next;          // [B, H] residual-stream input of the next step
     int H;
-    int advance;            // 1: write token / embedding / advance state (on-device greedy loop)
+    int advance;            // 0: report the argmax only; 1: feed it back (token, next embedding, kv_len/pos + 1);
+                            // 2: advance kv_len/pos and gather embed[state.token] WITHOUT replacing the token (caller-chosen input)
+    float* norm_out;        // optional [B, K]: the RMS-normalised input (x * w * rstd), written by CTA 0 (NORM kernels)
+    const uint32_t* force_tokens;  // optional [out_stride]: teacher forcing -- token fed back at step s is force_tokens[s] (argmax still reported)
 };
 
 struct AttnDecArgs {

@@ -356,6 +356,7 @@ decode_persistent_kernel(PersistArgs a) {
             const Geom g = phase_geom(a, gp);
             const Slab sl = warp_slab(g, warp, lane);
             const int K8 = g.K >> 3;
+            PK_PROF(7);
             // ---- activation staging: xs <- input (* RMSNorm weight), 1/rms ----
             const float* nw = (kind == 0) ? ly.ln1 : (kind == 2) ? ly.ln2 : (kind == 4) ? a.final_norm : nullptr;
             if (kind == 1) {
@@ -392,10 +393,12 @@ decode_persistent_kernel(PersistArgs a) {
                     xs[i] = lo;
                     xs[K8 + i] = hi;
                 }
+                PK_PROF(8);
                 if (nw) {
                     const float tot = block_sum(ssq, red);
                     if (tid == 0) rstd_s = rsqrtf(tot / (float)g.K + a.eps);
                 }
+                PK_PROF(9);
             }
             for (int i = tid; i < sl.rpc; i += PK_THREADS) acc_s[i] = 0.f;
             __syncthreads();

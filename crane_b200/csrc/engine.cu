@@ -187,6 +187,36 @@ struct crane_b200_model {
     SeqState* state = nullptr;
     uint32_t* out_tokens = nullptr;
     int out_cap = 8192;
+    // multiple output heads / extra embedding tables (Qwen3-TTS code predictor: lm_head.{g}, codec_embedding.{g})
+    std::vector<bf16*> heads;          // heads[g]; the single-head models only use lm_head
+    std::vector<bf16*> emb_tables;     // emb_tables[g]: [table_rows, H]
+    int table_rows = 0;
+    float* hidden_out = nullptr;       // [B, H] post-final-norm hidden state of the last pass (norm_out of the head GEMV)
+    struct HeadOverride {              // per-pass head / gather / forcing selection used by lm_head_last_row
+        const bf16* head = nullptr; const bf16* gather = nullptr; bool gather_set = false;
+        const uint32_t* force = nullptr; float* logits = nullptr;
+    } hov;
+    bool owns_stream = true;
+    // Qwen3-TTS composite: this model is the talker, `cp` the code predictor
+    bool is_tts = false;
+    crane_b200_model* cp = nullptr;
+    int tts_groups = 0, tts_Ht = 0, tts_Vt = 0, tts_eos = 0;
+    bf16 *tts_text_emb = nullptr, *tts_fc1 = nullptr, *tts_fc2 = nullptr;
+    float *tts_b1 = nullptr, *tts_b2 = nullptr;
+    int tts_loaded = 0;
+    float* tts_contrib = nullptr;      // [n_trailing + 1, H] trailing-text rows then the tts_pad row
+    int tts_n_trailing = 0, tts_max_frames = 0, tts_prefill_len = 0, tts_frames_done = 0;
+    uint32_t *tts_frames = nullptr, *tts_force = nullptr;   // [max_frames, groups]
+    int* tts_ctrl = nullptr;           // [4]: step, done_step (-1 while running), -, -
+    unsigned char* tts_seen = nullptr; // [V] first codes generated so far (repetition penalty is applied once per distinct token)
+    float *tts_first_logits = nullptr; // [V] penalised / masked copy used by the selector
+    std::string cp_json;
+    void tts_setup();
+    void tts_load(const std::string& name, int dt, const int64_t* shape, int ndim, const void* data);
+    void tts_text_project(const uint32_t* ids, size_t n, float* out_host);
+    void tts_prefill(const float* embeds, size_t P, const float* trailing, size_t nt, const float* pad);
+    void tts_frame(float rep_penalty, bool forced, int frame);
+    const bf16** tts_tables_dev = nullptr;
     int* block_table = nullptr;
     SeqState* h_state = nullptr;      // pinned
     uint32_t* h_tokens = nullptr;     // pinned
@@ -308,7 +338,8 @@ struct crane_b200_model {
 void crane_b200_model::parse_config(const char* json) {
     cbjson::Value root = cbjson::Parser(json).parse();
     if (root.type != cbjson::Value::OBJ) fail(CRANE_B200_INVALID_ARG, "config must be a JSON object");
-    const cbjson::Value& tc = root.has("text_config") ? root.at("text_config") : root;
+    is_tts = root.has("talker_config");
+    const cbjson::Value& tc = root.has("text_config") ? root.at("text_config") : is_tts ? root.at("talker_config") : root;
     is_vl = root.has("vision_config");
     V = (int)tc.integer("vocab_size");
     H = (int)tc.integer("hidden_size");
@@ -321,6 +352,27 @@ void crane_b200_model::parse_config(const char* json) {
     theta = tc.number("rope_theta", 1000000.0);
     if (tc.has("rope_parameters") && tc.at("rope_parameters").has("rope_theta")) theta = tc.at("rope_parameters").number("rope_theta", theta);
     tied = root.boolean("tie_word_embeddings", tc.boolean("tie_word_embeddings", true));
+    if (is_tts) {
+        tied = false;                    // codec_embedding and codec_head are separate tensors
+        tts_groups = (int)tc.integer("num_code_groups", 16);
+        tts_Ht = (int)tc.integer("text_hidden_size", 2048);
+        tts_Vt = (int)tc.integer("text_vocab_size", 151936);
+        tts_eos = (int)tc.integer("codec_eos_token_id", 0);
+        if (tts_Ht % 64 || tts_Ht % 32) fail(CRANE_B200_UNSUPPORTED, "text_hidden_size %d", tts_Ht);
+        const cbjson::Value& cc = tc.at("code_predictor_config");
+        if (cc.integer("hidden_size") != tc.integer("hidden_size"))
+            fail(CRANE_B200_UNSUPPORTED, "code predictor hidden_size != talker hidden_size (small_to_mtp_projection) is not supported");
+        char buf[1024];
+        snprintf(buf, sizeof buf,
+                 "{\"vocab_size\": %lld, \"hidden_size\": %lld, \"intermediate_size\": %lld, \"num_hidden_layers\": %lld, "
+                 "\"num_attention_heads\": %lld, \"num_key_value_heads\": %lld, \"head_dim\": %lld, \"rms_norm_eps\": %g, "
+                 "\"rope_theta\": %.1f, \"tie_word_embeddings\": false, \"engine\": {\"max_seq_len\": 64, \"persistent\": false}}",
+                 cc.integer("vocab_size", 2048), cc.integer("hidden_size"), cc.integer("intermediate_size"), cc.integer("num_hidden_layers"),
+                 cc.integer("num_attention_heads"), cc.integer("num_key_value_heads"), cc.integer("head_dim", 128), cc.number("rms_norm_eps", 1e-6),
+                 cc.number("rope_theta", 1000000.0));
+        cp_json = buf;
+        if ((int)cc.integer("num_code_groups", tts_groups) != tts_groups) fail(CRANE_B200_INVALID_ARG, "num_code_groups differs between talker and code predictor");
+    }
     const cbjson::Value* rs = tc.has("rope_scaling") ? &tc.at("rope_scaling") : (tc.has("rope_parameters") ? &tc.at("rope_parameters") : nullptr);
     if (rs && rs->has("mrope_section"))
         for (const auto& v : rs->at("mrope_section").arr) mrope_section.push_back((int)v.num);
@@ -583,6 +635,7 @@ bool crane_b200_model::load_vision_tensor(const std::string& n, int dt, const in
 }
 
 void crane_b200_model::load_tensor(const std::string& name_in, int dt, const int64_t* shape, int ndim, const void* data) {
+    if (is_tts && name_in.rfind("talker.", 0) == 0) { tts_load(name_in, dt, shape, ndim, data); return; }
     const std::string name = gguf_to_hf(name_in);
     if (finalized) fail(CRANE_B200_INVALID_ARG, "load_tensor after finalize");
     if (dt < 0 || dt > 2) fail(CRANE_B200_INVALID_ARG, "tensor %s: unknown dtype %d", name.c_str(), dt);
@@ -594,6 +647,26 @@ void crane_b200_model::load_tensor(const std::string& name_in, int dt, const int
                 fail(CRANE_B200_INVALID_ARG, "unknown vision tensor %s", name.c_str());
             return;
         }
+    if (name.rfind("lm_head.", 0) == 0 && name != "lm_head.weight") {       // lm_head.{g}.weight: extra output heads
+        const int g = std::atoi(name.substr(8).c_str());
+        if (g < 0 || g >= 64) fail(CRANE_B200_INVALID_ARG, "tensor %s: head index", name.c_str());
+        want_shape(name, shape, ndim, {V, H});
+        if ((int)heads.size() <= g) heads.resize(g + 1, nullptr);
+        if (!heads[g]) heads[g] = dalloc<bf16>((size_t)V * H);
+        up_bf16(heads[g], data, dt, (size_t)V * H);
+        if (g == 0) { lm_head = heads[0]; got_lm_head = true; }
+        return;
+    }
+    if (name.rfind("embed_tables.", 0) == 0) {                                 // embed_tables.{g}.weight: extra [rows, H] tables
+        const int g = std::atoi(name.substr(13).c_str());
+        if (g < 0 || g >= 64 || ndim != 2 || shape[1] != H) fail(CRANE_B200_INVALID_ARG, "tensor %s: bad table", name.c_str());
+        if (table_rows && table_rows != (int)shape[0]) fail(CRANE_B200_INVALID_ARG, "tensor %s: table rows differ", name.c_str());
+        table_rows = (int)shape[0];
+        if ((int)emb_tables.size() <= g) emb_tables.resize(g + 1, nullptr);
+        if (!emb_tables[g]) emb_tables[g] = dalloc<bf16>((size_t)table_rows * H);
+        up_bf16(emb_tables[g], data, dt, (size_t)table_rows * H);
+        return;
+    }
     if (name == "lm_head.weight") {
         want_shape(name, shape, ndim, {V, H});
         if (!tied) {
@@ -820,6 +893,7 @@ void crane_b200_model::finalize() {
     attn_dec = dalloc<float>((size_t)B * q_dim());
     act_dec = dalloc<float>((size_t)B * I);
     logits = dalloc<float>((size_t)B * V);
+    hidden_out = dalloc<float>((size_t)B * H);
     part_o = dalloc<float>((size_t)B * nh * ATTN_NSPLIT * D);
     part_ml = dalloc<float>((size_t)B * nh * ATTN_NSPLIT * 2);
     part_val = dalloc<float>((size_t)B * num_sms);
@@ -841,7 +915,7 @@ void crane_b200_model::finalize() {
         players = dalloc<PLayer>(L);
         CUDA_OK(cudaMemcpy(players, pl.data(), L * sizeof(PLayer), cudaMemcpyHostToDevice));
         grid_bar = dalloc<unsigned int>(64);
-        if (getenv("CRANE_B200_PROF")) { pk_prof = dalloc<unsigned long long>(8); CUDA_OK(cudaMemset(pk_prof, 0, 64)); }
+        if (getenv("CRANE_B200_PROF")) { pk_prof = dalloc<unsigned long long>(16); CUDA_OK(cudaMemset(pk_prof, 0, 128)); }
     }
     CUDA_OK(cudaMallocHost((void**)&h_state, sizeof(SeqState) * B));
     CUDA_OK(cudaMallocHost((void**)&h_tokens, sizeof(uint32_t) * out_cap));
@@ -849,6 +923,7 @@ void crane_b200_model::finalize() {
     CUDA_OK(cudaEventCreate(&pev1));
     CUDA_OK(cudaEventCreate(&dev0));
     CUDA_OK(cudaEventCreate(&dev1));
+    if (is_tts) tts_setup();
     CUDA_OK(cudaDeviceSynchronize());
     finalized = true;
 }
@@ -951,8 +1026,10 @@ void crane_b200_model::reset_recurrent_state() {
 void crane_b200_model::lm_head_last_row(const float* xrow, int advance, int B) {
     GemvArgs h = {};
     h.part_val = part_val; h.part_idx = part_idx; h.ticket = ticket; h.state = state; h.out_tokens = out_tokens; h.out_stride = out_cap;
-    h.embed = embed; h.x_next = x_dec; h.H = H; h.advance = advance;
-    linear_decode(GEMV_LOGITS_ARGMAX, true, lm_head, q_lm_head, qt_lm, V, H, xrow, H, final_norm, logits, V, &h, B);
+    h.embed = hov.gather_set ? hov.gather : embed; h.x_next = x_dec; h.H = H; h.advance = advance;
+    h.norm_out = hidden_out; h.force_tokens = hov.force;
+    linear_decode(GEMV_LOGITS_ARGMAX, true, hov.head ? hov.head : lm_head, q_lm_head, hov.head ? 0 : qt_lm, V, H, xrow, H, final_norm,
+                  hov.logits ? hov.logits : logits, V, &h, B);
 }
 
 // One decode step (layers + lm_head), replayed from a CUDA graph when capture is available.
@@ -997,13 +1074,13 @@ void crane_b200_model::decode_steps(int n_steps, int advance) {
         LAUNCH_OK(decode_persistent_launch(stream, p, num_sms));
         ++launches;
         if (pk_prof && n_steps > 8) {   // CRANE_B200_PROF=1: per-phase device time of CTA 0 (the CRANE_PROF spans of ops/prof.rs:37-61)
-            unsigned long long h[8];
+            unsigned long long h[16];
             CUDA_OK(cudaStreamSynchronize(stream));
-            CUDA_OK(cudaMemcpy(h, pk_prof, 64, cudaMemcpyDeviceToHost));
-            CUDA_OK(cudaMemset(pk_prof, 0, 64));
-            const char* names[7] = {"attention", "attn_barrier", "staging", "stream", "epilogue", "barrier", "token"};
+            CUDA_OK(cudaMemcpy(h, pk_prof, 128, cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemset(pk_prof, 0, 128));
+            const char* names[10] = {"attention", "attn_barrier", "stage_tail", "stream", "epilogue", "barrier", "token", "geom", "stage_load", "stage_reduce"};
             fprintf(stderr, "[crane_b200 prof] per step (us):");
-            for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f", names[i], (double)h[i] / 1e3 / n_steps);
+            for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.1f", names[i], (double)h[i] / 1e3 / n_steps);
             fprintf(stderr, "\n");
         }
         return;
@@ -1282,6 +1359,15 @@ int crane_b200_create(const char* config_json, int device_ordinal, crane_b200_mo
         m->parse_config(config_json);
         CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
         m->alloc_weights();
+        if (m->is_tts) {                 // code predictor = a second dense decoder on the same stream
+            std::unique_ptr<crane_b200_model> c(new crane_b200_model());
+            c->device = device_ordinal; c->num_sms = m->num_sms;
+            c->parse_config(m->cp_json.c_str());
+            c->stream = m->stream; c->owns_stream = false;
+            c->alloc_weights();
+            c->got_embed = true;         // its inputs come from the codec embedding tables, not embed_tokens
+            m->cp = c.release();
+        }
     } catch (const EngineError& e) {
         g_create_error = e.msg;
         for (void* p : m->allocs) cudaFree(p);
@@ -1299,12 +1385,13 @@ void crane_b200_destroy(crane_b200_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
+    if (m->cp) { crane_b200_destroy(m->cp); m->cp = nullptr; }
     for (auto& g : m->graph_step) if (g) cudaGraphExecDestroy(g);
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_state) cudaFreeHost(m->h_state);
     if (m->h_tokens) cudaFreeHost(m->h_tokens);
     for (cudaEvent_t e : {m->pev0, m->pev1, m->dev0, m->dev1}) if (e) cudaEventDestroy(e);
-    if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->stream && m->owns_stream) cudaStreamDestroy(m->stream);
     delete m;
 }
 
@@ -1710,3 +1797,5 @@ int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* w, int M, 
 }
 
 }  // extern "C"
+
+#include "engine_tts.inc"

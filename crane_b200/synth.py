@@ -118,6 +118,41 @@ TINY_QWEN3_5 = {
 }
 
 
+QWEN3_TTS_0_6B = {
+    "model_type": "qwen3_tts",
+    "tts_bos_token_id": 151672, "tts_eos_token_id": 151673, "tts_pad_token_id": 151671,
+    "talker_config": {
+        "vocab_size": 3072, "hidden_size": 1024, "intermediate_size": 3072, "num_hidden_layers": 28,
+        "num_attention_heads": 16, "num_key_value_heads": 8, "head_dim": 128, "rms_norm_eps": 1e-6, "rope_theta": 1000000.0,
+        "num_code_groups": 16, "text_hidden_size": 2048, "text_vocab_size": 151936, "max_position_embeddings": 32768,
+        "codec_eos_token_id": 2150, "codec_think_id": 2154, "codec_nothink_id": 2155, "codec_think_bos_id": 2156,
+        "codec_think_eos_id": 2157, "codec_pad_id": 2148, "codec_bos_id": 2149,
+        "code_predictor_config": {
+            "vocab_size": 2048, "hidden_size": 1024, "intermediate_size": 3072, "num_hidden_layers": 5,
+            "num_attention_heads": 16, "num_key_value_heads": 8, "head_dim": 128, "rms_norm_eps": 1e-6, "rope_theta": 1000000.0,
+            "num_code_groups": 16, "max_position_embeddings": 32768,
+        },
+    },
+}
+
+TINY_QWEN3_TTS = {
+    "model_type": "qwen3_tts",
+    "tts_bos_token_id": 1021, "tts_eos_token_id": 1022, "tts_pad_token_id": 1020,
+    "talker_config": {
+        "vocab_size": 1280, "hidden_size": 256, "intermediate_size": 512, "num_hidden_layers": 2,
+        "num_attention_heads": 4, "num_key_value_heads": 2, "head_dim": 128, "rms_norm_eps": 1e-6, "rope_theta": 1000000.0,
+        "num_code_groups": 4, "text_hidden_size": 512, "text_vocab_size": 1024, "max_position_embeddings": 4096,
+        "codec_eos_token_id": 1270, "codec_think_id": 1274, "codec_nothink_id": 1275, "codec_think_bos_id": 1276,
+        "codec_think_eos_id": 1277, "codec_pad_id": 1268, "codec_bos_id": 1269,
+        "code_predictor_config": {
+            "vocab_size": 256, "hidden_size": 256, "intermediate_size": 512, "num_hidden_layers": 2,
+            "num_attention_heads": 4, "num_key_value_heads": 2, "head_dim": 128, "rms_norm_eps": 1e-6, "rope_theta": 1000000.0,
+            "num_code_groups": 4, "max_position_embeddings": 4096,
+        },
+    },
+}
+
+
 def text_config(cfg: dict) -> dict:
     return cfg.get("text_config", cfg)
 
@@ -268,7 +303,39 @@ def vision_tensor_specs(vc: dict, prefix: str = "model.visual."):
         yield p + "linear_fc2.bias", (vc["out_hidden_size"],), "bias"
 
 
+def qwen3_tts_tensor_specs(cfg: dict):
+    """Qwen3-TTS talker + code predictor (names: crane-core/src/models/qwen3_tts/modeling.rs:297-345,513-575):
+    `talker.model.*` backbone, `talker.codec_head`, `talker.text_projection.*`, `talker.code_predictor.*`."""
+    tk = cfg["talker_config"]
+    cp = tk["code_predictor_config"]
+    H, Ht = tk["hidden_size"], tk["text_hidden_size"]
+    yield "talker.model.codec_embedding.weight", (tk["vocab_size"], H), "embed"
+    yield "talker.model.text_embedding.weight", (tk["text_vocab_size"], Ht), "embed"
+    yield "talker.text_projection.linear_fc1.weight", (Ht, Ht), "linear"
+    yield "talker.text_projection.linear_fc1.bias", (Ht,), "bias"
+    yield "talker.text_projection.linear_fc2.weight", (H, Ht), "linear"
+    yield "talker.text_projection.linear_fc2.bias", (H,), "bias"
+    for name, shape, kind in text_tensor_specs(dict(tk, tie_word_embeddings=True), "talker.model."):
+        if "embed_tokens" not in name:
+            yield name, shape, kind
+    yield "talker.codec_head.weight", (tk["vocab_size"], H), "linear"
+    n = cp["num_code_groups"] - 1
+    for g in range(n):
+        yield f"talker.code_predictor.model.codec_embedding.{g}.weight", (cp["vocab_size"], H), "embed"
+    for name, shape, kind in text_tensor_specs(dict(cp, tie_word_embeddings=True), "talker.code_predictor.model."):
+        if "embed_tokens" not in name:
+            yield name, shape, kind
+    for g in range(n):
+        yield f"talker.code_predictor.lm_head.{g}.weight", (cp["vocab_size"], cp["hidden_size"]), "linear"
+    if cp["hidden_size"] != H:
+        yield "talker.code_predictor.small_to_mtp_projection.weight", (cp["hidden_size"], H), "linear"
+        yield "talker.code_predictor.small_to_mtp_projection.bias", (cp["hidden_size"],), "bias"
+
+
 def tensor_specs(cfg: dict):
+    if cfg.get("model_type") == "qwen3_tts":
+        yield from qwen3_tts_tensor_specs(cfg)
+        return
     if cfg.get("model_type", "").startswith("qwen3_5"):
         yield from qwen3_5_tensor_specs(cfg)
     elif cfg.get("model_type") == "qwen3_vl":

@@ -167,6 +167,27 @@ CRANE_B200_API int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token
 /* The MRoPE counter (`next_mrope_pos`, vlm.rs:272-282). */
 CRANE_B200_API uint32_t crane_b200_next_mrope_pos(const crane_b200_model* m);
 
+/* ---- Qwen3-TTS codec-LM surface (crane-core/src/models/qwen3_tts/modeling.rs) ------------------------------------ */
+/* A `qwen3_tts` config (talker_config + code_predictor_config) makes the handle a talker with an embedded code predictor;
+ * tensors are registered under their checkpoint names (`talker.model.*`, `talker.codec_head.*`, `talker.text_projection.*`,
+ * `talker.code_predictor.*`, modeling.rs:297-345,513-575).
+ * text_embedding -> ResizeMlp (fc1+bias, SiLU, fc2+bias) for `n` text ids -> [n, hidden] f32 host (modeling.rs:244-268,612-614). */
+CRANE_B200_API int crane_b200_tts_text_project(crane_b200_model* m, const uint32_t* text_ids, size_t n, float* out_host);
+/* Rows of the talker codec_embedding (group = -1) or of code-predictor codec_embedding[group] -> [n, hidden] f32 host. */
+CRANE_B200_API int crane_b200_tts_codec_embed(crane_b200_model* m, int group, const uint32_t* ids, size_t n, float* out_host);
+/* Talker prefill over caller-assembled embeddings (`build_prefill_embeds`, modeling.rs:597-726, stays host glue) and the per-step
+ * text contributions of the frame loop: trailing_text [n_trailing, hidden] then the tts_pad row (modeling.rs:1546-1552). */
+CRANE_B200_API int crane_b200_tts_prefill(crane_b200_model* m, const float* embeds, size_t prefill_len, const float* trailing_text,
+                                          size_t n_trailing, const float* tts_pad_embed);
+/* The frame loop of `generate_speech_codes` / `generate_one_frame` (modeling.rs:1492-1568,1677-1749): per frame the first
+ * code from codec_head (repetition penalty over previous first codes, suppress window [V-1024, V) \ {EOS}, EOS held back for
+ * 2 frames), 15 code-predictor passes (`CodePredictor::predict`, :373-479), the summed-embedding next input and one talker
+ * pass -- all on the device, greedy (the reference's seeded host sampler is not pinned) or teacher-forced from
+ * `forced_frames` [max_frames, groups].  frames_out [max_frames, groups]; optional logits for parity:
+ * first_logits_out [max_frames, codec_vocab] (raw codec_head logits), group_logits_out [max_frames, groups-1, cp_vocab]. */
+CRANE_B200_API int crane_b200_tts_generate(crane_b200_model* m, size_t max_frames, float repetition_penalty, const uint32_t* forced_frames,
+                                           uint32_t* frames_out, size_t* n_frames_out, float* first_logits_out, float* group_logits_out);
+
 /* ---- profiling (crane-core/src/ops/prof.rs:37-243 `CRANE_PROF`) ----------------------------------- */
 /* Device time (ms, CUDA events on the engine stream) of the last prefill pass and last decode run. */
 CRANE_B200_API int crane_b200_last_timing(const crane_b200_model* m, float* prefill_ms, float* decode_ms, size_t* decode_steps);

@@ -375,3 +375,40 @@ def test_batched_decode_matches_per_sequence_decode(quant):
     with pytest.raises(crane_b200.CraneB200Error):
         m.decode_batch([seqs[0], seqs[0]], [1, 2])
     m.close()
+
+
+# ---- Qwen3-TTS codec-LM frame loop (config 5): talker + 16-pass code predictor on the device ----------------------------------
+
+def test_tts_frame_loop_against_oracle():
+    from oracle.qwen3_tts import Qwen3TTSOracle
+    cfg = synth.TINY_QWEN3_TTS
+    w = dict(synth.synth_checkpoint(cfg))
+    m = crane_b200.Qwen3TTSModel(cfg, device=0, max_seq_len=256)
+    m.load_checkpoint(w.items())
+    orc = Qwen3TTSOracle(cfg, w)
+    ids = synth.synth_token_ids(7, cfg["talker_config"]["text_vocab_size"] - 8, "tts-gpu")
+    # host glue + text projection / embedding gathers
+    pre_o, trail_o, pad_o = orc.build_prefill_embeds(ids)
+    pre, trail, pad = m.build_prefill_embeds(list(ids))
+    e_glue = max(rel_err(pre, pre_o.numpy()), rel_err(trail, trail_o.numpy()), rel_err(pad, pad_o.numpy()))
+    # greedy oracle frames, then teacher-force the same codes through the engine and compare every head's logits
+    n = 6
+    frames_o, trace = orc.generate_codes(ids, n, repetition_penalty=1.05)
+    assert len(frames_o) == n
+    frames, fl, gl = m.generate_codes(ids, n, repetition_penalty=1.05, forced_frames=frames_o, want_logits=True)
+    assert frames.shape == (n, cfg["talker_config"]["num_code_groups"]) and np.array_equal(frames, np.array(frames_o, np.uint32))
+    raw_first = [(t["hidden"] @ orc.w["talker.codec_head.weight"].T).numpy() for t in trace]
+    e_first = max(rel_err(fl[i], raw_first[i]) for i in range(n))
+    e_group = max(rel_err(gl[i], trace[i]["group_logits"].numpy()) for i in range(n))
+    print(f"tts: glue {e_glue:.3e}, first-code logits {e_first:.3e}, code-predictor logits {e_group:.3e}")
+    assert e_glue < PREFILL_TOL and e_first < PREFILL_TOL and e_group < PREFILL_TOL
+    # free-running greedy on the device: equal to the oracle's greedy frames up to the first near-tie
+    g = m.generate_codes(ids, n, repetition_penalty=1.05)
+    same = 0
+    for a, b in zip(g.tolist(), frames_o):
+        if a != b:
+            break
+        same += 1
+    print(f"tts greedy: {same}/{n} frames identical to the oracle")
+    assert same >= 1 and g.shape[1] == cfg["talker_config"]["num_code_groups"]
+    m.close()

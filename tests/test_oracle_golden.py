@@ -209,3 +209,26 @@ def test_ggml_dequant_matches_gguf_package():
     # gguf's own Q8_0 encoder decodes identically through ours
     raw = quants.quantize(x, T.Q8_0)
     assert np.array_equal(gq.dequantize(raw, "Q8_0", 1024), quants.dequantize(raw, T.Q8_0))
+
+
+# ---- Qwen3-TTS frame loop (oracle-only properties; the decoder stack itself is the HF-pinned Qwen3 oracle) ----------------------
+
+def test_tts_oracle_frame_loop_properties():
+    from oracle.qwen3_tts import Qwen3TTSOracle
+    cfg = synth.TINY_QWEN3_TTS
+    o = Qwen3TTSOracle(cfg, _weights(cfg))
+    ids = synth.synth_token_ids(5, 1000, "tts-cpu")
+    pre, trail, pad = o.build_prefill_embeds(ids)
+    # qwen3_tts/modeling.rs:597-726: role prefix (3) + overlaid codec prefix (nothink, think_bos, think_eos, pad = 4) + first text/bos (1)
+    assert pre.shape == (8, 256) and trail.shape == (5, 256) and pad.shape == (256,)
+    frames, trace = o.generate_codes(ids, 4, repetition_penalty=1.05)
+    G, eos, V = cfg["talker_config"]["num_code_groups"], cfg["talker_config"]["codec_eos_token_id"], cfg["talker_config"]["vocab_size"]
+    assert all(len(f) == G for f in frames)
+    # suppress window [V-1024, V) \\ {EOS} and EOS held back for the first two frames (:1470-1524)
+    for step, t in enumerate(trace):
+        lg = t["first_logits"].numpy()
+        assert np.all(np.isneginf(lg[[i for i in range(V - 1024, V) if i != eos]]))
+        assert (step >= 2) or np.isneginf(lg[eos])
+    # teacher forcing reproduces the same logits (KV / code-predictor cache handling is consistent)
+    _, trace2 = o.generate_codes(ids, 4, repetition_penalty=1.05, forced_frames=frames)
+    assert all(torch.allclose(a["group_logits"], b["group_logits"]) for a, b in zip(trace, trace2))
