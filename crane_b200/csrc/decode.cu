@@ -24,6 +24,9 @@ namespace cb {
 #ifndef GV_DEPTH
 #define GV_DEPTH 2
 #endif
+#ifndef GV_MINB                    // CTAs per SM the GEMV is compiled for (2 lets the next launch's CTA prime its ring early)
+#define GV_MINB 1
+#endif
 constexpr int GV_SEG_CHUNKS = 4;                       // 512-byte chunks per pipeline slot (2 KB)
 constexpr int GV_SEG_BYTES = GV_SEG_CHUNKS * 512;
 constexpr int GV_THREADS = GV_WARPS * 32;
@@ -36,7 +39,7 @@ __device__ __forceinline__ void cp_async_commit_g() { asm volatile("cp.async.com
 template <int N> __device__ __forceinline__ void cp_async_wait_g() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int B, int EPI, bool NORM>
-__global__ void __launch_bounds__(GV_THREADS, 1)
+__global__ void __launch_bounds__(GV_THREADS, GV_MINB)
 gemv_kernel(GemvArgs a) {
     extern __shared__ __align__(1024) unsigned char gsm[];
     // layout: [rings: GV_WARPS * GV_DEPTH * 2 KB][xs: B * K f32][acc: B * rpc f32]

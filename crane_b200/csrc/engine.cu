@@ -260,6 +260,8 @@ struct crane_b200_model {
     float last_prefill_ms = 0.f, last_decode_ms = 0.f;
     size_t last_decode_steps = 0;
     uint64_t launches = 0;
+    uint64_t graph_launches[3] = {0, 0, 0};
+    unsigned char* xq_buf = nullptr;   // activations quantised for the quantised GEMVs (xquant_launch)
     std::string last_error;
 
     // ---------------------------------------------------------------------------------------------
@@ -288,7 +290,7 @@ struct crane_b200_model {
     void load_tensor_ggml(const std::string& name, int qt, const int64_t* shape, int ndim, const void* data, size_t nbytes);
     unsigned char* up_quant(int qt, const void* data, size_t rows, int K, unsigned char* dst = nullptr, size_t dst_row_pitch = 0);
     void linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
-                       const float* norm_w, float* y, int ldy, const GemvArgs* extra = nullptr, int B = 1);
+                       const float* norm_w, float* y, int ldy, const GemvArgs* extra = nullptr, int B = 1, bool reuse_xq = false);
     const bf16* dequant_for_gemm(const unsigned char* qw, int qt, size_t rows, int K, size_t row_offset = 0);
     bool load_text_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
     bool load_vision_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
@@ -778,13 +780,17 @@ void crane_b200_model::load_tensor_ggml(const std::string& name_in, int qt, cons
 
 // One decode-path linear: bf16 GEMV or quantised GEMV with the same fused epilogue.
 void crane_b200_model::linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
-                                     const float* norm_w, float* y, int ldy, const GemvArgs* extra, int B) {
+                                     const float* norm_w, float* y, int ldy, const GemvArgs* extra, int B, bool reuse_xq) {
     GemvArgs g = extra ? *extra : GemvArgs{};
     g.N = N; g.K = K; g.x = xin; g.ldx = ldx; g.norm_w = norm_w; g.eps = eps; g.y = y; g.ldy = ldy;
     if (qt) {
         QGemvArgs qa;
         g.W = reinterpret_cast<const bf16*>(qw);
-        qa.g = g; qa.qtype = qt; qa.epi = epi; qa.norm = norm ? 1 : 0;
+        qa.g = g; qa.qtype = qt; qa.epi = epi; qa.norm = norm ? 1 : 0; qa.xq = xq_buf;
+        if (!reuse_xq) {     // same input (and norm) as the previous quantised linear: k and v after q
+            LAUNCH_OK(xquant_launch(stream, B, xin, ldx, K, norm ? norm_w : nullptr, eps, xq_buf, use_pdl));
+            ++launches;
+        }
         LAUNCH_OK(qgemv_launch(stream, B, qa, num_sms, use_pdl));
     } else {
         g.W = w;
@@ -821,6 +827,7 @@ void crane_b200_model::finalize() {
             if (l.qt_down) mx = std::max(mx, (size_t)H * I);
         }
         if (mx) { dq_scratch = dalloc<bf16>(mx); dq_scratch_elems = mx; }
+        xq_buf = dalloc<unsigned char>(xquant_bytes(std::max(max_batch, 1), std::max(std::max(H, I), q_dim())));
     }
     for (int i = 0; i < L; ++i) {
         // full: q,k,v,o (1|2|4|8) gate,up,down (16|32|64) ln1,ln2 (128|256) q_norm,k_norm (512|1024)
@@ -974,8 +981,8 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) 
             if (l.qt_q) {   // GGUF keeps q/k/v as separate quantised matrices (qwen3/modeling.rs:252-255): three GEMVs into one qkv row
                 const int qs = nh * q_stride(), kvd = nkv * D;
                 linear_decode(GEMV_STORE, true, nullptr, l.q_wq, l.qt_q, qs, H, x_dec, H, l.ln1, qkv_dec, qkv_dim(), nullptr, B);
-                linear_decode(GEMV_STORE, true, nullptr, l.q_wk, l.qt_k, kvd, H, x_dec, H, l.ln1, qkv_dec + qs, qkv_dim(), nullptr, B);
-                linear_decode(GEMV_STORE, true, nullptr, l.q_wv, l.qt_v, kvd, H, x_dec, H, l.ln1, qkv_dec + qs + kvd, qkv_dim(), nullptr, B);
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wk, l.qt_k, kvd, H, x_dec, H, l.ln1, qkv_dec + qs, qkv_dim(), nullptr, B, true);
+                linear_decode(GEMV_STORE, true, nullptr, l.q_wv, l.qt_v, kvd, H, x_dec, H, l.ln1, qkv_dec + qs + kvd, qkv_dim(), nullptr, B, true);
             } else {
                 linear_decode(GEMV_STORE, true, l.wqkv, nullptr, 0, qkv_dim(), H, x_dec, H, l.ln1, qkv_dec, qkv_dim(), nullptr, B);
             }
@@ -1046,13 +1053,13 @@ void crane_b200_model::decode_step_graphed(int advance) {
         }
         if (ok) ok = cudaGraphInstantiate(&graph_step[advance], g, 0) == cudaSuccess;
         if (g) cudaGraphDestroy(g);
+        graph_launches[advance] = launches - before;     // kernels one replay stands for
         launches = before;
         if (!ok) { graph_failed = true; graph_step[advance] = nullptr; cudaGetLastError(); }
     }
     if (graph_step[advance]) {
         CUDA_OK(cudaGraphLaunch(graph_step[advance], stream));
-        for (const auto& l : layers) launches += l.full ? (l.qt_q ? 7 : 5) : 9;
-        launches += 1;
+        launches += graph_launches[advance];
     } else {
         enqueue_decode_step(advance, false);
     }

@@ -46,236 +46,339 @@ __device__ __forceinline__ float f16_bits_to_float(uint32_t h) { return __half2f
 __device__ __forceinline__ int dp4a_s(int a, int b, int c) { return __dp4a(a, b, c); }
 
 template <int QT> struct QTraits;
-template <> struct QTraits<QT_Q4_K> { static constexpr int SB = 144, LPS = 2, DEPTH = 3; };
-template <> struct QTraits<QT_Q6_K> { static constexpr int SB = 224, LPS = 2, DEPTH = 2; };
-template <> struct QTraits<QT_Q8_0> { static constexpr int SB = 272, LPS = 4, DEPTH = 3; };
+template <> struct QTraits<QT_Q4_K> { static constexpr int SB = 144; };
+template <> struct QTraits<QT_Q6_K> { static constexpr int SB = 224; };
+template <> struct QTraits<QT_Q8_0> { static constexpr int SB = 272; };
 
-// Quantised activation of one sequence in shared memory.
-struct XQ {
-    const int* q;       // [K/4]   int8 x 4
-    const float* dx;    // [K/32]  block scale
-    const float* sx;    // [K/32]  dx * sum(q) over the block (for the Q4_K minima)
-    const int* isum16;  // [K/16]  sum(q) over 16 elements (for the Q6_K -32 offset)
+// Quantised activations in shared memory, B sequences back to back, each:
+//   [K int8 | K/32 float2 {d, d * sum(q)} | K/16 i32 sum(q) per 16 elements]
+// The int8 part is stored in 16-byte granules XOR-swizzled by the 128-element group index, so the 8 lanes of an LDS.128
+// phase (2 super-blocks x 4 quarters) hit 8 different bank groups.
+__device__ __forceinline__ int xq_swz(int byte_off) {
+    const int g = byte_off >> 4;
+    return ((g ^ ((g >> 3) & 7)) << 4) | (byte_off & 15);
+}
+
+// One lane's slice of the activations for a k-tile: 64 elements of one super-block, held in registers while the warp
+// walks the rows of the tile (the weights are read once from shared memory, the activations once per tile).
+//   Q4_K / Q8_0: quarter q = elements [64q, 64q + 64)                       -> blocks 2q, 2q + 1
+//   Q6_K       : half h = q >> 1, lq = q & 1: elements 128h + 32t + 16lq + [0, 16), t = 0..3 (ggml's q1..q4 interleave)
+template <int QT, int B>
+struct XSlice {
+    int4 q[B][4];
+    float d[B][4];      // Q4_K: {d0, d0*sum0, d1, d1*sum1}; Q6_K: d of blocks 4h + t; Q8_0: {d0, d1, -, -}
+    float s[B][4];      // Q6_K only: 32 * d_t * isum16_t
+    __device__ __forceinline__ void load(const unsigned char* xbase, size_t xb, int K, int sbk_abs, int qq) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const unsigned char* xq = xbase + (size_t)b * xb;
+            const float2* ds = reinterpret_cast<const float2*>(xq + K);
+            const int* is16 = reinterpret_cast<const int*>(xq + K + (K / 32) * 8);
+            if constexpr (QT == QT_Q6_K) {
+                const int h = qq >> 1, lq = qq & 1;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int e = sbk_abs * 256 + 128 * h + 32 * t + 16 * lq;
+                    q[b][t] = *reinterpret_cast<const int4*>(xq + xq_swz(e));
+                    d[b][t] = ds[e >> 5].x;
+                    s[b][t] = 32.f * d[b][t] * (float)is16[e >> 4];
+                }
+            } else {
+                const int e = sbk_abs * 256 + 64 * qq;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) q[b][t] = *reinterpret_cast<const int4*>(xq + xq_swz(e + 16 * t));
+                const float4 v = *reinterpret_cast<const float4*>(ds + (e >> 5));
+                d[b][0] = v.x; d[b][1] = v.y; d[b][2] = v.z; d[b][3] = v.w;
+            }
+        }
+    }
 };
 
-// Partial dot of one lane's share of a super-block (elements [e0, e0 + 256/LPS) of the row) with the activation.
-template <int QT>
-__device__ __forceinline__ float sb_part_dot(const unsigned char* sb, int part, int e0, const XQ& x) {
+__device__ __forceinline__ int dot16(const int4& w0, const int4& w1, const int4& x0, const int4& x1) {
+    int s = 0;
+    s = dp4a_s(w0.x, x0.x, s); s = dp4a_s(w0.y, x0.y, s); s = dp4a_s(w0.z, x0.z, s); s = dp4a_s(w0.w, x0.w, s);
+    s = dp4a_s(w1.x, x1.x, s); s = dp4a_s(w1.y, x1.y, s); s = dp4a_s(w1.z, x1.z, s); s = dp4a_s(w1.w, x1.w, s);
+    return s;
+}
+__device__ __forceinline__ int dot8(const int4& w, const int4& x) {
+    int s = 0;
+    s = dp4a_s(w.x, x.x, s); s = dp4a_s(w.y, x.y, s); s = dp4a_s(w.z, x.z, s); s = dp4a_s(w.w, x.w, s);
+    return s;
+}
+
+// acc[b] += (this lane's 64 elements of super-block `sb`) . x[b]; weight bits are unpacked once for all B sequences.
+template <int QT, int B>
+__device__ __forceinline__ void sb_quarter_dot(const unsigned char* sb, int qq, const XSlice<QT, B>& x, float* acc) {
     if constexpr (QT == QT_Q4_K) {
-        // half `part` = sub-blocks 4p .. 4p+3
-        const uint4 hdr = *reinterpret_cast<const uint4*>(sb);
+        const uint4 hdr = *reinterpret_cast<const uint4*>(sb);         // f16 d | f16 dmin | 12 packed 6-bit scales / mins
         const float d = f16_bits_to_float(hdr.x & 0xffffu), dmin = f16_bits_to_float(hdr.x >> 16);
-        const unsigned char* sc8 = reinterpret_cast<const unsigned char*>(&hdr) + 4;     // 12 packed bytes
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {            // 32 qs bytes -> sub-blocks (ja, ja+1)
-            const int ja = 4 * part + 2 * c;
-            int sca, ma, scb, mb;
-            {   // ggml get_scale_min_k4
-                auto get = [&](int j, int& sc, int& m) {
-                    if (j < 4) { sc = sc8[j] & 63; m = sc8[j + 4] & 63; }
-                    else { sc = (sc8[j + 4] & 0xF) | ((sc8[j - 4] >> 6) << 4); m = (sc8[j + 4] >> 4) | ((sc8[j] >> 6) << 4); }
-                };
-                get(ja, sca, ma);
-                get(ja + 1, scb, mb);
-            }
-            const uint4* qp = reinterpret_cast<const uint4*>(sb + 16 + 64 * part + 32 * c);
-            const uint4 w0 = qp[0], w1 = qp[1];
-            const int ea = e0 + 64 * c;          // first element of sub-block ja in the row
-            const int4* xa = reinterpret_cast<const int4*>(x.q + (ea >> 2));
-            const int4* xb = reinterpret_cast<const int4*>(x.q + ((ea + 32) >> 2));
-            const int4 xa0 = xa[0], xa1 = xa[1], xb0 = xb[0], xb1 = xb[1];
-            int sa = 0, sb2 = 0;
-            sa = dp4a_s(w0.x & 0x0F0F0F0F, xa0.x, sa); sb2 = dp4a_s((w0.x >> 4) & 0x0F0F0F0F, xb0.x, sb2);
-            sa = dp4a_s(w0.y & 0x0F0F0F0F, xa0.y, sa); sb2 = dp4a_s((w0.y >> 4) & 0x0F0F0F0F, xb0.y, sb2);
-            sa = dp4a_s(w0.z & 0x0F0F0F0F, xa0.z, sa); sb2 = dp4a_s((w0.z >> 4) & 0x0F0F0F0F, xb0.z, sb2);
-            sa = dp4a_s(w0.w & 0x0F0F0F0F, xa0.w, sa); sb2 = dp4a_s((w0.w >> 4) & 0x0F0F0F0F, xb0.w, sb2);
-            sa = dp4a_s(w1.x & 0x0F0F0F0F, xa1.x, sa); sb2 = dp4a_s((w1.x >> 4) & 0x0F0F0F0F, xb1.x, sb2);
-            sa = dp4a_s(w1.y & 0x0F0F0F0F, xa1.y, sa); sb2 = dp4a_s((w1.y >> 4) & 0x0F0F0F0F, xb1.y, sb2);
-            sa = dp4a_s(w1.z & 0x0F0F0F0F, xa1.z, sa); sb2 = dp4a_s((w1.z >> 4) & 0x0F0F0F0F, xb1.z, sb2);
-            sa = dp4a_s(w1.w & 0x0F0F0F0F, xa1.w, sa); sb2 = dp4a_s((w1.w >> 4) & 0x0F0F0F0F, xb1.w, sb2);
-            const int ba = ea >> 5;
-            acc += d * ((float)sca * x.dx[ba] * (float)sa + (float)scb * x.dx[ba + 1] * (float)sb2)
-                 - dmin * ((float)ma * x.sx[ba] + (float)mb * x.sx[ba + 1]);
+        // ggml get_scale_min_k4 for sub-blocks ja = 2q, ja + 1
+        const int sh = 16 * (qq & 1);
+        const uint32_t ya = hdr.y >> sh, za = hdr.z >> sh, wa = hdr.w >> sh;
+        int sca, ma, scb, mb;
+        if (qq < 2) {
+            sca = ya & 63; ma = za & 63; scb = (ya >> 8) & 63; mb = (za >> 8) & 63;
+        } else {
+            sca = (wa & 0xF) | (((ya >> 6) & 3) << 4);        ma = ((wa >> 4) & 0xF) | (((za >> 6) & 3) << 4);
+            scb = ((wa >> 8) & 0xF) | (((ya >> 14) & 3) << 4); mb = ((wa >> 12) & 0xF) | (((za >> 14) & 3) << 4);
         }
-        return acc;
+        const uint4* qp = reinterpret_cast<const uint4*>(sb + 16 + 32 * qq);
+        const uint4 w0 = qp[0], w1 = qp[1];
+        int4 lo0, lo1, hi0, hi1;
+        lo0.x = w0.x & 0x0F0F0F0F; lo0.y = w0.y & 0x0F0F0F0F; lo0.z = w0.z & 0x0F0F0F0F; lo0.w = w0.w & 0x0F0F0F0F;
+        lo1.x = w1.x & 0x0F0F0F0F; lo1.y = w1.y & 0x0F0F0F0F; lo1.z = w1.z & 0x0F0F0F0F; lo1.w = w1.w & 0x0F0F0F0F;
+        hi0.x = (w0.x >> 4) & 0x0F0F0F0F; hi0.y = (w0.y >> 4) & 0x0F0F0F0F; hi0.z = (w0.z >> 4) & 0x0F0F0F0F; hi0.w = (w0.w >> 4) & 0x0F0F0F0F;
+        hi1.x = (w1.x >> 4) & 0x0F0F0F0F; hi1.y = (w1.y >> 4) & 0x0F0F0F0F; hi1.z = (w1.z >> 4) & 0x0F0F0F0F; hi1.w = (w1.w >> 4) & 0x0F0F0F0F;
+        const float dsa = d * (float)sca, dsb = d * (float)scb, dma = dmin * (float)ma, dmb = dmin * (float)mb;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int sa = dot16(lo0, lo1, x.q[b][0], x.q[b][1]);
+            const int sb2 = dot16(hi0, hi1, x.q[b][2], x.q[b][3]);
+            acc[b] += dsa * x.d[b][0] * (float)sa + dsb * x.d[b][2] * (float)sb2 - dma * x.d[b][1] - dmb * x.d[b][3];
+        }
     } else if constexpr (QT == QT_Q6_K) {
-        // half `part` = elements [128p, 128p + 128): ql[64p..], qh[32p..], scales[8p..]
+        const int h = qq >> 1, lq = qq & 1;
         const float d = f16_bits_to_float(*reinterpret_cast<const unsigned short*>(sb + 208));
-        const signed char* sc = reinterpret_cast<const signed char*>(sb + 192 + 8 * part);
-        float acc = 0.f;
+        const uint2 scw = *reinterpret_cast<const uint2*>(sb + 192 + 8 * h);        // 8 int8 scales of this half
+        const uint4 A = *reinterpret_cast<const uint4*>(sb + 64 * h + 16 * lq);
+        const uint4 Bq = *reinterpret_cast<const uint4*>(sb + 64 * h + 32 + 16 * lq);
+        const uint4 Hh = *reinterpret_cast<const uint4*>(sb + 128 + 32 * h + 16 * lq);
+        int4 q1, q2, q3, q4;
+#define CB_Q6(c) \
+        q1.c = (A.c & 0x0F0F0F0F) | ((Hh.c & 0x03030303) << 4); \
+        q2.c = (Bq.c & 0x0F0F0F0F) | (((Hh.c >> 2) & 0x03030303) << 4); \
+        q3.c = ((A.c >> 4) & 0x0F0F0F0F) | (((Hh.c >> 4) & 0x03030303) << 4); \
+        q4.c = ((Bq.c >> 4) & 0x0F0F0F0F) | (((Hh.c >> 6) & 0x03030303) << 4);
+        CB_Q6(x) CB_Q6(y) CB_Q6(z) CB_Q6(w)
+#undef CB_Q6
+        // scale of group t is byte 2t + lq of the half's 8 scales
+        const float s1 = d * (float)(signed char)((scw.x >> (8 * lq)) & 0xff), s2 = d * (float)(signed char)((scw.x >> (16 + 8 * lq)) & 0xff);
+        const float s3 = d * (float)(signed char)((scw.y >> (8 * lq)) & 0xff), s4 = d * (float)(signed char)((scw.y >> (16 + 8 * lq)) & 0xff);
 #pragma unroll
-        for (int l4 = 0; l4 < 8; ++l4) {         // 4 consecutive l per step
-            const uint32_t A = *reinterpret_cast<const uint32_t*>(sb + 64 * part + 4 * l4);
-            const uint32_t Bq = *reinterpret_cast<const uint32_t*>(sb + 64 * part + 32 + 4 * l4);
-            const uint32_t Hh = *reinterpret_cast<const uint32_t*>(sb + 128 + 32 * part + 4 * l4);
-            const int q1 = (A & 0x0F0F0F0F) | ((Hh & 0x03030303) << 4);
-            const int q2 = (Bq & 0x0F0F0F0F) | (((Hh >> 2) & 0x03030303) << 4);
-            const int q3 = ((A >> 4) & 0x0F0F0F0F) | (((Hh >> 4) & 0x03030303) << 4);
-            const int q4 = ((Bq >> 4) & 0x0F0F0F0F) | (((Hh >> 6) & 0x03030303) << 4);
-            const int e = e0 + 4 * l4;           // element of q1; q2/q3/q4 at +32/+64/+96
-            const int g = l4 >> 2;               // l / 16
-            const int x1 = x.q[e >> 2], x2 = x.q[(e + 32) >> 2], x3 = x.q[(e + 64) >> 2], x4 = x.q[(e + 96) >> 2];
-            // (q - 32) . x = q . x - 32 * sum(x) : the -32 term is applied once per 16-element group below
-            acc += d * ((float)sc[g] * x.dx[e >> 5] * (float)dp4a_s(q1, x1, 0) + (float)sc[2 + g] * x.dx[(e + 32) >> 5] * (float)dp4a_s(q2, x2, 0) +
-                        (float)sc[4 + g] * x.dx[(e + 64) >> 5] * (float)dp4a_s(q3, x3, 0) + (float)sc[6 + g] * x.dx[(e + 96) >> 5] * (float)dp4a_s(q4, x4, 0));
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {            // 8 groups of 16 elements in this half
-            const int e = e0 + 16 * g;
-            acc -= d * (float)sc[g] * x.dx[e >> 5] * 32.f * (float)x.isum16[e >> 4];
-        }
-        return acc;
+        for (int b = 0; b < B; ++b)      // (q - 32) . x = q . x - 32 sum(x)
+            acc[b] += s1 * (x.d[b][0] * (float)dot8(q1, x.q[b][0]) - x.s[b][0]) + s2 * (x.d[b][1] * (float)dot8(q2, x.q[b][1]) - x.s[b][1]) +
+                      s3 * (x.d[b][2] * (float)dot8(q3, x.q[b][2]) - x.s[b][2]) + s4 * (x.d[b][3] * (float)dot8(q4, x.q[b][3]) - x.s[b][3]);
     } else {
-        // Q8_0, quarter `part` = 64 elements = blocks 2p, 2p+1
-        float acc = 0.f;
+        const int4* wq = reinterpret_cast<const int4*>(sb + 64 * qq);
+        const int4 w0 = wq[0], w1 = wq[1], w2 = wq[2], w3 = wq[3];
+        const uint32_t dd = *reinterpret_cast<const uint32_t*>(sb + 256 + 4 * qq);
+        const float d0 = f16_bits_to_float(dd & 0xffffu), d1 = f16_bits_to_float(dd >> 16);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int blk = 2 * part + c;
-            const float d = f16_bits_to_float(*reinterpret_cast<const unsigned short*>(sb + 256 + 2 * blk));
-            const int4* wq = reinterpret_cast<const int4*>(sb + 32 * blk);
-            const int e = e0 + 32 * c;
-            const int4* xq = reinterpret_cast<const int4*>(x.q + (e >> 2));
-            const int4 w0 = wq[0], w1 = wq[1], x0 = xq[0], x1 = xq[1];
-            int s = 0;
-            s = dp4a_s(w0.x, x0.x, s); s = dp4a_s(w0.y, x0.y, s); s = dp4a_s(w0.z, x0.z, s); s = dp4a_s(w0.w, x0.w, s);
-            s = dp4a_s(w1.x, x1.x, s); s = dp4a_s(w1.y, x1.y, s); s = dp4a_s(w1.z, x1.z, s); s = dp4a_s(w1.w, x1.w, s);
-            acc += d * x.dx[e >> 5] * (float)s;
-        }
-        return acc;
+        for (int b = 0; b < B; ++b)
+            acc[b] += d0 * x.d[b][0] * (float)dot16(w0, w1, x.q[b][0], x.q[b][1]) + d1 * x.d[b][2] * (float)dot16(w2, w3, x.q[b][2], x.q[b][3]);
     }
 }
 
-constexpr int QG_WARPS = 16;
-constexpr int QG_THREADS = QG_WARPS * 32;
+// Sum N per-lane values over the warp in N + log2(32/N) - 1 shuffles (recursive halving): on return every lane holds in
+// v[0] the warp total of value `idx`.
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane, int& idx) {
+    idx = 0;
+    int off = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        if (up) idx += n / 2;
+    }
+    for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
 
+// ------------------------------------------------------------------------------------------------ activation quantiser
+// One CTA per sequence: x (f32, optionally times the RMSNorm weight; 1/rms kept aside) -> int8 per 32-element block in
+// exactly the shared-memory image the GEMV consumes (see xq_swz), written once to global so the 148 GEMV CTAs fetch
+// 1.5 B/element with one bulk copy each instead of re-reading and re-quantising 4 B/element.
+constexpr int XQ_THREADS = 1024;
+__host__ __device__ inline size_t xq_seq_bytes(int K) { return (size_t)K + (size_t)(K / 32) * 8 + (size_t)(K / 16) * 4; }
+
+__global__ void __launch_bounds__(XQ_THREADS, 1)
+xquant_kernel(const float* __restrict__ x, int ldx, int K, const float* __restrict__ norm_w, float eps, int B, unsigned char* __restrict__ out) {
+    __shared__ float red[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* xq = out + (size_t)b * xq_seq_bytes(K);
+    float2* dsp = reinterpret_cast<float2*>(xq + K);
+    int* isp = reinterpret_cast<int*>(xq + K + (K / 32) * 8);
+    pdl_wait();
+    pdl_launch_dependents();
+    float ssq = 0.f;
+    for (int g = warp; g < K / 128; g += XQ_THREADS / 32) {          // 4 blocks per warp pass, 4 elements per lane
+        const int e = g * 128 + lane * 4;
+        float4 w = *reinterpret_cast<const float4*>(x + (size_t)b * ldx + e);
+        if (norm_w) {
+            ssq += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
+            const float4 nw = *reinterpret_cast<const float4*>(norm_w + e);
+            w.x *= nw.x; w.y *= nw.y; w.z *= nw.z; w.w *= nw.w;
+        }
+        float amax = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fmaxf(fabsf(w.z), fabsf(w.w)));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+        const float d = amax / 127.f;
+        int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (d > 0.f) { q0 = __float2int_rn(w.x / d); q1 = __float2int_rn(w.y / d); q2 = __float2int_rn(w.z / d); q3 = __float2int_rn(w.w / d); }
+        *reinterpret_cast<uint32_t*>(xq + xq_swz(e)) =
+            (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
+        int s16 = q0 + q1 + q2 + q3;
+        s16 += __shfl_xor_sync(0xffffffffu, s16, 1); s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
+        const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 4);
+        if ((lane & 3) == 0) isp[e >> 4] = s16;
+        if ((lane & 7) == 0) dsp[e >> 5] = make_float2(d, d * (float)s32);
+    }
+    const float tot = block_sum(ssq, red);
+    if (tid == 0) reinterpret_cast<float*>(out + (size_t)B * xq_seq_bytes(K))[b] = norm_w ? rsqrtf(tot / (float)K + eps) : 1.f;
+}
+
+size_t xquant_bytes(int B, int K) { return (size_t)B * xq_seq_bytes(K) + 16; }
+
+int xquant_launch(cudaStream_t st, int B, const float* x, int ldx, int K, const float* norm_w, float eps, unsigned char* out, bool pdl) {
+    if ((K % 256) != 0 || B < 1 || B > 4) return -1000;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B);
+    cfg.blockDim = dim3(XQ_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, xquant_kernel, x, ldx, K, norm_w, eps, B, out);
+}
+
+#ifndef QG_R_DEF                    // tools/qgemv_bench.cu sweeps these
+#define QG_R_DEF 4
+#define QG_DEPTH_DEF 2
+#define QG_W1_DEF 16
+#define QG_W4_DEF 12
+#endif
+constexpr int QG_R = QG_R_DEF;     // rows per tile
+constexpr int QG_KT = 8;           // super-blocks per tile row (32 lanes x 64 elements)
+constexpr int QG_DEPTH = QG_DEPTH_DEF;   // tiles in flight per warp
+__host__ __device__ constexpr int qg_warps(int B) { return B >= 4 ? QG_W4_DEF : QG_W1_DEF; }
+
+// One CTA per SM owns a contiguous block of output rows.  Work unit = tile of QG_R rows x QG_KT super-blocks; a warp takes
+// a contiguous range of tiles (k fastest), streams each through its private cp.async ring, keeps its activation slice in
+// registers and one f32 accumulator per (row, sequence), and flushes them to the CTA's shared row accumulators when it
+// moves on to another row group.
 template <int B, int QT>
-__global__ void __launch_bounds__(QG_THREADS, 1)
+__global__ void __launch_bounds__(qg_warps(B) * 32, 1)
 qgemv_kernel(QGemvArgs qa) {
     using TR = QTraits<QT>;
-    constexpr int SBP = 32 / TR::LPS;                  // super-blocks per warp pass
-    constexpr int SLOT = SBP * TR::SB;                 // bytes per ring slot
-    constexpr int CPS = SLOT / 16;                     // 16-byte chunks per slot
+    constexpr int QG_MAXW = qg_warps(B);
+    const int QG_WARPS = (int)(blockDim.x >> 5);       // chosen at launch so rings + activations fit in shared memory
+    const int QG_THREADS = (int)blockDim.x;
+    constexpr int ROWB = QG_KT * TR::SB;               // bytes of one tile row
+    constexpr int SLOT = QG_R * ROWB;                  // bytes per ring slot
     const GemvArgs& a = qa.g;
     extern __shared__ __align__(1024) unsigned char qsm[];
-    // layout: [rings: QG_WARPS * DEPTH * SLOT][per b: xq K | dx K/32 f32 | sx K/32 f32 | isum16 K/16 i32][acc B * rpc f32]
+    // layout: [rings: QG_WARPS * DEPTH * SLOT][per b: xq K | {d, d*sum} K/32 float2 | isum16 K/16 i32][1/rms B f32, 16 B][acc B * rpc f32]
     const int K = a.K;
     const size_t xb = (size_t)K + (size_t)(K / 32) * 8 + (size_t)(K / 16) * 4;       // bytes of quantised activation per sequence
-    unsigned char* xbase = qsm + (size_t)QG_WARPS * TR::DEPTH * SLOT;
+    unsigned char* xbase = qsm + (size_t)QG_WARPS * QG_DEPTH * SLOT;
     const int rows_per_unit = (qa.epi == GEMV_SILU_MUL) ? 2 : 1;
     const int units = a.N / rows_per_unit;
     const int upc = (units + gridDim.x - 1) / gridDim.x;
     const int rpc = upc * rows_per_unit;
     const int r0 = blockIdx.x * rpc;
     const int nrows = max(0, min(a.N, r0 + rpc) - r0);
-    float* acc_s = reinterpret_cast<float*>(xbase + (size_t)B * xb);
-    __shared__ float red[32];
-    __shared__ float rstd_s[B];
-    __shared__ float wbest_v[QG_WARPS][B];
-    __shared__ int wbest_i[QG_WARPS][B];
+    float* acc_s = reinterpret_cast<float*>(xbase + (size_t)B * xb + 16);
+    __shared__ uint64_t xbar;
+    __shared__ float wbest_v[QG_MAXW][B];
+    __shared__ int wbest_i[QG_MAXW][B];
     __shared__ int is_last_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t spr = (uint32_t)(K >> 8);                                          // super-blocks per row
-    const uint32_t total_sb = (uint32_t)nrows * spr;
-    const uint32_t total_pass = (total_sb + SBP - 1) / SBP;
-    const uint32_t ppw = (total_pass + QG_WARPS - 1) / QG_WARPS;                      // passes per warp
-    const uint32_t sb_begin = min(total_sb, (uint32_t)warp * ppw * SBP);
-    const uint32_t sb_end = min(total_sb, ((uint32_t)warp + 1) * ppw * SBP);
-    const uint32_t npass = (sb_end - sb_begin + SBP - 1) / SBP;
-    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.W) + ((size_t)r0 * spr + sb_begin) * TR::SB;
-    unsigned char* ring = qsm + (size_t)warp * TR::DEPTH * SLOT;
+    const uint32_t nkt = (spr + QG_KT - 1) / QG_KT;                                   // k-tiles per row
+    // rows per tile: QG_R when that leaves every warp at least two tiles, fewer for short row blocks (q/k/v/o projections)
+    uint32_t R = QG_R;
+    while (R > 1 && (((uint32_t)nrows + R - 1) / R) * nkt < 2u * (uint32_t)QG_WARPS) R >>= 1;
+    const uint32_t nrg = ((uint32_t)nrows + R - 1) / R;                               // row groups
+    const uint32_t ntile = nrg * nkt;
+    const uint32_t tpw = (ntile + QG_WARPS - 1) / QG_WARPS;
+    const uint32_t t_begin = min(ntile, (uint32_t)warp * tpw), t_end = min(ntile, ((uint32_t)warp + 1) * tpw);
+    const uint32_t nt = t_end - t_begin;
+    const unsigned char* wbase = reinterpret_cast<const unsigned char*>(a.W) + (size_t)r0 * spr * TR::SB;
+    unsigned char* ring = qsm + (size_t)warp * QG_DEPTH * SLOT;
     const uint32_t ring_u32 = smem_u32(ring);
 
     auto issue = [&](uint32_t p) {
-        if (p < npass) {
-            const uint32_t nsb = min((uint32_t)SBP, sb_end - sb_begin - p * SBP);
-            const uint32_t nchunk = nsb * TR::SB / 16;
-            const unsigned char* src = gsrc + (size_t)p * SLOT;
-            const uint32_t dst = ring_u32 + (p % TR::DEPTH) * SLOT;
-            for (uint32_t c = lane; c < nchunk; c += 32)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + (size_t)c * 16) : "memory");
+        if (p < nt) {
+            const uint32_t t = t_begin + p, rg = t / nkt, kt = t - rg * nkt;
+            const uint32_t nr = min(R, (uint32_t)nrows - rg * R);
+            const uint32_t cpr = min((uint32_t)QG_KT, spr - kt * QG_KT) * (TR::SB / 16);      // 16-byte chunks per tile row
+            const uint32_t dst = ring_u32 + (p % QG_DEPTH) * SLOT;
+            for (uint32_t r = 0; r < nr; ++r) {
+                const unsigned char* src = wbase + ((size_t)(rg * R + r) * spr + (size_t)kt * QG_KT) * TR::SB;
+                for (uint32_t c = lane; c < cpr; c += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * ROWB + c * 16), "l"(src + (size_t)c * 16) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll
-    for (int p = 0; p < TR::DEPTH; ++p) issue((uint32_t)p);
+    for (int p = 0; p < QG_DEPTH; ++p) issue((uint32_t)p);
     for (int i = tid; i < B * rpc; i += QG_THREADS) acc_s[i] = 0.f;
+    if (tid == 0) { mbar_init(&xbar, 1); fence_barrier_init(); }
+    __syncthreads();
 
     pdl_wait();
     pdl_launch_dependents();
 
-    // ---- quantise the activation(s): int8 per 32-element block, RMSNorm weight folded in, 1/rms kept aside ----
-#pragma unroll
-    for (int b = 0; b < B; ++b) {
-        unsigned char* xq = xbase + (size_t)b * xb;
-        float* dxp = reinterpret_cast<float*>(xq + K);
-        float* sxp = dxp + K / 32;
-        int* isp = reinterpret_cast<int*>(sxp + K / 32);
-        float ssq = 0.f;
-        for (int blk = warp; blk < K / 32; blk += QG_WARPS) {
-            float v = a.x[(size_t)b * a.ldx + blk * 32 + lane];
-            if (qa.norm) { ssq += v * v; v *= a.norm_w[blk * 32 + lane]; }
-            const float amax = warp_max(fabsf(v));
-            const float d = amax / 127.f;
-            const int q = (d > 0.f) ? __float2int_rn(v / d) : 0;
-            xq[blk * 32 + lane] = (unsigned char)(signed char)q;
-            int s16 = q;
-            s16 += __shfl_xor_sync(0xffffffffu, s16, 1); s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
-            s16 += __shfl_xor_sync(0xffffffffu, s16, 4); s16 += __shfl_xor_sync(0xffffffffu, s16, 8);
-            const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 16);
-            if ((lane & 15) == 0) isp[blk * 2 + (lane >> 4)] = s16;
-            if (lane == 0) { dxp[blk] = d; sxp[blk] = d * (float)s32; }
-        }
-        if (qa.norm) {
-            const float tot = block_sum(ssq, red);
-            if (tid == 0) rstd_s[b] = rsqrtf(tot / (float)K + a.eps);
-        }
+    // ---- fetch the activations quantised by xquant_kernel: one bulk copy of the ready-made shared-memory image ----
+    const uint32_t xbytes = (uint32_t)(B * xb) + 16u;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&xbar, xbytes);
+        bulk_load(xbase, qa.xq, xbytes, &xbar);
     }
-    __syncthreads();
+    mbar_wait(&xbar, 0);
+    const float* rstd_s = reinterpret_cast<const float*>(xbase + (size_t)B * xb);
 
-    // ---- stream this warp's super-blocks ----
+    // ---- stream this warp's tiles ----
     {
-        const int part = lane % TR::LPS;
-        const int sl = lane / TR::LPS;                         // super-block slot inside the pass
-        const bool whole_row_pass = (spr % SBP) == 0;          // a pass never straddles rows: one reduction per pass
-        for (uint32_t p = 0; p < npass; ++p) {
-            asm volatile("cp.async.wait_group %0;" ::"n"(TR::DEPTH - 1) : "memory");
+        const int sbk = lane >> 2, qq = lane & 3;              // this lane's super-block within the tile row and its quarter
+        XSlice<QT, B> xs;
+        float acc[QG_R * B];
+#pragma unroll
+        for (int i = 0; i < QG_R * B; ++i) acc[i] = 0.f;
+        uint32_t cur_rg = 0xffffffffu, cur_kt = 0xffffffffu;
+        auto flush = [&]() {
+            int idx;
+            warp_reduce_scatter<QG_R * B>(acc, lane, idx);
+            const int r = idx / B, b = idx % B;
+            const uint32_t row = cur_rg * R + r;
+            if ((lane & (32 / (QG_R * B) - 1)) == 0 && (uint32_t)r < R && row < (uint32_t)nrows) atomicAdd(&acc_s[(size_t)b * rpc + row], acc[0]);
+#pragma unroll
+            for (int i = 0; i < QG_R * B; ++i) acc[i] = 0.f;
+        };
+        for (uint32_t p = 0; p < nt; ++p) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(QG_DEPTH - 1) : "memory");
             __syncwarp();
-            const uint32_t sbi = sb_begin + p * SBP + sl;      // super-block index inside the CTA's row block
-            const bool valid = sbi < sb_end;
-            const uint32_t row = valid ? sbi / spr : 0;
-            const uint32_t sbk = sbi - row * spr;
-            const unsigned char* sb = ring + (p % TR::DEPTH) * SLOT + sl * TR::SB;
-            const int e0 = (int)sbk * 256 + part * (256 / TR::LPS);
-            float part_acc[B];
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-                part_acc[b] = 0.f;
-                if (valid) {
-                    const unsigned char* xq = xbase + (size_t)b * xb;
-                    XQ x;
-                    x.q = reinterpret_cast<const int*>(xq);
-                    x.dx = reinterpret_cast<const float*>(xq + K);
-                    x.sx = x.dx + K / 32;
-                    x.isum16 = reinterpret_cast<const int*>(x.sx + K / 32);
-                    part_acc[b] = sb_part_dot<QT>(sb, part, e0, x);
-                }
+            const uint32_t t = t_begin + p, rg = t / nkt, kt = t - rg * nkt;
+            if (rg != cur_rg) {
+                if (cur_rg != 0xffffffffu) flush();
+                cur_rg = rg;
             }
-            if (whole_row_pass) {
-                const uint32_t prow = (sb_begin + p * SBP) / spr;
+            const bool active = kt * QG_KT + sbk < spr;
+            if (kt != cur_kt) {
+                if (active) xs.load(xbase, xb, K, (int)(kt * QG_KT) + sbk, qq);
+                cur_kt = kt;
+            }
+            const uint32_t nr = min(R, (uint32_t)nrows - rg * R);
+            const unsigned char* sb = ring + (p % QG_DEPTH) * SLOT + sbk * TR::SB;
+            if (active) {
 #pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    const float v = warp_sum(part_acc[b]);
-                    if (lane == 0) atomicAdd(&acc_s[(size_t)b * rpc + prow], v);
-                }
-            } else if (valid) {
-#pragma unroll
-                for (int b = 0; b < B; ++b) atomicAdd(&acc_s[(size_t)b * rpc + row], part_acc[b]);
+                for (int r = 0; r < QG_R; ++r)
+                    if ((uint32_t)r < nr) sb_quarter_dot<QT, B>(sb + r * ROWB, qq, xs, acc + r * B);
             }
             __syncwarp();
-            issue(p + TR::DEPTH);
+            issue(p + QG_DEPTH);
         }
+        if (cur_rg != 0xffffffffu) flush();
     }
     __syncthreads();
 
@@ -370,8 +473,12 @@ static int qgemv_launch_t(cudaStream_t st, const QGemvArgs& qa, int num_sms, boo
     const int rpu = qa.epi == GEMV_SILU_MUL ? 2 : 1;
     const int rpc = ((a.N / rpu) + num_sms - 1) / num_sms * rpu;
     const size_t xb = (size_t)a.K + (size_t)(a.K / 32) * 8 + (size_t)(a.K / 16) * 4;
-    const size_t smem = (size_t)QG_WARPS * TR::DEPTH * (32 / TR::LPS) * TR::SB + (size_t)B * xb + (size_t)B * rpc * 4 + 16;
-    if (smem > 227 * 1024) return -1000;
+    const size_t fixed = (size_t)B * xb + 16 + (size_t)B * rpc * 4 + 16, slot = (size_t)QG_DEPTH * QG_R * QG_KT * TR::SB;
+    int QG_WARPS = qg_warps(B);
+    while (QG_WARPS > 4 && fixed + QG_WARPS * slot > 226 * 1024) --QG_WARPS;
+    const int QG_THREADS = QG_WARPS * 32;
+    const size_t smem = fixed + QG_WARPS * slot;
+    if (smem > 226 * 1024) return -1000;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(qgemv_kernel<B, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

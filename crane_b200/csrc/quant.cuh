@@ -22,11 +22,16 @@ inline int q_src_block_elems(int qt) { return qt == QT_Q8_0 ? 32 : 256; }
 void q_repack_rows(int qt, const unsigned char* src, unsigned char* dst, size_t rows, int K);
 
 struct QGemvArgs {
-    GemvArgs g;        // W is reinterpreted as the quantised bytes; epilogue fields as for the bf16 GEMV
+    GemvArgs g;        // W is reinterpreted as the quantised bytes; epilogue fields as for the bf16 GEMV; g.x / g.norm_w unused
     int qtype;
     int epi;           // GemvEpi
-    int norm;          // fold RMSNorm (g.norm_w) into the activation
+    int norm;          // the activations were RMS-normalised by xquant_launch: scale the outputs by its 1/rms
+    const unsigned char* xq;   // activations of the B sequences, quantised by xquant_launch (xquant_bytes(B, K) bytes)
 };
+
+// Quantise B activation rows (f32, row stride ldx; times norm_w when non-null) for qgemv_launch.
+size_t xquant_bytes(int B, int K);
+int xquant_launch(cudaStream_t st, int B, const float* x, int ldx, int K, const float* norm_w, float eps, unsigned char* out, bool pdl);
 
 int qgemv_launch(cudaStream_t st, int B, const QGemvArgs& a, int num_sms, bool pdl);
 // rows x K quantised -> bf16 row-major (prefill GEMM operand)
