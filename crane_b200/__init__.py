@@ -78,7 +78,7 @@ _SIGNATURES = {
     "crane_b200_next_mrope_pos": (C.c_uint32, [C.c_void_p]),
     "crane_b200_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_size_t)]),
     "crane_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
-    "crane_b200_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+    "crane_b200_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int]),
 }
 
@@ -384,8 +384,8 @@ class Qwen3TTSModel(Engine):
         return (frames[:k], fl[:k], gl[:k]) if want_logits else frames[:k]
 
 
-def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_init=None, use_simt=False, device=0):
-    """Kernel-level test hook: epilogue(A[M,K] x W[N,K]^T) with bf16 bit-pattern inputs."""
+def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_init=None, use_simt=False, device=0, a_lo_bits=None):
+    """Kernel-level test hook: epilogue((A + A_lo)[M,K] x W[N,K]^T) with bf16 bit-pattern inputs."""
     lib = load_library()
     M, K = a_bits.shape
     N = w_bits.shape[0]
@@ -393,7 +393,9 @@ def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_in
     cols = N // 2 if mode == EPI_SILU_MUL_BF16 else N
     out = np.zeros((M, cols), dtype=np.uint16 if half else np.float32) if out_init is None else np.ascontiguousarray(out_init).copy()
     b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
-    rc = lib.crane_b200_op_gemm(device, _ptr(np.ascontiguousarray(a_bits)), _ptr(np.ascontiguousarray(w_bits)), M, N, K, mode,
+    alo = None if a_lo_bits is None else np.ascontiguousarray(a_lo_bits)
+    rc = lib.crane_b200_op_gemm(device, _ptr(np.ascontiguousarray(a_bits)), None if alo is None else _ptr(alo),
+                                _ptr(np.ascontiguousarray(w_bits)), M, N, K, mode,
                                 None if b is None else _ptr(b), _ptr(out), 1 if use_simt else 0)
     if rc != OK:
         raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())

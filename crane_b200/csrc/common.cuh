@@ -41,7 +41,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);   // .x = a (low half), .y = b
     return *reinterpret_cast<uint32_t*>(&t);
 }
+// (a, b) -> packed bf16 pair `hi` and the packed bf16 pair `lo` of the rounding residuals: a ~= hi.x + lo.x to ~16 mantissa bits
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16(a, b);
+    lo = pack_bf16(a - bf16lo(hi), b - bf16hi(hi));
+}
 __device__ __forceinline__ float round_bf16(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+// the value a (hi, lo) bf16 pair reproduces
+__device__ __forceinline__ float round_bf16_split(float a) {
+    const float h = round_bf16(a);
+    return h + round_bf16(a - h);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

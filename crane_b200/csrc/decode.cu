@@ -395,6 +395,9 @@ attn_decode_kernel(AttnDecArgs a) {
     extern __shared__ __align__(16) unsigned char asm_[];
     bf16* k_t = reinterpret_cast<bf16*>(asm_);
     bf16* v_t = k_t + TILE * D;
+    bf16* kl_t = v_t + TILE * D;          // split precision only: low-order planes of the same tile
+    bf16* vl_t = kl_t + TILE * D;
+    const bool split_kv = a.kv_lo_off != 0;
     float* mo_s = reinterpret_cast<float*>(asm_);          // [NW][NREP][D], aliases the tiles after the token loop
     __shared__ float q_s[NREP][D];
     __shared__ float knew_s[D], vnew_s[D];
@@ -429,6 +432,11 @@ attn_decode_kernel(AttnDecArgs a) {
             const uint32_t kd = smem_u32(k_t + r * D + ch * 8), vd = smem_u32(v_t + r * D + ch * 8);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd), "l"(a.k_pool + off) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd), "l"(a.v_pool + off) : "memory");
+            if (split_kv) {
+                const uint32_t kld = smem_u32(kl_t + r * D + ch * 8), vld = smem_u32(vl_t + r * D + ch * 8);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kld), "l"(a.k_pool + a.kv_lo_off + off) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vld), "l"(a.v_pool + a.kv_lo_off + off) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -484,12 +492,12 @@ attn_decode_kernel(AttnDecArgs a) {
                 for (int jj = 0; jj < NE; ++jj) if (jj == (lo ? j + RJ : j - RJ)) other = e[jj];
                 r = lo ? (e[j] * c - other * s) : (other * s + e[j] * c);
             }
-            dst[lane + 32 * j] = is_k ? round_bf16(r) : r;
+            dst[lane + 32 * j] = is_k ? (split_kv ? round_bf16_split(r) : round_bf16(r)) : r;
         }
     }
     if (split == s_last && warp == NW - 1) {
         const float* vsrc = qkv + q_span + kv_dim + kvh * D;
-        for (int i = lane; i < D; i += 32) vnew_s[i] = round_bf16(vsrc[i]);
+        for (int i = lane; i < D; i += 32) vnew_s[i] = split_kv ? round_bf16_split(vsrc[i]) : round_bf16(vsrc[i]);
     }
     __syncthreads();
     if (split == s_last) {   // append the new token to its page
@@ -497,8 +505,13 @@ attn_decode_kernel(AttnDecArgs a) {
         const int page = bt[t / KV_PAGE];
         const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
         for (int i = tid; i < D; i += 256) {
-            a.k_pool[off + i] = __float2bfloat16_rn(knew_s[i]);
-            a.v_pool[off + i] = __float2bfloat16_rn(vnew_s[i]);
+            const bf16 kh = __float2bfloat16_rn(knew_s[i]), vh = __float2bfloat16_rn(vnew_s[i]);
+            a.k_pool[off + i] = kh;
+            a.v_pool[off + i] = vh;
+            if (split_kv) {
+                a.k_pool[a.kv_lo_off + off + i] = __float2bfloat16_rn(knew_s[i] - __bfloat162float(kh));
+                a.v_pool[a.kv_lo_off + off + i] = __float2bfloat16_rn(vnew_s[i] - __bfloat162float(vh));
+            }
         }
     }
 
@@ -532,6 +545,14 @@ attn_decode_kernel(AttnDecArgs a) {
                 kf[4] = bf16lo(kr.z); kf[5] = bf16hi(kr.z); kf[6] = bf16lo(kr.w); kf[7] = bf16hi(kr.w);
                 vf[0] = bf16lo(vr.x); vf[1] = bf16hi(vr.x); vf[2] = bf16lo(vr.y); vf[3] = bf16hi(vr.y);
                 vf[4] = bf16lo(vr.z); vf[5] = bf16hi(vr.z); vf[6] = bf16lo(vr.w); vf[7] = bf16hi(vr.w);
+                if (split_kv) {
+                    const uint4 kl = *reinterpret_cast<const uint4*>(kl_t + r * D + gl * EPL);
+                    const uint4 vl = *reinterpret_cast<const uint4*>(vl_t + r * D + gl * EPL);
+                    kf[0] += bf16lo(kl.x); kf[1] += bf16hi(kl.x); kf[2] += bf16lo(kl.y); kf[3] += bf16hi(kl.y);
+                    kf[4] += bf16lo(kl.z); kf[5] += bf16hi(kl.z); kf[6] += bf16lo(kl.w); kf[7] += bf16hi(kl.w);
+                    vf[0] += bf16lo(vl.x); vf[1] += bf16hi(vl.x); vf[2] += bf16lo(vl.y); vf[3] += bf16hi(vl.y);
+                    vf[4] += bf16lo(vl.z); vf[5] += bf16hi(vl.z); vf[6] += bf16lo(vl.w); vf[7] += bf16hi(vl.w);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < EPL; ++j) { kf[j] = 0.f; vf[j] = 0.f; }
@@ -646,12 +667,12 @@ attn_decode_kernel(AttnDecArgs a) {
 
 template <int D, int NREP>
 static int attn_decode_launch_t(cudaStream_t st, int B, const AttnDecArgs& a, bool pdl) {
-    constexpr int SMEM = 65536;
-    static bool set = false;
-    if (!set) {
+    const int SMEM = a.kv_lo_off ? 131072 : 65536;
+    static int set = 0;
+    if (set < SMEM) {
         cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<D, NREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return (int)e;
-        set = true;
+        set = SMEM;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.nkv * ATTN_NSPLIT, B);

@@ -77,6 +77,7 @@ struct AttnDecArgs {
     int nh, nkv;
     float scale;
     float* out;              // [B, nh*D] f32
+    long long kv_lo_off;     // split precision: element offset of the pools' low-order planes (0 = plain bf16 pages)
 };
 
 int gemv_max_group(int K, int N, int num_sms);

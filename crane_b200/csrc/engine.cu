@@ -262,6 +262,15 @@ struct crane_b200_model {
     uint64_t launches = 0;
     uint64_t graph_launches[3] = {0, 0, 0};
     unsigned char* xq_buf = nullptr;   // activations quantised for the quantised GEMVs (xquant_launch)
+    // Split precision (default): every bf16 activation operand / KV page has a low-order plane (x = hi + lo) so the prefill
+    // tensor-core path carries ~16 mantissa bits; lo_* = element offset of that plane from the buffer base, 0 when off.
+    bool split = true;
+    long long lo_xn = 0, lo_q = 0, lo_attn = 0, lo_act = 0, lo_kv = 0;
+    long long lo_vpvb = 0, lo_vxn = 0, lo_vqkvb = 0, lo_vattn = 0, lo_vact = 0, lo_vm1 = 0;
+    bf16* dalloc_act(size_t n, long long& lo_off) {     // bf16 activation buffer (+ its lo plane)
+        lo_off = split ? (long long)n : 0;
+        return dalloc<bf16>(split ? 2 * n : n);
+    }
     std::string last_error;
 
     // ---------------------------------------------------------------------------------------------
@@ -327,9 +336,11 @@ struct crane_b200_model {
     void gdn_args(GdnArgs& g, const LayerW& l, int S, const float* proj, float* conv, float* qn, float* kn, float* gb, float* y) const;
     void reset_recurrent_state();
     void encode_images(const float* pv, const uint32_t* grid, size_t n_images);
-    void gemm(const bf16* A, int lda, const bf16* W, int M, int N, int K, int mode, void* out, int ldo, const float* bias) {
-        GemmEpi ep{out, ldo, bias, mode};
-        LAUNCH_OK(gemm_bf16_launch(stream, A, lda, W, M, N, K, ep, use_simt));
+    // a_lo / out_lo: element offsets of the low-order planes of A and of a bf16 `out` (0 = plain bf16)
+    void gemm(const bf16* A, long long a_lo, int lda, const bf16* W, int M, int N, int K, int mode, void* out, int ldo, const float* bias,
+              long long out_lo = 0) {
+        GemmEpi ep{out, out_lo ? (void*)((bf16*)out + out_lo) : nullptr, ldo, bias, mode};
+        LAUNCH_OK(gemm_bf16_launch(stream, A, a_lo ? A + a_lo : nullptr, lda, W, M, N, K, ep, use_simt));
         ++launches;
     }
 };
@@ -415,12 +426,16 @@ void crane_b200_model::parse_config(const char* json) {
         use_simt = e.string("gemm", "tcgen05") == "simt";
         use_graphs = e.boolean("graphs", true);
         use_pdl = e.boolean("pdl", true);
+        const std::string prec = e.string("precision", "split");
+        if (prec == "bf16") split = false;
+        else if (prec != "split") fail(CRANE_B200_INVALID_ARG, "engine.precision must be \"split\" or \"bf16\"");
         if (e.string("vit_act", "erf") == "tanh") vit_gelu_mode = EPI_GELU_TANH_BF16;
         if (e.string("merger_act", "tanh") == "erf") merger_gelu_mode = EPI_GELU_ERF_BF16;
     }
     if (const char* g = getenv("CRANE_B200_GEMM")) use_simt = std::string(g) == "simt";
     if (const char* g = getenv("CRANE_B200_GRAPHS")) use_graphs = std::string(g) != "0";
     if (const char* g = getenv("CRANE_B200_PDL")) use_pdl = std::string(g) != "0";
+    if (const char* g = getenv("CRANE_B200_PRECISION")) split = std::string(g) != "bf16";
     if (root.has("engine")) use_persistent = root.at("engine").boolean("persistent", false);
     if (const char* g = getenv("CRANE_B200_PERSISTENT")) use_persistent = std::string(g) != "0";
     if (max_batch < 1 || max_batch > 64) fail(CRANE_B200_INVALID_ARG, "max_batch %d (1..64 sequence slots)", max_batch);
@@ -873,8 +888,8 @@ void crane_b200_model::finalize() {
     const size_t page_elems = (size_t)nkv * KV_PAGE * D;
     for (auto& l : layers) {
         if (l.full) {
-            l.k_pool = dalloc<bf16>((size_t)max_batch * max_pages * page_elems);
-            l.v_pool = dalloc<bf16>((size_t)max_batch * max_pages * page_elems);
+            l.k_pool = dalloc_act((size_t)max_batch * max_pages * page_elems, lo_kv);
+            l.v_pool = dalloc_act((size_t)max_batch * max_pages * page_elems, lo_kv);
         } else {   // GdnLayerCache (ops/gdn/cache.rs:15-45): conv window + [Hv, K, V] f32 state, zero-initialised
             l.conv_state = dalloc<float>((size_t)conv_dim() * ck);
             l.rec_state = dalloc<float>((size_t)nv * dk * dv);
@@ -912,7 +927,7 @@ void crane_b200_model::finalize() {
     CUDA_OK(cudaMemset(counters, 0, (size_t)B * nkv * sizeof(unsigned int)));
     CUDA_OK(cudaMemset(ticket, 0, sizeof(unsigned int)));
     CUDA_OK(cudaMemset(state, 0, B * sizeof(SeqState)));
-    use_persistent = use_persistent && !hybrid && !any_quant && decode_persistent_supported(D, nh / nkv, H, I, q_dim(), nkv, num_sms);
+    use_persistent = use_persistent && !hybrid && !any_quant && !split && decode_persistent_supported(D, nh / nkv, H, I, q_dim(), nkv, num_sms);
     if (use_persistent) {
         std::vector<PLayer> pl(L);
         for (int i = 0; i < L; ++i) {
@@ -944,15 +959,15 @@ void crane_b200_model::ensure_prefill_ws(int S) {
     const int cap = (S + 127) / 128 * 128;
     x = dalloc<float>((size_t)cap * H);
     qkv = dalloc<float>((size_t)cap * qkv_dim());
-    xn = dalloc<bf16>((size_t)cap * H);
-    q_bf = dalloc<bf16>((size_t)cap * q_dim());
-    attn_bf = dalloc<bf16>((size_t)cap * std::max(q_dim(), value_dim()));
+    xn = dalloc_act((size_t)cap * H, lo_xn);
+    q_bf = dalloc_act((size_t)cap * q_dim(), lo_q);
+    attn_bf = dalloc_act((size_t)cap * std::max(q_dim(), value_dim()), lo_attn);
     if (hybrid) {
         g_proj = dalloc<float>((size_t)cap * gdn_in_pad); g_conv = dalloc<float>((size_t)cap * conv_dim());
         g_qn = dalloc<float>((size_t)cap * nk * dk); g_kn = dalloc<float>((size_t)cap * nk * dk);
         g_gb = dalloc<float>((size_t)cap * nv * 2); g_y = dalloc<float>((size_t)cap * value_dim());
     }
-    act_bf = dalloc<bf16>((size_t)cap * I);
+    act_bf = dalloc_act((size_t)cap * I, lo_act);
     ids_dev = dalloc<uint32_t>(cap);
     pos3_dev = dalloc<int>((size_t)3 * cap);
     rows_dev = dalloc<int>(cap);
@@ -991,7 +1006,7 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) 
             a.q_norm_w = l.qn; a.k_norm_w = l.kn; a.eps = eps; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.axis_of = axis_of;
             a.state = state; a.block_table = block_table; a.max_pages = max_pages; a.k_pool = l.k_pool; a.v_pool = l.v_pool;
             a.nh = nh; a.nkv = nkv; a.scale = 1.0f / std::sqrt((float)D);
-            a.out = attn_dec;
+            a.out = attn_dec; a.kv_lo_off = lo_kv;
             LAUNCH_OK(attn_decode_launch(stream, B, D, a, pdl));
             ++launches;   // attention
             linear_decode(GEMV_RESID, false, l.wo, l.q_wo, l.qt_o, H, q_dim(), attn_dec, q_dim(), nullptr, x_dec, H, nullptr, B);
@@ -1128,7 +1143,7 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     const int qd = q_dim();
     for (int li = 0; li < L; ++li) {
         LayerW& l = layers[li];
-        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln1, eps, xn));
+        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln1, eps, xn, lo_xn));
         if (l.full) {
             const bf16* wqkv = l.wqkv;
             if (l.qt_q) {   // dequantise q | k | v into consecutive rows of the scratch -> one merged GEMM
@@ -1137,31 +1152,32 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
                 dequant_for_gemm(l.q_wk, l.qt_k, kvd, H, qs);
                 wqkv = dequant_for_gemm(l.q_wv, l.qt_v, kvd, H, qs + kvd);
             }
-            gemm(xn, H, wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
+            gemm(xn, lo_xn, H, wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
             RopeAppendArgs ra = {};
             ra.qkv = qkv; ra.q_stride = q_stride(); ra.rot_half = rot_half;
             ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
             ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = bt_cur(); ra.k_pool = l.k_pool; ra.v_pool = l.v_pool;
-            ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf;
+            ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf; ra.q_lo_off = lo_q; ra.kv_lo_off = lo_kv;
             LAUNCH_OK(rope_append_launch(stream, D, ra));
             FlashArgs fa = {};
             fa.q = q_bf; fa.q_stride = qd; fa.k_pool = l.k_pool; fa.v_pool = l.v_pool; fa.block_table = bt_cur(); fa.nh = nh; fa.nkv = nkv;
             fa.out = attn_bf; fa.o_stride = qd; fa.S = S; fa.kv_offset = (int)start_pos; fa.scale = 1.0f / std::sqrt((float)D); fa.nseq = 1;
+            fa.q_lo_off = lo_q; fa.kv_lo_off = lo_kv; fa.out_lo_off = lo_attn;
             LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
-            if (hybrid) { LAUNCH_OK(gate_mul_launch(stream, attn_bf, qkv, S, nh, D, q_stride(), qkv_dim())); ++launches; }
-            gemm(attn_bf, qd, l.qt_o ? dequant_for_gemm(l.q_wo, l.qt_o, H, qd) : l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
+            if (hybrid) { LAUNCH_OK(gate_mul_launch(stream, attn_bf, qkv, S, nh, D, q_stride(), qkv_dim(), lo_attn)); ++launches; }
+            gemm(attn_bf, lo_attn, qd, l.qt_o ? dequant_for_gemm(l.q_wo, l.qt_o, H, qd) : l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
         } else {
-            gemm(xn, H, l.w_in, S, gdn_in_pad, H, EPI_STORE_F32, g_proj, gdn_in_pad, nullptr);
+            gemm(xn, lo_xn, H, l.w_in, S, gdn_in_pad, H, EPI_STORE_F32, g_proj, gdn_in_pad, nullptr);
             GdnArgs ga;
             gdn_args(ga, l, S, g_proj, g_conv, g_qn, g_kn, g_gb, g_y);
-            ga.out_bf16 = attn_bf;
+            ga.out_bf16 = attn_bf; ga.out_lo_off = lo_attn;
             LAUNCH_OK(gdn_forward_launch(stream, ga));
-            gemm(attn_bf, value_dim(), l.w_out, S, H, value_dim(), EPI_RESID_F32, x, H, nullptr);
+            gemm(attn_bf, lo_attn, value_dim(), l.w_out, S, H, value_dim(), EPI_RESID_F32, x, H, nullptr);
             launches += 3;
         }
-        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln2, eps, xn));
-        gemm(xn, H, l.qt_gu ? dequant_for_gemm(l.q_wgu, l.qt_gu, (size_t)2 * I, H) : l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr);
-        gemm(act_bf, I, l.qt_down ? dequant_for_gemm(l.q_wdown, l.qt_down, H, I) : l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
+        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln2, eps, xn, lo_xn));
+        gemm(xn, lo_xn, H, l.qt_gu ? dequant_for_gemm(l.q_wgu, l.qt_gu, (size_t)2 * I, H) : l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr, lo_act);
+        gemm(act_bf, lo_act, I, l.qt_down ? dequant_for_gemm(l.q_wdown, l.qt_down, H, I) : l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
         launches += 4;
         if (n_vis > 0 && li < (int)v_deepstack.size()) {   // DeepStack (qwen3_vl/text.rs:262-268)
             LAUNCH_OK(set_rows_launch(stream, x, H, rows_dev, n_vis, ds_embeds + (size_t)li * n_vis * H, true));
@@ -1200,12 +1216,12 @@ void crane_b200_model::ensure_vision_ws(int N) {
     v_cos = dalloc<float>((size_t)cap * (v_hd / 2));
     v_sin = dalloc<float>((size_t)cap * (v_hd / 2));
     v_w4 = dalloc<float>((size_t)4 * cap);
-    v_pvb = dalloc<bf16>((size_t)cap * pk);
-    v_xn = dalloc<bf16>((size_t)cap * v_H);
-    v_qkvb = dalloc<bf16>((size_t)cap * 3 * v_H);
-    v_attn = dalloc<bf16>((size_t)cap * v_H);
-    v_act = dalloc<bf16>((size_t)cap * v_I);
-    v_m1 = dalloc<bf16>((size_t)(cap / m2) * mh);
+    v_pvb = dalloc_act((size_t)cap * pk, lo_vpvb);
+    v_xn = dalloc_act((size_t)cap * v_H, lo_vxn);
+    v_qkvb = dalloc_act((size_t)cap * 3 * v_H, lo_vqkvb);
+    v_attn = dalloc_act((size_t)cap * v_H, lo_vattn);
+    v_act = dalloc_act((size_t)cap * v_I, lo_vact);
+    v_m1 = dalloc_act((size_t)(cap / m2) * mh, lo_vm1);
     v_idx4 = dalloc<int>((size_t)4 * cap);
     v_seq_start = dalloc<int>(cap);
     v_seq_len = dalloc<int>(cap);
@@ -1278,35 +1294,36 @@ void crane_b200_model::encode_images(const float* pv, const uint32_t* grid, size
     CUDA_OK(cudaMemcpyAsync(v_sin, sn.data(), sn.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaMemcpyAsync(v_seq_start, sstart.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream));
     CUDA_OK(cudaMemcpyAsync(v_seq_len, slen.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream));
-    LAUNCH_OK(cast_f32_bf16_launch(stream, v_pv, v_pvb, (size_t)N * pk));
+    LAUNCH_OK(cast_f32_bf16_launch(stream, v_pv, v_pvb, (size_t)N * pk, lo_vpvb));
     CUDA_OK(cudaStreamSynchronize(stream));   // host staging vectors go out of scope below
 
     // patch embed: Conv3d(kernel == stride) == GEMM [N, C*T*P*P] x [Hv, C*T*P*P]^T + bias (vision.rs:46-58)
-    gemm(v_pvb, pk, v_wpatch, N, v_H, pk, EPI_STORE_F32, v_x, v_H, v_bpatch);
+    gemm(v_pvb, lo_vpvb, pk, v_wpatch, N, v_H, pk, EPI_STORE_F32, v_x, v_H, v_bpatch);
     LAUNCH_OK(vit_pos_embed_add_launch(stream, v_x, N, v_H, v_pos, v_idx4, v_w4));
     launches += 2;
     const int Ng = N / m2;
     auto run_merger = [&](MergerW& m, float* out) {
-        if (m.post) LAUNCH_OK(layernorm_rows_launch(stream, v_x, Ng, mh, m.nw, m.nb, 1e-6f, v_xn));
-        else LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, m.nw, m.nb, 1e-6f, v_xn));
-        gemm(v_xn, mh, m.w1, Ng, mh, mh, merger_gelu_mode, v_m1, mh, m.b1);
-        gemm(v_m1, mh, m.w2, Ng, v_out, mh, EPI_STORE_F32, out, v_out, m.b2);
+        if (m.post) LAUNCH_OK(layernorm_rows_launch(stream, v_x, Ng, mh, m.nw, m.nb, 1e-6f, v_xn, lo_vxn));
+        else LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, m.nw, m.nb, 1e-6f, v_xn, lo_vxn));
+        gemm(v_xn, lo_vxn, mh, m.w1, Ng, mh, mh, merger_gelu_mode, v_m1, mh, m.b1, lo_vm1);
+        gemm(v_m1, lo_vm1, mh, m.w2, Ng, v_out, mh, EPI_STORE_F32, out, v_out, m.b2);
         ++launches;
     };
     for (int bi = 0; bi < v_depth; ++bi) {
         VitBlockW& b = vblocks[bi];
-        LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, b.n1w, b.n1b, 1e-6f, v_xn));
-        gemm(v_xn, v_H, b.wqkv, N, 3 * v_H, v_H, EPI_STORE_F32, v_qkv, 3 * v_H, b.bqkv);
-        LAUNCH_OK(vit_rope_launch(stream, v_qkv, N, v_nh, v_hd, v_cos, v_sin, v_qkvb));
+        LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, b.n1w, b.n1b, 1e-6f, v_xn, lo_vxn));
+        gemm(v_xn, lo_vxn, v_H, b.wqkv, N, 3 * v_H, v_H, EPI_STORE_F32, v_qkv, 3 * v_H, b.bqkv);
+        LAUNCH_OK(vit_rope_launch(stream, v_qkv, N, v_nh, v_hd, v_cos, v_sin, v_qkvb, lo_vqkvb));
         FlashArgs fa = {};
         fa.q = v_qkvb; fa.q_stride = 3 * v_H; fa.k = v_qkvb + v_H; fa.v = v_qkvb + 2 * v_H; fa.kv_stride = 3 * v_H;
         fa.nh = v_nh; fa.nkv = v_nh; fa.out = v_attn; fa.o_stride = v_H; fa.seq_start = v_seq_start; fa.seq_len = v_seq_len;
         fa.scale = 1.0f / std::sqrt((float)v_hd); fa.nseq = nseq; fa.max_len = max_len;
+        fa.q_lo_off = lo_vqkvb; fa.kv_lo_off = lo_vqkvb; fa.out_lo_off = lo_vattn;
         LAUNCH_OK(flash_prefill_launch(stream, v_hd, false, false, fa));
-        gemm(v_attn, v_H, b.wproj, N, v_H, v_H, EPI_RESID_F32, v_x, v_H, b.bproj);
-        LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, b.n2w, b.n2b, 1e-6f, v_xn));
-        gemm(v_xn, v_H, b.wfc1, N, v_I, v_H, vit_gelu_mode, v_act, v_I, b.bfc1);
-        gemm(v_act, v_I, b.wfc2, N, v_H, v_I, EPI_RESID_F32, v_x, v_H, b.bfc2);
+        gemm(v_attn, lo_vattn, v_H, b.wproj, N, v_H, v_H, EPI_RESID_F32, v_x, v_H, b.bproj);
+        LAUNCH_OK(layernorm_rows_launch(stream, v_x, N, v_H, b.n2w, b.n2b, 1e-6f, v_xn, lo_vxn));
+        gemm(v_xn, lo_vxn, v_H, b.wfc1, N, v_I, v_H, vit_gelu_mode, v_act, v_I, b.bfc1, lo_vact);
+        gemm(v_act, lo_vact, v_I, b.wfc2, N, v_H, v_I, EPI_RESID_F32, v_x, v_H, b.bfc2);
         launches += 4;
         for (size_t j = 0; j < v_deepstack.size(); ++j)
             if (v_deepstack[j] == bi) run_merger(v_ds_mergers[j], ds_embeds + j * (size_t)Ng * v_out);
@@ -1370,6 +1387,7 @@ int crane_b200_create(const char* config_json, int device_ordinal, crane_b200_mo
             std::unique_ptr<crane_b200_model> c(new crane_b200_model());
             c->device = device_ordinal; c->num_sms = m->num_sms;
             c->parse_config(m->cp_json.c_str());
+            c->split = m->split;
             c->stream = m->stream; c->owns_stream = false;
             c->alloc_weights();
             c->got_embed = true;         // its inputs come from the codec embedding tables, not embed_tokens
@@ -1478,7 +1496,7 @@ uint64_t crane_b200_active_kv_cache_bytes(const crane_b200_model* m) {
     if (!m) return 0;
     uint64_t full = 0;
     for (int f : m->layer_is_full) full += f;
-    return (uint64_t)m->kv_len * m->nkv * m->D * 2 /*K,V*/ * 2 /*bf16*/ * full +
+    return (uint64_t)m->kv_len * m->nkv * m->D * 2 /*K,V*/ * (m->split ? 4 : 2) /*bf16 (+ lo plane)*/ * full +
            (m->hybrid ? (uint64_t)(m->L - full) * ((uint64_t)m->nv * m->dk * m->dv + (uint64_t)m->conv_dim() * m->ck) * 4 : 0);
 }
 uint64_t crane_b200_kernel_launches(const crane_b200_model* m) { return m ? m->launches : 0; }
@@ -1772,8 +1790,8 @@ int crane_b200_last_timing(const crane_b200_model* m, float* prefill_ms, float* 
     return CRANE_B200_OK;
 }
 
-int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* w, int M, int N, int K, int mode, const float* bias, void* out_inout,
-                       int use_simt) {
+int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* a_lo, const uint16_t* w, int M, int N, int K, int mode, const float* bias,
+                       void* out_inout, int use_simt) {
     if (!a || !w || !out_inout) return CRANE_B200_INVALID_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return CRANE_B200_CUDA_ERROR;
     const bool half_out = (mode == EPI_STORE_BF16 || mode == EPI_SILU_MUL_BF16 || mode == EPI_GELU_ERF_BF16 || mode == EPI_GELU_TANH_BF16);
@@ -1783,14 +1801,15 @@ int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* w, int M, 
     float* db = nullptr;
     void* dout = nullptr;
     int rc = CRANE_B200_CUDA_ERROR;
-    if (cudaMalloc(&da, (size_t)M * K * 2) == cudaSuccess && cudaMalloc(&dw, (size_t)N * K * 2) == cudaSuccess &&
+    if (cudaMalloc(&da, (size_t)M * K * 2 * 2) == cudaSuccess && cudaMalloc(&dw, (size_t)N * K * 2) == cudaSuccess &&
         cudaMalloc(&dout, out_bytes) == cudaSuccess && (!bias || cudaMalloc(&db, (size_t)N * 4) == cudaSuccess)) {
         cudaMemcpy(da, a, (size_t)M * K * 2, cudaMemcpyHostToDevice);
         cudaMemcpy(dw, w, (size_t)N * K * 2, cudaMemcpyHostToDevice);
         cudaMemcpy(dout, out_inout, out_bytes, cudaMemcpyHostToDevice);
         if (bias) cudaMemcpy(db, bias, (size_t)N * 4, cudaMemcpyHostToDevice);
-        GemmEpi ep{dout, out_cols, db, mode};
-        const int r = gemm_bf16_launch(nullptr, da, K, dw, M, N, K, ep, use_simt != 0);
+        if (a_lo) cudaMemcpy(da + (size_t)M * K, a_lo, (size_t)M * K * 2, cudaMemcpyHostToDevice);
+        GemmEpi ep{dout, nullptr, out_cols, db, mode};
+        const int r = gemm_bf16_launch(nullptr, da, a_lo ? da + (size_t)M * K : nullptr, K, dw, M, N, K, ep, use_simt != 0);
         if (r == -1000) rc = CRANE_B200_UNSUPPORTED;
         else if (r == 0 && cudaDeviceSynchronize() == cudaSuccess) {
             cudaMemcpy(out_inout, dout, out_bytes, cudaMemcpyDeviceToHost);

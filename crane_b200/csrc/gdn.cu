@@ -165,7 +165,11 @@ gdn_gated_norm_kernel(GdnArgs a) {
     for (int i = lane; i < a.dv; i += 32) {
         const float o = yr[i] * rstd * a.norm_w[i] * silu_f(zr[i]);
         const size_t idx = ((size_t)t * a.nv + h) * a.dv + i;
-        if (a.out_bf16) a.out_bf16[idx] = __float2bfloat16_rn(o);
+        if (a.out_bf16) {
+            const bf16 hi = __float2bfloat16_rn(o);
+            a.out_bf16[idx] = hi;
+            if (a.out_lo_off) a.out_bf16[a.out_lo_off + idx] = __float2bfloat16_rn(o - __bfloat162float(hi));
+        }
         if (a.out_f32) a.out_f32[idx] = o;
     }
 }

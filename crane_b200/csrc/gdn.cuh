@@ -27,6 +27,7 @@ struct GdnArgs {
     // outputs (one of)
     bf16* out_bf16;              // [S, value_dim]  gated-norm output as the out_proj GEMM operand (prefill)
     float* out_f32;              // [S, value_dim]  (decode: GEMV input)
+    long long out_lo_off;        // split precision: element offset of out_bf16's low-order plane (0 = none)
 };
 
 int gdn_forward_launch(cudaStream_t st, const GdnArgs& a);

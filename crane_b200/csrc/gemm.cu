@@ -91,13 +91,19 @@ __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int m, int n, flo
             *reinterpret_cast<float4*>(o + j) = r;
         }
     } else if constexpr (MODE == EPI_SILU_MUL_BF16) {
-        bf16* o = reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ldo + (n >> 1);
-        uint32_t p[8];
+        const size_t off = (size_t)m * ep.ldo + (n >> 1);
+        uint32_t p[8], q[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            p[j] = pack_bf16(silu_f(v[4 * j]) * v[4 * j + 1], silu_f(v[4 * j + 2]) * v[4 * j + 3]);
+            split_bf16x2(silu_f(v[4 * j]) * v[4 * j + 1], silu_f(v[4 * j + 2]) * v[4 * j + 3], p[j], q[j]);
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + off;
         *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+        if (ep.out_lo != nullptr) {
+            bf16* ol = reinterpret_cast<bf16*>(ep.out_lo) + off;
+            *reinterpret_cast<uint4*>(ol) = make_uint4(q[0], q[1], q[2], q[3]);
+            *reinterpret_cast<uint4*>(ol + 8) = make_uint4(q[4], q[5], q[6], q[7]);
+        }
     } else {
         if constexpr (MODE == EPI_GELU_ERF_BF16) {
 #pragma unroll
@@ -106,11 +112,17 @@ __device__ __forceinline__ void epi_store32(const GemmEpi& ep, int m, int n, flo
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
         }
-        bf16* o = reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ldo + n;
+        const size_t off = (size_t)m * ep.ldo + n;
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + off;
+        bf16* ol = ep.out_lo != nullptr ? reinterpret_cast<bf16*>(ep.out_lo) + off : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                          pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+        for (int j = 0; j < 32; j += 8) {
+            uint32_t p[4], q[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) split_bf16x2(v[j + 2 * t], v[j + 2 * t + 1], p[t], q[t]);
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(p[0], p[1], p[2], p[3]);
+            if (ol != nullptr) *reinterpret_cast<uint4*>(ol + j) = make_uint4(q[0], q[1], q[2], q[3]);
+        }
     }
 }
 
@@ -123,20 +135,22 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_SMEM_BUDGET = 192 * 1024;
 
-template <int BN>
+template <int BN, bool SPLIT>
 struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES * (SPLIT ? 2 : 1) + B_BYTES;     // [A hi | A lo (SPLIT) | B]
     static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int MODE>
+// SPLIT: the activation operand comes as two bf16 planes A = hi + lo (lo = bf16(x - hi), ~16 mantissa bits together); the
+// weight tile is fetched once and multiplied by both, accumulating into the same TMEM columns: D = hi.W^T + lo.W^T.
+template <int BN, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmB,
                GemmEpi ep, int M, int N, int K) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, SPLIT>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -151,6 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
+        if (SPLIT) tma_prefetch_desc(&tmAlo);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
@@ -168,9 +183,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                uint8_t* b_dst = a_dst + Cfg::A_BYTES * (SPLIT ? 2 : 1);
                 mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                 tma_load_2d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m0);
+                if (SPLIT) tma_load_2d(a_dst + Cfg::A_BYTES, &tmAlo, &full_bar[s], kb * GEMM_BK, m0);
                 tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n0);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
@@ -184,11 +200,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
                 const uint64_t adesc = make_smem_desc_sw128(a_addr);
-                const uint64_t bdesc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+                const uint64_t aldesc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+                const uint64_t bdesc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES * (SPLIT ? 2 : 1));
 #pragma unroll
                 for (int k = 0; k < GEMM_BK / 16; ++k) {
                     // +32 B per K=16 step inside the 128 B swizzle atom -> +2 in the >>4-encoded start address
                     umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    if (SPLIT) umma_bf16(tmem_base, aldesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);             // frees the smem stage once these MMAs retire
                 if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -223,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // =====================================================================================
 template <int MODE>
 __global__ void __launch_bounds__(128)
-gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, GemmEpi ep, int M, int N, int K) {
+gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ A_lo, int lda, const bf16* __restrict__ W, GemmEpi ep, int M, int N, int K) {
     __shared__ float ws[32][65];
     const int m = blockIdx.y * 128 + threadIdx.x;
     const int n0 = blockIdx.x * 32;
@@ -239,7 +257,8 @@ gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W
         __syncthreads();
         if (m < M) {
             for (int c = 0; c < 64; ++c) {
-                const float a = __bfloat162float(A[(size_t)m * lda + k0 + c]);
+                float a = __bfloat162float(A[(size_t)m * lda + k0 + c]);
+                if (A_lo != nullptr) a += __bfloat162float(A_lo[(size_t)m * lda + k0 + c]);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = fmaf(a, ws[j][c], acc[j]);
             }
@@ -282,29 +301,30 @@ static bool make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, ui
     return r == CUDA_SUCCESS;
 }
 
-template <int BN, int MODE>
-static int launch_tc(cudaStream_t stream, const bf16* A, int lda, const bf16* W, int M, int N, int K, const GemmEpi& epi) {
-    using Cfg = GemmCfg<BN>;
-    CUtensorMap tmA, tmB;
+template <int BN, int MODE, bool SPLIT>
+static int launch_tc(cudaStream_t stream, const bf16* A, const bf16* A_lo, int lda, const bf16* W, int M, int N, int K, const GemmEpi& epi) {
+    using Cfg = GemmCfg<BN, SPLIT>;
+    CUtensorMap tmA, tmAlo, tmB;
     if (!make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1001;
+    if (!make_tmap_bf16(&tmAlo, SPLIT ? A_lo : A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1001;
     if (!make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN)) return -1001;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     dim3 grid((N + BN - 1) / BN, (M + GEMM_BM - 1) / GEMM_BM);
-    gemm_tc_kernel<BN, MODE><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, epi, M, N, K);
+    gemm_tc_kernel<BN, MODE, SPLIT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmAlo, tmB, epi, M, N, K);
     return (int)cudaGetLastError();
 }
 
 template <int MODE>
-static int launch_mode(cudaStream_t stream, const bf16* A, int lda, const bf16* W, int M, int N, int K,
+static int launch_mode(cudaStream_t stream, const bf16* A, const bf16* A_lo, int lda, const bf16* W, int M, int N, int K,
                        const GemmEpi& epi, bool use_simt) {
     if (use_simt) {
         dim3 grid(N / 32, (M + 127) / 128);
-        gemm_simt_kernel<MODE><<<grid, 128, 0, stream>>>(A, lda, W, epi, M, N, K);
+        gemm_simt_kernel<MODE><<<grid, 128, 0, stream>>>(A, A_lo, lda, W, epi, M, N, K);
         return (int)cudaGetLastError();
     }
     // Tile width: fill the 148 SMs in as few waves as possible, wider tiles on ties.
@@ -319,23 +339,30 @@ static int launch_mode(cudaStream_t stream, const bf16* A, int lda, const bf16* 
         eff *= (bn == 256 ? 1.0 : bn == 128 ? 0.95 : 0.80);   // narrower tiles re-read A from smem more often
         if (eff > best) { best = eff; best_bn = bn; }
     }
+    if (A_lo != nullptr) {
+        switch (best_bn) {
+            case 256: return launch_tc<256, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi);
+            case 128: return launch_tc<128, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi);
+            default:  return launch_tc<64, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi);
+        }
+    }
     switch (best_bn) {
-        case 256: return launch_tc<256, MODE>(stream, A, lda, W, M, N, K, epi);
-        case 128: return launch_tc<128, MODE>(stream, A, lda, W, M, N, K, epi);
-        default:  return launch_tc<64, MODE>(stream, A, lda, W, M, N, K, epi);
+        case 256: return launch_tc<256, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi);
+        case 128: return launch_tc<128, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi);
+        default:  return launch_tc<64, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi);
     }
 }
 
-int gemm_bf16_launch(cudaStream_t stream, const bf16* A, int lda, const bf16* W, int M, int N, int K,
+int gemm_bf16_launch(cudaStream_t stream, const bf16* A, const bf16* A_lo, int lda, const bf16* W, int M, int N, int K,
                      const GemmEpi& epi, bool use_simt) {
     if (M <= 0 || N <= 0 || K <= 0 || (K % GEMM_BK) != 0 || (N % 32) != 0 || (lda % 8) != 0) return -1000;
     switch (epi.mode) {
-        case EPI_STORE_F32:      return launch_mode<EPI_STORE_F32>(stream, A, lda, W, M, N, K, epi, use_simt);
-        case EPI_STORE_BF16:     return launch_mode<EPI_STORE_BF16>(stream, A, lda, W, M, N, K, epi, use_simt);
-        case EPI_RESID_F32:      return launch_mode<EPI_RESID_F32>(stream, A, lda, W, M, N, K, epi, use_simt);
-        case EPI_SILU_MUL_BF16:  return launch_mode<EPI_SILU_MUL_BF16>(stream, A, lda, W, M, N, K, epi, use_simt);
-        case EPI_GELU_ERF_BF16:  return launch_mode<EPI_GELU_ERF_BF16>(stream, A, lda, W, M, N, K, epi, use_simt);
-        case EPI_GELU_TANH_BF16: return launch_mode<EPI_GELU_TANH_BF16>(stream, A, lda, W, M, N, K, epi, use_simt);
+        case EPI_STORE_F32:      return launch_mode<EPI_STORE_F32>(stream, A, A_lo, lda, W, M, N, K, epi, use_simt);
+        case EPI_STORE_BF16:     return launch_mode<EPI_STORE_BF16>(stream, A, A_lo, lda, W, M, N, K, epi, use_simt);
+        case EPI_RESID_F32:      return launch_mode<EPI_RESID_F32>(stream, A, A_lo, lda, W, M, N, K, epi, use_simt);
+        case EPI_SILU_MUL_BF16:  return launch_mode<EPI_SILU_MUL_BF16>(stream, A, A_lo, lda, W, M, N, K, epi, use_simt);
+        case EPI_GELU_ERF_BF16:  return launch_mode<EPI_GELU_ERF_BF16>(stream, A, A_lo, lda, W, M, N, K, epi, use_simt);
+        case EPI_GELU_TANH_BF16: return launch_mode<EPI_GELU_TANH_BF16>(stream, A, A_lo, lda, W, M, N, K, epi, use_simt);
         default: return -1000;
     }
 }

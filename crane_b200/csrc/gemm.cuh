@@ -27,6 +27,7 @@ enum GemmEpiMode : int {
 
 struct GemmEpi {
     void* out;
+    void* out_lo;       // bf16-output modes: optional second plane receiving bf16(value - bf16(value)) (split-precision operand)
     int ldo;            // leading dimension of `out` in elements
     const float* bias;  // [N] or nullptr
     int mode;
@@ -36,7 +37,8 @@ struct TmaEncoder;  // host: resolves cuTensorMapEncodeTiled once
 
 // Host API.  `use_simt` selects the slow debugging kernel (bring-up A/B only).
 // Returns cudaError_t (as int) or -1000 for unsupported shapes.
-int gemm_bf16_launch(cudaStream_t stream, const bf16* A, int lda, const bf16* W, int M, int N, int K,
+// `A_lo` (nullable): low-order plane of a split-precision activation operand, same shape/stride as A (see gemm.cu).
+int gemm_bf16_launch(cudaStream_t stream, const bf16* A, const bf16* A_lo, int lda, const bf16* W, int M, int N, int K,
                      const GemmEpi& epi, bool use_simt);
 
 }  // namespace cb

@@ -28,7 +28,7 @@ int embed_rows_launch(cudaStream_t st, const uint32_t* ids, int S, const bf16* e
 
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-rmsnorm_rows_kernel(const float* __restrict__ x, int H, const float* __restrict__ w, float eps, bf16* __restrict__ out) {
+rmsnorm_rows_kernel(const float* __restrict__ x, int H, const float* __restrict__ w, float eps, bf16* __restrict__ out, long long lo_off) {
     __shared__ float red[32];
     const float* xr = x + (size_t)blockIdx.x * H;
     float ssq = 0.f;
@@ -41,19 +41,22 @@ rmsnorm_rows_kernel(const float* __restrict__ x, int H, const float* __restrict_
     for (int i = threadIdx.x * 4; i < H; i += 1024) {
         const float4 v = *reinterpret_cast<const float4*>(xr + i);
         const float4 g = *reinterpret_cast<const float4*>(w + i);
-        *reinterpret_cast<uint2*>(o + i) = make_uint2(pack_bf16(v.x * rstd * g.x, v.y * rstd * g.y),
-                                                      pack_bf16(v.z * rstd * g.z, v.w * rstd * g.w));
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(v.x * rstd * g.x, v.y * rstd * g.y, h0, l0);
+        split_bf16x2(v.z * rstd * g.z, v.w * rstd * g.w, h1, l1);
+        *reinterpret_cast<uint2*>(o + i) = make_uint2(h0, h1);
+        if (lo_off) *reinterpret_cast<uint2*>(o + lo_off + i) = make_uint2(l0, l1);
     }
 }
-int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out) {
+int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out, long long lo_off) {
     if (H % 4) return -1000;
-    rmsnorm_rows_kernel<<<S, 256, 0, st>>>(x, H, w, eps, out);
+    rmsnorm_rows_kernel<<<S, 256, 0, st>>>(x, H, w, eps, out, lo_off);
     return (int)cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, int W, const float* __restrict__ w, const float* __restrict__ b,
-                      float eps, bf16* __restrict__ out) {
+                      float eps, bf16* __restrict__ out, long long lo_off) {
     __shared__ float red[32];
     const float* xr = x + (size_t)blockIdx.x * W;
     float s = 0.f;
@@ -74,14 +77,16 @@ layernorm_rows_kernel(const float* __restrict__ x, int W, const float* __restric
         const float4 v = *reinterpret_cast<const float4*>(xr + i);
         const float4 g = *reinterpret_cast<const float4*>(w + i);
         const float4 bb = *reinterpret_cast<const float4*>(b + i);
-        *reinterpret_cast<uint2*>(o + i) =
-            make_uint2(pack_bf16((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y),
-                       pack_bf16((v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w));
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y, h0, l0);
+        split_bf16x2((v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w, h1, l1);
+        *reinterpret_cast<uint2*>(o + i) = make_uint2(h0, h1);
+        if (lo_off) *reinterpret_cast<uint2*>(o + lo_off + i) = make_uint2(l0, l1);
     }
 }
-int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out) {
+int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out, long long lo_off) {
     if (W % 4) return -1000;
-    layernorm_rows_kernel<<<rows, 256, 0, st>>>(x, W, w, b, eps, out);
+    layernorm_rows_kernel<<<rows, 256, 0, st>>>(x, W, w, b, eps, out, lo_off);
     return (int)cudaGetLastError();
 }
 
@@ -105,7 +110,12 @@ rope_append_kernel(RopeAppendArgs a) {
         const float* src = row + q_span + kv_dim + kvh * D;
         bf16* dst = a.v_pool + (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
 #pragma unroll
-        for (int j = 0; j < NE; ++j) dst[lane + 32 * j] = __float2bfloat16_rn(src[lane + 32 * j]);
+        for (int j = 0; j < NE; ++j) {
+            const float v = src[lane + 32 * j];
+            const bf16 h = __float2bfloat16_rn(v);
+            dst[lane + 32 * j] = h;
+            if (a.kv_lo_off) dst[a.kv_lo_off + lane + 32 * j] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
         return;
     }
     const bool is_k = vec >= a.nh;
@@ -138,7 +148,10 @@ rope_append_kernel(RopeAppendArgs a) {
             for (int jj = 0; jj < NE; ++jj) if (jj == (lo ? j + RJ : j - RJ)) other = e[jj];
             r = lo ? (e[j] * c - other * sn) : (other * sn + e[j] * c);
         }
-        dst[lane + 32 * j] = __float2bfloat16_rn(r);
+        const bf16 h = __float2bfloat16_rn(r);
+        dst[lane + 32 * j] = h;
+        const long long lo_off = is_k ? a.kv_lo_off : a.q_lo_off;
+        if (lo_off) dst[lo_off + lane + 32 * j] = __float2bfloat16_rn(r - __bfloat162float(h));
     }
 }
 int rope_append_launch(cudaStream_t st, int D, const RopeAppendArgs& a) {
@@ -173,16 +186,21 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int D, bool CAUSAL, bool PAGED>
+// SPLIT: q, k, v (and the probabilities) are hi + lo bf16 pairs; every product keeps its three leading terms
+//   S = qh.kh + qh.kl + ql.kh          O += ph.vh + ph.vl + pl.vh
+// so the result carries ~16 mantissa bits instead of 8 (the f32-oracle parity mode; 3x the tensor work of 4 % of the flops).
+template <int D, bool CAUSAL, bool PAGED, bool SPLIT>
 __global__ void __launch_bounds__(128)
 flash_prefill_kernel(FlashArgs a) {
     constexpr int BM = 64, BN = 64;
     constexpr int LDS = D + 8;                 // padded row (elements): conflict-free ldmatrix
-    constexpr int TILE = BN * LDS;             // elements per K or V tile
+    constexpr int TILE = BN * LDS;             // elements per K or V tile plane
     constexpr int CPR = D / 8;                 // 16-byte chunks per row
+    constexpr int P = SPLIT ? 2 : 1;           // planes per operand
+    constexpr int STG = (SPLIT && D > 128) ? 1 : 2;
     extern __shared__ __align__(16) unsigned char fsm[];
-    bf16* q_s = reinterpret_cast<bf16*>(fsm);
-    bf16* kv_s = q_s + BM * LDS;               // [2 stages][K tile | V tile]
+    bf16* q_s = reinterpret_cast<bf16*>(fsm);  // [P][BM x LDS]
+    bf16* kv_s = q_s + P * BM * LDS;           // [STG][K hi | K lo | V hi | V lo]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tq = lane & 3;
@@ -202,10 +220,11 @@ flash_prefill_kernel(FlashArgs a) {
         const int qr = q0 + r;
         const bf16* src = a.q + (size_t)(row0 + min(qr, S - 1)) * a.q_stride + head * D + ch * 8;
         cp_async16(smem_u32(q_s + r * LDS + ch * 8), src, qr < S ? 16 : 0);
+        if (SPLIT) cp_async16(smem_u32(q_s + BM * LDS + r * LDS + ch * 8), src + a.q_lo_off, qr < S ? 16 : 0);
     }
     auto load_kv = [&](int tile, int stage) {
-        bf16* ks = kv_s + stage * 2 * TILE;
-        bf16* vs = ks + TILE;
+        bf16* ks = kv_s + stage * 2 * P * TILE;
+        bf16* vs = ks + P * TILE;
         const int kv0 = tile * BN;
         for (int c = tid; c < BN * CPR; c += 128) {
             const int r = c / CPR, ch = c % CPR;
@@ -222,6 +241,10 @@ flash_prefill_kernel(FlashArgs a) {
             }
             cp_async16(smem_u32(ks + r * LDS + ch * 8), ksrc, ok ? 16 : 0);
             cp_async16(smem_u32(vs + r * LDS + ch * 8), vsrc, ok ? 16 : 0);
+            if (SPLIT) {
+                cp_async16(smem_u32(ks + TILE + r * LDS + ch * 8), ksrc + a.kv_lo_off, ok ? 16 : 0);
+                cp_async16(smem_u32(vs + TILE + r * LDS + ch * 8), vsrc + a.kv_lo_off, ok ? 16 : 0);
+            }
         }
     };
     load_kv(0, 0);
@@ -232,38 +255,71 @@ flash_prefill_kernel(FlashArgs a) {
     for (int i = 0; i < D / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
     float m_row[2] = {-INFINITY, -INFINITY}, l_row[2] = {0.f, 0.f};
     const float sl2 = a.scale * 1.4426950408889634f;
-    uint32_t qf[D / 16][4];
+    uint32_t qf[SPLIT ? 1 : D / 16][4];        // plain mode keeps the Q fragments in registers; SPLIT re-reads them from smem
 
     for (int tile = 0; tile < n_tiles; ++tile) {
-        const int stage = tile & 1;
-        if (tile + 1 < n_tiles) load_kv(tile + 1, stage ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
+        const int stage = (STG == 2) ? (tile & 1) : 0;
+        if (STG == 2) {
+            if (tile + 1 < n_tiles) load_kv(tile + 1, stage ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
-        if (tile == 0) {
+        if (!SPLIT && tile == 0) {
 #pragma unroll
             for (int kk = 0; kk < D / 16; ++kk) {
                 const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int c = kk * 16 + (lane >> 4) * 8;
-                ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(q_s + r * LDS + c));
+                ldmatrix_x4(qf[SPLIT ? 0 : kk][0], qf[SPLIT ? 0 : kk][1], qf[SPLIT ? 0 : kk][2], qf[SPLIT ? 0 : kk][3], smem_u32(q_s + r * LDS + c));
             }
         }
-        const bf16* ks = kv_s + stage * 2 * TILE;
-        const bf16* vs = ks + TILE;
+        const bf16* ks = kv_s + stage * 2 * P * TILE;
+        const bf16* vs = ks + P * TILE;
         // ---- S = Q K^T ----
         float s_acc[BN / 8][4];
 #pragma unroll
         for (int j = 0; j < BN / 8; ++j) { s_acc[j][0] = s_acc[j][1] = s_acc[j][2] = s_acc[j][3] = 0.f; }
+        if constexpr (!SPLIT) {
 #pragma unroll
-        for (int j = 0; j < BN / 8; ++j) {
+            for (int j = 0; j < BN / 8; ++j) {
 #pragma unroll
+                for (int kk = 0; kk < D / 16; kk += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    const int r = j * 8 + (lane & 7);
+                    const int c = kk * 16 + (lane >> 3) * 8;
+                    ldmatrix_x4(b0, b1, b2, b3, smem_u32(ks + r * LDS + c));
+                    mma_bf16_16816(s_acc[j], qf[SPLIT ? 0 : kk], b0, b1);
+                    mma_bf16_16816(s_acc[j], qf[SPLIT ? 0 : kk + 1], b2, b3);
+                }
+            }
+        } else {
+#pragma unroll 1
             for (int kk = 0; kk < D / 16; kk += 2) {
-                uint32_t b0, b1, b2, b3;
-                const int r = j * 8 + (lane & 7);
-                const int c = kk * 16 + (lane >> 3) * 8;
-                ldmatrix_x4(b0, b1, b2, b3, smem_u32(ks + r * LDS + c));
-                mma_bf16_16816(s_acc[j], qf[kk], b0, b1);
-                mma_bf16_16816(s_acc[j], qf[kk + 1], b2, b3);
+                uint32_t qh0[4], qh1[4], ql0[4], ql1[4];
+                {
+                    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int c = kk * 16 + (lane >> 4) * 8;
+                    ldmatrix_x4(qh0[0], qh0[1], qh0[2], qh0[3], smem_u32(q_s + r * LDS + c));
+                    ldmatrix_x4(qh1[0], qh1[1], qh1[2], qh1[3], smem_u32(q_s + r * LDS + c + 16));
+                    ldmatrix_x4(ql0[0], ql0[1], ql0[2], ql0[3], smem_u32(q_s + BM * LDS + r * LDS + c));
+                    ldmatrix_x4(ql1[0], ql1[1], ql1[2], ql1[3], smem_u32(q_s + BM * LDS + r * LDS + c + 16));
+                }
+#pragma unroll
+                for (int j = 0; j < BN / 8; ++j) {
+                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                    const int r = j * 8 + (lane & 7);
+                    const int c = kk * 16 + (lane >> 3) * 8;
+                    ldmatrix_x4(h0, h1, h2, h3, smem_u32(ks + r * LDS + c));
+                    ldmatrix_x4(l0, l1, l2, l3, smem_u32(ks + TILE + r * LDS + c));
+                    mma_bf16_16816(s_acc[j], ql0, h0, h1);      // small terms first
+                    mma_bf16_16816(s_acc[j], ql1, h2, h3);
+                    mma_bf16_16816(s_acc[j], qh0, l0, l1);
+                    mma_bf16_16816(s_acc[j], qh1, l2, l3);
+                    mma_bf16_16816(s_acc[j], qh0, h0, h1);
+                    mma_bf16_16816(s_acc[j], qh1, h2, h3);
+                }
             }
         }
         // ---- mask + online softmax (rows g and g+8 of this warp's 16) ----
@@ -312,22 +368,31 @@ flash_prefill_kernel(FlashArgs a) {
         // ---- O += P V ----
 #pragma unroll
         for (int kt = 0; kt < BN / 16; ++kt) {
-            uint32_t pa[4];
-            pa[0] = pack_bf16(s_acc[2 * kt][0], s_acc[2 * kt][1]);
-            pa[1] = pack_bf16(s_acc[2 * kt][2], s_acc[2 * kt][3]);
-            pa[2] = pack_bf16(s_acc[2 * kt + 1][0], s_acc[2 * kt + 1][1]);
-            pa[3] = pack_bf16(s_acc[2 * kt + 1][2], s_acc[2 * kt + 1][3]);
+            uint32_t pa[4], pl[4];
+            split_bf16x2(s_acc[2 * kt][0], s_acc[2 * kt][1], pa[0], pl[0]);
+            split_bf16x2(s_acc[2 * kt][2], s_acc[2 * kt][3], pa[1], pl[1]);
+            split_bf16x2(s_acc[2 * kt + 1][0], s_acc[2 * kt + 1][1], pa[2], pl[2]);
+            split_bf16x2(s_acc[2 * kt + 1][2], s_acc[2 * kt + 1][3], pa[3], pl[3]);
 #pragma unroll
             for (int dj = 0; dj < D / 8; dj += 2) {
                 uint32_t b0, b1, b2, b3;
                 const int r = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int c = dj * 8 + (lane >> 4) * 8;
                 ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(vs + r * LDS + c));
+                if constexpr (SPLIT) {
+                    uint32_t c0, c1, c2, c3;
+                    ldmatrix_x4_trans(c0, c1, c2, c3, smem_u32(vs + TILE + r * LDS + c));
+                    mma_bf16_16816(o_acc[dj], pl, b0, b1);
+                    mma_bf16_16816(o_acc[dj + 1], pl, b2, b3);
+                    mma_bf16_16816(o_acc[dj], pa, c0, c1);
+                    mma_bf16_16816(o_acc[dj + 1], pa, c2, c3);
+                }
                 mma_bf16_16816(o_acc[dj], pa, b0, b1);
                 mma_bf16_16816(o_acc[dj + 1], pa, b2, b3);
             }
         }
         __syncthreads();   // everyone done with this stage before it is refilled
+        if (STG == 1 && tile + 1 < n_tiles) { load_kv(tile + 1, 0); cp_async_commit(); }
     }
     cp_async_wait<0>();
     // ---- normalise and store ----
@@ -343,48 +408,61 @@ flash_prefill_kernel(FlashArgs a) {
             const float inv = 1.f / l_row[r];
             bf16* o = a.out + (size_t)(row0 + qrow) * a.o_stride + head * D;
 #pragma unroll
-            for (int i = 0; i < D / 8; ++i)
-                *reinterpret_cast<uint32_t*>(o + i * 8 + tq * 2) = pack_bf16(o_acc[i][2 * r] * inv, o_acc[i][2 * r + 1] * inv);
+            for (int i = 0; i < D / 8; ++i) {
+                uint32_t hi, lo;
+                split_bf16x2(o_acc[i][2 * r] * inv, o_acc[i][2 * r + 1] * inv, hi, lo);
+                *reinterpret_cast<uint32_t*>(o + i * 8 + tq * 2) = hi;
+                if (SPLIT) *reinterpret_cast<uint32_t*>(o + a.out_lo_off + i * 8 + tq * 2) = lo;
+            }
         }
     }
 }
 
-template <int D, bool CAUSAL, bool PAGED>
+template <int D, bool CAUSAL, bool PAGED, bool SPLIT>
 static int flash_launch_t(cudaStream_t st, const FlashArgs& a) {
-    constexpr int SMEM = (64 * (D + 8) + 4 * 64 * (D + 8)) * 2;
+    constexpr int P = SPLIT ? 2 : 1, STG = (SPLIT && D > 128) ? 1 : 2;
+    constexpr int SMEM = (P * 64 * (D + 8) + STG * 2 * P * 64 * (D + 8)) * 2;
+    static_assert(SMEM <= 227 * 1024, "flash tile does not fit");
     static bool set = false;
     if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(flash_prefill_kernel<D, CAUSAL, PAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return (int)e;
         set = true;
     }
     const int max_len = a.seq_len ? a.max_len : a.S;
     dim3 grid((max_len + 63) / 64, a.nh, a.seq_len ? a.nseq : 1);
-    flash_prefill_kernel<D, CAUSAL, PAGED><<<grid, 128, SMEM, st>>>(a);
+    flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT><<<grid, 128, SMEM, st>>>(a);
     return (int)cudaGetLastError();
 }
 
 int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const FlashArgs& a) {
-    if (D == 128 && causal && paged) return flash_launch_t<128, true, true>(st, a);
-    if (D == 256 && causal && paged) return flash_launch_t<256, true, true>(st, a);
-    if (D == 64 && !causal && !paged) return flash_launch_t<64, false, false>(st, a);
-    if (D == 128 && !causal && !paged) return flash_launch_t<128, false, false>(st, a);
+    const bool split = a.q_lo_off != 0;
+    if (split && (a.kv_lo_off == 0 || a.out_lo_off == 0)) return -1000;
+    if (D == 128 && causal && paged) return split ? flash_launch_t<128, true, true, true>(st, a) : flash_launch_t<128, true, true, false>(st, a);
+    if (D == 256 && causal && paged) return split ? flash_launch_t<256, true, true, true>(st, a) : flash_launch_t<256, true, true, false>(st, a);
+    if (D == 64 && !causal && !paged) return split ? flash_launch_t<64, false, false, true>(st, a) : flash_launch_t<64, false, false, false>(st, a);
+    if (D == 128 && !causal && !paged) return split ? flash_launch_t<128, false, false, true>(st, a) : flash_launch_t<128, false, false, false>(st, a);
     return -1000;
 }
 
 // attn[s, h*D + i] *= sigmoid(gate), gate = qkv[s, h*q_stride + D + i]   (qwen3_5/modeling.rs:556-563)
 __global__ void __launch_bounds__(256)
-gate_mul_kernel(bf16* __restrict__ attn, const float* __restrict__ qkv, int nh, int D, int q_stride, int row_width) {
+gate_mul_kernel(bf16* __restrict__ attn, const float* __restrict__ qkv, int nh, int D, int q_stride, int row_width, long long lo_off) {
     const int s = blockIdx.x;
     for (int i = threadIdx.x; i < nh * D; i += blockDim.x) {
         const int h = i / D, d = i % D;
         const float g = qkv[(size_t)s * row_width + h * q_stride + D + d];
-        const float v = __bfloat162float(attn[(size_t)s * nh * D + i]);
-        attn[(size_t)s * nh * D + i] = __float2bfloat16_rn(v / (1.0f + expf(-g)));
+        bf16* p = attn + (size_t)s * nh * D + i;
+        float v = __bfloat162float(*p);
+        if (lo_off) v += __bfloat162float(p[lo_off]);
+        v = v / (1.0f + expf(-g));
+        const bf16 hi = __float2bfloat16_rn(v);
+        *p = hi;
+        if (lo_off) p[lo_off] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
 }
-int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh, int D, int q_stride, int row_width) {
-    gate_mul_kernel<<<S, 256, 0, st>>>(attn, qkv, nh, D, q_stride, row_width);
+int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh, int D, int q_stride, int row_width, long long lo_off) {
+    gate_mul_kernel<<<S, 256, 0, st>>>(attn, qkv, nh, D, q_stride, row_width, lo_off);
     return (int)cudaGetLastError();
 }
 
@@ -409,17 +487,21 @@ int set_rows_launch(cudaStream_t st, float* x, int H, const int* rows, int n, co
 }
 
 __global__ void __launch_bounds__(256)
-cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4) {
+cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4, long long lo_off) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(src)[i];
-        reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(v.x, v.y, h0, l0);
+        split_bf16x2(v.z, v.w, h1, l1);
+        reinterpret_cast<uint2*>(dst)[i] = make_uint2(h0, h1);
+        if (lo_off) reinterpret_cast<uint2*>(dst + lo_off)[i] = make_uint2(l0, l1);
     }
 }
-int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n) {
+int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n, long long lo_off) {
     if (n % 4) return -1000;
     const size_t n4 = n / 4;
     const int grid = (int)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
-    cast_f32_bf16_kernel<<<grid, 256, 0, st>>>(src, dst, n4);
+    cast_f32_bf16_kernel<<<grid, 256, 0, st>>>(src, dst, n4, lo_off);
     return (int)cudaGetLastError();
 }
 
@@ -447,7 +529,12 @@ int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const flo
 // cos/sin [N, hd/2] (full-width cat(emb, emb) of the reference collapses to a half-split rotation).
 __global__ void __launch_bounds__(256)
 vit_rope_kernel(const float* __restrict__ qkv, int nh, int hd, const float* __restrict__ cs, const float* __restrict__ sn,
-                bf16* __restrict__ out) {
+                bf16* __restrict__ out, long long lo_off) {
+    auto put = [&](bf16* p, float v) {
+        const bf16 h = __float2bfloat16_rn(v);
+        *p = h;
+        if (lo_off) p[lo_off] = __float2bfloat16_rn(v - __bfloat162float(h));
+    };
     const int p = blockIdx.x;
     const int half = hd / 2;
     const int Hv = nh * hd;
@@ -460,13 +547,13 @@ vit_rope_kernel(const float* __restrict__ qkv, int nh, int hd, const float* __re
         const float* v = row + which * Hv + h * hd;
         const float x1 = v[j], x2 = v[j + half];
         bf16* o = orow + which * Hv + h * hd;
-        o[j] = __float2bfloat16_rn(x1 * c - x2 * s);
-        o[j + half] = __float2bfloat16_rn(x2 * c + x1 * s);
+        put(o + j, x1 * c - x2 * s);
+        put(o + j + half, x2 * c + x1 * s);
     }
-    for (int i = threadIdx.x; i < Hv; i += blockDim.x) orow[2 * Hv + i] = __float2bfloat16_rn(row[2 * Hv + i]);
+    for (int i = threadIdx.x; i < Hv; i += blockDim.x) put(orow + 2 * Hv + i, row[2 * Hv + i]);
 }
-int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out) {
-    vit_rope_kernel<<<N, 256, 0, st>>>(qkv, nh, hd, cos, sin, out);
+int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out, long long lo_off) {
+    vit_rope_kernel<<<N, 256, 0, st>>>(qkv, nh, hd, cos, sin, out, lo_off);
     return (int)cudaGetLastError();
 }
 

@@ -24,6 +24,8 @@ struct RopeAppendArgs {
     bf16* v_pool;
     int nh, nkv;
     bf16* q_out;             // [S, nh * D]
+    long long q_lo_off;      // split precision: element offset of the low-order plane of q_out (0 = none)
+    long long kv_lo_off;     // ... and of the K / V pools
 };
 
 struct FlashArgs {
@@ -41,17 +43,20 @@ struct FlashArgs {
     float scale;
     int nseq;
     int max_len;                        // max query rows over sequences (grid sizing)
+    // split precision (x = hi + lo, both bf16): element offsets of the low-order planes, 0 = plain bf16
+    long long q_lo_off, kv_lo_off, out_lo_off;
 };
 
 int embed_rows_launch(cudaStream_t st, const uint32_t* ids, int S, const bf16* embed, int H, float* x);
-int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out);
-int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out);
+// bf16 outputs take `lo_off`: element offset (from `out`) of a second plane receiving bf16(v - bf16(v)); 0 = none
+int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out, long long lo_off = 0);
+int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out, long long lo_off = 0);
 int rope_append_launch(cudaStream_t st, int D, const RopeAppendArgs& a);
 int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const FlashArgs& a);
-int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh, int D, int q_stride, int row_width);
+int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh, int D, int q_stride, int row_width, long long lo_off = 0);
 int set_rows_launch(cudaStream_t st, float* x, int H, const int* rows, int n, const float* src, bool add);
-int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n);
+int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n, long long lo_off = 0);
 int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const float* table, const int* idx4, const float* w4);
-int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out);
+int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out, long long lo_off = 0);
 
 }  // namespace cb

@@ -195,8 +195,9 @@ CRANE_B200_API int crane_b200_last_timing(const crane_b200_model* m, float* pref
 CRANE_B200_API uint64_t crane_b200_kernel_launches(const crane_b200_model* m);
 
 /* ---- kernel-level test hooks (used by tests/ only; host buffers in, host buffers out) ------------ */
-/* C[M,N] = epilogue(A[M,K] bf16 x W[N,K]^T bf16); mode = cb::GemmEpiMode; out dtype follows the mode. */
-CRANE_B200_API int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* w, int M, int N, int K, int mode,
+/* C[M,N] = epilogue((A + A_lo)[M,K] bf16 x W[N,K]^T bf16); a_lo = optional low-order plane of a split-precision A
+ * (NULL: plain bf16); mode = cb::GemmEpiMode; out dtype follows the mode. */
+CRANE_B200_API int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* a_lo, const uint16_t* w, int M, int N, int K, int mode,
                        const float* bias, void* out_inout, int use_simt);
 
 #ifdef __cplusplus

@@ -1,10 +1,11 @@
 """GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the committed fixtures.
 
-Tolerances ("rel" = max|a-b| / max|b| over a logits vector, the bar BASELINE.json states as <=1e-3 rel on bf16 logits;
-the measured values are printed so they can be tightened):
+Tolerances ("rel" = max|a-b| / max|b| over a logits vector; BASELINE.json's bar is <=1e-3 rel against the f32 CPU path;
+the measured values are printed):
   * kernel-level GEMM, f32 output ...... 1e-5  (same bf16 inputs, f32 accumulation, different order)
-  * decode path (f32 activations, bf16 KV pages) ......... 1e-2
-  * prefill path (bf16 tensor-core operands, f32 residual) 2e-2
+  * default engine (split precision: hi+lo bf16 operands and KV pages) ... 1e-3 everywhere (measured ~1e-5 .. 3e-5)
+  * "precision": "bf16" fast mode (plain bf16 operands / pages) .......... 1e-2 decode, 2e-2 prefill (measured 4e-3 .. 1e-2)
+  * GGUF-quantised linears (int8 activation blocks, oracle = f32 x . dequant(W); parity unpinned) ... 3e-2 / 5e-2
 Greedy tokens must match the oracle wherever the oracle's own top-2 margin exceeds the measured logit error.
 """
 import numpy as np
@@ -19,8 +20,10 @@ from oracle.qwen3_vl import Qwen3VLOracle
 
 pytestmark = pytest.mark.gpu
 
-DECODE_TOL = 1e-2
-PREFILL_TOL = 2e-2
+DECODE_TOL = 1e-3          # default (split-precision) engine: the north-star bar
+PREFILL_TOL = 1e-3
+FAST_DECODE_TOL = 1e-2     # "precision": "bf16"
+FAST_PREFILL_TOL = 2e-2
 
 
 def _bf16(x):
@@ -42,6 +45,22 @@ def test_gemm_store_f32(shape, simt):
     assert e < 1e-5
     out = crane_b200.op_gemm(a_bits, w_bits, crane_b200.EPI_STORE_F32, bias=bias, use_simt=simt)
     assert rel_err(out, ref + bias) < 1e-5
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["simt", "tcgen05"])
+def test_gemm_split_precision(simt):
+    """A = hi + lo (two bf16 planes): the product carries ~16 mantissa bits of the f32 activations."""
+    M, N, K = 300, 512, 1024
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((M, K), dtype=np.float32)
+    hi_bits, hi = _bf16(a)
+    lo_bits, lo = _bf16(a - hi)
+    w_bits, w = _bf16(rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K))
+    ref = a.astype(np.float64) @ w.astype(np.float64).T
+    e_plain = rel_err(crane_b200.op_gemm(hi_bits, w_bits, crane_b200.EPI_STORE_F32, use_simt=simt), ref)
+    e_split = rel_err(crane_b200.op_gemm(hi_bits, w_bits, crane_b200.EPI_STORE_F32, use_simt=simt, a_lo_bits=lo_bits), ref)
+    print(f"gemm split simt={simt}: plain bf16 {e_plain:.3e}, split {e_split:.3e}")
+    assert e_split < 3e-5 and e_plain > 10 * e_split
 
 
 @pytest.mark.parametrize("simt", [True, False], ids=["simt", "tcgen05"])
@@ -67,6 +86,15 @@ def test_gemm_epilogues(simt):
         assert rel_err(out, torch.nn.functional.gelu(x, approximate=approx).numpy()) < 5e-3
 
 
+# (gemm kernel, precision mode): the default engine twice (debug SIMT GEMM / tcgen05 GEMM) + the plain-bf16 fast mode
+MODES = [("simt", "split"), ("tcgen05", "split"), ("tcgen05", "bf16")]
+MODE_IDS = ["simt-split", "tcgen05-split", "tcgen05-bf16"]
+
+
+def _tols(precision):
+    return (PREFILL_TOL, DECODE_TOL) if precision == "split" else (FAST_PREFILL_TOL, FAST_DECODE_TOL)
+
+
 def _model(cfg, cls=crane_b200.Qwen3Model, **opts):
     w = dict(synth.synth_checkpoint(cfg))
     m = cls(cfg, device=0, max_seq_len=opts.pop("max_seq_len", 512), **opts)
@@ -75,10 +103,11 @@ def _model(cfg, cls=crane_b200.Qwen3Model, **opts):
 
 
 @pytest.mark.parametrize("name,cfg", [("tiny_qwen3", synth.TINY_QWEN3), ("tiny_qwen3_untied", synth.TINY_QWEN3_UNTIED)])
-@pytest.mark.parametrize("gemm", ["simt", "tcgen05"])
-def test_tiny_qwen3_against_hf_fixture(name, cfg, gemm):
+@pytest.mark.parametrize("gemm,precision", MODES, ids=MODE_IDS)
+def test_tiny_qwen3_against_hf_fixture(name, cfg, gemm, precision):
     g = golden(name)
-    m, _ = _model(cfg, gemm=gemm)
+    ptol, dtol = _tols(precision)
+    m, _ = _model(cfg, gemm=gemm, precision=precision)
     toks = [int(t) for t in g["prompt"]]
     errs = []
     for step in range(g["logits"].shape[0]):
@@ -90,8 +119,8 @@ def test_tiny_qwen3_against_hf_fixture(name, cfg, gemm):
         if top2[1] - top2[0] > 4 * e * np.abs(g["logits"][step]).max():
             assert int(np.argmax(lg)) == int(g["tokens"][step]), f"step {step}"
         toks.append(int(g["tokens"][step]))
-    print(f"{name} gemm={gemm}: prefill rel {errs[0]:.3e}, decode rel max {max(errs[1:]):.3e}")
-    assert errs[0] < PREFILL_TOL and max(errs[1:]) < DECODE_TOL
+    print(f"{name} gemm={gemm} {precision}: prefill rel {errs[0]:.3e}, decode rel max {max(errs[1:]):.3e}")
+    assert errs[0] < ptol and max(errs[1:]) < dtol
     m.close()
 
 
@@ -138,7 +167,7 @@ def test_on_device_greedy_loop_matches_host_loop_and_oracle():
     # identical to the oracle up to the first near-tie of the oracle itself
     for i, (a, b) in enumerate(zip(dev, ref_toks)):
         if a != b:
-            assert margins[i] < 0.05, f"token {i}: {a} vs oracle {b} with margin {margins[i]}"
+            assert margins[i] < 2e-3, f"token {i}: {a} vs oracle {b} with margin {margins[i]}"   # only an oracle near-tie may differ
             break
     print(f"greedy: {sum(int(a == b) for a, b in zip(dev, ref_toks))}/24 tokens equal, min oracle margin {min(margins):.3f}")
     m.close()
@@ -163,12 +192,13 @@ def test_forward_embeds_and_errors():
     m.close()
 
 
-@pytest.mark.parametrize("gemm", ["simt", "tcgen05"])
-def test_tiny_qwen3_vl_against_fixture(gemm):
+@pytest.mark.parametrize("gemm,precision", MODES, ids=MODE_IDS)
+def test_tiny_qwen3_vl_against_fixture(gemm, precision):
     cfg = synth.TINY_QWEN3_VL
     g = golden("tiny_qwen3_vl")
+    ptol, dtol = _tols(precision)
     pv, grid = synth.patchify(g["image"])
-    m, w = _model(cfg, cls=crane_b200.Qwen3VLModel, gemm=gemm)
+    m, w = _model(cfg, cls=crane_b200.Qwen3VLModel, gemm=gemm, precision=precision)
     img, ds = m.encode_images(pv, [grid], want_deepstack=3)
     e_img, e_ds = rel_err(img, g["ref_image_embeds"]), rel_err(ds, g["ref_deepstack"])
     lg = m.forward(g["prompt"], pv, [grid], 0)
@@ -180,11 +210,11 @@ def test_tiny_qwen3_vl_against_fixture(gemm):
         lg = m.decode_step(tok, S + step - 1)
         errs.append(rel_err(lg, g["ref_logits"][step]))
         tok = int(g["ref_tokens"][step])
-    print(f"tiny_qwen3_vl gemm={gemm}: image {e_img:.3e} deepstack {e_ds:.3e} prefill {e0:.3e} decode {max(errs):.3e}")
-    assert e_img < PREFILL_TOL and e_ds < PREFILL_TOL and e0 < PREFILL_TOL and max(errs) < DECODE_TOL
+    print(f"tiny_qwen3_vl gemm={gemm} {precision}: image rel {e_img:.3e} deepstack rel {e_ds:.3e} prefill rel {e0:.3e} decode rel {max(errs):.3e}")
+    assert e_img < ptol and e_ds < ptol and e0 < ptol and max(errs) < dtol
     # HF's activation choice through the engine switch
-    m2, _ = _model(cfg, cls=crane_b200.Qwen3VLModel, gemm=gemm, vit_act="tanh", merger_act="erf")
-    assert rel_err(m2.forward(g["prompt"], pv, [grid], 0), g["hf_logits"][0]) < PREFILL_TOL
+    m2, _ = _model(cfg, cls=crane_b200.Qwen3VLModel, gemm=gemm, precision=precision, vit_act="tanh", merger_act="erf")
+    assert rel_err(m2.forward(g["prompt"], pv, [grid], 0), g["hf_logits"][0]) < ptol
     m.close(); m2.close()
 
 
@@ -201,25 +231,26 @@ def test_vl_generate_matches_oracle():
         ref.append(int(orc.decode_step(ref[-1], len(ids) + i).numpy().argmax()))
     got = m.generate(ids, pv, [grid], 8)
     print("vl generate:", list(got), "oracle:", ref)
-    assert len(got) == 8
+    assert [int(x) for x in got] == ref
     m.close()
 
 
 # ---- Qwen3.5 hybrid: Gated-Delta-Net layers + gated attention with partial rotary (config 3) ----------------
 
-@pytest.mark.parametrize("gemm", ["simt", "tcgen05"])
-def test_tiny_qwen3_5_against_hf_fixture(gemm):
+@pytest.mark.parametrize("gemm,precision", MODES, ids=MODE_IDS)
+def test_tiny_qwen3_5_against_hf_fixture(gemm, precision):
     cfg = synth.TINY_QWEN3_5
     g = golden("tiny_qwen3_5")
-    m, _ = _model(cfg, cls=crane_b200.Qwen3_5Model, gemm=gemm)
+    ptol, _ = _tols(precision)
+    m, _ = _model(cfg, cls=crane_b200.Qwen3_5Model, gemm=gemm, precision=precision)
     toks = [int(t) for t in g["prompt"]]
     errs = []
     for step in range(g["logits"].shape[0]):
         ctx = toks if step == 0 else toks[-1:]
         errs.append(rel_err(m.forward_step(ctx, len(toks) - len(ctx)), g["logits"][step]))
         toks.append(int(g["tokens"][step]))
-    print(f"tiny_qwen3_5 gemm={gemm}: prefill rel {errs[0]:.3e}, decode rel max {max(errs[1:]):.3e}")
-    assert errs[0] < PREFILL_TOL and max(errs[1:]) < PREFILL_TOL
+    print(f"tiny_qwen3_5 gemm={gemm} {precision}: prefill rel {errs[0]:.3e}, decode rel max {max(errs[1:]):.3e}")
+    assert errs[0] < ptol and max(errs[1:]) < ptol
     m.close()
 
 
