@@ -148,6 +148,7 @@ def run_cpu(cfg, weights, n_decode, steps, warmup):
     orc = Qwen3VLOracle(cfg, {k: v for k, v in weights}, max_pos=2048)
     ids, pv, grid = make_request(cfg)
     pre_t, dec_t, toks = [], [], 0
+    first_logits, tok_list = None, []
     with torch.no_grad():
         for it in range(warmup + steps):
             orc.clear_kv_cache()
@@ -155,8 +156,10 @@ def run_cpu(cfg, weights, n_decode, steps, warmup):
             lg = orc.prefill(ids, pv, [grid])
             t1 = time.perf_counter()
             tok = int(lg.argmax())
+            first_logits, tok_list = lg.numpy().copy(), [tok]
             for i in range(n_decode):
                 tok = int(orc.decode_step(tok, len(ids) + i).argmax())
+                tok_list.append(tok)
             t2 = time.perf_counter()
             if it >= warmup:
                 pre_t.append(t1 - t0)
@@ -165,7 +168,8 @@ def run_cpu(cfg, weights, n_decode, steps, warmup):
     n_patches = pv.shape[0]
     fl = prefill_flops(cfg, len(ids), n_patches, n_patches // 4)
     return {"decode_tok_s": toks / sum(dec_t), "prefill_tflops": fl / (sum(pre_t) / len(pre_t)) / 1e12,
-            "prefill_s": sum(pre_t) / len(pre_t), "cores": cores, "ms_per_step": 1e3 * (sum(pre_t) + sum(dec_t)) / steps}
+            "prefill_s": sum(pre_t) / len(pre_t), "cores": cores, "ms_per_step": 1e3 * (sum(pre_t) + sum(dec_t)) / steps,
+            "prefill_logits": first_logits, "tokens": tok_list}
 
 
 def main():
@@ -187,7 +191,8 @@ def main():
     base = {"metric": "decode_tok_per_s", "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "weights": "seeded synthetic N(0,1/fan_in) rounded to bf16",
-                       "l2": "per-token weight stream 3.44 GB >> 126 MB L2 (inputs larger than L2)", "parallelism": f"dp{args.gpus} (replicas)"}}
+                       "l2": "per-token weight stream 3.44 GB >> 126 MB L2 (inputs larger than L2)", "parallelism": f"dp{args.gpus} (replicas)",
+                       "precision": os.environ.get("CRANE_B200_PRECISION", "split") + " (split = hi+lo bf16 operands / KV pages, parity mode)"}}
 
     # ---------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -233,12 +238,15 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- device-resident leg: prefill via the public call, decode with the on-device greedy loop ----
+    gpu_out = {}
+
     def request_device():
         model.clear_kv_cache()
         lg = model.forward(ids, pv_pinned, [grid], 0)
         first = int(np.argmax(lg))
         toks = model.decode_greedy(first, S, N_DECODE)
         t = model.last_timing()
+        gpu_out["prefill_logits"], gpu_out["tokens"] = lg, [first] + [int(x) for x in toks]
         return t["prefill_ms"], t["decode_ms"], toks
 
     for _ in range(args.warmup):
@@ -319,6 +327,11 @@ def main():
         out["cpu_baseline"] = {"value": r["decode_tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
                                "prefill_tflops": r["prefill_tflops"],
                                "sample": f"1 warm-up + 1 timed request: ViT+prefill(454) + {n_dec} decode tokens, torch f32, {r['cores']} threads"}
+        # full-size parity on the same request: GPU prefill logits and greedy tokens against the oracle's
+        ref, got = r["prefill_logits"].reshape(-1), np.asarray(gpu_out["prefill_logits"]).reshape(-1)
+        same = sum(int(a == b) for a, b in zip(gpu_out["tokens"], r["tokens"]))
+        out["parity"] = {"prefill_logits_rel": float(np.abs(got - ref).max() / np.abs(ref).max()),
+                         "greedy_tokens_equal": f"{same}/{len(r['tokens'])}", "against": "oracle (torch f32) on the same full-size request"}
     print(json.dumps(out))
     model.close()
     if dist is not None:
