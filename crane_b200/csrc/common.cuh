@@ -98,6 +98,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ---- programmatic dependent launch ---------------------------------------------------
+// ---- programmatic dependent launch ----------------------------------------------------
+// Every kernel of the decode AND prefill chains is launched with programmaticStreamSerialization: it may start while its
+// predecessor drains, runs whatever does not depend on it (barrier/TMEM setup, weight prefetch), then blocks in pdl_wait() until
+// the predecessor has completed and flushed.  A kernel launched this way MUST call pdl_wait() before touching activations.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -107,6 +111,21 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
     return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+
+
+// Host: launch `kernel` on `st`, as a programmatic dependent of the previous kernel in the stream when `pdl`.
+inline bool& prefill_pdl() { static bool on = true; return on; }
+template <typename... KArgs, typename... Args>
+inline int launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace cb

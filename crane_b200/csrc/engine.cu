@@ -340,6 +340,7 @@ struct crane_b200_model {
     void gemm(const bf16* A, long long a_lo, int lda, const bf16* W, int M, int N, int K, int mode, void* out, int ldo, const float* bias,
               long long out_lo = 0) {
         GemmEpi ep{out, out_lo ? (void*)((bf16*)out + out_lo) : nullptr, ldo, bias, mode};
+        ep.w_dynamic = dq_scratch != nullptr && W == dq_scratch;
         LAUNCH_OK(gemm_bf16_launch(stream, A, a_lo ? A + a_lo : nullptr, lda, W, M, N, K, ep, use_simt));
         ++launches;
     }
@@ -435,6 +436,7 @@ void crane_b200_model::parse_config(const char* json) {
     if (const char* g = getenv("CRANE_B200_GEMM")) use_simt = std::string(g) == "simt";
     if (const char* g = getenv("CRANE_B200_GRAPHS")) use_graphs = std::string(g) != "0";
     if (const char* g = getenv("CRANE_B200_PDL")) use_pdl = std::string(g) != "0";
+    cb::prefill_pdl() = use_pdl;          // process-wide: the prefill-side launchers read it
     if (const char* g = getenv("CRANE_B200_PRECISION")) split = std::string(g) != "bf16";
     if (root.has("engine")) use_persistent = root.at("engine").boolean("persistent", false);
     if (const char* g = getenv("CRANE_B200_PERSISTENT")) use_persistent = std::string(g) != "0";
@@ -1814,6 +1816,41 @@ int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* a_lo, cons
         else if (r == 0 && cudaDeviceSynchronize() == cudaSuccess) {
             cudaMemcpy(out_inout, dout, out_bytes, cudaMemcpyDeviceToHost);
             rc = CRANE_B200_OK;
+            if (getenv("CRANE_B200_GEMM_PROF") && !use_simt) {      // tile timeline + event timing of this shape (tools/gemm_probe.py)
+                const size_t max_tiles = 8192;
+                unsigned long long* dprof = nullptr;
+                cudaMalloc(&dprof, max_tiles * 8 * sizeof(unsigned long long));
+                GemmEpi ep2 = ep;
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                for (int i = 0; i < 5; ++i) gemm_bf16_launch(nullptr, da, a_lo ? da + (size_t)M * K : nullptr, K, dw, M, N, K, ep2, false);
+                cudaEventRecord(e0, nullptr);
+                for (int i = 0; i < 20; ++i) gemm_bf16_launch(nullptr, da, a_lo ? da + (size_t)M * K : nullptr, K, dw, M, N, K, ep2, false);
+                cudaEventRecord(e1, nullptr);
+                cudaDeviceSynchronize();
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                cudaMemset(dprof, 0, max_tiles * 8 * sizeof(unsigned long long));
+                ep2.prof = dprof;
+                gemm_bf16_launch(nullptr, da, a_lo ? da + (size_t)M * K : nullptr, K, dw, M, N, K, ep2, false);
+                cudaDeviceSynchronize();
+                std::vector<unsigned long long> hp(max_tiles * 8);
+                cudaMemcpy(hp.data(), dprof, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                unsigned long long t0 = ~0ull, t1 = 0;
+                size_t n = 0;
+                for (size_t i = 0; i < max_tiles; ++i) if (hp[8 * i]) { t0 = std::min(t0, hp[8 * i]); t1 = std::max(t1, hp[8 * i + 6]); ++n; }
+                double acc[6] = {0, 0, 0, 0, 0, 0}, start_max = 0;
+                for (size_t i = 0; i < max_tiles; ++i) if (hp[8 * i]) {
+                    for (int j = 0; j < 6; ++j) acc[j] += (double)((long long)hp[8 * i + j + 1] - (long long)hp[8 * i + j]);
+                    start_max = std::max(start_max, (double)(hp[8 * i] - t0));
+                }
+                fprintf(stderr, "gemm_prof M=%d N=%d K=%d split=%d: %.2f us/launch back-to-back (%.1f TFLOP/s); one launch: %zu CTAs, span %.2f us, last CTA start +%.2f us; "
+                        "per-CTA mean ns: setup %.0f | first operands %.0f | mainloop issue %.0f | accumulator wait %.0f | epilogue %.0f\n",
+                        M, N, K, a_lo ? 1 : 0, ms * 1e3 / 20, 2.0 * M * N * K / (ms * 1e-3 / 20) / 1e12, n, (t1 - t0) / 1e3, start_max / 1e3,
+                        acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n);
+                cudaFree(dprof);
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+            }
         } else {
             g_create_error = std::string("op_gemm: ") + cudaGetErrorString(cudaGetLastError()) + " rc=" + std::to_string(r);
         }

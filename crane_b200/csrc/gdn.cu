@@ -19,6 +19,8 @@ constexpr int GDN_MAX_CK = 8;
 
 __global__ void __launch_bounds__(128)
 gdn_conv_kernel(GdnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
     const int c = blockIdx.x * 128 + threadIdx.x;
     const int t = blockIdx.y;
@@ -34,6 +36,8 @@ gdn_conv_kernel(GdnArgs a) {
 
 __global__ void __launch_bounds__(128)
 gdn_conv_state_kernel(GdnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
     const int c = blockIdx.x * 128 + threadIdx.x;
     if (c >= conv_dim) return;
@@ -48,6 +52,8 @@ gdn_conv_state_kernel(GdnArgs a) {
 // grid (S), 256 threads: warps normalise the 2*nk q/k head vectors of timestep t; threads < nv compute the gates.
 __global__ void __launch_bounds__(256)
 gdn_prep_kernel(GdnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int t = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
@@ -82,6 +88,8 @@ __device__ __forceinline__ int gdn_pad(int k) { return k + (k >> 5) * 4; }
 
 __global__ void __launch_bounds__(128)
 gdn_recur_kernel(GdnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int DK = 128, KP = DK + 16;
     __shared__ __align__(16) float q_s[GDN_TC][KP];
     __shared__ __align__(16) float k_s[GDN_TC][KP];
@@ -151,6 +159,8 @@ gdn_recur_kernel(GdnArgs a) {
 // One warp per (t, value head): y * rsqrt(mean(y^2) + eps) * w * silu(z)
 __global__ void __launch_bounds__(128)
 gdn_gated_norm_kernel(GdnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (gw >= a.S * a.nv) return;
@@ -177,12 +187,13 @@ gdn_gated_norm_kernel(GdnArgs a) {
 int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     if (a.dk != 128 || (a.dv % 32) != 0 || a.ck > GDN_MAX_CK || a.nv > 256 || (a.nv % a.nk) != 0) return -1000;
     const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
-    gdn_conv_kernel<<<dim3((conv_dim + 127) / 128, a.S), 128, 0, st>>>(a);
-    gdn_conv_state_kernel<<<(conv_dim + 127) / 128, 128, 0, st>>>(a);
-    gdn_prep_kernel<<<a.S, 256, 0, st>>>(a);
-    gdn_recur_kernel<<<a.nv * (a.dv / 32), 128, 0, st>>>(a);
-    gdn_gated_norm_kernel<<<(a.S * a.nv + 3) / 4, 128, 0, st>>>(a);
-    return (int)cudaGetLastError();
+    const bool pdl = prefill_pdl();
+    int r = launch_k(gdn_conv_kernel, dim3((conv_dim + 127) / 128, a.S), dim3(128), 0, st, pdl, a);
+    if (!r) r = launch_k(gdn_conv_state_kernel, dim3((conv_dim + 127) / 128), dim3(128), 0, st, pdl, a);
+    if (!r) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);
+    if (!r) r = launch_k(gdn_recur_kernel, dim3(a.nv * (a.dv / 32)), dim3(128), 0, st, pdl, a);
+    if (!r) r = launch_k(gdn_gated_norm_kernel, dim3((a.S * a.nv + 3) / 4), dim3(128), 0, st, pdl, a);
+    return r;
 }
 
 }  // namespace cb

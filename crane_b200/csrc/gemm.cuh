@@ -31,6 +31,8 @@ struct GemmEpi {
     int ldo;            // leading dimension of `out` in elements
     const float* bias;  // [N] or nullptr
     int mode;
+    bool w_dynamic = false;   // W was written by an earlier kernel of the chain (dequantised scratch): no weight prefetch before the dependency wait
+    unsigned long long* prof = nullptr;   // optional: 8 globaltimer stamps per CTA (tile timeline, tools/gemm_probe.py)
 };
 
 struct TmaEncoder;  // host: resolves cuTensorMapEncodeTiled once

@@ -14,6 +14,8 @@ namespace cb {
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embed_rows_kernel(const uint32_t* __restrict__ ids, const bf16* __restrict__ embed, int H, float* __restrict__ x) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int s = blockIdx.x;
     const bf16* row = embed + (size_t)ids[s] * H;
     for (int i = threadIdx.x * 2; i < H; i += 512) {
@@ -22,13 +24,14 @@ embed_rows_kernel(const uint32_t* __restrict__ ids, const bf16* __restrict__ emb
     }
 }
 int embed_rows_launch(cudaStream_t st, const uint32_t* ids, int S, const bf16* embed, int H, float* x) {
-    embed_rows_kernel<<<S, 256, 0, st>>>(ids, embed, H, x);
-    return (int)cudaGetLastError();
+    return launch_k(embed_rows_kernel, dim3(S), dim3(256), 0, st, prefill_pdl(), ids, embed, H, x);
 }
 
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 rmsnorm_rows_kernel(const float* __restrict__ x, int H, const float* __restrict__ w, float eps, bf16* __restrict__ out, long long lo_off) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[32];
     const float* xr = x + (size_t)blockIdx.x * H;
     float ssq = 0.f;
@@ -50,13 +53,14 @@ rmsnorm_rows_kernel(const float* __restrict__ x, int H, const float* __restrict_
 }
 int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out, long long lo_off) {
     if (H % 4) return -1000;
-    rmsnorm_rows_kernel<<<S, 256, 0, st>>>(x, H, w, eps, out, lo_off);
-    return (int)cudaGetLastError();
+    return launch_k(rmsnorm_rows_kernel, dim3(S), dim3(256), 0, st, prefill_pdl(), x, H, w, eps, out, lo_off);
 }
 
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, int W, const float* __restrict__ w, const float* __restrict__ b,
                       float eps, bf16* __restrict__ out, long long lo_off) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[32];
     const float* xr = x + (size_t)blockIdx.x * W;
     float s = 0.f;
@@ -86,8 +90,7 @@ layernorm_rows_kernel(const float* __restrict__ x, int W, const float* __restric
 }
 int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, const float* w, const float* b, float eps, bf16* out, long long lo_off) {
     if (W % 4) return -1000;
-    layernorm_rows_kernel<<<rows, 256, 0, st>>>(x, W, w, b, eps, out, lo_off);
-    return (int)cudaGetLastError();
+    return launch_k(layernorm_rows_kernel, dim3(rows), dim3(256), 0, st, prefill_pdl(), x, W, w, b, eps, out, lo_off);
 }
 
 // -------------------------------------------------------------------------------------
@@ -95,6 +98,8 @@ int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, cons
 template <int D>
 __global__ void __launch_bounds__(128)
 rope_append_kernel(RopeAppendArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NE = D / 32;
     const int lane = threadIdx.x & 31;
     const int nvec = a.nh + 2 * a.nkv;
@@ -158,11 +163,10 @@ int rope_append_launch(cudaStream_t st, int D, const RopeAppendArgs& a) {
     if (a.rot_half < 32 || (a.rot_half % 32) != 0 || 2 * a.rot_half > D) return -1000;
     const int nwarps = a.S * (a.nh + 2 * a.nkv);
     const int grid = (nwarps + 3) / 4;
-    if (D == 128) rope_append_kernel<128><<<grid, 128, 0, st>>>(a);
-    else if (D == 256) rope_append_kernel<256><<<grid, 128, 0, st>>>(a);
-    else if (D == 64) rope_append_kernel<64><<<grid, 128, 0, st>>>(a);
-    else return -1000;
-    return (int)cudaGetLastError();
+    if (D == 128) return launch_k(rope_append_kernel<128>, dim3(grid), dim3(128), 0, st, prefill_pdl(), a);
+    if (D == 256) return launch_k(rope_append_kernel<256>, dim3(grid), dim3(128), 0, st, prefill_pdl(), a);
+    if (D == 64) return launch_k(rope_append_kernel<64>, dim3(grid), dim3(128), 0, st, prefill_pdl(), a);
+    return -1000;
 }
 
 // -------------------------------------------------------------------------------------
@@ -192,6 +196,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int D, bool CAUSAL, bool PAGED, bool SPLIT>
 __global__ void __launch_bounds__(128)
 flash_prefill_kernel(FlashArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int BM = 64, BN = 64;
     constexpr int LDS = D + 8;                 // padded row (elements): conflict-free ldmatrix
     constexpr int TILE = BN * LDS;             // elements per K or V tile plane
@@ -431,8 +437,7 @@ static int flash_launch_t(cudaStream_t st, const FlashArgs& a) {
     }
     const int max_len = a.seq_len ? a.max_len : a.S;
     dim3 grid((max_len + 63) / 64, a.nh, a.seq_len ? a.nseq : 1);
-    flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT><<<grid, 128, SMEM, st>>>(a);
-    return (int)cudaGetLastError();
+    return launch_k(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, grid, dim3(128), SMEM, st, prefill_pdl(), a);
 }
 
 int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const FlashArgs& a) {
@@ -448,6 +453,8 @@ int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const 
 // attn[s, h*D + i] *= sigmoid(gate), gate = qkv[s, h*q_stride + D + i]   (qwen3_5/modeling.rs:556-563)
 __global__ void __launch_bounds__(256)
 gate_mul_kernel(bf16* __restrict__ attn, const float* __restrict__ qkv, int nh, int D, int q_stride, int row_width, long long lo_off) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int s = blockIdx.x;
     for (int i = threadIdx.x; i < nh * D; i += blockDim.x) {
         const int h = i / D, d = i % D;
@@ -462,13 +469,14 @@ gate_mul_kernel(bf16* __restrict__ attn, const float* __restrict__ qkv, int nh, 
     }
 }
 int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh, int D, int q_stride, int row_width, long long lo_off) {
-    gate_mul_kernel<<<S, 256, 0, st>>>(attn, qkv, nh, D, q_stride, row_width, lo_off);
-    return (int)cudaGetLastError();
+    return launch_k(gate_mul_kernel, dim3(S), dim3(256), 0, st, prefill_pdl(), attn, qkv, nh, D, q_stride, row_width, lo_off);
 }
 
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 set_rows_kernel(float* __restrict__ x, int H, const int* __restrict__ rows, const float* __restrict__ src, int add) {
+    pdl_wait();
+    pdl_launch_dependents();
     float* dst = x + (size_t)rows[blockIdx.x] * H;
     const float* s = src + (size_t)blockIdx.x * H;
     for (int i = threadIdx.x * 4; i < H; i += 1024) {
@@ -482,12 +490,13 @@ set_rows_kernel(float* __restrict__ x, int H, const int* __restrict__ rows, cons
 }
 int set_rows_launch(cudaStream_t st, float* x, int H, const int* rows, int n, const float* src, bool add) {
     if (n <= 0) return 0;
-    set_rows_kernel<<<n, 256, 0, st>>>(x, H, rows, src, add ? 1 : 0);
-    return (int)cudaGetLastError();
+    return launch_k(set_rows_kernel, dim3(n), dim3(256), 0, st, prefill_pdl(), x, H, rows, src, add ? 1 : 0);
 }
 
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n4, long long lo_off) {
+    pdl_wait();
+    pdl_launch_dependents();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(src)[i];
         uint32_t h0, l0, h1, l1;
@@ -501,14 +510,15 @@ int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n,
     if (n % 4) return -1000;
     const size_t n4 = n / 4;
     const int grid = (int)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
-    cast_f32_bf16_kernel<<<grid, 256, 0, st>>>(src, dst, n4, lo_off);
-    return (int)cudaGetLastError();
+    return launch_k(cast_f32_bf16_kernel, dim3(grid), dim3(256), 0, st, prefill_pdl(), src, dst, n4, lo_off);
 }
 
 // x[p] += sum_c w4[c][p] * table[idx4[c][p]]      (bilinear pos-embed, qwen3_5/vision.rs:445-459)
 __global__ void __launch_bounds__(256)
 vit_pos_embed_add_kernel(float* __restrict__ x, int N, int Hv, const float* __restrict__ table,
                          const int* __restrict__ idx4, const float* __restrict__ w4) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int p = blockIdx.x;
     int id[4]; float w[4];
 #pragma unroll
@@ -521,8 +531,7 @@ vit_pos_embed_add_kernel(float* __restrict__ x, int N, int Hv, const float* __re
     }
 }
 int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const float* table, const int* idx4, const float* w4) {
-    vit_pos_embed_add_kernel<<<N, 256, 0, st>>>(x, N, Hv, table, idx4, w4);
-    return (int)cudaGetLastError();
+    return launch_k(vit_pos_embed_add_kernel, dim3(N), dim3(256), 0, st, prefill_pdl(), x, N, Hv, table, idx4, w4);
 }
 
 // qkv f32 [N, 3, nh, hd] -> bf16 same layout; q and k rotated in f32 with the 2-D (row, col) table
@@ -530,6 +539,8 @@ int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const flo
 __global__ void __launch_bounds__(256)
 vit_rope_kernel(const float* __restrict__ qkv, int nh, int hd, const float* __restrict__ cs, const float* __restrict__ sn,
                 bf16* __restrict__ out, long long lo_off) {
+    pdl_wait();
+    pdl_launch_dependents();
     auto put = [&](bf16* p, float v) {
         const bf16 h = __float2bfloat16_rn(v);
         *p = h;
@@ -553,8 +564,7 @@ vit_rope_kernel(const float* __restrict__ qkv, int nh, int hd, const float* __re
     for (int i = threadIdx.x; i < Hv; i += blockDim.x) put(orow + 2 * Hv + i, row[2 * Hv + i]);
 }
 int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out, long long lo_off) {
-    vit_rope_kernel<<<N, 256, 0, st>>>(qkv, nh, hd, cos, sin, out, lo_off);
-    return (int)cudaGetLastError();
+    return launch_k(vit_rope_kernel, dim3(N), dim3(256), 0, st, prefill_pdl(), qkv, nh, hd, cos, sin, out, lo_off);
 }
 
 }  // namespace cb

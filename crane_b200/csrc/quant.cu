@@ -524,6 +524,8 @@ int qgemv_launch(cudaStream_t st, int B, const QGemvArgs& qa, int num_sms, bool 
 template <int QT>
 __global__ void __launch_bounds__(256)
 q_dequant_kernel(const unsigned char* __restrict__ w, size_t nsb, bf16* __restrict__ out) {
+    pdl_wait();                 // `out` is a scratch an earlier GEMM of the chain may still be reading
+    pdl_launch_dependents();
     const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
     const size_t sbi = gid >> 5;
     const int g = (int)(gid & 31);               // elements [8g, 8g+8)
@@ -576,9 +578,9 @@ int q_dequant_bf16_launch(cudaStream_t st, int qt, const unsigned char* w, size_
     const size_t threads = nsb * 32;
     const unsigned int grid = (unsigned int)((threads + 255) / 256);
     switch (qt) {
-        case QT_Q4_K: q_dequant_kernel<QT_Q4_K><<<grid, 256, 0, st>>>(w, nsb, out); break;
-        case QT_Q6_K: q_dequant_kernel<QT_Q6_K><<<grid, 256, 0, st>>>(w, nsb, out); break;
-        case QT_Q8_0: q_dequant_kernel<QT_Q8_0><<<grid, 256, 0, st>>>(w, nsb, out); break;
+        case QT_Q4_K: return launch_k(q_dequant_kernel<QT_Q4_K>, dim3(grid), dim3(256), 0, st, prefill_pdl(), w, nsb, out);
+        case QT_Q6_K: return launch_k(q_dequant_kernel<QT_Q6_K>, dim3(grid), dim3(256), 0, st, prefill_pdl(), w, nsb, out);
+        case QT_Q8_0: return launch_k(q_dequant_kernel<QT_Q8_0>, dim3(grid), dim3(256), 0, st, prefill_pdl(), w, nsb, out);
         default: return -1000;
     }
     return (int)cudaGetLastError();
