@@ -151,6 +151,24 @@ def test_chunked_prefill_incremental_decode_and_argmax():
     m.close()
 
 
+def test_long_context_decode_multiple_kv_tiles():
+    """Context long enough that every KV split of the decode attention walks several shared-memory tiles."""
+    cfg = synth.TINY_QWEN3
+    m, w = _model(cfg, max_seq_len=2560)
+    orc = Qwen3Oracle(cfg, w, max_pos=2560)
+    ids = synth.synth_token_ids(2300, cfg["vocab_size"], "long")
+    ref = orc.forward(ids, 0).numpy()
+    e0 = rel_err(m.forward_step(ids, 0), ref)
+    errs, tok = [], int(np.argmax(ref))
+    for i in range(3):
+        ref = orc.forward([tok], 2300 + i).numpy()
+        errs.append(rel_err(m.forward_step([tok], 2300 + i), ref))
+        tok = int(np.argmax(ref))
+    print(f"long context (2300 + 3): prefill rel {e0:.3e}, decode rel max {max(errs):.3e}")
+    assert e0 < PREFILL_TOL and max(errs) < DECODE_TOL
+    m.close()
+
+
 def test_on_device_greedy_loop_matches_host_loop_and_oracle():
     cfg = synth.TINY_QWEN3
     m, w = _model(cfg)
