@@ -301,6 +301,11 @@ def main():
         return
 
     peaks = load_peaks()
+    traffic = None           # DRAM bytes of one decode step measured by ncu (tools/profile.sh + tools/summarize_ncu.py traffic)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        pass
     ctx_avg = S + N_DECODE / 2
     bytes_tok = decode_bytes_per_token(cfg, ctx_avg)
     step_s = (sum(dec_ms) / 1e3) / (args.steps * N_DECODE)         # this rank's device time per decode step
@@ -316,7 +321,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peaks["source"],
+                     "traffic": traffic["decode_step_dram_bytes"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None, "peak_source": peaks["source"],
                      "kernel": "decode step = 5 GEMV/attention launches x 28 layers + lm_head (cb::gemv_kernel dominates)",
                      "algorithmic_bytes_per_launch": bytes_tok, "launch": "one decode step (graph replay), mean ctx %d" % ctx_avg},
     })

@@ -48,6 +48,42 @@ def report(path, out):
             f.write(",".join('"' + r[i] + '"' if "," in r[i] else r[i] for i in idx) + "\n")
 
 
+def _raw(path):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    out = []
+    for r in rows[2:]:
+        d = {}
+        for h, u, v in zip(hdr, units, r):
+            d[h] = (v, u)
+        out.append(d)
+    return out
+
+
+def _bytes(d, key):
+    v, u = d[key]
+    x = float(v.replace(",", ""))
+    return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+
+def traffic(prefix, dst):
+    """DRAM bytes of one decode step from the full captures prof_gemv_/prof_lmhead_/prof_attn_<tag>.ncu-rep:
+    28 x (qkv + o + gate_up + down GEMV + attention) + lm_head, each = dram__bytes_read.sum + dram__bytes_write.sum of its launch."""
+    import json
+    tag = prefix
+    gemv = _raw(f"gpurun_out/prof_gemv_{tag}.ncu-rep")
+    head = _raw(f"gpurun_out/prof_lmhead_{tag}.ncu-rep")
+    attn = _raw(f"gpurun_out/prof_attn_{tag}.ncu-rep")
+    per = lambda d: _bytes(d, "dram__bytes_read.sum") + _bytes(d, "dram__bytes_write.sum")
+    names = [d["Kernel Name"][0] for d in gemv]
+    layer = sum(per(d) for d in gemv[:4])                      # four consecutive GEMVs of a layer (any rotation of qkv, o, gate_up, down)
+    step = 28 * (layer + per(attn[0])) + per(head[0])
+    json.dump({"decode_step_dram_bytes": step, "layer_gemv_dram_bytes": layer, "lm_head_dram_bytes": per(head[0]),
+               "attention_dram_bytes": per(attn[0]), "gemv_kernels": names[:4],
+               "source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch ({tag})"}, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
     kind, src, dst = sys.argv[1:4]
-    {"launches": launches, "report": report}[kind](src, dst)
+    {"launches": launches, "report": report, "traffic": traffic}[kind](src, dst)
