@@ -198,12 +198,13 @@ __global__ void __launch_bounds__(128)
 flash_prefill_kernel(FlashArgs a) {
     pdl_wait();
     pdl_launch_dependents();
-    constexpr int BM = 64, BN = 64;
+    constexpr int BM = 64;
+    constexpr int BN = (SPLIT && D > 128) ? 32 : 64;     // D = 256 with hi+lo planes: half-page key tiles keep the double buffer in 227 KB
     constexpr int LDS = D + 8;                 // padded row (elements): conflict-free ldmatrix
     constexpr int TILE = BN * LDS;             // elements per K or V tile plane
     constexpr int CPR = D / 8;                 // 16-byte chunks per row
     constexpr int P = SPLIT ? 2 : 1;           // planes per operand
-    constexpr int STG = (SPLIT && D > 128) ? 1 : 2;
+    constexpr int STG = 2;
     extern __shared__ __align__(16) unsigned char fsm[];
     bf16* q_s = reinterpret_cast<bf16*>(fsm);  // [P][BM x LDS]
     bf16* kv_s = q_s + P * BM * LDS;           // [STG][K hi | K lo | V hi | V lo]
@@ -238,8 +239,8 @@ flash_prefill_kernel(FlashArgs a) {
             const bool ok = t < T;
             const bf16 *ksrc, *vsrc;
             if (PAGED) {
-                const int page = a.block_table[tile];     // BN == KV_PAGE
-                const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + r) * D + ch * 8;
+                const int page = a.block_table[kv0 / KV_PAGE];     // a tile is a whole page or an aligned half of one
+                const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + (kv0 % KV_PAGE) + r) * D + ch * 8;
                 ksrc = a.k_pool + off; vsrc = a.v_pool + off;
             } else {
                 const size_t off = (size_t)(row0 + (ok ? t : 0)) * a.kv_stride + kvh * D + ch * 8;
@@ -426,8 +427,8 @@ flash_prefill_kernel(FlashArgs a) {
 
 template <int D, bool CAUSAL, bool PAGED, bool SPLIT>
 static int flash_launch_t(cudaStream_t st, const FlashArgs& a) {
-    constexpr int P = SPLIT ? 2 : 1, STG = (SPLIT && D > 128) ? 1 : 2;
-    constexpr int SMEM = (P * 64 * (D + 8) + STG * 2 * P * 64 * (D + 8)) * 2;
+    constexpr int P = SPLIT ? 2 : 1, STG = 2, BN = (SPLIT && D > 128) ? 32 : 64;
+    constexpr int SMEM = (P * 64 * (D + 8) + STG * 2 * P * BN * (D + 8)) * 2;
     static_assert(SMEM <= 227 * 1024, "flash tile does not fit");
     static bool set = false;
     if (!set) {
