@@ -47,6 +47,8 @@ _SIGNATURES = {
     "crane_b200_last_error": (C.c_char_p, [C.c_void_p]),
     "crane_b200_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
     "crane_b200_load_tensor_ggml": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_size_t]),
+    "crane_b200_load_safetensors": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "crane_b200_load_gguf": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "crane_b200_finalize": (C.c_int, [C.c_void_p]),
     "crane_b200_forward_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(Logits)]),
     "crane_b200_forward_step_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]),
@@ -149,6 +151,18 @@ class Engine:
             raise TypeError(f"{name}: unsupported dtype {a.dtype}")
         shape = (C.c_int64 * a.ndim)(*a.shape)
         self._ck(self.lib.crane_b200_load_tensor(self.h, name.encode(), dt, shape, a.ndim, _ptr(a)))
+
+    def load_safetensors(self, path: str):
+        """Register every tensor of a .safetensors file (native reader); returns (loaded, skipped)."""
+        a, s = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self.lib.crane_b200_load_safetensors(self.h, os.fsencode(path), C.byref(a), C.byref(s)))
+        return a.value, s.value
+
+    def load_gguf(self, path: str):
+        """Register every tensor of a GGUF file (native reader, quantised blocks kept as they are); returns (loaded, skipped)."""
+        a, s = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self.lib.crane_b200_load_gguf(self.h, os.fsencode(path), C.byref(a), C.byref(s)))
+        return a.value, s.value
 
     def load_tensor_ggml(self, name: str, ggml_type: int, shape, raw: np.ndarray):
         """Raw ggml blocks (uint8) of a [rows, cols] tensor; ggml_type 8 = Q8_0, 12 = Q4_K, 14 = Q6_K."""

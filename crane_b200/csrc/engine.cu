@@ -297,6 +297,8 @@ struct crane_b200_model {
     void alloc_weights();
     void load_tensor(const std::string& name, int dt, const int64_t* shape, int ndim, const void* data);
     void load_tensor_ggml(const std::string& name, int qt, const int64_t* shape, int ndim, const void* data, size_t nbytes);
+    void load_safetensors_file(const char* path, size_t* n_loaded, size_t* n_skipped);
+    void load_gguf_file(const char* path, size_t* n_loaded, size_t* n_skipped);
     unsigned char* up_quant(int qt, const void* data, size_t rows, int K, unsigned char* dst = nullptr, size_t dst_row_pitch = 0);
     void linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
                        const float* norm_w, float* y, int ldy, const GemvArgs* extra = nullptr, int B = 1, bool reuse_xq = false);
@@ -1862,3 +1864,4 @@ int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* a_lo, cons
 }  // extern "C"
 
 #include "engine_tts.inc"
+#include "engine_loaders.inc"

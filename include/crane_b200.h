@@ -85,6 +85,13 @@ CRANE_B200_API int crane_b200_load_tensor(crane_b200_model* m, const char* name,
  * crane-core/src/ops/linear.rs:23-48): decode streams the quantised bytes, prefill dequantises one matrix at a time. */
 CRANE_B200_API int crane_b200_load_tensor_ggml(crane_b200_model* m, const char* name, int ggml_type, const int64_t* shape, int ndim,
                                                const void* data, size_t nbytes);
+/* Whole-file readers: every tensor of a .safetensors file (`VarBuilder::from_mmaped_safetensors`,
+ * crane-core/src/models/qwen3/model.rs:91-92) or of a GGUF v2/v3 file (`gguf_file::Content::read` + `Qwen3Model::from_gguf`,
+ * crane-core/src/models/qwen3/modeling.rs:821-935) is registered under its own name; quantised GGUF tensors keep their blocks.
+ * Tensors the engine has no use for are skipped and counted in *n_skipped (both counters optional).  The model config still
+ * comes from crane_b200_create (GGUF metadata is not interpreted).  Call once per shard, then crane_b200_finalize. */
+CRANE_B200_API int crane_b200_load_safetensors(crane_b200_model* m, const char* path, size_t* n_loaded, size_t* n_skipped);
+CRANE_B200_API int crane_b200_load_gguf(crane_b200_model* m, const char* path, size_t* n_loaded, size_t* n_skipped);
 /* All tensors registered: merge QKV / gate-up, build rotary tables, allocate KV pages + workspaces. */
 CRANE_B200_API int crane_b200_finalize(crane_b200_model* m);
 

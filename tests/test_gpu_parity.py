@@ -461,3 +461,84 @@ def test_tts_frame_loop_against_oracle():
     print(f"tts greedy: {same}/{n} frames identical to the oracle")
     assert same >= 1 and g.shape[1] == cfg["talker_config"]["num_code_groups"]
     m.close()
+
+
+# ---- native checkpoint readers: a .safetensors file and a GGUF file read by the library itself ---------------------
+
+HF_TO_GGUF = {"input_layernorm.weight": "attn_norm.weight", "post_attention_layernorm.weight": "ffn_norm.weight",
+              "self_attn.q_proj.weight": "attn_q.weight", "self_attn.k_proj.weight": "attn_k.weight", "self_attn.v_proj.weight": "attn_v.weight",
+              "self_attn.o_proj.weight": "attn_output.weight", "self_attn.q_norm.weight": "attn_q_norm.weight",
+              "self_attn.k_norm.weight": "attn_k_norm.weight", "mlp.gate_proj.weight": "ffn_gate.weight", "mlp.up_proj.weight": "ffn_up.weight",
+              "mlp.down_proj.weight": "ffn_down.weight"}
+
+
+def _gguf_name(hf):
+    if hf == "model.embed_tokens.weight":
+        return "token_embd.weight"
+    if hf == "model.norm.weight":
+        return "output_norm.weight"
+    if hf == "lm_head.weight":
+        return "output.weight"
+    _, _, idx, rest = hf.split(".", 3)
+    return f"blk.{idx}.{HF_TO_GGUF[rest]}"
+
+
+def test_safetensors_file_reader(tmp_path):
+    import safetensors.torch
+    cfg = synth.TINY_QWEN3_UNTIED
+    w = dict(synth.synth_checkpoint(cfg))
+    ids = synth.synth_token_ids(33, cfg["vocab_size"], "st")
+    ref_m, _ = _model(cfg)
+    ref = ref_m.forward_step(ids, 0)
+    ref_m.close()
+    # bf16 matrices, f32 vectors, plus a tensor the engine has no use for
+    tensors = {k: (torch.from_numpy(v).to(torch.bfloat16) if v.ndim == 2 else torch.from_numpy(v)) for k, v in w.items()}
+    tensors["model.rotary_emb.inv_freq"] = torch.arange(64, dtype=torch.float32)
+    path = str(tmp_path / "model.safetensors")
+    safetensors.torch.save_file(tensors, path)
+    m = crane_b200.Qwen3Model(cfg, device=0, max_seq_len=512)
+    loaded, skipped = m.load_safetensors(path)
+    m.finalize()
+    assert loaded == len(w) and skipped == 1
+    assert np.array_equal(m.forward_step(ids, 0), ref)           # same bytes in, same logits out
+    with pytest.raises(crane_b200.CraneB200Error):
+        m.load_safetensors(str(tmp_path / "missing.safetensors"))
+    m.close()
+
+
+def test_gguf_file_reader(tmp_path):
+    import gguf
+    from oracle import ggml_quant as gq
+    cfg = synth.TINY_QWEN3_UNTIED
+    w = dict(synth.synth_checkpoint(cfg))
+    ids = synth.synth_token_ids(33, cfg["vocab_size"], "gg")
+    ref_m, _ = _quantised_model(cfg, Q4_K_M_LIKE)                 # the same blocks, registered tensor by tensor
+    ref = ref_m.forward_step(ids, 0)
+    ref_tok = ref_m.generate(ids, max_new_tokens=4)
+    ref_m.close()
+    path = str(tmp_path / "model.gguf")
+    wr = gguf.GGUFWriter(path, "qwen3")
+    wr.add_uint32("qwen3.block_count", cfg["num_hidden_layers"])
+    wr.add_string("general.name", "tiny")
+    wr.add_array("tokenizer.ggml.tokens", ["a", "b", "c"])        # metadata of every value kind has to be skipped correctly
+    qtypes = {"Q4_K": gguf.GGMLQuantizationType.Q4_K, "Q6_K": gguf.GGMLQuantizationType.Q6_K, "Q8_0": gguf.GGMLQuantizationType.Q8_0}
+    for name, arr in w.items():
+        qt = next((t for suf, t in Q4_K_M_LIKE.items() if name.endswith(suf)), None)
+        if qt is None or arr.ndim != 2:
+            wr.add_tensor(_gguf_name(name), np.ascontiguousarray(arr, dtype=np.float32))
+        else:
+            raw = np.ascontiguousarray(gq.quantize(arr, qt)).reshape(arr.shape[0], -1)
+            wr.add_tensor(_gguf_name(name), raw, raw_dtype=qtypes[qt])
+    wr.add_tensor("rope_freqs.weight", np.ones(64, np.float32))
+    wr.write_header_to_file()
+    wr.write_kv_data_to_file()
+    wr.write_tensors_to_file()
+    wr.close()
+    m = crane_b200.Qwen3Model(cfg, device=0, max_seq_len=512)
+    loaded, skipped = m.load_gguf(path)
+    m.finalize()
+    assert loaded == len(w) and skipped == 1
+    assert np.array_equal(m.forward_step(ids, 0), ref)
+    m.clear_kv_cache()
+    assert list(m.generate(ids, max_new_tokens=4)) == list(ref_tok)
+    m.close()
