@@ -83,17 +83,23 @@ gdn_prep_kernel(GdnArgs a) {
 }
 
 // grid (nv * dv/32), 128 threads.  dk == 128.
-constexpr int GDN_TC = 16;
+// The S steps are strictly sequential, so a step's latency is everything: the two 32-term dots run as 4 independent FMA chains
+// (one per float4 component), and the per-step operands (q, k, v, decay, beta) stream through a double-buffered cp.async ring of
+// GDN_TC-step chunks so no step ever waits on global memory.
+constexpr int GDN_TC = 32;
+constexpr int GDN_KP = 128 + 16;                   // padded row: 4 floats of skew per 32 (conflict-free float4 reads by the 4 lanes of a column)
 __device__ __forceinline__ int gdn_pad(int k) { return k + (k >> 5) * 4; }
+constexpr size_t GDN_RECUR_SMEM = (size_t)2 * GDN_TC * (2 * GDN_KP + 32 + 2) * sizeof(float);
 
 __global__ void __launch_bounds__(128)
 gdn_recur_kernel(GdnArgs a) {
     pdl_wait();
-    constexpr int DK = 128, KP = DK + 16;
-    __shared__ __align__(16) float q_s[GDN_TC][KP];
-    __shared__ __align__(16) float k_s[GDN_TC][KP];
-    __shared__ float v_s[GDN_TC][32];
-    __shared__ float gb_s[GDN_TC][2];
+    constexpr int DK = 128, KP = GDN_KP;
+    extern __shared__ __align__(16) float gsm[];
+    float* q_s = gsm;                               // [2][TC][KP]
+    float* k_s = q_s + 2 * GDN_TC * KP;             // [2][TC][KP]
+    float* v_s = k_s + 2 * GDN_TC * KP;             // [2][TC][32]
+    float* gb_s = v_s + 2 * GDN_TC * 32;            // [2][TC][2]
     const int tiles = a.dv / 32;
     const int h = blockIdx.x / tiles, vt = blockIdx.x % tiles;
     const int kh = h / (a.nv / a.nk);
@@ -107,49 +113,67 @@ gdn_recur_kernel(GdnArgs a) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) s[i] = sp[(size_t)i * a.dv];
 
-    for (int t0 = 0; t0 < a.S; t0 += GDN_TC) {
+    auto prefetch = [&](int t0, int buf) {
         const int nt = min(GDN_TC, a.S - t0);
-        __syncthreads();
-        for (int i = tid; i < nt * DK; i += 128) {
-            const int tt = i / DK, k = i % DK;
-            q_s[tt][gdn_pad(k)] = a.qn[((size_t)(t0 + tt) * a.nk + kh) * DK + k];
-            k_s[tt][gdn_pad(k)] = a.kn[((size_t)(t0 + tt) * a.nk + kh) * DK + k];
+        if (nt > 0) {
+            for (int i = tid; i < nt * 32; i += 128) {       // 32 16-byte pieces of q and of k per step
+                const int tt = i >> 5, c = i & 31;
+                const size_t src = ((size_t)(t0 + tt) * a.nk + kh) * DK + c * 4;
+                const int dst = (buf * GDN_TC + tt) * KP + gdn_pad(c * 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(q_s + dst)), "l"(a.qn + src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(k_s + dst)), "l"(a.kn + src) : "memory");
+            }
+            for (int i = tid; i < nt * 8; i += 128) {
+                const int tt = i >> 3, c = i & 7;
+                const float* src = a.conv_out + (size_t)(t0 + tt) * conv_dim + 2 * a.nk * a.dk + h * a.dv + vt * 32 + c * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(v_s + (buf * GDN_TC + tt) * 32 + c * 4)), "l"(src) : "memory");
+            }
+            if (tid < nt) {
+                const float* src = a.gb + ((size_t)(t0 + tid) * a.nv + h) * 2;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(gb_s + (buf * GDN_TC + tid) * 2)), "l"(src) : "memory");
+            }
         }
-        for (int i = tid; i < nt * 32; i += 128) {
-            const int tt = i / 32, c = i % 32;
-            v_s[tt][c] = a.conv_out[(size_t)(t0 + tt) * conv_dim + 2 * a.nk * a.dk + h * a.dv + vt * 32 + c];
-        }
-        if (tid < nt * 2) gb_s[tid / 2][tid % 2] = a.gb[((size_t)(t0 + tid / 2) * a.nv + h) * 2 + (tid % 2)];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < a.S; t0 += GDN_TC, buf ^= 1) {
+        const int nt = min(GDN_TC, a.S - t0);
+        prefetch(t0 + GDN_TC, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         for (int tt = 0; tt < nt; ++tt) {
-            const float decay = gb_s[tt][0], beta = gb_s[tt][1];
-            const float4* kp = reinterpret_cast<const float4*>(&k_s[tt][gdn_pad(32 * c4)]);
-            const float4* qp = reinterpret_cast<const float4*>(&q_s[tt][gdn_pad(32 * c4)]);
-            float kv = 0.f;
+            const float decay = gb_s[(buf * GDN_TC + tt) * 2], beta = gb_s[(buf * GDN_TC + tt) * 2 + 1];
+            const float4* kp = reinterpret_cast<const float4*>(k_s + (buf * GDN_TC + tt) * KP + gdn_pad(32 * c4));
+            const float4* qp = reinterpret_cast<const float4*>(q_s + (buf * GDN_TC + tt) * KP + gdn_pad(32 * c4));
+            float4 kr[8];
+            float kx = 0.f, ky = 0.f, kz = 0.f, kw = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 k4 = kp[i];
+                kr[i] = kp[i];
                 s[4 * i + 0] *= decay; s[4 * i + 1] *= decay; s[4 * i + 2] *= decay; s[4 * i + 3] *= decay;
-                kv = fmaf(s[4 * i + 0], k4.x, kv); kv = fmaf(s[4 * i + 1], k4.y, kv);
-                kv = fmaf(s[4 * i + 2], k4.z, kv); kv = fmaf(s[4 * i + 3], k4.w, kv);
+                kx = fmaf(s[4 * i + 0], kr[i].x, kx); ky = fmaf(s[4 * i + 1], kr[i].y, ky);
+                kz = fmaf(s[4 * i + 2], kr[i].z, kz); kw = fmaf(s[4 * i + 3], kr[i].w, kw);
             }
+            float kv = (kx + ky) + (kz + kw);
             kv += __shfl_xor_sync(0xffffffffu, kv, 1);
             kv += __shfl_xor_sync(0xffffffffu, kv, 2);
-            const float delta = (v_s[tt][col_local] - kv) * beta;
-            float y = 0.f;
+            const float delta = (v_s[(buf * GDN_TC + tt) * 32 + col_local] - kv) * beta;
+            float yx = 0.f, yy = 0.f, yz = 0.f, yw = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 k4 = kp[i];
                 const float4 q4 = qp[i];
-                s[4 * i + 0] = fmaf(k4.x, delta, s[4 * i + 0]); y = fmaf(s[4 * i + 0], q4.x, y);
-                s[4 * i + 1] = fmaf(k4.y, delta, s[4 * i + 1]); y = fmaf(s[4 * i + 1], q4.y, y);
-                s[4 * i + 2] = fmaf(k4.z, delta, s[4 * i + 2]); y = fmaf(s[4 * i + 2], q4.z, y);
-                s[4 * i + 3] = fmaf(k4.w, delta, s[4 * i + 3]); y = fmaf(s[4 * i + 3], q4.w, y);
+                s[4 * i + 0] = fmaf(kr[i].x, delta, s[4 * i + 0]); yx = fmaf(s[4 * i + 0], q4.x, yx);
+                s[4 * i + 1] = fmaf(kr[i].y, delta, s[4 * i + 1]); yy = fmaf(s[4 * i + 1], q4.y, yy);
+                s[4 * i + 2] = fmaf(kr[i].z, delta, s[4 * i + 2]); yz = fmaf(s[4 * i + 2], q4.z, yz);
+                s[4 * i + 3] = fmaf(kr[i].w, delta, s[4 * i + 3]); yw = fmaf(s[4 * i + 3], q4.w, yw);
             }
+            float y = (yx + yy) + (yz + yw);
             y += __shfl_xor_sync(0xffffffffu, y, 1);
             y += __shfl_xor_sync(0xffffffffu, y, 2);
             if (c4 == 0) a.y[((size_t)(t0 + tt) * a.nv + h) * a.dv + col] = y;
         }
+        __syncthreads();                               // this buffer is refilled by the prefetch of the next iteration
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) sp[(size_t)i * a.dv] = s[i];
@@ -193,7 +217,11 @@ int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     if (!r) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);
     // NOT a programmatic dependent: launched early, its 64 long-running CTAs land wherever the previous kernel leaves room and
     // pile up several to an SM; launched after it, they spread one per SM (measured: 4.4 vs 2.4 ms per layer at 4096 tokens)
-    if (!r) r = launch_k(gdn_recur_kernel, dim3(a.nv * (a.dv / 32)), dim3(128), 0, st, false, a);
+    if (!r) {
+        static bool set = false;
+        if (!set) { cudaFuncSetAttribute(gdn_recur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GDN_RECUR_SMEM); set = true; }
+        r = launch_k(gdn_recur_kernel, dim3(a.nv * (a.dv / 32)), dim3(128), GDN_RECUR_SMEM, st, false, a);
+    }
     if (!r) r = launch_k(gdn_gated_norm_kernel, dim3((a.S * a.nv + 3) / 4), dim3(128), 0, st, pdl, a);
     return r;
 }
