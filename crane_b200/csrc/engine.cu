@@ -1025,7 +1025,7 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) 
             GemvArgs o = {};
             o.W = l.w_out; o.N = H; o.K = value_dim(); o.x = gd_out; o.ldx = value_dim(); o.y = x_dec; o.ldy = H;
             LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
-            launches += 7;
+            launches += (nk == nv && dv == 128 && B == 1) ? 3 : 7;     // gdn_forward_launch: one fused kernel or five
         }
         linear_decode(GEMV_SILU_MUL, true, l.wgu, l.q_wgu, l.qt_gu, 2 * I, H, x_dec, H, l.ln2, act_dec, I, nullptr, B);
         linear_decode(GEMV_RESID, false, l.wdown, l.q_wdown, l.qt_down, H, I, act_dec, I, nullptr, x_dec, H, nullptr, B);

@@ -208,10 +208,107 @@ gdn_gated_norm_kernel(GdnArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Decode (S == 1) fast path: the five stages above for ONE token in ONE launch.  Everything a value head needs is head-local when
+// nk == nv (its own q / k / v channels of the conv, its 128 x 128 state, its gates), so one 512-thread CTA per head does
+// conv + state shift -> l2norm / gates -> one recurrence step -> gated RMSNorm.  Same arithmetic, four launches fewer per layer.
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+gdn_decode_kernel(GdnArgs a) {
+    constexpr int DK = 128, DV = 128;
+    __shared__ __align__(16) float q_s[DK], k_s[DK], v_s[DV], y_s[DV];
+    __shared__ float red[32];
+    __shared__ float gate_s[2];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int key_dim = a.nk * DK, conv_dim = 2 * key_dim + a.nv * DV;
+    // ---- depthwise causal conv (window = last ck-1 cached inputs + this token) + SiLU, and the state shift ----
+    if (tid < 3 * DK) {
+        const int which = tid / DK, i = tid % DK;                 // 0: q, 1: k, 2: v
+        const int c = which == 0 ? h * DK + i : which == 1 ? key_dim + h * DK + i : 2 * key_dim + h * DV + i;
+        float* st = a.conv_state + (size_t)c * a.ck;
+        const float xin = a.proj[c];
+        float acc = 0.f;
+        for (int j = 0; j < a.ck; ++j) {
+            const float hv = (j + 1 < a.ck) ? st[j + 1] : xin;
+            acc = fmaf(a.conv_w[(size_t)c * a.ck + j], hv, acc);
+        }
+        for (int j = 0; j + 1 < a.ck; ++j) st[j] = st[j + 1];      // one thread per channel: in-order shift is safe
+        st[a.ck - 1] = xin;
+        (which == 0 ? q_s : which == 1 ? k_s : v_s)[i] = silu_f(acc);
+    }
+    if (tid == 3 * DK) {
+        const float* pr = a.proj + conv_dim + a.nv * DV;
+        const float b = pr[h], av = pr[a.nv + h];
+        gate_s[0] = expf(a.neg_exp_a[h] * logf(1.0f + expf(av + a.dt_bias[h])));
+        gate_s[1] = 1.0f / (1.0f + expf(-b));
+    }
+    __syncthreads();
+    // ---- l2norm(q) / sqrt(dk), l2norm(k) ----
+    if (warp < 2) {
+        float* vsrc = warp == 0 ? q_s : k_s;
+        float e[4], ssq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { e[j] = vsrc[lane + 32 * j]; ssq += e[j] * e[j]; }
+        ssq = warp_sum(ssq);
+        float sc = 1.0f / sqrtf(ssq + 1e-6f);
+        if (warp == 0) sc *= 1.0f / sqrtf((float)DK);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vsrc[lane + 32 * j] = e[j] * sc;
+    }
+    __syncthreads();
+    // ---- one step of the gated delta rule: 4 lanes per state column ----
+    const int col = tid >> 2, c4 = tid & 3;
+    float* sp = a.rec_state + ((size_t)h * DK + 32 * c4) * DV + col;
+    const float decay = gate_s[0], beta = gate_s[1];
+    float s[32];
+    float kx = 0.f, ky = 0.f, kz = 0.f, kw = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[i] = sp[(size_t)i * DV] * decay;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 k4 = *reinterpret_cast<const float4*>(k_s + 32 * c4 + 4 * i);
+        kx = fmaf(s[4 * i + 0], k4.x, kx); ky = fmaf(s[4 * i + 1], k4.y, ky);
+        kz = fmaf(s[4 * i + 2], k4.z, kz); kw = fmaf(s[4 * i + 3], k4.w, kw);
+    }
+    float kv = (kx + ky) + (kz + kw);
+    kv += __shfl_xor_sync(0xffffffffu, kv, 1);
+    kv += __shfl_xor_sync(0xffffffffu, kv, 2);
+    const float delta = (v_s[col] - kv) * beta;
+    float yx = 0.f, yy = 0.f, yz = 0.f, yw = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 k4 = *reinterpret_cast<const float4*>(k_s + 32 * c4 + 4 * i);
+        const float4 q4 = *reinterpret_cast<const float4*>(q_s + 32 * c4 + 4 * i);
+        s[4 * i + 0] = fmaf(k4.x, delta, s[4 * i + 0]); yx = fmaf(s[4 * i + 0], q4.x, yx);
+        s[4 * i + 1] = fmaf(k4.y, delta, s[4 * i + 1]); yy = fmaf(s[4 * i + 1], q4.y, yy);
+        s[4 * i + 2] = fmaf(k4.z, delta, s[4 * i + 2]); yz = fmaf(s[4 * i + 2], q4.z, yz);
+        s[4 * i + 3] = fmaf(k4.w, delta, s[4 * i + 3]); yw = fmaf(s[4 * i + 3], q4.w, yw);
+    }
+    float y = (yx + yy) + (yz + yw);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sp[(size_t)i * DV] = s[i];
+    if (c4 == 0) y_s[col] = y;
+    __syncthreads();
+    // ---- rmsnorm(y) * w * silu(z) ----
+    const float yv = tid < DV ? y_s[tid] : 0.f;
+    const float tot = block_sum(yv * yv, red);
+    if (tid < DV) {
+        const float rstd = rsqrtf(tot / (float)DV + a.eps);
+        const float z = a.proj[conv_dim + h * DV + tid];
+        a.out_f32[(size_t)h * DV + tid] = yv * rstd * a.norm_w[tid] * silu_f(z);
+    }
+}
+
 int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     if (a.dk != 128 || (a.dv % 32) != 0 || a.ck > GDN_MAX_CK || a.nv > 256 || (a.nv % a.nk) != 0) return -1000;
     const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
     const bool pdl = prefill_pdl();
+    if (a.S == 1 && a.nk == a.nv && a.dv == 128 && a.ck >= 2 && a.out_f32 != nullptr && a.out_bf16 == nullptr)
+        return launch_k(gdn_decode_kernel, dim3(a.nv), dim3(512), 0, st, pdl, a);
     int r = launch_k(gdn_conv_kernel, dim3((conv_dim + 127) / 128, a.S), dim3(128), 0, st, pdl, a);
     if (!r) r = launch_k(gdn_conv_state_kernel, dim3((conv_dim + 127) / 128), dim3(128), 0, st, pdl, a);
     if (!r) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);

@@ -272,9 +272,11 @@ def test_tiny_qwen3_5_against_hf_fixture(gemm, precision):
     m.close()
 
 
-def test_qwen3_5_chunked_prefill_state_handoff_and_decode():
+@pytest.mark.parametrize("equal_heads", [False, True], ids=["nk<nv", "nk==nv"])
+def test_qwen3_5_chunked_prefill_state_handoff_and_decode(equal_heads):
+    """nk == nv (the shape of Qwen3.5-0.8B) takes the single-launch GDN decode kernel, nk < nv the five-kernel path."""
     from oracle.qwen3_5 import Qwen3_5Oracle
-    cfg = synth.TINY_QWEN3_5
+    cfg = dict(synth.TINY_QWEN3_5, linear_num_key_heads=4) if equal_heads else synth.TINY_QWEN3_5
     m, w = _model(cfg, cls=crane_b200.Qwen3_5Model)
     orc = Qwen3_5Oracle(cfg, w)
     ids = synth.synth_token_ids(90, cfg["vocab_size"], "q35-gpu")
