@@ -114,6 +114,22 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 
 
+// Host: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE -- one process may drive a handle on every GPU of the box --
+// so each launcher remembers, per device, the largest opt-in it has already made for its kernel instantiation.
+constexpr int CB_MAX_DEV = 64;
+struct SmemOptIn { size_t bytes[CB_MAX_DEV] = {}; };
+template <typename K>
+inline int ensure_dyn_smem(K kernel, size_t bytes, SmemOptIn& seen) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= CB_MAX_DEV) return (int)cudaErrorInvalidDevice;
+    if (bytes > seen.bytes[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        seen.bytes[dev] = bytes;
+    }
+    return 0;
+}
+
 // Host: launch `kernel` on `st`, as a programmatic dependent of the previous kernel in the stream when `pdl`.
 inline bool& prefill_pdl() { static bool on = true; return on; }
 template <typename... KArgs, typename... Args>

@@ -297,12 +297,8 @@ template <int B, int EPI, bool NORM>
 static int gemv_launch_t(cudaStream_t st, const GemvArgs& a, int num_sms, bool pdl) {
     const size_t smem = gemv_smem_bytes(B, a.K, a.N, EPI == GEMV_SILU_MUL ? 2 : 1, num_sms);
     if (smem > 227 * 1024) return -1000;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_kernel<B, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
+    static SmemOptIn seen;
+    if (const int e = ensure_dyn_smem(gemv_kernel<B, EPI, NORM>, smem, seen)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms);
     cfg.blockDim = dim3(GV_THREADS);
@@ -668,12 +664,8 @@ attn_decode_kernel(AttnDecArgs a) {
 template <int D, int NREP>
 static int attn_decode_launch_t(cudaStream_t st, int B, const AttnDecArgs& a, bool pdl) {
     const int SMEM = a.kv_lo_off ? 131072 : 65536;
-    static int set = 0;
-    if (set < SMEM) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<D, NREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return (int)e;
-        set = SMEM;
-    }
+    static SmemOptIn seen;
+    if (const int e = ensure_dyn_smem(attn_decode_kernel<D, NREP>, (size_t)SMEM, seen)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.nkv * ATTN_NSPLIT, B);
     cfg.blockDim = dim3(256);

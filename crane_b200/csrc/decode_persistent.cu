@@ -540,12 +540,8 @@ template <int NREP>
 static int launch_t(cudaStream_t st, const PersistArgs& a, int num_sms) {
     const size_t smem = decode_persistent_smem(a, num_sms);
     if (smem > 227 * 1024) return -1000;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(decode_persistent_kernel<NREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
+    static SmemOptIn seen;
+    if (const int e = ensure_dyn_smem(decode_persistent_kernel<NREP>, smem, seen)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms);
     cfg.blockDim = dim3(PK_THREADS);

@@ -315,9 +315,9 @@ int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     // NOT a programmatic dependent: launched early, its 64 long-running CTAs land wherever the previous kernel leaves room and
     // pile up several to an SM; launched after it, they spread one per SM (measured: 4.4 vs 2.4 ms per layer at 4096 tokens)
     if (!r) {
-        static bool set = false;
-        if (!set) { cudaFuncSetAttribute(gdn_recur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GDN_RECUR_SMEM); set = true; }
-        r = launch_k(gdn_recur_kernel, dim3(a.nv * (a.dv / 32)), dim3(128), GDN_RECUR_SMEM, st, false, a);
+        static SmemOptIn seen;
+        r = ensure_dyn_smem(gdn_recur_kernel, GDN_RECUR_SMEM, seen);
+        if (!r) r = launch_k(gdn_recur_kernel, dim3(a.nv * (a.dv / 32)), dim3(128), GDN_RECUR_SMEM, st, false, a);
     }
     if (!r) r = launch_k(gdn_gated_norm_kernel, dim3((a.S * a.nv + 3) / 4), dim3(128), 0, st, pdl, a);
     return r;

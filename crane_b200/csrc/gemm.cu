@@ -445,12 +445,8 @@ static int launch_tc(cudaStream_t stream, const bf16* A, const bf16* A_lo, int l
     if (!make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM / cx)) return -1001;
     if (!make_tmap_bf16(&tmAlo, SPLIT ? A_lo : A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM / cx)) return -1001;
     if (!make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN / cy)) return -1001;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static SmemOptIn seen;
+    if (const int e = ensure_dyn_smem(gemm_tc_kernel<BN, MODE, SPLIT>, (size_t)Cfg::SMEM_BYTES, seen)) return e;
     dim3 grid((N + BN - 1) / BN, ((M + GEMM_BM - 1) / GEMM_BM + cy - 1) / cy * cy);   // whole clusters; surplus tiles are all-OOB
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

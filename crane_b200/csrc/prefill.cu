@@ -430,12 +430,8 @@ static int flash_launch_t(cudaStream_t st, const FlashArgs& a) {
     constexpr int P = SPLIT ? 2 : 1, STG = 2, BN = (SPLIT && D > 128) ? 32 : 64;
     constexpr int SMEM = (P * 64 * (D + 8) + STG * 2 * P * BN * (D + 8)) * 2;
     static_assert(SMEM <= 227 * 1024, "flash tile does not fit");
-    static bool set = false;
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return (int)e;
-        set = true;
-    }
+    static SmemOptIn seen;
+    if (const int e = ensure_dyn_smem(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, (size_t)SMEM, seen)) return e;
     const int max_len = a.seq_len ? a.max_len : a.S;
     dim3 grid((max_len + 63) / 64, a.nh, a.seq_len ? a.nseq : 1);
     return launch_k(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, grid, dim3(128), SMEM, st, prefill_pdl(), a);

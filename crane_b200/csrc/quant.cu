@@ -479,12 +479,8 @@ static int qgemv_launch_t(cudaStream_t st, const QGemvArgs& qa, int num_sms, boo
     const int QG_THREADS = QG_WARPS * 32;
     const size_t smem = fixed + QG_WARPS * slot;
     if (smem > 226 * 1024) return -1000;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(qgemv_kernel<B, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
+    static SmemOptIn seen;
+    if (const int e = ensure_dyn_smem(qgemv_kernel<B, QT>, smem, seen)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms);
     cfg.blockDim = dim3(QG_THREADS);
