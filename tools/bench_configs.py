@@ -34,8 +34,28 @@ def cheap(shape, kind):
     return np.tile(BLOCK, reps)[:n].reshape(shape)
 
 
+GGML_TYPE_ID = {"Q8_0": 8, "Q4_K": 12, "Q6_K": 14}
+
+
+def fake_blocks(rows, K, qt):
+    """Syntactically valid ggml blocks with random codes and small f16 scales (timing only: the values are irrelevant, and this tool
+    must not touch oracle/).  Layouts: Q8_0 [f16 d | 32 i8]; Q4_K [f16 d | f16 dmin | 12 B scales | 128 B nibbles]; Q6_K [128 ql | 64 qh | 16 i8 | f16 d]."""
+    small = np.frombuffer(np.float16(0.01).tobytes(), np.uint8)
+    if qt == "Q8_0":
+        b = rng.integers(0, 256, (rows, K // 32, 34), dtype=np.uint8)
+        b[..., 0:2] = small
+    elif qt == "Q4_K":
+        b = rng.integers(0, 256, (rows, K // 256, 144), dtype=np.uint8)
+        b[..., 0:2] = small
+        b[..., 2:4] = small
+    else:
+        b = rng.integers(0, 256, (rows, K // 256, 210), dtype=np.uint8)
+        b[..., 192:208] = rng.integers(0, 16, (rows, K // 256, 16), dtype=np.uint8)
+        b[..., 208:210] = small
+    return b.reshape(rows, -1)
+
+
 def load_cheap(m, cfg, quant=None):
-    from oracle import ggml_quant as gq          # only to fabricate valid ggml blocks for the timing run
     qcache = {}
     for name, shape, kind in synth.tensor_specs(cfg):
         qt = None
@@ -44,9 +64,9 @@ def load_cheap(m, cfg, quant=None):
         if qt:
             key = (qt, shape[1])
             if key not in qcache:
-                qcache[key] = gq.quantize((rng.standard_normal((64, shape[1])) * 0.02).astype(np.float32), qt)
+                qcache[key] = fake_blocks(64, shape[1], qt)
             raw = np.tile(qcache[key], ((shape[0] + 63) // 64, 1))[:shape[0]]
-            m.load_tensor_ggml(name, gq.GGML_TYPE_ID[qt], shape, raw)
+            m.load_tensor_ggml(name, GGML_TYPE_ID[qt], shape, raw)
         else:
             m.load_tensor(name, cheap(shape, kind))
     m.finalize()
