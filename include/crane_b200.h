@@ -64,8 +64,10 @@ typedef struct {
 /* Create an engine for one model on one GPU.  `config_json` is the checkpoint's HF config.json text
  * (qwen3: crane-core/src/models/qwen3/modeling.rs:94-130 `Config`; qwen3_vl: text_config + vision_config
  * as crane-core/src/models/qwen3_5/config.rs:112-137) optionally extended with an "engine" object:
- *   {"max_seq_len": 4096, "max_batch": 1, "gemm": "tcgen05"|"simt", "graphs": true,
- *    "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf"}
+ *   {"max_seq_len": 4096, "max_batch": 1, "gemm": "tcgen05"|"simt", "graphs": true, "pdl": true,
+ *    "precision": "split"|"bf16", "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf"}
+ * "precision": "split" (default) carries every bf16 tensor-core operand and KV page as a hi + lo pair (~16 mantissa bits:
+ * logits within ~3e-5 of the f32 CPU path); "bf16" is the plain-bf16 fast mode (~1e-2, what the reference's GPU path does).
  * Replaces `model_factory::create_backend` / `Qwen3Backend::new`
  * (crane-serve/src/engine/model_factory.rs:471-560, backend.rs:615-625). */
 CRANE_B200_API int crane_b200_create(const char* config_json, int device_ordinal, crane_b200_model** out);
