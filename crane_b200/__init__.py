@@ -49,6 +49,7 @@ _SIGNATURES = {
     "crane_b200_load_tensor_ggml": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_size_t]),
     "crane_b200_load_safetensors": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "crane_b200_load_gguf": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "crane_b200_gguf_config": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "crane_b200_finalize": (C.c_int, [C.c_void_p]),
     "crane_b200_forward_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(Logits)]),
     "crane_b200_forward_step_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]),
@@ -296,6 +297,15 @@ class Engine:
 class Qwen3Model(Engine):
     """`crane_core::models::qwen3::Model` (qwen3/model.rs:34-349) without the tokenizer."""
 
+    @classmethod
+    def from_gguf(cls, path: str, device: int = 0, **engine_opts):
+        """`Model::new_with_format(.., Gguf, ..)` -> `Qwen3Model::from_gguf` (qwen3/modeling.rs:821-935): config from the file's
+        metadata, tensors (quantised blocks included) from the file itself."""
+        m = cls(gguf_config(path), device=device, **engine_opts)
+        m.load_gguf(path)
+        m.finalize()
+        return m
+
     def generate(self, input_ids, max_new_tokens: int = 128, eos_token_id=(), temperature=None):
         """`ModelForCausalLM::generate` (generation/based.rs:5-34); greedy only (temperature None => ArgMax,
         qwen3/model.rs:281-284).  Sampling stays on the caller's side of the boundary."""
@@ -396,6 +406,17 @@ class Qwen3TTSModel(Engine):
                                                   _ptr(frames), C.byref(n), None if fl is None else _ptr(fl), None if gl is None else _ptr(gl)))
         k = int(n.value)
         return (frames[:k], fl[:k], gl[:k]) if want_logits else frames[:k]
+
+
+def gguf_config(path: str) -> dict:
+    """config.json of a GGUF checkpoint, derived by the library from the file's metadata (pure host code, no GPU needed)."""
+    lib = load_library()
+    buf = C.create_string_buffer(2048)
+    need = C.c_size_t(0)
+    rc = lib.crane_b200_gguf_config(os.fsencode(path), buf, len(buf), C.byref(need))
+    if rc != OK:
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+    return json.loads(buf.value.decode())
 
 
 def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_init=None, use_simt=False, device=0, a_lo_bits=None):

@@ -94,6 +94,12 @@ CRANE_B200_API int crane_b200_load_tensor_ggml(crane_b200_model* m, const char* 
  * comes from crane_b200_create (GGUF metadata is not interpreted).  Call once per shard, then crane_b200_finalize. */
 CRANE_B200_API int crane_b200_load_safetensors(crane_b200_model* m, const char* path, size_t* n_loaded, size_t* n_skipped);
 CRANE_B200_API int crane_b200_load_gguf(crane_b200_model* m, const char* path, size_t* n_loaded, size_t* n_skipped);
+/* The config.json text of a GGUF checkpoint, derived from its metadata with the reference's recipe (`Qwen3Model::from_gguf`,
+ * crane-core/src/models/qwen3/modeling.rs:821-905: head counts, key_length default 128, block_count, embedding_length,
+ * feed_forward_length, context_length, rms epsilon, rope base; vocab from token_embd.weight; tied iff no output.weight).
+ * Pure host code (no GPU, no handle): feed the text to crane_b200_create, then crane_b200_load_gguf the same file.
+ * *needed receives the byte count including the terminator; errors are reported through crane_b200_last_error(NULL). */
+CRANE_B200_API int crane_b200_gguf_config(const char* path, char* json_out, size_t capacity, size_t* needed);
 /* All tensors registered: merge QKV / gate-up, build rotary tables, allocate KV pages + workspaces. */
 CRANE_B200_API int crane_b200_finalize(crane_b200_model* m);
 

@@ -45,3 +45,37 @@ def test_null_and_bad_config_are_errors_not_crashes():
     assert lib.crane_b200_forward_step(None, None, 0, 0, None) == crane_b200.INVALID_ARG
     assert lib.crane_b200_num_layers(None) == 0
     lib.crane_b200_destroy(None)
+
+
+def test_gguf_metadata_to_config_is_pure_host_code(tmp_path):
+    """`crane_b200_gguf_config` follows Qwen3Model::from_gguf's recipe (qwen3/modeling.rs:821-905) and needs no GPU."""
+    import gguf
+    import numpy as np
+    path = str(tmp_path / "meta.gguf")
+    wr = gguf.GGUFWriter(path, "qwen3")
+    wr.add_uint32("qwen3.block_count", 3)
+    wr.add_uint32("qwen3.embedding_length", 256)
+    wr.add_uint32("qwen3.feed_forward_length", 512)
+    wr.add_uint32("qwen3.attention.head_count", 8)
+    wr.add_uint32("qwen3.attention.head_count_kv", 2)
+    wr.add_float32("qwen3.rope.freq_base", 10000.0)
+    wr.add_float32("qwen3.attention.layer_norm_rms_epsilon", 1e-5)
+    wr.add_array("tokenizer.ggml.tokens", ["a", "b", "c"])
+    wr.add_tensor("token_embd.weight", np.zeros((1000, 256), np.float32))
+    wr.add_tensor("blk.0.attn_q_norm.weight", np.ones(128, np.float32))
+    wr.write_header_to_file()
+    wr.write_kv_data_to_file()
+    wr.write_tensors_to_file()
+    wr.close()
+    cfg = crane_b200.gguf_config(path)
+    assert cfg["model_type"] == "qwen3" and cfg["vocab_size"] == 1000 and cfg["hidden_size"] == 256 and cfg["intermediate_size"] == 512
+    assert cfg["num_hidden_layers"] == 3 and cfg["num_attention_heads"] == 8 and cfg["num_key_value_heads"] == 2
+    assert cfg["head_dim"] == 128 and cfg["max_position_embeddings"] == 32768           # the reference's defaults
+    assert abs(cfg["rope_theta"] - 1e4) < 1e-3 and abs(cfg["rms_norm_eps"] - 1e-5) < 1e-9
+    assert cfg["tie_word_embeddings"] is True and cfg["use_qk_norm"] is True
+    # missing required key / not a GGUF file: error code + message, no crash
+    bad = str(tmp_path / "bad.gguf")
+    open(bad, "wb").write(b"not a gguf file at all")
+    import pytest
+    with pytest.raises(crane_b200.CraneB200Error):
+        crane_b200.gguf_config(bad)

@@ -521,6 +521,13 @@ def test_gguf_file_reader(tmp_path):
     path = str(tmp_path / "model.gguf")
     wr = gguf.GGUFWriter(path, "qwen3")
     wr.add_uint32("qwen3.block_count", cfg["num_hidden_layers"])
+    wr.add_uint32("qwen3.embedding_length", cfg["hidden_size"])
+    wr.add_uint32("qwen3.feed_forward_length", cfg["intermediate_size"])
+    wr.add_uint32("qwen3.attention.head_count", cfg["num_attention_heads"])
+    wr.add_uint32("qwen3.attention.head_count_kv", cfg["num_key_value_heads"])
+    wr.add_uint32("qwen3.attention.key_length", cfg["head_dim"])
+    wr.add_float32("qwen3.rope.freq_base", float(cfg["rope_theta"]))
+    wr.add_float32("qwen3.attention.layer_norm_rms_epsilon", float(cfg["rms_norm_eps"]))
     wr.add_string("general.name", "tiny")
     wr.add_array("tokenizer.ggml.tokens", ["a", "b", "c"])        # metadata of every value kind has to be skipped correctly
     qtypes = {"Q4_K": gguf.GGMLQuantizationType.Q4_K, "Q6_K": gguf.GGMLQuantizationType.Q6_K, "Q8_0": gguf.GGMLQuantizationType.Q8_0}
@@ -544,3 +551,7 @@ def test_gguf_file_reader(tmp_path):
     m.clear_kv_cache()
     assert list(m.generate(ids, max_new_tokens=4)) == list(ref_tok)
     m.close()
+    # config from the file's own metadata (Qwen3Model::from_gguf): no config.json involved
+    m2 = crane_b200.Qwen3Model.from_gguf(path, device=0, max_seq_len=512)
+    assert rel_err(m2.forward_step(ids, 0), ref) < 1e-6          # (f32 epsilon / rope base read back from the metadata)
+    m2.close()
