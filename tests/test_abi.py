@@ -79,3 +79,22 @@ def test_gguf_metadata_to_config_is_pure_host_code(tmp_path):
     import pytest
     with pytest.raises(crane_b200.CraneB200Error):
         crane_b200.gguf_config(bad)
+
+
+def test_every_entry_point_survives_null_arguments():
+    """No entry point may crash, abort or throw across the ABI: all-NULL / zero arguments give an error status (or a neutral 0)."""
+    lib = crane_b200.load_library()
+    for name, (res, args) in crane_b200._SIGNATURES.items():
+        call = []
+        for a in args:
+            if a in (ctypes.c_int, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64):
+                call.append(0)
+            elif a in (ctypes.c_float, ctypes.c_double):
+                call.append(0.0)
+            else:
+                call.append(None)
+        r = getattr(lib, name)(*call)
+        if res is ctypes.c_int:
+            assert r <= 0, f"{name}(NULL...) returned {r}"
+        elif res in (ctypes.c_uint64, ctypes.c_size_t, ctypes.c_uint32):
+            assert r == 0, f"{name}(NULL...) returned {r}"
