@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "decode.cuh"
-#include "decode_persistent.cuh"
+#include "decode_ll.cuh"
 #include "gdn.cuh"
 #include "gemm.cuh"
 #include "json_min.h"
@@ -147,10 +147,15 @@ struct crane_b200_model {
     int nk = 0, nv = 0, dk = 0, dv = 0, ck = 4, gdn_in = 0, gdn_in_pad = 0, rot_half = 0, full_interval = 4;
     std::vector<int> layer_is_full;
     int max_seq = 4096, max_batch = 1, max_pages = 0;
-    bool use_simt = false, use_graphs = true, use_pdl = true, use_persistent = false;
-    PLayer* players = nullptr;
-    unsigned int* grid_bar = nullptr;
-    unsigned long long* pk_prof = nullptr;
+    bool use_simt = false, use_graphs = true, use_pdl = true, use_persistent = true;
+    // persistent decode kernel (decode_ll.cu): exchange buffers of (value, tag) pairs, the tag counter, the timeout flag
+    unsigned long long *ll_xa = nullptr, *ll_xb = nullptr, *ll_qkv = nullptr, *ll_att = nullptr, *ll_act = nullptr, *ll_part = nullptr, *ll_amax = nullptr;
+    unsigned int ll_tag = 0;
+    unsigned int* ll_err = nullptr;
+    unsigned int* h_ll_err = nullptr;      // pinned
+    unsigned long long* ll_prof = nullptr;
+    void ll_err_fetch();                   // enqueue the D2H copy of the flag (before a stream sync the caller does anyway)
+    void ll_err_verify();                  // after that sync
     // vision
     int v_depth = 0, v_H = 0, v_I = 0, v_nh = 0, v_hd = 0, v_patch = 16, v_merge = 2, v_tpatch = 2, v_in = 3, v_out = 0,
         v_npos = 0, v_side = 0;
@@ -440,7 +445,7 @@ void crane_b200_model::parse_config(const char* json) {
     if (const char* g = getenv("CRANE_B200_PDL")) use_pdl = std::string(g) != "0";
     cb::prefill_pdl() = use_pdl;          // process-wide: the prefill-side launchers read it
     if (const char* g = getenv("CRANE_B200_PRECISION")) split = std::string(g) != "bf16";
-    if (root.has("engine")) use_persistent = root.at("engine").boolean("persistent", false);
+    if (root.has("engine")) use_persistent = root.at("engine").boolean("persistent", true);
     if (const char* g = getenv("CRANE_B200_PERSISTENT")) use_persistent = std::string(g) != "0";
     if (max_batch < 1 || max_batch > 64) fail(CRANE_B200_INVALID_ARG, "max_batch %d (1..64 sequence slots)", max_batch);
     max_seq = (max_seq + KV_PAGE - 1) / KV_PAGE * KV_PAGE;
@@ -931,17 +936,24 @@ void crane_b200_model::finalize() {
     CUDA_OK(cudaMemset(counters, 0, (size_t)B * nkv * sizeof(unsigned int)));
     CUDA_OK(cudaMemset(ticket, 0, sizeof(unsigned int)));
     CUDA_OK(cudaMemset(state, 0, B * sizeof(SeqState)));
-    use_persistent = use_persistent && !hybrid && !any_quant && !split && decode_persistent_supported(D, nh / nkv, H, I, q_dim(), nkv, num_sms);
+    // single-sequence bf16 decode runs as ONE persistent launch per call (decode_ll.cu) when the geometry allows it
+    use_persistent = use_persistent && !hybrid && !any_quant && !is_tts && owns_stream && L <= LL_MAX_LAYERS &&
+                     decode_ll_supported(D, rot_half, nh, nkv, H, I, q_dim(), qkv_dim(), V, num_sms);
     if (use_persistent) {
-        std::vector<PLayer> pl(L);
-        for (int i = 0; i < L; ++i) {
-            const LayerW& l = layers[i];
-            pl[i] = PLayer{l.wqkv, l.wo, l.wgu, l.wdown, l.ln1, l.ln2, l.qn, l.kn, l.k_pool, l.v_pool};
-        }
-        players = dalloc<PLayer>(L);
-        CUDA_OK(cudaMemcpy(players, pl.data(), L * sizeof(PLayer), cudaMemcpyHostToDevice));
-        grid_bar = dalloc<unsigned int>(64);
-        if (getenv("CRANE_B200_PROF")) { pk_prof = dalloc<unsigned long long>(16); CUDA_OK(cudaMemset(pk_prof, 0, 128)); }
+        int coop = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        use_persistent = coop != 0;
+    }
+    if (use_persistent) {
+        auto pairs = [&](size_t n) { auto* p = dalloc<unsigned long long>(n); CUDA_OK(cudaMemset(p, 0, n * 8)); return p; };
+        ll_xa = pairs(H); ll_xb = pairs(H); ll_qkv = pairs(qkv_dim()); ll_att = pairs(q_dim()); ll_act = pairs(I);
+        ll_part = pairs(decode_ll_part_pairs(num_sms, nh, nkv));
+        ll_amax = pairs((size_t)2 * num_sms);
+        ll_err = dalloc<unsigned int>(1);
+        CUDA_OK(cudaMemset(ll_err, 0, sizeof(unsigned int)));
+        CUDA_OK(cudaMallocHost((void**)&h_ll_err, sizeof(unsigned int)));
+        *h_ll_err = 0;
+        if (getenv("CRANE_B200_PROF")) { ll_prof = dalloc<unsigned long long>(16); CUDA_OK(cudaMemset(ll_prof, 0, 128)); }
     }
     CUDA_OK(cudaMallocHost((void**)&h_state, sizeof(SeqState) * B));
     CUDA_OK(cudaMallocHost((void**)&h_tokens, sizeof(uint32_t) * out_cap));
@@ -1086,32 +1098,57 @@ void crane_b200_model::decode_step_graphed(int advance) {
 
 // n dependent decode steps: one persistent launch when available, else n graph replays / kernel chains.
 void crane_b200_model::decode_steps(int n_steps, int advance) {
-    if (use_persistent) {
-        PersistArgs p = {};
+    if (use_persistent && (advance == 1 || (advance == 0 && n_steps == 1))) {
+        LLArgs p = {};
         p.L = L; p.H = H; p.I = I; p.V = V; p.nh = nh; p.nkv = nkv; p.qkv_dim = qkv_dim(); p.q_dim = q_dim();
         p.eps = eps; p.scale = 1.0f / std::sqrt((float)D);
-        p.layers = players; p.lm_head = lm_head; p.final_norm = final_norm; p.embed = embed;
-        p.cos_tab = cos_tab; p.sin_tab = sin_tab; p.axis_of = axis_of; p.state = state; p.block_table = bt_cur();
-        p.x = x_dec; p.qkv = qkv_dec; p.act = act_dec; p.logits = logits; p.part_o = part_o; p.part_ml = part_ml;
-        p.part_val = part_val; p.part_idx = part_idx; p.out_tokens = out_tokens; p.barrier = grid_bar;
-        p.n_steps = n_steps; p.advance = advance; p.prof = pk_prof;
-        p.xs_floats = std::max(std::max(H, I), std::max(q_dim(), PK_WARPS_C * (nh / nkv) * 128));
-        CUDA_OK(cudaMemsetAsync(grid_bar, 0, 64 * sizeof(unsigned int), stream));
-        LAUNCH_OK(decode_persistent_launch(stream, p, num_sms));
+        for (int i = 0; i < L; ++i) {
+            const LayerW& l = layers[i];
+            p.layers[i] = LLLayer{l.wqkv, l.wo, l.wgu, l.wdown, l.ln1, l.ln2, l.qn, l.kn, l.k_pool, l.v_pool};
+        }
+        p.lm_head = lm_head; p.final_norm = final_norm; p.embed = embed;
+        p.cos_tab = cos_tab; p.sin_tab = sin_tab; p.axis_of = axis_of; p.state = state; p.block_table = block_table; p.max_pages = max_pages;
+        p.kv_lo_off = lo_kv; p.x_io = x_dec; p.logits = logits; p.out_tokens = out_tokens;
+        p.xa = ll_xa; p.xb = ll_xb; p.qkv = ll_qkv; p.att = ll_att; p.act = ll_act; p.part = ll_part; p.amax = ll_amax;
+        const unsigned int need = ll_tags_per_launch(L, n_steps);
+        if (ll_tag > 0xffffffffu - need - 1u) {       // tag space exhausted (once per ~10^8 tokens): start over from clean buffers
+            for (auto* b : {ll_xa, ll_xb}) CUDA_OK(cudaMemsetAsync(b, 0, (size_t)H * 8, stream));
+            CUDA_OK(cudaMemsetAsync(ll_qkv, 0, (size_t)qkv_dim() * 8, stream));
+            CUDA_OK(cudaMemsetAsync(ll_att, 0, (size_t)q_dim() * 8, stream));
+            CUDA_OK(cudaMemsetAsync(ll_act, 0, (size_t)I * 8, stream));
+            CUDA_OK(cudaMemsetAsync(ll_part, 0, decode_ll_part_pairs(num_sms, nh, nkv) * 8, stream));
+            CUDA_OK(cudaMemsetAsync(ll_amax, 0, (size_t)2 * num_sms * 8, stream));
+            ll_tag = 0;
+        }
+        p.tag_base = ll_tag;
+        ll_tag += need;
+        p.n_steps = n_steps; p.advance = advance; p.err = ll_err; p.prof = ll_prof;
+        LAUNCH_OK(decode_ll_launch(stream, p, num_sms));
         ++launches;
-        if (pk_prof && n_steps > 8) {   // CRANE_B200_PROF=1: per-phase device time of CTA 0 (the CRANE_PROF spans of ops/prof.rs:37-61)
+        if (ll_prof && n_steps > 8) {   // CRANE_B200_PROF=1: where CTA 0's first thread spent its cycles (the CRANE_PROF spans of ops/prof.rs:37-61)
             unsigned long long h[16];
             CUDA_OK(cudaStreamSynchronize(stream));
-            CUDA_OK(cudaMemcpy(h, pk_prof, 128, cudaMemcpyDeviceToHost));
-            CUDA_OK(cudaMemset(pk_prof, 0, 128));
-            const char* names[10] = {"attention", "attn_barrier", "stage_tail", "stream", "epilogue", "barrier", "token", "geom", "stage_load", "stage_reduce"};
-            fprintf(stderr, "[crane_b200 prof] per step (us):");
-            for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.1f", names[i], (double)h[i] / 1e3 / n_steps);
+            CUDA_OK(cudaMemcpy(h, ll_prof, 128, cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemset(ll_prof, 0, 128));
+            const char* names[8] = {"init", "wait_x", "stream", "cta_barrier", "attention", "merge", "epilogue", "token"};
+            fprintf(stderr, "[crane_b200 prof] cycles per step:");
+            for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / n_steps);
             fprintf(stderr, "\n");
         }
         return;
     }
     for (int i = 0; i < n_steps; ++i) decode_step_graphed(advance);
+}
+
+// The persistent kernel bounds every wait; a wait that gave up leaves garbage behind and raises this flag (read at sync points).
+void crane_b200_model::ll_err_fetch() {
+    if (ll_err) CUDA_OK(cudaMemcpyAsync(h_ll_err, ll_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+}
+void crane_b200_model::ll_err_verify() {
+    if (!ll_err || *h_ll_err == 0) return;
+    CUDA_OK(cudaMemsetAsync(ll_err, 0, sizeof(unsigned int), stream));
+    *h_ll_err = 0;
+    fail(CRANE_B200_CUDA_ERROR, "persistent decode kernel: a dependency wait timed out (results discarded)");
 }
 
 // =================================================================================================
@@ -1419,6 +1456,7 @@ void crane_b200_destroy(crane_b200_model* m) {
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_state) cudaFreeHost(m->h_state);
     if (m->h_tokens) cudaFreeHost(m->h_tokens);
+    if (m->h_ll_err) cudaFreeHost(m->h_ll_err);
     for (cudaEvent_t e : {m->pev0, m->pev1, m->dev0, m->dev1}) if (e) cudaEventDestroy(e);
     if (m->stream && m->owns_stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -1478,7 +1516,9 @@ int crane_b200_forward_step_argmax(crane_b200_model* m, const uint32_t* ids, siz
     if (r != CRANE_B200_OK) return r;
     API_BEGIN(m)
     CUDA_OK(cudaMemcpyAsync(m->h_tokens, m->out_tokens, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    m->ll_err_fetch();
     CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->ll_err_verify();
     *token_out = m->h_tokens[0];
     API_END(m)
 }
@@ -1527,7 +1567,9 @@ int crane_b200_copy_logits(crane_b200_model* m, float* host_out, size_t n_floats
     need_ready(m);
     if (!host_out || n_floats > (size_t)m->V) fail(CRANE_B200_INVALID_ARG, "copy_logits: bad arguments");
     CUDA_OK(cudaMemcpyAsync(host_out, m->logits, n_floats * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    m->ll_err_fetch();
     CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->ll_err_verify();
     API_END(m)
 }
 
@@ -1565,7 +1607,9 @@ int crane_b200_decode_greedy(crane_b200_model* m, uint32_t first_token, size_t s
     m->decode_steps((int)n_steps, 1);
     CUDA_OK(cudaEventRecord(m->dev1, m->stream));
     CUDA_OK(cudaMemcpyAsync(m->h_tokens, m->out_tokens, n_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    m->ll_err_fetch();
     CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->ll_err_verify();
     m->last_decode_steps = n_steps;
     m->kv_len = start_pos + n_steps;
     m->next_mrope_pos += (uint32_t)n_steps;

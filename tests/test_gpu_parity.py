@@ -191,6 +191,35 @@ def test_on_device_greedy_loop_matches_host_loop_and_oracle():
     m.close()
 
 
+@pytest.mark.parametrize("cfg_name", ["tiny_qwen3", "tiny_qwen3_untied"])
+def test_persistent_decode_kernel_matches_kernel_chain(cfg_name):
+    """The single-launch decode (decode_ll.cu: tagged activation exchange, no grid barrier) against the graph of PDL-chained
+    kernels: same tokens from the on-device loop, logits equal to f32 summation-order noise, and both within the bar of the oracle."""
+    cfg = synth.TINY_QWEN3 if cfg_name == "tiny_qwen3" else synth.TINY_QWEN3_UNTIED
+    w = dict(synth.synth_checkpoint(cfg))
+    ids = synth.synth_token_ids(70, cfg["vocab_size"], "ll")
+    out = {}
+    for persistent in (True, False):
+        m = crane_b200.Qwen3Model(cfg, device=0, max_seq_len=512, persistent=persistent)
+        m.load_checkpoint(w.items())
+        first = m.forward_step_argmax(ids, 0)
+        toks = list(m.decode_greedy(first, len(ids), 40))                       # 40 steps in one launch (persistent) / 40 graph replays
+        lg = m.forward_step([toks[-1]], len(ids) + 40)                           # single step, logits out
+        lens = (m.kv_len(), m.kernel_launches())
+        more = list(m.decode_greedy(int(np.argmax(lg)), len(ids) + 41, 5))      # a second launch continues from the first one's state
+        out[persistent] = (first, toks, lg, more, lens)
+        m.close()
+    a, b = out[True], out[False]
+    e = rel_err(a[2], b[2])
+    print(f"persistent vs chain ({cfg_name}): logits rel {e:.3e}; launches {a[4][1]} vs {b[4][1]}")
+    assert a[0] == b[0] and a[1] == b[1] and a[3] == b[3] and a[4][0] == b[4][0] == len(ids) + 41
+    assert e < 1e-5
+    orc = Qwen3Oracle(cfg, w)
+    ref = orc.forward(list(ids) + [a[0]] + a[1], 0).numpy()
+    assert rel_err(a[2], ref) < DECODE_TOL
+    assert a[4][1] < b[4][1] // 10                                               # it really was one launch per call
+
+
 def test_forward_embeds_and_errors():
     cfg = synth.TINY_QWEN3
     m, w = _model(cfg)
