@@ -38,6 +38,23 @@ class Logits(C.Structure):
     _fields_ = [("device_ptr", C.c_void_p), ("rows", C.c_size_t), ("vocab", C.c_size_t), ("stream", C.c_void_p)]
 
 
+class Sampling(C.Structure):
+    """`crane_b200_sampling` (include/crane_b200.h): the per-sequence fields `sampling::sample` reads."""
+    _fields_ = [("temperature", C.c_float), ("top_p", C.c_float), ("top_k", C.c_int32), ("repetition_penalty", C.c_float),
+                ("frequency_penalty", C.c_float), ("presence_penalty", C.c_float), ("context", C.c_void_p), ("n_context", C.c_size_t),
+                ("uniforms", C.c_void_p), ("seed", C.c_uint64)]
+
+
+def make_sampling(temperature=0.0, top_p=0.0, top_k=0, repetition_penalty=1.0, frequency_penalty=0.0, presence_penalty=0.0, context=(),
+                  uniforms=None, seed=0):
+    """-> (Sampling, keep-alive arrays)."""
+    ctx = np.ascontiguousarray(list(context), dtype=np.uint32)
+    uni = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float32)
+    s = Sampling(float(temperature or 0.0), float(top_p or 0.0), int(top_k or 0), float(repetition_penalty), float(frequency_penalty),
+                 float(presence_penalty), ctx.ctypes.data if ctx.size else None, ctx.size, None if uni is None else uni.ctypes.data, int(seed))
+    return s, (ctx, uni)
+
+
 _lib = None
 
 # name -> (restype, argtypes): must list every symbol include/crane_b200.h declares
@@ -70,6 +87,14 @@ _SIGNATURES = {
     "crane_b200_seq_free": (C.c_int, [C.c_void_p, C.c_int]),
     "crane_b200_seq_select": (C.c_int, [C.c_void_p, C.c_int]),
     "crane_b200_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "crane_b200_sample": (C.c_int, [C.c_void_p, C.POINTER(Sampling), C.POINTER(C.c_uint32)]),
+    "crane_b200_forward_step_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(Sampling), C.POINTER(C.c_uint32)]),
+    "crane_b200_decode_batch_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Sampling), C.c_void_p]),
+    "crane_b200_topk": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "crane_b200_op_qlinear": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p,
+                                        C.c_float, C.c_void_p]),
+    "crane_b200_op_topk": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "crane_b200_op_sample": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Sampling), C.POINTER(C.c_uint32), C.c_void_p]),
     "crane_b200_encode_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "crane_b200_vl_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                         C.POINTER(Logits)]),
@@ -255,6 +280,37 @@ class Engine:
         self._ck(self.lib.crane_b200_decode_batch(self.h, _ptr(sq), _ptr(tk), sq.size, n_steps, _ptr(out), None if lg is None else _ptr(lg)))
         return out, lg
 
+    # ---- device-side sampling (crane-serve/src/engine/sampling.rs) ----
+    def sample(self, **kw) -> int:
+        """`sampling::sample` on the logits of the last forward call (they never leave the device)."""
+        sp, keep = make_sampling(**kw)
+        tok = C.c_uint32()
+        self._ck(self.lib.crane_b200_sample(self.h, C.byref(sp), C.byref(tok)))
+        return int(tok.value)
+
+    def forward_step_sample(self, ids, start_pos: int, **kw) -> int:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        sp, keep = make_sampling(**kw)
+        tok = C.c_uint32()
+        self._ck(self.lib.crane_b200_forward_step_sample(self.h, _ptr(ids), ids.size, start_pos, C.byref(sp), C.byref(tok)))
+        return int(tok.value)
+
+    def decode_batch_sample(self, seqs, tokens, params):
+        """One decode round with per-sequence sampling; params = list of make_sampling keyword dicts."""
+        sq = np.ascontiguousarray(seqs, dtype=np.int32)
+        tk = np.ascontiguousarray(tokens, dtype=np.uint32)
+        made = [make_sampling(**p) for p in params]
+        arr = (Sampling * len(made))(*[m[0] for m in made])
+        out = np.empty(sq.size, dtype=np.uint32)
+        self._ck(self.lib.crane_b200_decode_batch_sample(self.h, _ptr(sq), _ptr(tk), sq.size, arr, _ptr(out)))
+        return out
+
+    def topk(self, k: int):
+        idx = np.empty(k, dtype=np.uint32)
+        val = np.empty(k, dtype=np.float32)
+        self._ck(self.lib.crane_b200_topk(self.h, k, _ptr(idx), _ptr(val)))
+        return idx, val
+
     # ---- vision-language surface ----
     def encode_images(self, pixel_values, grid_thw, want_deepstack: int = 0):
         pv = np.ascontiguousarray(pixel_values, dtype=np.float32)
@@ -435,3 +491,41 @@ def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_in
     if rc != OK:
         raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
     return out
+
+
+def op_topk(logits: np.ndarray, k: int, device=0) -> np.ndarray:
+    """`crane_core::ops::topk_indices` on caller logits (kernel-level test hook)."""
+    lib = load_library()
+    x = np.ascontiguousarray(logits, dtype=np.float32)
+    out = np.empty(k, dtype=np.uint32)
+    rc = lib.crane_b200_op_topk(device, _ptr(x), x.size, k, _ptr(out))
+    if rc != OK:
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+    return out
+
+
+def op_sample(logits: np.ndarray, device=0, **kw):
+    """`sampling::sample` on caller logits -> (token, logits after penalties)."""
+    lib = load_library()
+    x = np.ascontiguousarray(logits, dtype=np.float32)
+    sp, keep = make_sampling(**kw)
+    tok = C.c_uint32()
+    after = np.empty_like(x)
+    rc = lib.crane_b200_op_sample(device, _ptr(x), x.size, C.byref(sp), C.byref(tok), _ptr(after))
+    if rc != OK:
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+    return int(tok.value), after
+
+
+def op_qlinear(x: np.ndarray, raw: np.ndarray, ggml_type: int, n: int, norm_w=None, eps: float = 1e-6, device=0) -> np.ndarray:
+    """Quantised linear of x [m, k] through the decode kernels (kernel-level test hook) -> [m, n] f32."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    m, k = x.shape
+    y = np.empty((m, n), np.float32)
+    nw = None if norm_w is None else np.ascontiguousarray(norm_w, dtype=np.float32)
+    rc = lib.crane_b200_op_qlinear(device, _ptr(x), m, k, _ptr(raw), raw.size, ggml_type, n, None if nw is None else _ptr(nw), eps, _ptr(y))
+    if rc != OK:
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+    return y

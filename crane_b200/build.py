@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcrane_b200.so")
-SOURCES = ["gemm.cu", "decode.cu", "decode_ll.cu", "prefill.cu", "gdn.cu", "quant.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "decode.cu", "decode_ll.cu", "prefill.cu", "gdn.cu", "quant.cu", "sampler.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--threads", "2"]
 

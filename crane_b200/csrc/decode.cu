@@ -260,6 +260,7 @@ gemv_kernel(GemvArgs a) {
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
+                if ((unsigned)bi >= (unsigned)a.N) bi = 0;       // an all-NaN row has no maximum: never gather from an out-of-range id
                 if (lane == 0) {
                     SeqState* s = a.state + b;
                     if (a.out_tokens) a.out_tokens[(size_t)b * a.out_stride + s->step] = (uint32_t)bi;

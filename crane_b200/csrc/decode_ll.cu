@@ -4,19 +4,25 @@
 // Why.  A batch-1 decode step of Qwen3-VL-2B is 141 dependent bandwidth-bound phases (113 weight matrices + 28 attentions) of
 // 1.3-96 us of HBM time each.  As separate kernels every phase boundary costs ~2.5 us during which the HBM pipe is idle
 // (round 1: 50 % of the HBM roofline); a grid barrier per phase costs about the same.  Here:
-//   * one CTA per SM stays resident; each of its 16 warps owns a fixed (column group, row lane) of every weight matrix and
-//     streams it through a private cp.async ring (DEPTH x 2 KB per warp, 192 KB per SM).  The prefetch cursor is independent of
-//     the consumption cursor and runs ahead across phase, layer and token boundaries: while a warp waits for its input
-//     activations the next matrices keep arriving, so a dependency stall shorter than the ring (~4 us of HBM time) costs no
-//     bandwidth;
+//   * one CTA per SM stays resident; each of its 8 warps owns a fixed column range of every weight matrix and streams it, in
+//     tiles of 16 rows x 64 columns, through a private cp.async ring (12 x 2 KB per warp, 192 KB per SM).  The prefetch cursor
+//     is independent of the consumption cursor and runs ahead across phase, layer and token boundaries: while a warp waits
+//     for its input activations the next matrices keep arriving, so a dependency stall shorter than the ring (~4 us of HBM
+//     time) costs no bandwidth;
+//   * the products run on the tensor cores -- not for flops (the step is HBM-bound) but for instruction count: a 2 KB tile is
+//     4 ldmatrix + 4 mma.sync (m16n8k16, weights = A from the ring, activations = the B columns (hi, lo) of a split-bf16
+//     pair, f32 accumulate) where FMA lanes need ~110 instructions, so whatever landed during a wait is consumed at
+//     shared-memory speed and the stream catches up with its prefetch;
 //   * activations cross SMs as 8-byte (value, tag) pairs written with one store and polled by their consumers (the NCCL
 //     "LL" protocol applied to a GEMV chain): no separate flag, no fence, no barrier -- one L2 round trip per dependency.  A
-//     warp polls only the 256*ncc columns it owns and keeps them in registers for the whole phase (no shared-memory staging,
-//     no block barrier at phase start); RMSNorm is folded in (weights multiplied at load, 1/rms applied in the epilogue);
+//     warp polls only the columns it owns and keeps them in registers as B fragments for the whole phase (no shared-memory
+//     staging, no block barrier at phase start); RMSNorm is folded in (weights multiplied at load, 1/rms applied in the
+//     epilogue);
 //   * attention runs as nkv x nsplit CTA items (K/V straight from the pages into registers, loads issued before the query is
 //     polled), partials are published as pairs and merged by the CTA that owns the head (one split per lane, shuffles).
-// Arithmetic is identical to the multi-kernel path (decode.cu): f32 activations / residual, bf16 weights, split-precision KV
-// pages, lowest-index argmax.  Reference being replaced: the per-token loop of `Model::generate`
+// Arithmetic: f32 residual stream and accumulation, bf16 weights (exact), activations enter the products as hi + lo bf16 pairs
+// (~16 mantissa bits, the engine's split precision -- the multi-kernel path of decode.cu multiplies by the f32 value itself),
+// split-precision KV pages, lowest-index argmax.  Reference being replaced: the per-token loop of `Model::generate`
 // (crane-core/src/models/qwen3/model.rs:298-331) over `Qwen3Model::forward` (qwen3/modeling.rs:942-1036) and the server's
 // decode rounds (crane-serve/src/engine/mod.rs:898-1008).
 #include "decode_ll.cuh"
@@ -26,8 +32,8 @@
 
 namespace cb {
 
-#ifndef LL_POLL_LIMIT
-#define LL_POLL_LIMIT (1u << 22)        // failed polls before a wait is declared dead (~seconds); the launch then drains
+#ifndef LL_WAIT_CYCLES
+#define LL_WAIT_CYCLES (1ll << 31)      // SM cycles (~1 s) before a wait is declared dead; the launch then drains
 #endif
 constexpr int LL_SEG_BYTES = 2048;      // ring slot = 4 chunks of 512 B (one chunk = 256 bf16 of one row)
 constexpr int LL_MAX_SPLIT = 32;        // attention splits per KV head (one per lane in the merge)
@@ -55,156 +61,177 @@ __device__ __forceinline__ unsigned long long ld_pair1(const unsigned long long*
 __device__ __forceinline__ uint32_t pair_tag(unsigned long long u) { return (uint32_t)(u >> 32); }
 __device__ __forceinline__ float pair_val(unsigned long long u) { return __uint_as_float((uint32_t)u); }
 
-// Bounded waiting: a wait that never completes (a bug, or a peer that died) must not hang the GPU.  After LL_POLL_LIMIT failed
-// polls the thread raises *err; every waiter gives up as soon as it sees the flag, and the launch drains with garbage results
+// Bounded waiting: a wait that never completes (a bug, or a peer that died) must not hang the GPU.  After LL_WAIT_CYCLES
+// cycles of waiting the thread raises *err; every waiter gives up as soon as it sees the flag, and the launch drains with garbage results
 // that the host discards (CRANE_B200_CUDA_ERROR).
 struct Waiter {
-    unsigned int* err;
+    unsigned int* err;         // [0] flag, [1..7] who gave up first: site, cta, warp, step, phase, tag wanted, tag seen;
+                               // [16 + cta * LL_WARPS + warp] what each warp was last seen waiting for: step << 20 | phase << 8 | site
     bool dead;
-    __device__ __forceinline__ bool again(uint32_t& it) {
+    uint32_t where;            // step << 12 | phase (diagnostics only)
+    __device__ __forceinline__ bool again(uint32_t& it, long long& t0, uint32_t site, uint32_t want, uint32_t seen) {
         if (dead) return false;
         if ((++it & 255u) == 0u) {
+            if (it == 256u) {
+                t0 = clock64();
+                if ((threadIdx.x & 31) == 0) err[16 + blockIdx.x * LL_WARPS + (threadIdx.x >> 5)] = ((where >> 12) << 20) | ((where & 0xfffu) << 8) | site;
+            }
             unsigned int e = *reinterpret_cast<volatile unsigned int*>(err);
-            if (it >= LL_POLL_LIMIT) { atomicExch(err, 1u); e = 1u; }
+            if (e == 0u && clock64() - t0 > LL_WAIT_CYCLES) {
+                if (atomicCAS(err, 0u, 1u) == 0u) {
+                    err[1] = site; err[2] = blockIdx.x; err[3] = threadIdx.x >> 5; err[4] = where >> 12; err[5] = where & 0xfffu; err[6] = want; err[7] = seen;
+                }
+                e = 1u;
+            }
             if (__any_sync(0xffffffffu, e != 0u)) { dead = true; return false; }
         }
         return true;
     }
 };
 
-// Sum 8 per-lane values over the warp in 7 + 2 shuffles (recursive halving): on return v[0] of every lane holds the warp total
-// of value `idx` (lanes with equal idx hold the same total; idx = (lane >> 2) bit-reversed over 3 bits, see below).
-__device__ __forceinline__ void ll_reduce_scatter8(float (&v)[8], int lane, int& idx) {
-    idx = 0;
-    int off = 16;
-#pragma unroll
-    for (int n = 8; n > 1; n >>= 1, off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = up ? v[i] : v[i + n / 2];
-            const float keep = up ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-        if (up) idx += n / 2;
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 // ---- phase geometry --------------------------------------------------------------------------------------------------
-struct PDesc {                 // one weight matrix as seen by this CTA
-    const unsigned char* W;
-    int N, K, rpc, r0, nrows;
-    LLGeom g;
+// A weight matrix [N, K] as seen by one CTA (row block [r0, r0 + nrows)) and one warp (columns [col0, col0 + 64 * ncs)): the warp
+// walks its block in tiles of 16 rows x 64 columns = one 2 KB ring slot = four m16n8k16 tensor-core steps.  Only five distinct
+// shapes exist (qkv, o, gate/up, down, lm_head): computed once per launch into shared memory, so switching phase costs a table read.
+struct WGeo {
+    unsigned long long base_off;   // bytes from the matrix start to (row r0, column col0)
+    uint32_t nslots;               // ring slots of this warp in the phase: row tiles x ncs (0: the warp idles -- K < 64 * warps)
+    int r0, nrows, ntiles;         // row block of the CTA, in tiles of 16 rows
+    int K, ncs, col0;              // ncs = 64-column steps per warp
+    int pad;
 };
-__device__ __forceinline__ PDesc phase_desc(const LLArgs& a, int p) {      // p = 0 .. 4L (4L = lm_head)
-    PDesc d;
-    int rpu = 1;
-    if (p >= 4 * a.L) { d.W = reinterpret_cast<const unsigned char*>(a.lm_head); d.N = a.V; d.K = a.H; }
-    else {
-        const LLLayer& l = a.layers[p >> 2];
-        switch (p & 3) {
-            case 0: d.W = reinterpret_cast<const unsigned char*>(l.wqkv); d.N = a.qkv_dim; d.K = a.H; break;
-            case 1: d.W = reinterpret_cast<const unsigned char*>(l.wo); d.N = a.H; d.K = a.q_dim; break;
-            case 2: d.W = reinterpret_cast<const unsigned char*>(l.wgu); d.N = 2 * a.I; d.K = a.H; rpu = 2; break;
-            default: d.W = reinterpret_cast<const unsigned char*>(l.wdown); d.N = a.H; d.K = a.I; break;
-        }
-    }
-    const int units = d.N / rpu;
-    const int upc = (units + (int)gridDim.x - 1) / (int)gridDim.x;
-    d.rpc = upc * rpu;
-    d.r0 = (int)blockIdx.x * d.rpc;
-    d.nrows = max(0, min(d.N, d.r0 + d.rpc) - d.r0);
-    ll_geom(d.K, d.g);
-    return d;
+__host__ __device__ inline int ll_active_warps(int K) {        // warps that share the columns of a row: K = 64 * ncs * active
+    int aw = LL_WARPS;
+    while (aw > 1 && (K % (64 * aw)) != 0) aw >>= 1;
+    return aw;
 }
-struct WDesc {                 // ... and by one warp: chunk q of the warp = row (rl + RL * (q / ncc)), column chunk (cg * ncc + q % ncc)
-    const unsigned char* base;
-    uint32_t nq, nmy;
-    size_t row_stride;
-    int cg, rl;
-};
-__device__ __forceinline__ WDesc warp_desc(const PDesc& d, int warp, int lane) {
-    WDesc w;
-    w.cg = warp % d.g.G;
-    w.rl = warp / d.g.G;
-    w.nmy = d.nrows > w.rl ? (uint32_t)((d.nrows - w.rl + d.g.RL - 1) / d.g.RL) : 0u;
-    w.nq = w.nmy * (uint32_t)d.g.ncc;
-    w.base = d.W + ((size_t)(d.r0 + w.rl) * d.K + (size_t)w.cg * d.g.ncc * 256) * 2 + lane * 16;
-    w.row_stride = (size_t)d.g.RL * d.K * 2;
-    return w;
+__device__ __forceinline__ int phase_kind(int p, int L) { return (p == 4 * L) ? 4 : (p & 3); }   // 0 qkv, 1 o, 2 gate/up, 3 down, 4 lm_head
+__device__ __forceinline__ const unsigned char* phase_weights(const LLArgs& a, int p) {
+    if (p >= 4 * a.L) return reinterpret_cast<const unsigned char*>(a.lm_head);
+    const LLLayer& l = a.layers[p >> 2];
+    const bf16* w = (p & 3) == 0 ? l.wqkv : (p & 3) == 1 ? l.wo : (p & 3) == 2 ? l.wgu : l.wdown;
+    return reinterpret_cast<const unsigned char*>(w);
+}
+__device__ void fill_geometry(const LLArgs& a, WGeo* wg /* [5] of this warp */, int warp) {
+    for (int kind = 0; kind < 5; ++kind) {
+        int N, K, rpu = 1;
+        switch (kind) {
+            case 0: N = a.qkv_dim; K = a.H; break;
+            case 1: N = a.H; K = a.q_dim; break;
+            case 2: N = 2 * a.I; K = a.H; rpu = 2; break;
+            case 3: N = a.H; K = a.I; break;
+            default: N = a.V; K = a.H; break;
+        }
+        const int aw = ll_active_warps(K);
+        const int units = N / rpu;
+        const int upc = (units + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int rpc = upc * rpu;
+        WGeo w;
+        w.r0 = (int)blockIdx.x * rpc;
+        w.nrows = max(0, min(N, w.r0 + rpc) - w.r0);
+        w.ntiles = (w.nrows + 15) / 16;
+        w.K = K; w.pad = 0;
+        w.ncs = K / (64 * aw);
+        w.col0 = warp * 64 * w.ncs;
+        w.nslots = warp < aw ? (uint32_t)(w.ntiles * w.ncs) : 0u;
+        w.base_off = ((unsigned long long)w.r0 * K + (unsigned long long)w.col0) * 2;
+        wg[kind] = w;
+    }
 }
 
 // prefetch cursor of one warp: runs over the phases of all steps, independent of what the warp is consuming
 struct Cursor {
-    const unsigned char* base;
-    size_t row_stride, row_off;
-    uint32_t nq, q, cc, ncc;
-    uint32_t gp, gp_end;        // global phase index (step * n_phase + p) and its end
-    uint32_t seq;               // non-empty slots issued so far
+    const unsigned char* tile;  // (first row of the current row tile, first column of the warp) of the matrix being prefetched
+    uint32_t row_bytes;         // K * 2
+    int rows_left;              // rows of the CTA's block from the current tile on
+    int cs, ncs;                // 64-column step inside the tile
+    uint32_t left;              // slots of this phase still to issue
+    int step, p;                // phase being prefetched; step == n_steps: past the end
+    uint32_t slot;              // byte offset of the next ring slot to fill
 };
 
-// Position the cursor on the first phase (from pf.gp on) in which this warp owns chunks.  Out of line: it runs once per phase
-// per warp, and the streaming loops that call it stay small.
-__device__ __noinline__ void cursor_enter(const LLArgs& a, Cursor& pf, int n_phase, int warp, int lane) {
+// Position the cursor on the first phase (from (pf.step, pf.p) on) in which this warp owns slots.  Inlined on purpose: the
+// cursor must stay in registers -- with 227 KB of shared memory carved out there is no L1 left, so anything that lives in local
+// memory (a struct whose address is passed to a real call, a spilled register) costs an L2 round trip per access.
+__device__ __forceinline__ void cursor_enter(const LLArgs& a, Cursor& pf, const WGeo* wg) {
+    const int n_phase = 4 * a.L + 1;
     for (;;) {
-        if (pf.gp >= pf.gp_end) { pf.nq = 0; pf.q = 0; return; }
-        const PDesc d = phase_desc(a, (int)(pf.gp % (uint32_t)n_phase));
-        const WDesc w = warp_desc(d, warp, lane);
-        if (w.nq != 0) {
-            pf.base = w.base; pf.row_stride = w.row_stride; pf.row_off = 0; pf.nq = w.nq; pf.q = 0; pf.cc = 0;
-            pf.ncc = (uint32_t)d.g.ncc;
+        if (pf.p >= n_phase) { pf.p = 0; ++pf.step; }
+        if (pf.step >= a.n_steps) { pf.left = 0; return; }
+        const WGeo& w = wg[phase_kind(pf.p, a.L)];
+        if (w.nslots != 0) {
+            pf.tile = phase_weights(a, pf.p) + w.base_off;
+            pf.row_bytes = (uint32_t)w.K * 2u; pf.rows_left = w.nrows; pf.cs = 0; pf.ncs = w.ncs; pf.left = w.nslots;
             return;
         }
-        ++pf.gp;
+        ++pf.p;
     }
 }
 
-// ---- activation slice of a warp: poll the pairs of its 256 * NCC columns into registers -------------------------------
-template <int NCC>
-__device__ __forceinline__ void load_x(const unsigned long long* buf, uint32_t tag, int cg, int lane, const float* norm_w,
-                                       float (&xr)[NCC][8], float& ssq, Waiter& wt) {
-    float g[NCC][8];
-    if (norm_w != nullptr) {          // immutable: in flight while the activations are still being produced
+// ---- tensor-core pieces: A = 16 weight rows x 16 columns (ldmatrix from the ring slot), B = the activations as the columns
+// (hi, lo, 0, ...) of a 16 x 8 operand, D = f32.  One mma.sync does 16 rows x 16 columns for both halves of the split activation.
+__device__ __forceinline__ void ll_ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ll_mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ---- activation slice of a warp: poll the pairs of its 64 * NCS columns and shape them into tensor-core B fragments --------------
+// B (k x n, "col") of m16n8k16: lane l holds rows k = 2 (l % 4) + {0, 1} (b0) and + {8, 9} (b1) of column n = l / 4.  Column 0 carries
+// hi = bf16(x), column 1 lo = bf16(x - hi) (~16 mantissa bits together, the weights are exact in bf16), the other six are zero.
+// Every lane fetches two adjacent pairs of each 64-column step (one 16-byte load, the whole step = 512 contiguous bytes per
+// warp), folds the RMSNorm weight in, splits, and the fragments are dealt out with shuffles: lanes 0-3 receive the hi halves,
+// lanes 4-7 the lo halves, the rest hold zeros.  The sum of squares of the raw values comes back through `ssq` (per lane).
+template <int NCS, bool NORM>
+__device__ __forceinline__ void load_xb(const unsigned long long* buf, uint32_t tag, int col0, int lane, const float* norm_w,
+                                        uint32_t (&xb)[NCS * 4][2], float& ssq, Waiter& wt) {
+    const int c_lane = col0 + 2 * lane;                   // this lane's two columns inside each 64-column step
+    float2 g[NORM ? NCS : 1];
+    if (NORM) {                                           // immutable: in flight while the activations are still being produced
 #pragma unroll
-        for (int cc = 0; cc < NCC; ++cc) {
-            const float4* gp = reinterpret_cast<const float4*>(norm_w + (size_t)(cg * NCC + cc) * 256 + lane * 8);
-            const float4 g0 = gp[0], g1 = gp[1];
-            g[cc][0] = g0.x; g[cc][1] = g0.y; g[cc][2] = g0.z; g[cc][3] = g0.w;
-            g[cc][4] = g1.x; g[cc][5] = g1.y; g[cc][6] = g1.z; g[cc][7] = g1.w;
-        }
+        for (int cs = 0; cs < NCS; ++cs) g[cs] = *reinterpret_cast<const float2*>(norm_w + c_lane + 64 * cs);
     }
+    float v0[NCS], v1[NCS];
     uint32_t it = 0;
+    long long wt0 = 0;
     for (;;) {
         bool ok = true;
+        uint32_t seen = tag;
 #pragma unroll
-        for (int cc = 0; cc < NCC; ++cc) {
-            const unsigned long long* p = buf + (size_t)(cg * NCC + cc) * 256 + lane * 8;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                unsigned long long u0, u1;
-                ld_pair2(p + 2 * j, u0, u1);
-                ok = ok && pair_tag(u0) == tag && pair_tag(u1) == tag;
-                xr[cc][2 * j] = pair_val(u0);
-                xr[cc][2 * j + 1] = pair_val(u1);
-            }
+        for (int cs = 0; cs < NCS; ++cs) {
+            unsigned long long u0, u1;
+            ld_pair2(buf + c_lane + 64 * cs, u0, u1);
+            if (pair_tag(u0) != tag) { ok = false; seen = pair_tag(u0); }
+            if (pair_tag(u1) != tag) { ok = false; seen = pair_tag(u1); }
+            v0[cs] = pair_val(u0); v1[cs] = pair_val(u1);
         }
         if (__all_sync(0xffffffffu, ok)) break;
-        if (!wt.again(it)) break;
+        if (!wt.again(it, wt0, 1u, tag, seen)) break;
     }
     ssq = 0.f;
+    const int kq = lane & 3;
+    const bool is_lo = (lane & 4) != 0, act = lane < 8;
 #pragma unroll
-    for (int cc = 0; cc < NCC; ++cc)
+    for (int cs = 0; cs < NCS; ++cs) {
+        float a0 = v0[cs], a1 = v1[cs];
+        if (NORM) { ssq = fmaf(a0, a0, fmaf(a1, a1, ssq)); a0 *= g[cs].x; a1 *= g[cs].y; }
+        uint32_t hp, lp;
+        split_bf16x2(a0, a1, hp, lp);                     // (hi, lo) packed pairs of columns (2 lane, 2 lane + 1)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            ssq = fmaf(xr[cc][j], xr[cc][j], ssq);
-            if (norm_w != nullptr) xr[cc][j] *= g[cc][j];
+        for (int ks = 0; ks < 4; ++ks) {
+            // columns 16 ks + 2 kq + {0, 1} live in lane 8 ks + kq, columns + {8, 9} in lane 8 ks + kq + 4
+            const uint32_t h0 = __shfl_sync(0xffffffffu, hp, 8 * ks + kq), l0 = __shfl_sync(0xffffffffu, lp, 8 * ks + kq);
+            const uint32_t h1 = __shfl_sync(0xffffffffu, hp, 8 * ks + kq + 4), l1 = __shfl_sync(0xffffffffu, lp, 8 * ks + kq + 4);
+            xb[cs * 4 + ks][0] = act ? (is_lo ? l0 : h0) : 0u;
+            xb[cs * 4 + ks][1] = act ? (is_lo ? l1 : h1) : 0u;
         }
+    }
 }
 
 // =====================================================================================================================
-template <int DEPTH>
+template <int DEPTH, bool DIAG>
 __global__ void __launch_bounds__(LL_THREADS, 1)
 decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
     constexpr int D = 128;
@@ -220,6 +247,7 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
     __shared__ float wbest_v[LL_WARPS];
     __shared__ int wbest_i[LL_WARPS];
     __shared__ uint32_t tok_s;
+    __shared__ WGeo wgeo_s[LL_WARPS][5];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -227,43 +255,62 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
     const int NREP = a.nh / a.nkv;
     const uint32_t tag0 = a.tag_base;
     const uint32_t tstride = (uint32_t)(a.L + 2);
-    Waiter wt{a.err, false};
+    Waiter wt{a.err, false, 0u};
 
-    long long tprof = clock64();
+    long long tprof = DIAG ? clock64() : 0ll;
     auto prof = [&](int slot) {
-        if (a.prof != nullptr && cta == 0 && tid == 0) {
+        if (DIAG && a.prof != nullptr && cta == 0 && tid == 0) {
             const long long now = clock64();
             a.prof[slot] += (unsigned long long)(now - tprof);
             tprof = now;
         }
     };
 
+    // optional event trace of a few warps (tools/ll_trace.py): where the time of a phase goes, on a common clock
+    int tr_s = -1, tr_p = 0, tr_n = 0;
+    const int tr_cta = cta == 0 ? 0 : cta == 73 ? 1 : cta == 140 ? 2 : -1, tr_w = warp == 0 ? 0 : warp == 5 ? 1 : -1;
+    const bool tr_on = DIAG && a.trace != nullptr && lane == 0 && tr_cta >= 0 && tr_w >= 0;
+    unsigned long long* tr = a.trace + (size_t)((tr_cta < 0 ? 0 : tr_cta) * 2 + (tr_w < 0 ? 0 : tr_w)) * LL_TRACE_CAP * 2;
+    auto trace = [&](int ev) {
+        if (DIAG && tr_on && tr_s == a.trace_step && tr_n < LL_TRACE_CAP) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tr[2 * tr_n] = (unsigned long long)(ev | (tr_p << 8));
+            tr[2 * tr_n + 1] = t;
+            ++tr_n;
+        }
+    };
+
     // ---- prefetch cursor ---------------------------------------------------------------------------------------------
-    unsigned char* ring = lsm + (size_t)warp * DEPTH * LL_SEG_BYTES + lane * 16;
-    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t ring_u32 = smem_u32(lsm + (size_t)warp * DEPTH * LL_SEG_BYTES);
+    if (lane == 0) fill_geometry(a, wgeo_s[warp], warp);
+    __syncwarp();
+    const WGeo* wg = wgeo_s[warp];
     Cursor pf;
-    pf.gp = 0; pf.gp_end = (uint32_t)a.n_steps * (uint32_t)n_phase; pf.seq = 0;
-    auto pf_enter = [&]() { cursor_enter(a, pf, n_phase, warp, lane); };
-    auto issue_next = [&]() {         // one ring slot (<= 4 chunks, never across a phase boundary) + exactly one commit
-        if (pf.q < pf.nq) {
-            const uint32_t dst = ring_u32 + (pf.seq % DEPTH) * LL_SEG_BYTES;
+    pf.step = 0; pf.p = 0; pf.slot = 0;
+    auto pf_enter = [&]() { cursor_enter(a, pf, wg); };
+    // a slot = 16 rows x 128 bytes; 16-byte segment j of row r sits at r * 128 + ((j ^ (r & 7)) << 4) so that the eight rows an
+    // ldmatrix phase reads fall into eight different bank groups.  Lane l copies segment (l & 7) of rows (l >> 3) + 4 i.
+    const uint32_t cp_row = (uint32_t)(lane >> 3), cp_seg = (uint32_t)(lane & 7);
+    auto issue_next = [&]() {         // one ring slot (never across a phase boundary) + exactly one commit
+        if (pf.left != 0) {
+            const uint32_t dst = ring_u32 + pf.slot;
+            const unsigned char* src = pf.tile + (size_t)pf.cs * 128 + cp_seg * 16;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (pf.q < pf.nq) {
-                    ll_cp16(dst + c * 512, pf.base + pf.row_off + (size_t)pf.cc * 512);
-                    ++pf.q;
-                    if (++pf.cc == pf.ncc) { pf.cc = 0; pf.row_off += pf.row_stride; }
-                }
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t r = cp_row + 4u * i;
+                if ((int)r < pf.rows_left) ll_cp16(dst + r * 128u + ((cp_seg ^ (r & 7u)) << 4), src + (size_t)r * pf.row_bytes);
             }
-            ++pf.seq;
-            if (pf.q >= pf.nq) { ++pf.gp; pf_enter(); }
+            pf.slot = (pf.slot + LL_SEG_BYTES == DEPTH * LL_SEG_BYTES) ? 0u : pf.slot + LL_SEG_BYTES;
+            if (++pf.cs == pf.ncs) { pf.cs = 0; pf.tile += (size_t)16 * pf.row_bytes; pf.rows_left -= 16; }
+            if (--pf.left == 0) { ++pf.p; pf_enter(); }
         }
         ll_commit();
     };
     pf_enter();
 #pragma unroll 1
     for (int i = 0; i < DEPTH; ++i) issue_next();
-    uint32_t cseq = 0;                // slots consumed so far
+    uint32_t cslot = 0;               // byte offset of the next ring slot to consume
 
     // ---- sequence state, residual slice, first input ----------------------------------------------------------------------
     const SeqState st0 = a.state[0];
@@ -292,11 +339,14 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
             const int kind = (p == 4 * a.L) ? 4 : (p & 3);  // 0 qkv, 1 o-proj, 2 gate/up, 3 down, 4 lm_head
             const int l = min(p >> 2, a.L - 1);
             const uint32_t tagl = tstep + (uint32_t)(p >> 2) + 1u;      // tag of layer l's buffers; lm_head input = tag (s, L)
+            wt.where = ((uint32_t)s << 12) | (uint32_t)p;
+            if (DIAG) { tr_s = s; tr_p = p; }
 
             // ============================ attention of layer l (between the QKV and the O projections) ============================
             if (kind == 1) {
                 const LLLayer& ly = a.layers[l];
                 const int nsplit = max(1, min(min(grid / a.nkv, LL_MAX_SPLIT), (T + 31) / 32));
+                trace(7);
                 if (cta < a.nkv * nsplit) {
                     const int kvh = cta / nsplit, split = cta % nsplit;
                     const int chunk = (T + nsplit - 1) / nsplit;
@@ -305,10 +355,11 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                     const bool owner = (split == (T - 1) / chunk);
                     const bool split_kv = a.kv_lo_off != 0;
                     const int half = lane >> 4, hl = lane & 15;
-                    const int npass = t_end > t0 ? (t_end - t0 + 31) / 32 : 0;
+                    constexpr int TPP = 2 * LL_WARPS;                   // tokens per pass: two per warp (16 lanes each)
+                    const int npass = t_end > t0 ? (t_end - t0 + TPP - 1) / TPP : 0;
                     uint4 kh = make_uint4(0, 0, 0, 0), kl = kh, vh = kh, vl = kh;
                     auto load_pass = [&](int ps, uint4& rkh, uint4& rkl, uint4& rvh, uint4& rvl) {
-                        const int t = t0 + ps * 32 + warp * 2 + half;
+                        const int t = t0 + ps * TPP + warp * 2 + half;
                         rkh = make_uint4(0, 0, 0, 0); rkl = rkh; rvh = rkh; rvl = rkh;
                         if (t < t_end) {
                             const int page = __ldg(bt + t / KV_PAGE);
@@ -320,31 +371,35 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                     };
                     if (npass > 0) load_pass(0, kh, kl, vh, vl);        // in flight while the query is still being produced
                     // ---- q (NREP heads), and on the owning split the new k / v: poll, RMSNorm, rotate ----
-                    if (warp < NREP + 2 && (warp < NREP || owner)) {
-                        const bool is_k = warp == NREP, is_v = warp == NREP + 1;
-                        const unsigned long long* src = a.qkv + (is_v ? a.q_dim + a.nkv * D + kvh * D : is_k ? a.q_dim + kvh * D : (kvh * NREP + warp) * D);
+                    for (int vec = warp; vec < NREP + 2; vec += LL_WARPS) {
+                        if (vec >= NREP && !owner) continue;
+                        const bool is_k = vec == NREP, is_v = vec == NREP + 1;
+                        const unsigned long long* src = a.qkv + (is_v ? a.q_dim + a.nkv * D + kvh * D : is_k ? a.q_dim + kvh * D : (kvh * NREP + vec) * D);
                         const float* nw = is_k ? ly.kn : ly.qn;
                         float nwv[4], cs_c[4], cs_s[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             nwv[j] = is_v ? 1.f : nw[lane + 32 * j];
                             const int i = lane + 32 * (j & 1);           // rotary pair (j, j + 2): column i = lane + 32 * (j mod 2)
-                            const int pp = pos3[a.axis_of[i]];
+                            const int ax = a.axis_of[i];
+                            const int pp = ax == 0 ? pos3[0] : ax == 1 ? pos3[1] : pos3[2];   // no dynamically indexed local array: there is no L1
                             cs_c[j] = a.cos_tab[(size_t)pp * (D / 2) + i];
                             cs_s[j] = a.sin_tab[(size_t)pp * (D / 2) + i];
                         }
                         float e[4];
                         uint32_t it = 0;
+    long long wt0 = 0;
                         for (;;) {
                             bool ok = true;
+                            uint32_t seen = tagl;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const unsigned long long u = ld_pair1(src + lane + 32 * j);
-                                ok = ok && pair_tag(u) == tagl;
+                                if (pair_tag(u) != tagl) { ok = false; seen = pair_tag(u); }
                                 e[j] = pair_val(u);
                             }
                             if (__all_sync(0xffffffffu, ok)) break;
-                            if (!wt.again(it)) break;
+                            if (!wt.again(it, wt0, 2u, tagl, seen)) break;
                         }
                         if (is_v) {
 #pragma unroll
@@ -360,12 +415,13 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                             r[1] = e[1] * cs_c[1] - e[3] * cs_s[1];
                             r[2] = e[0] * cs_s[2] + e[2] * cs_c[2];
                             r[3] = e[1] * cs_s[3] + e[3] * cs_c[3];
-                            float* dst = is_k ? knew_s : q_s[warp];
+                            float* dst = is_k ? knew_s : q_s[vec];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) dst[lane + 32 * j] = is_k ? (split_kv ? round_bf16_split(r[j]) : round_bf16(r[j])) : r[j];
                         }
                     }
                     __syncthreads();
+                    trace(8);
                     // ---- head groups of <= 2 query heads share every K/V register ----
                     const int HG = (NREP & 1) ? 1 : 2;
 #pragma unroll 1
@@ -382,7 +438,7 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                         for (int ps = 0; ps < npass; ++ps) {
                             uint4 nkh = make_uint4(0, 0, 0, 0), nkl = nkh, nvh = nkh, nvl = nkh;
                             if (ps + 1 < npass) load_pass(ps + 1, nkh, nkl, nvh, nvl);
-                            const bool valid = (t0 + ps * 32 + warp * 2 + half) < t_end;
+                            const bool valid = (t0 + ps * TPP + warp * 2 + half) < t_end;
                             float kf[8], vf[8];
                             kf[0] = bf16lo(kh.x); kf[1] = bf16hi(kh.x); kf[2] = bf16lo(kh.y); kf[3] = bf16hi(kh.y);
                             kf[4] = bf16lo(kh.z); kf[5] = bf16hi(kh.z); kf[6] = bf16lo(kh.w); kf[7] = bf16hi(kh.w);
@@ -494,152 +550,162 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                     }
                 }
                 prof(4);
+                trace(9);
                 // ---- split merge of head `cta`: one split per lane, 8 output columns per warp ----
                 if (cta < a.nh) {
                     const int h = cta, kvh = h / NREP, hh = h % NREP;
                     const bool have = lane < nsplit;
                     const unsigned long long* src = a.part + ((size_t)(kvh * nsplit + (have ? lane : 0)) * NREP + hh) * LL_PART_STRIDE;
-                    float ov[8], ms = -INFINITY, lsum = 0.f;
+                    constexpr int CPW = D / LL_WARPS;               // output columns per warp
+                    float ov[CPW], ms = -INFINITY, lsum = 0.f;
                     uint32_t it = 0;
+    long long wt0 = 0;
                     for (;;) {
                         bool ok = true;
+                        uint32_t seen = tagl;
                         if (have) {
                             unsigned long long u0, u1;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                ld_pair2(src + warp * 8 + 2 * j, u0, u1);
-                                ok = ok && pair_tag(u0) == tagl && pair_tag(u1) == tagl;
+                            for (int j = 0; j < CPW / 2; ++j) {
+                                ld_pair2(src + warp * CPW + 2 * j, u0, u1);
+                                if (pair_tag(u0) != tagl) { ok = false; seen = pair_tag(u0); }
+                                if (pair_tag(u1) != tagl) { ok = false; seen = pair_tag(u1); }
                                 ov[2 * j] = pair_val(u0); ov[2 * j + 1] = pair_val(u1);
                             }
                             ld_pair2(src + 128, u0, u1);
-                            ok = ok && pair_tag(u0) == tagl && pair_tag(u1) == tagl;
+                            if (pair_tag(u0) != tagl) { ok = false; seen = pair_tag(u0); }
+                            if (pair_tag(u1) != tagl) { ok = false; seen = pair_tag(u1); }
                             ms = pair_val(u0); lsum = pair_val(u1);
                         }
                         if (__all_sync(0xffffffffu, ok)) break;
-                        if (!wt.again(it)) break;
+                        if (!wt.again(it, wt0, 3u, tagl, seen)) break;
                     }
                     if (!have) {
                         ms = -INFINITY; lsum = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) ov[j] = 0.f;
+                        for (int j = 0; j < CPW; ++j) ov[j] = 0.f;
                     }
                     const float M = warp_max(ms);
                     const float c = (ms == -INFINITY) ? 0.f : __expf(ms - M);
                     const float Ls = warp_sum(lsum * c);
                     float outv = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < CPW; ++j) {
                         const float t = warp_sum(ov[j] * c);
                         if (lane == j) outv = t;
                     }
-                    if (lane < 8) st_pair(a.att + (size_t)h * D + warp * 8 + lane, outv / Ls, tagl);
+                    if (lane < CPW) st_pair(a.att + (size_t)h * D + warp * CPW + lane, outv / Ls, tagl);
                 }
                 prof(5);
+                trace(10);
             }
 
             // ============================ weight phase: y = W . x over this CTA's row block ============================
-            const PDesc d = phase_desc(a, p);
-            const WDesc w = warp_desc(d, warp, lane);
+            const WGeo w = wg[kind];
             const LLLayer& ly = a.layers[l];
             const float* nw = (kind == 0) ? ly.ln1 : (kind == 2) ? ly.ln2 : (kind == 4) ? a.final_norm : nullptr;
             const unsigned long long* xin = (kind == 0 || kind == 4) ? a.xa : (kind == 1) ? a.att : (kind == 2) ? a.xb : a.act;
             float* acc = acc_s + (gphase & 1u) * max_rows;
             float* ssq_p = &ssq_s[gphase & 3u];
 
-            auto run = [&](auto ncc_tag) {
-                constexpr int NCC = decltype(ncc_tag)::value;
-                float xr[NCC][8];
+            auto run = [&](auto ncs_tag, auto norm_tag) {
+                constexpr int NCS = decltype(ncs_tag)::value;
+                constexpr bool NORM = decltype(norm_tag)::value;
+                // A CTA reads an exchange buffer only in phases where it owns rows: every such read is waited for, transitively, by
+                // whoever overwrites the buffer next (each writer needs the outputs of all row owners of the phase before).  A read
+                // nobody depends on could be overtaken by the next layer's values and would then never see its tag.
+                if (w.nslots == 0) return;
+                trace(1);
+                uint32_t xb[NCS * 4][2];
                 float ssq = 0.f;
-                const bool stat = nw != nullptr && w.rl == 0;     // this warp's columns count towards the RMSNorm statistic
-                if (w.nq == 0 && !stat) return;                    // no rows of this matrix for this warp
-                load_x<NCC>(xin, tagl, w.cg, lane, nw, xr, ssq, wt);
-                if (stat) {
+                load_xb<NCS, NORM>(xin, tagl, w.col0, lane, nw, xb, ssq, wt);
+                if (NORM) {
                     ssq = warp_sum(ssq);
                     if (lane == 0) atomicAdd(ssq_p, ssq);
                 }
                 prof(1);
-                uint32_t q = 0;
+                trace(2);
+                // ldmatrix addresses of this lane inside a slot: row (lane & 7) + 8 * ((lane >> 3) & 1), 16-byte segment 2 ks + (lane >> 4)
+                const uint32_t lrow = (uint32_t)(lane & 7) + (((uint32_t)lane >> 3) & 1u) * 8u;
+                const uint32_t lbase = ring_u32 + lrow * 128u;
+                const uint32_t lsw = lrow & 7u, lhalf = (uint32_t)lane >> 4;
 #pragma unroll 1
-                for (uint32_t b = 0; q < w.nq; ++b) {            // batches of 8 rows of this warp = 2 * NCC ring slots
-                    float av[8];
+                for (int rt = 0; rt < w.ntiles; ++rt) {
+                    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) av[i] = 0.f;
+                    for (int cs = 0; cs < NCS; ++cs) {
+                        ll_wait<DEPTH - 1>();
+                        __syncwarp();
+                        trace(3);
+                        const uint32_t sb = lbase + cslot;
+                        uint32_t af[4][4];
 #pragma unroll
-                    for (int sl = 0; sl < 2 * NCC; ++sl) {
-                        if (q < w.nq) {                            // warp-uniform
-                            ll_wait<DEPTH - 1>();
-                            __syncwarp();
-                            const unsigned char* sp = ring + (cseq % DEPTH) * LL_SEG_BYTES;
-                            uint4 wv[4];
+                        for (int ks = 0; ks < 4; ++ks)
+                            ll_ldmatrix_x4(af[ks][0], af[ks][1], af[ks][2], af[ks][3], sb + (((2u * ks + lhalf) ^ lsw) << 4));
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (q + c < w.nq) wv[c] = *reinterpret_cast<const uint4*>(sp + c * 512);
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const int i = sl * 4 + c;          // compile-time: row i / NCC of the batch, column chunk i % NCC
-                                if (q + c < w.nq) {
-                                    const float* xv = xr[i % NCC];
-                                    float t = av[i / NCC];
-                                    t = fmaf(bf16lo(wv[c].x), xv[0], t); t = fmaf(bf16hi(wv[c].x), xv[1], t);
-                                    t = fmaf(bf16lo(wv[c].y), xv[2], t); t = fmaf(bf16hi(wv[c].y), xv[3], t);
-                                    t = fmaf(bf16lo(wv[c].z), xv[4], t); t = fmaf(bf16hi(wv[c].z), xv[5], t);
-                                    t = fmaf(bf16lo(wv[c].w), xv[6], t); t = fmaf(bf16hi(wv[c].w), xv[7], t);
-                                    av[i / NCC] = t;
-                                }
-                            }
-                            q += 4;
-                            __syncwarp();                          // every lane has its slot data in registers
-                            issue_next();
-                            ++cseq;
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (ks & 1) ll_mma_16816(d1, af[ks][0], af[ks][1], af[ks][2], af[ks][3], xb[cs * 4 + ks][0], xb[cs * 4 + ks][1]);
+                            else ll_mma_16816(d0, af[ks][0], af[ks][1], af[ks][2], af[ks][3], xb[cs * 4 + ks][0], xb[cs * 4 + ks][1]);
                         }
+                        __syncwarp();                              // every lane has its fragments: the slot may be refilled
+                        issue_next();
+                        cslot = (cslot + LL_SEG_BYTES == DEPTH * LL_SEG_BYTES) ? 0u : cslot + LL_SEG_BYTES;
                     }
-                    int idx;
-                    ll_reduce_scatter8(av, lane, idx);
-                    const uint32_t rloc = b * 8u + (uint32_t)idx;
-                    if ((lane & 3) == 0 && rloc < w.nmy) atomicAdd(&acc[w.rl + d.g.RL * (int)rloc], av[0]);
+                    // D: lane l holds rows l / 4 and l / 4 + 8, columns 2 (l % 4) + {0, 1}; columns 0 and 1 are the hi and lo products
+                    if ((lane & 3) == 0) {
+                        const int r = rt * 16 + (lane >> 2);
+                        if (r < w.nrows) atomicAdd(&acc[r], (d0[0] + d1[0]) + (d0[1] + d1[1]));
+                        if (r + 8 < w.nrows) atomicAdd(&acc[r + 8], (d0[2] + d1[2]) + (d0[3] + d1[3]));
+                    }
                 }
             };
-            switch (d.g.ncc) {
-                case 1: run(std::integral_constant<int, 1>{}); break;
-                case 2: run(std::integral_constant<int, 2>{}); break;
-                case 3: run(std::integral_constant<int, 3>{}); break;
-                default: run(std::integral_constant<int, 4>{}); break;
+            // (columns per warp, with / without RMSNorm): the norm phases read K = hidden_size, the widest slices are MLP down-projections
+            const bool norm = nw != nullptr;
+            using TT = std::true_type; using FF = std::false_type;
+            switch (w.ncs) {
+                case 1: if (norm) run(std::integral_constant<int, 1>{}, TT{}); else run(std::integral_constant<int, 1>{}, FF{}); break;
+                case 2: if (norm) run(std::integral_constant<int, 2>{}, TT{}); else run(std::integral_constant<int, 2>{}, FF{}); break;
+                case 4: if (norm) run(std::integral_constant<int, 4>{}, TT{}); else run(std::integral_constant<int, 4>{}, FF{}); break;
+                case 8: if (norm) run(std::integral_constant<int, 8>{}, TT{}); else run(std::integral_constant<int, 8>{}, FF{}); break;
+                default: run(std::integral_constant<int, 12>{}, FF{}); break;
             }
             prof(2);
+            trace(4);
             __syncthreads();
             prof(3);
+            trace(5);
 
             // ============================ epilogue: publish this CTA's rows ============================
-            const float rstd = (nw != nullptr) ? rsqrtf(*ssq_p / (float)d.K + a.eps) : 1.f;
+            const float rstd = (nw != nullptr) ? rsqrtf(*ssq_p / (float)w.K + a.eps) : 1.f;
             if (tid == 0) ssq_s[(gphase + 2u) & 3u] = 0.f;          // last read two phases ago, next written two phases from now
             if (kind == 0) {
-                for (int i = tid; i < d.nrows; i += LL_THREADS) {
-                    st_pair(a.qkv + d.r0 + i, acc[i] * rstd, tagl);
+                for (int i = tid; i < w.nrows; i += LL_THREADS) {
+                    st_pair(a.qkv + w.r0 + i, acc[i] * rstd, tagl);
                     acc[i] = 0.f;
                 }
             } else if (kind == 1 || kind == 3) {
                 unsigned long long* dst = (kind == 1) ? a.xb : a.xa;
                 const uint32_t tg = (kind == 1) ? tagl : tagl + 1u;   // down-proj output = input of the next layer (or of the lm_head)
-                for (int i = tid; i < d.nrows; i += LL_THREADS) {
+                for (int i = tid; i < w.nrows; i += LL_THREADS) {
                     const float v = xres_s[i] + acc[i];
                     xres_s[i] = v;
-                    st_pair(dst + d.r0 + i, v, tg);
+                    st_pair(dst + w.r0 + i, v, tg);
                     acc[i] = 0.f;
                 }
             } else if (kind == 2) {
-                for (int u = tid; u < d.nrows / 2; u += LL_THREADS) {
+                for (int u = tid; u < w.nrows / 2; u += LL_THREADS) {
                     const float g = acc[2 * u] * rstd, up = acc[2 * u + 1] * rstd;
-                    st_pair(a.act + d.r0 / 2 + u, silu_f(g) * up, tagl);
+                    st_pair(a.act + w.r0 / 2 + u, silu_f(g) * up, tagl);
                     acc[2 * u] = 0.f; acc[2 * u + 1] = 0.f;
                 }
             } else {
                 // logits + (value, lowest index) argmax: per thread rows ascend, so the first maximum wins
                 float bv = -INFINITY; int bi = 0x7fffffff;
-                for (int i = tid; i < d.nrows; i += LL_THREADS) {
+                for (int i = tid; i < w.nrows; i += LL_THREADS) {
                     const float v = acc[i] * rstd;
-                    a.logits[d.r0 + i] = v;
+                    a.logits[w.r0 + i] = v;
                     acc[i] = 0.f;
-                    if (v > bv) { bv = v; bi = d.r0 + i; }
+                    if (v > bv) { bv = v; bi = w.r0 + i; }
                 }
 #pragma unroll
                 for (int ofs = 16; ofs > 0; ofs >>= 1) {
@@ -653,14 +719,17 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                     for (int ww = 1; ww < LL_WARPS; ++ww)
                         if (wbest_v[ww] > bv || (wbest_v[ww] == bv && wbest_i[ww] < bi)) { bv = wbest_v[ww]; bi = wbest_i[ww]; }
                     const uint32_t tg = tstep + (uint32_t)a.L + 2u;
-                    st_pair(a.amax + 2 * cta, bv, tg);
-                    st_pair(a.amax + 2 * cta + 1, __int_as_float(bi), tg);
+                    unsigned long long* am = a.amax + (size_t)(s & 1) * 2 * grid;     // two copies: a CTA nobody waits for may still be reading the last step's
+                    st_pair(am + 2 * cta, bv, tg);
+                    st_pair(am + 2 * cta + 1, __int_as_float(bi), tg);
                 }
             }
             prof(6);
+            trace(6);
         }
 
         // ============================ token: every CTA reduces the per-CTA maxima itself (no broadcast hop) ============================
+        wt.where = ((uint32_t)s << 12) | (uint32_t)n_phase;
         if (warp == 0) {
             const uint32_t tg = tstep + (uint32_t)a.L + 2u;
             float bv = -INFINITY; int bi = 0x7fffffff;
@@ -668,16 +737,19 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                 const int c = c0 + lane;
                 float v = -INFINITY; int ix = 0x7fffffff;
                 uint32_t it = 0;
+    long long wt0 = 0;
                 for (;;) {
                     bool ok = true;
+                    uint32_t seen = tg;
                     if (c < grid) {
                         unsigned long long u0, u1;
-                        ld_pair2(a.amax + 2 * c, u0, u1);
+                        ld_pair2(a.amax + (size_t)(s & 1) * 2 * grid + 2 * c, u0, u1);
                         ok = pair_tag(u0) == tg && pair_tag(u1) == tg;
+                        if (!ok) seen = pair_tag(u0) != tg ? pair_tag(u0) : pair_tag(u1);
                         v = pair_val(u0); ix = __float_as_int(pair_val(u1));
                     }
                     if (__all_sync(0xffffffffu, ok)) break;
-                    if (!wt.again(it)) break;
+                    if (!wt.again(it, wt0, 4u, tg, seen)) break;
                 }
                 if (c < grid && (v > bv || (v == bv && ix < bi))) { bv = v; bi = ix; }
             }
@@ -705,6 +777,8 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
         }
         __syncthreads();                                             // tok_s is rewritten by the next step
         prof(7);
+        if (DIAG) tr_p = n_phase;
+        trace(11);
     }
     if (cta == 0 && tid == 0) {
         SeqState* sp = a.state;
@@ -729,21 +803,25 @@ static size_t ll_smem(const LLArgs& a, int grid, int depth) {
 }
 
 bool decode_ll_supported(int D, int rot_half, int nh, int nkv, int H, int I, int q_dim, int qkv_dim, int V, int num_sms) {
-    LLGeom g;
     if (D != 128 || rot_half != 64 || nkv <= 0 || nh % nkv || nh / nkv > LL_MAX_NREP || nh > num_sms || nkv > num_sms) return false;
-    if (!ll_geom(H, g) || !ll_geom(I, g) || !ll_geom(q_dim, g)) return false;
+    auto cols_ok = [](int K, bool norm) { // every warp owns 64 * ncs columns, ncs one of the instantiated widths
+        if (K <= 0 || (K % 64) != 0) return false;
+        const int ncs = K / (64 * ll_active_warps(K));
+        return ncs == 1 || ncs == 2 || ncs == 4 || ncs == 8 || (!norm && ncs == 12);
+    };
+    if (!cols_ok(H, true) || !cols_ok(I, false) || !cols_ok(q_dim, false)) return false;
     if ((2 * I) % 2 || qkv_dim <= 0 || V <= 0) return false;
     LLArgs a = {};
     a.H = H; a.I = I; a.V = V; a.qkv_dim = qkv_dim;
-    return ll_smem(a, num_sms, 4) + 24 * 1024 <= 227 * 1024;       // static shared memory: ~22.5 KB
+    return ll_smem(a, num_sms, 64 / LL_WARPS) + 20 * 1024 <= 227 * 1024;     // + the static shared memory (~16 KB)
 }
 
 size_t decode_ll_part_pairs(int num_sms, int nh, int nkv) { return (size_t)num_sms * (size_t)(nh / nkv) * LL_PART_STRIDE; }
 
-template <int DEPTH>
+template <int DEPTH, bool DIAG>
 static int ll_launch_t(cudaStream_t st, const LLArgs& a, int grid, size_t smem, int max_rows) {
     static SmemOptIn seen;
-    if (const int e = ensure_dyn_smem(decode_ll_kernel<DEPTH>, smem, seen)) return e;
+    if (const int e = ensure_dyn_smem(decode_ll_kernel<DEPTH, DIAG>, smem, seen)) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(LL_THREADS);
@@ -754,22 +832,23 @@ static int ll_launch_t(cudaStream_t st, const LLArgs& a, int grid, size_t smem, 
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, decode_ll_kernel<DEPTH>, a, max_rows);
+    return (int)cudaLaunchKernelEx(&cfg, decode_ll_kernel<DEPTH, DIAG>, a, max_rows);
 }
 
 int decode_ll_launch(cudaStream_t st, const LLArgs& a, int num_sms) {
     const int mr = ll_max_rows(a, num_sms);
     static const int forced = [] { const char* e = getenv("CRANE_B200_LL_DEPTH"); return e ? atoi(e) : 0; }();
-    const size_t budget = 227 * 1024 - 23 * 1024;      // dynamic part: the kernel's static shared memory is ~22.5 KB
-    for (int depth : {6, 5, 4}) {
+    cudaFuncAttributes fa;
+    if (const cudaError_t e = cudaFuncGetAttributes(&fa, decode_ll_kernel<64 / LL_WARPS, true>)) return (int)e;
+    const size_t budget = 227 * 1024 - fa.sharedSizeBytes;      // dynamic part next to the kernel's static shared memory
+    for (int depth : {96 / LL_WARPS, 80 / LL_WARPS, 64 / LL_WARPS}) {
         if (forced && depth != forced) continue;
         const size_t smem = ll_smem(a, num_sms, depth);
         if (smem > budget) continue;
-        switch (depth) {
-            case 6: return ll_launch_t<6>(st, a, num_sms, smem, mr);
-            case 5: return ll_launch_t<5>(st, a, num_sms, smem, mr);
-            default: return ll_launch_t<4>(st, a, num_sms, smem, mr);
-        }
+        const bool diag = a.prof != nullptr || a.trace != nullptr;       // the instrumented build of the kernel only when asked for
+        if (depth == 96 / LL_WARPS) return diag ? ll_launch_t<96 / LL_WARPS, true>(st, a, num_sms, smem, mr) : ll_launch_t<96 / LL_WARPS, false>(st, a, num_sms, smem, mr);
+        if (depth == 80 / LL_WARPS) return diag ? ll_launch_t<80 / LL_WARPS, true>(st, a, num_sms, smem, mr) : ll_launch_t<80 / LL_WARPS, false>(st, a, num_sms, smem, mr);
+        return diag ? ll_launch_t<64 / LL_WARPS, true>(st, a, num_sms, smem, mr) : ll_launch_t<64 / LL_WARPS, false>(st, a, num_sms, smem, mr);
     }
     return -1000;
 }

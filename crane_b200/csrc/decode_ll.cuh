@@ -6,29 +6,17 @@
 
 namespace cb {
 
-constexpr int LL_WARPS = 16;
+constexpr int LL_WARPS = 8;           // 8 x 32 threads x 255 registers: nothing of the streaming loop may spill (no L1 is left beside 227 KB of shared memory)
 constexpr int LL_THREADS = LL_WARPS * 32;
-constexpr int LL_MAX_NCC = 4;        // 256-column chunks of a weight row one warp may own (activation slice held in registers)
 constexpr int LL_PART_STRIDE = 132;  // pairs per (attention item, head): 128 outputs, running max, running sum, 2 pad
 constexpr int LL_MAX_LAYERS = 64;
+constexpr int LL_TRACE_CAP = 4096;
 
 struct LLLayer {
     const bf16 *wqkv, *wo, *wgu, *wdown;
     const float *ln1, *ln2, *qn, *kn;
     bf16 *k_pool, *v_pool;
 };
-
-// How the 16 warps of a CTA share a [rows, K] row block: G column groups x RL row lanes; a warp owns `ncc` 256-column chunks of
-// every RL-th row, so the activation columns it needs never change during a phase (8 * ncc registers per lane).
-struct LLGeom { int G, RL, ncc; };
-__host__ __device__ inline bool ll_geom(int K, LLGeom& g) {
-    if (K <= 0 || (K & 255)) return false;
-    const int cpr = K >> 8;
-    int G = 1;
-    while (G < LL_WARPS && (cpr % (G * 2)) == 0) G *= 2;
-    g.G = G; g.RL = LL_WARPS / G; g.ncc = cpr / G;
-    return g.ncc <= LL_MAX_NCC;
-}
 
 struct LLArgs {
     int L, H, I, V, nh, nkv, qkv_dim, q_dim;
@@ -53,12 +41,14 @@ struct LLArgs {
     unsigned long long* att;       // [q_dim]
     unsigned long long* act;       // [I]
     unsigned long long* part;      // [grid, nrep, LL_PART_STRIDE] attention partials
-    unsigned long long* amax;      // [grid, 2] per-CTA (max logit, index)
+    unsigned long long* amax;      // [2 (step parity), grid, 2] per-CTA (max logit, index)
     unsigned int tag_base;         // tags of this launch are tag_base + 1 .. tag_base + n_steps * (L + 2)
     int n_steps;
     int advance;                   // 1: feed each argmax back as the next input
     unsigned int* err;             // [1] set when a wait timed out (the launch then drains without waiting)
-    unsigned long long* prof;      // optional [16] ns accumulators of CTA 0
+    unsigned long long* prof;      // optional [16] cycle accumulators of CTA 0
+    unsigned long long* trace;     // optional [6][LL_TRACE_CAP][2] (event | phase << 8, globaltimer ns) of CTAs 0 / 73 / 140, warps 0 / 9, during step trace_step
+    int trace_step;
 };
 
 // tags consumed by one launch (host advances its counter by this)

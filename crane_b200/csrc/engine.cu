@@ -23,6 +23,7 @@
 #include "json_min.h"
 #include "prefill.cuh"
 #include "quant.cuh"
+#include "sampler.cuh"
 
 using namespace cb;
 
@@ -133,6 +134,8 @@ struct MergerW {
 
 }  // namespace
 
+#include "engine_sampler.inc"
+
 struct crane_b200_model {
     // ---- configuration ----
     int device = 0, num_sms = 148;
@@ -154,6 +157,7 @@ struct crane_b200_model {
     unsigned int* ll_err = nullptr;
     unsigned int* h_ll_err = nullptr;      // pinned
     unsigned long long* ll_prof = nullptr;
+    unsigned long long* ll_trace = nullptr;   // CRANE_B200_LL_TRACE=<file>: event trace of one step (tools/ll_trace.py)
     void ll_err_fetch();                   // enqueue the D2H copy of the flag (before a stream sync the caller does anyway)
     void ll_err_verify();                  // after that sync
     // vision
@@ -169,9 +173,10 @@ struct crane_b200_model {
     bf16 *embed = nullptr, *lm_head = nullptr;
     unsigned char* q_lm_head = nullptr;   // quantised output head (GGUF `output.weight`, or the tied quantised `token_embd.weight`)
     int qt_lm = 0;
+    unsigned char* q_embed = nullptr;     // quantised embedding table: rows are dequantised as they are gathered (modules/embedding.rs:31-105)
+    int qt_embed = 0;
+    void embed_step_input(int B);         // x_dec <- embedding rows of state[b].token
     bool any_quant = false;
-    bf16* dq_scratch = nullptr;           // one dequantised weight matrix at a time for the prefill GEMMs
-    size_t dq_scratch_elems = 0;
     float* final_norm = nullptr;
     std::vector<LayerW> layers;
     bool got_embed = false, got_lm_head = false, got_final_norm = false, finalized = false;
@@ -223,12 +228,33 @@ struct crane_b200_model {
     void tts_frame(float rep_penalty, bool forced, int frame);
     const bf16** tts_tables_dev = nullptr;
     int* block_table = nullptr;
-    SeqState* h_state = nullptr;      // pinned
+    // Sequence state travels host -> device through a ring of pinned snapshots, one per call: the ABI hands out stream-ordered
+    // results, so a caller may issue the next call before the previous upload has run, and a single staging slot would be
+    // overwritten under it.  A slot is reused only after its own upload has completed (its event).
+    static constexpr int STATE_RING = 16, STATE_GROUP = 4;
+    SeqState* h_state_ring = nullptr; // pinned [STATE_RING][STATE_GROUP]
+    cudaEvent_t h_state_ev[STATE_RING] = {};
+    bool h_state_used[STATE_RING] = {};
+    int h_state_next = 0;
+    SeqState* h_state = nullptr;      // the slot being filled (stage_state)
+    SeqState* stage_state() {
+        const int i = h_state_next;
+        if (h_state_used[i]) CUDA_OK(cudaEventSynchronize(h_state_ev[i]));
+        h_state = h_state_ring + (size_t)i * STATE_GROUP;
+        return h_state;
+    }
+    void push_state(int nseq) {       // upload the staged snapshot(s) to the device-resident state
+        CUDA_OK(cudaMemcpyAsync(state, h_state, sizeof(SeqState) * nseq, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaEventRecord(h_state_ev[h_state_next], stream));
+        h_state_used[h_state_next] = true;
+        h_state_next = (h_state_next + 1) % STATE_RING;
+    }
     uint32_t* h_tokens = nullptr;     // pinned
     // prefill workspaces (grown on demand)
     int ws_S = 0;
     float *x = nullptr, *qkv = nullptr;
     bf16 *xn = nullptr, *q_bf = nullptr, *attn_bf = nullptr, *act_bf = nullptr;
+    float* rows_f32 = nullptr;         // [S, max(I, q_dim)] f32 rows in front of / behind a quantised linear in prefill
     float *g_proj = nullptr, *g_conv = nullptr, *g_qn = nullptr, *g_kn = nullptr, *g_gb = nullptr, *g_y = nullptr;   // GDN prefill workspaces
     float *gd_proj = nullptr, *gd_conv = nullptr, *gd_qn = nullptr, *gd_kn = nullptr, *gd_gb = nullptr, *gd_y = nullptr, *gd_out = nullptr;  // decode
     uint32_t* ids_dev = nullptr;
@@ -267,6 +293,7 @@ struct crane_b200_model {
     uint64_t launches = 0;
     uint64_t graph_launches[3] = {0, 0, 0};
     unsigned char* xq_buf = nullptr;   // activations quantised for the quantised GEMVs (xquant_launch)
+    int xq_mode_last = -1;
     // Split precision (default): every bf16 activation operand / KV page has a low-order plane (x = hi + lo) so the prefill
     // tensor-core path carries ~16 mantissa bits; lo_* = element offset of that plane from the buffer base, 0 when off.
     bool split = true;
@@ -276,6 +303,7 @@ struct crane_b200_model {
         lo_off = split ? (long long)n : 0;
         return dalloc<bf16>(split ? 2 * n : n);
     }
+    SamplerScratch sampler;
     std::string last_error;
 
     // ---------------------------------------------------------------------------------------------
@@ -307,7 +335,8 @@ struct crane_b200_model {
     unsigned char* up_quant(int qt, const void* data, size_t rows, int K, unsigned char* dst = nullptr, size_t dst_row_pitch = 0);
     void linear_decode(int epi, bool norm, const bf16* w, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx,
                        const float* norm_w, float* y, int ldy, const GemvArgs* extra = nullptr, int B = 1, bool reuse_xq = false);
-    const bf16* dequant_for_gemm(const unsigned char* qw, int qt, size_t rows, int K, size_t row_offset = 0);
+    void qlinear_rows(int epi, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx, const float* norm_w, float* y, int ldy,
+                      int S, bool reuse_xq = false);
     bool load_text_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
     bool load_vision_tensor(const std::string& n, int dt, const int64_t* shape, int ndim, const void* data);
     void finalize();
@@ -347,7 +376,6 @@ struct crane_b200_model {
     void gemm(const bf16* A, long long a_lo, int lda, const bf16* W, int M, int N, int K, int mode, void* out, int ldo, const float* bias,
               long long out_lo = 0) {
         GemmEpi ep{out, out_lo ? (void*)((bf16*)out + out_lo) : nullptr, ldo, bias, mode};
-        ep.w_dynamic = dq_scratch != nullptr && W == dq_scratch;
         LAUNCH_OK(gemm_bf16_launch(stream, A, a_lo ? A + a_lo : nullptr, lda, W, M, N, K, ep, use_simt));
         ++launches;
     }
@@ -754,18 +782,16 @@ void crane_b200_model::load_tensor_ggml(const std::string& name_in, int qt, cons
     const size_t want = (size_t)rows * (K / q_src_block_elems(qt)) * q_src_block_bytes(qt);
     if (nbytes != want) fail(CRANE_B200_INVALID_ARG, "tensor %s: %zu bytes, expected %zu", name.c_str(), nbytes, want);
     any_quant = true;
-    auto dequant_to = [&](bf16* dst) {      // device-side dequantisation into a bf16 matrix
-        unsigned char* tmpq = up_quant(qt, data, (size_t)rows, (int)K);
-        LAUNCH_OK(q_dequant_bf16_launch(stream, qt, tmpq, (size_t)rows, (int)K, dst));
-        CUDA_OK(cudaStreamSynchronize(stream));
-        return tmpq;
-    };
     if (name == "model.embed_tokens.weight") {
-        // rows are gathered as bf16 (whole table dequantised at load); a tied head streams the quantised bytes
+        // the table keeps its blocks; gathered rows are dequantised to f32 (QuantizedEmbedding, modules/embedding.rs:31-105);
+        // a tied head streams the same bytes
         want_shape(name, shape, ndim, {V, H});
-        unsigned char* qb = dequant_to(embed);
+        q_embed = up_quant(qt, data, (size_t)V, H);
+        qt_embed = qt;
+        dfree(embed);
+        embed = nullptr;
         got_embed = true;
-        if (tied) { q_lm_head = qb; qt_lm = qt; } else dfree(qb);
+        if (tied) { q_lm_head = q_embed; qt_lm = qt; lm_head = nullptr; }
         return;
     }
     if (name == "lm_head.weight") {
@@ -795,6 +821,7 @@ void crane_b200_model::load_tensor_ggml(const std::string& name_in, int qt, cons
         const size_t rb = (size_t)(H / 256) * q_sb_bytes(qt);
         if (!l.q_wgu) l.q_wgu = dalloc<unsigned char>((size_t)2 * I * rb);
         l.qt_gu = qt;
+        (up ? l.qt_up_seen : l.qt_gate_seen) = qt;
         up_quant(qt, data, I, H, l.q_wgu + (up ? rb : 0), 2 * rb);     // rows interleaved (gate_j, up_j)
         l.loaded |= up ? 32 : 16;
     }
@@ -811,8 +838,10 @@ void crane_b200_model::linear_decode(int epi, bool norm, const bf16* w, const un
         QGemvArgs qa;
         g.W = reinterpret_cast<const bf16*>(qw);
         qa.g = g; qa.qtype = qt; qa.epi = epi; qa.norm = norm ? 1 : 0; qa.xq = xq_buf;
-        if (!reuse_xq) {     // same input (and norm) as the previous quantised linear: k and v after q
-            LAUNCH_OK(xquant_launch(stream, B, xin, ldx, K, norm ? norm_w : nullptr, eps, xq_buf, use_pdl));
+        const int xmode = xq_mode_for(qt);
+        if (!reuse_xq || xmode != xq_mode_last) {     // same input (norm, block rule) as the previous quantised linear: k and v after q
+            LAUNCH_OK(xquant_launch(stream, B, xin, ldx, K, norm ? norm_w : nullptr, eps, xmode, xq_buf, use_pdl));
+            xq_mode_last = xmode;
             ++launches;
         }
         LAUNCH_OK(qgemv_launch(stream, B, qa, num_sms, use_pdl));
@@ -823,11 +852,18 @@ void crane_b200_model::linear_decode(int epi, bool norm, const bf16* w, const un
     ++launches;
 }
 
-// Prefill: dequantise `rows` x K into the shared bf16 scratch (at `row_offset` rows) and hand back the GEMM operand.
-const bf16* crane_b200_model::dequant_for_gemm(const unsigned char* qw, int qt, size_t rows, int K, size_t row_offset) {
-    LAUNCH_OK(q_dequant_bf16_launch(stream, qt, qw, rows, K, dq_scratch + row_offset * K));
-    ++launches;
-    return dq_scratch;
+// Prefill through a quantised linear: candle's `QMatMul::forward` quantises every activation ROW to Q8_K / Q8_0 blocks and takes
+// ggml integer dots whatever the number of rows (crane-core/src/ops/linear.rs:23-48), so S > 1 runs the same xquant + qgemv
+// kernels as decode, four rows per pass over the quantised weights.  (A tensor-core formulation would have to reproduce the
+// per-block integer dots exactly; the decode kernels already do.)
+void crane_b200_model::qlinear_rows(int epi, const unsigned char* qw, int qt, int N, int K, const float* xin, int ldx, const float* norm_w,
+                                    float* y, int ldy, int S, bool reuse_xq) {
+    for (int s0 = 0; s0 < S;) {
+        const int B = (S - s0 >= 4) ? 4 : (S - s0 >= 2) ? 2 : 1;
+        linear_decode(epi, norm_w != nullptr, nullptr, qw, qt, N, K, xin + (size_t)s0 * ldx, ldx, norm_w, y + (size_t)s0 * ldy, ldy, nullptr, B,
+                      reuse_xq && S <= 4);
+        s0 += B;
+    }
 }
 
 // =================================================================================================
@@ -846,12 +882,14 @@ void crane_b200_model::finalize() {
                 if (!(l.qt_q && l.qt_k && l.qt_v)) fail(CRANE_B200_UNSUPPORTED, "q/k/v must be all quantised or all bf16 within a layer");
                 mx = std::max(mx, (size_t)qkv_dim() * H);
             }
+            if ((l.qt_gate_seen != 0) != (l.qt_up_seen != 0) || (l.qt_gu && ((l.loaded & 48) != 48 || l.wgu != nullptr)))
+                fail(CRANE_B200_UNSUPPORTED, "gate_proj and up_proj of a layer must both be quantised (same ggml type) or both bf16");
             if (l.qt_o) mx = std::max(mx, (size_t)H * q_dim());
             if (l.qt_gu) mx = std::max(mx, (size_t)2 * I * H);
             if (l.qt_down) mx = std::max(mx, (size_t)H * I);
         }
-        if (mx) { dq_scratch = dalloc<bf16>(mx); dq_scratch_elems = mx; }
-        xq_buf = dalloc<unsigned char>(xquant_bytes(std::max(max_batch, 1), std::max(std::max(H, I), q_dim())));
+        (void)mx;
+        xq_buf = dalloc<unsigned char>(xquant_bytes(4, std::max(std::max(H, I), q_dim())));      // groups of <= 4 rows / sequences
     }
     for (int i = 0; i < L; ++i) {
         // full: q,k,v,o (1|2|4|8) gate,up,down (16|32|64) ln1,ln2 (128|256) q_norm,k_norm (512|1024)
@@ -948,14 +986,16 @@ void crane_b200_model::finalize() {
         auto pairs = [&](size_t n) { auto* p = dalloc<unsigned long long>(n); CUDA_OK(cudaMemset(p, 0, n * 8)); return p; };
         ll_xa = pairs(H); ll_xb = pairs(H); ll_qkv = pairs(qkv_dim()); ll_att = pairs(q_dim()); ll_act = pairs(I);
         ll_part = pairs(decode_ll_part_pairs(num_sms, nh, nkv));
-        ll_amax = pairs((size_t)2 * num_sms);
-        ll_err = dalloc<unsigned int>(1);
-        CUDA_OK(cudaMemset(ll_err, 0, sizeof(unsigned int)));
+        ll_amax = pairs((size_t)4 * num_sms);
+        ll_err = dalloc<unsigned int>(16 + num_sms * LL_WARPS);       // flag, first failing wait, per-CTA heartbeats (decode_ll.cu `Waiter`)
+        CUDA_OK(cudaMemset(ll_err, 0, sizeof(unsigned int) * (16 + num_sms * LL_WARPS)));
         CUDA_OK(cudaMallocHost((void**)&h_ll_err, sizeof(unsigned int)));
         *h_ll_err = 0;
         if (getenv("CRANE_B200_PROF")) { ll_prof = dalloc<unsigned long long>(16); CUDA_OK(cudaMemset(ll_prof, 0, 128)); }
+        if (getenv("CRANE_B200_LL_TRACE")) ll_trace = dalloc<unsigned long long>((size_t)6 * LL_TRACE_CAP * 2);
     }
-    CUDA_OK(cudaMallocHost((void**)&h_state, sizeof(SeqState) * B));
+    CUDA_OK(cudaMallocHost((void**)&h_state_ring, sizeof(SeqState) * STATE_RING * STATE_GROUP));
+    for (auto& e : h_state_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_OK(cudaMallocHost((void**)&h_tokens, sizeof(uint32_t) * out_cap));
     CUDA_OK(cudaEventCreate(&pev0));
     CUDA_OK(cudaEventCreate(&pev1));
@@ -970,7 +1010,7 @@ void crane_b200_model::ensure_prefill_ws(int S) {
     if (S <= ws_S) return;
     CUDA_OK(cudaStreamSynchronize(stream));
     for (void* p : {(void*)x, (void*)qkv, (void*)xn, (void*)q_bf, (void*)attn_bf, (void*)act_bf, (void*)ids_dev, (void*)pos3_dev,
-                    (void*)rows_dev, (void*)embeds_in, (void*)g_proj, (void*)g_conv, (void*)g_qn, (void*)g_kn, (void*)g_gb, (void*)g_y})
+                    (void*)rows_dev, (void*)embeds_in, (void*)rows_f32, (void*)g_proj, (void*)g_conv, (void*)g_qn, (void*)g_kn, (void*)g_gb, (void*)g_y})
         dfree(p);
     const int cap = (S + 127) / 128 * 128;
     x = dalloc<float>((size_t)cap * H);
@@ -988,6 +1028,7 @@ void crane_b200_model::ensure_prefill_ws(int S) {
     pos3_dev = dalloc<int>((size_t)3 * cap);
     rows_dev = dalloc<int>(cap);
     embeds_in = dalloc<float>((size_t)cap * H);
+    rows_f32 = any_quant ? dalloc<float>((size_t)cap * std::max(I, q_dim())) : nullptr;
     ws_S = cap;
 }
 
@@ -995,17 +1036,25 @@ void crane_b200_model::ensure_prefill_ws(int S) {
 // decode step
 // =================================================================================================
 void crane_b200_model::arm_state(uint32_t token, size_t start_pos, int p0, int p1, int p2) {
+    stage_state();
     h_state[0].kv_len = (int)start_pos;
     h_state[0].pos[0] = p0; h_state[0].pos[1] = p1; h_state[0].pos[2] = p2;
     h_state[0].token = token;
     h_state[0].step = 0;
     h_state[0].slot = cur;
-    CUDA_OK(cudaMemcpyAsync(state, h_state, sizeof(SeqState), cudaMemcpyHostToDevice, stream));
+    push_state(1);
+}
+
+// x_dec <- the embedding rows of state[b].token (bf16 table, or rows dequantised out of a quantised table)
+void crane_b200_model::embed_step_input(int B) {
+    if (q_embed) LAUNCH_OK(embed_rows_q_launch(stream, qt_embed, q_embed, H, nullptr, state, B, x_dec, false));
+    else LAUNCH_OK(embed_decode_launch(stream, B, embed, H, state, x_dec, false));
+    ++launches;
 }
 
 void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) {
     const bool pdl = use_pdl;
-    if (with_embed) { LAUNCH_OK(embed_decode_launch(stream, B, embed, H, state, x_dec, false)); ++launches; }
+    if (with_embed) embed_step_input(B);
     for (int li = 0; li < L; ++li) {
         LayerW& l = layers[li];
         if (l.full) {
@@ -1068,6 +1117,8 @@ void crane_b200_model::lm_head_last_row(const float* xrow, int advance, int B) {
     h.norm_out = hidden_out; h.force_tokens = hov.force;
     linear_decode(GEMV_LOGITS_ARGMAX, true, hov.head ? hov.head : lm_head, q_lm_head, hov.head ? 0 : qt_lm, V, H, xrow, H, final_norm,
                   hov.logits ? hov.logits : logits, V, &h, B);
+    // a quantised table cannot be gathered by the head's epilogue: the next input is dequantised by its own launch
+    if (advance && q_embed && !hov.gather_set) embed_step_input(B);
 }
 
 // One decode step (layers + lm_head), replayed from a CUDA graph when capture is available.
@@ -1117,14 +1168,21 @@ void crane_b200_model::decode_steps(int n_steps, int advance) {
             CUDA_OK(cudaMemsetAsync(ll_att, 0, (size_t)q_dim() * 8, stream));
             CUDA_OK(cudaMemsetAsync(ll_act, 0, (size_t)I * 8, stream));
             CUDA_OK(cudaMemsetAsync(ll_part, 0, decode_ll_part_pairs(num_sms, nh, nkv) * 8, stream));
-            CUDA_OK(cudaMemsetAsync(ll_amax, 0, (size_t)2 * num_sms * 8, stream));
+            CUDA_OK(cudaMemsetAsync(ll_amax, 0, (size_t)4 * num_sms * 8, stream));
             ll_tag = 0;
         }
         p.tag_base = ll_tag;
         ll_tag += need;
         p.n_steps = n_steps; p.advance = advance; p.err = ll_err; p.prof = ll_prof;
+        if (ll_trace && n_steps > 8) { CUDA_OK(cudaMemsetAsync(ll_trace, 0, (size_t)6 * LL_TRACE_CAP * 16, stream)); p.trace = ll_trace; p.trace_step = 6; }
         LAUNCH_OK(decode_ll_launch(stream, p, num_sms));
         ++launches;
+        if (p.trace) {
+            std::vector<unsigned long long> h((size_t)6 * LL_TRACE_CAP * 2);
+            CUDA_OK(cudaStreamSynchronize(stream));
+            CUDA_OK(cudaMemcpy(h.data(), ll_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+            if (FILE* f = fopen(getenv("CRANE_B200_LL_TRACE"), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        }
         if (ll_prof && n_steps > 8) {   // CRANE_B200_PROF=1: where CTA 0's first thread spent its cycles (the CRANE_PROF spans of ops/prof.rs:37-61)
             unsigned long long h[16];
             CUDA_OK(cudaStreamSynchronize(stream));
@@ -1146,9 +1204,22 @@ void crane_b200_model::ll_err_fetch() {
 }
 void crane_b200_model::ll_err_verify() {
     if (!ll_err || *h_ll_err == 0) return;
-    CUDA_OK(cudaMemsetAsync(ll_err, 0, sizeof(unsigned int), stream));
+    std::vector<unsigned int> d(16 + num_sms * LL_WARPS);
+    CUDA_OK(cudaMemcpy(d.data(), ll_err, d.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemsetAsync(ll_err, 0, sizeof(unsigned int) * d.size(), stream));
     *h_ll_err = 0;
-    fail(CRANE_B200_CUDA_ERROR, "persistent decode kernel: a dependency wait timed out (results discarded)");
+    static const char* sites[5] = {"?", "activation slice", "attention query", "attention split merge", "token argmax"};
+    // the warps that were waiting furthest behind are where the chain broke
+    unsigned int lo = ~0u;
+    for (size_t i = 16; i < d.size(); ++i) if (d[i] != 0 && d[i] < lo) lo = d[i];
+    std::string who;
+    int shown = 0;
+    for (size_t i = 16; i < d.size() && shown < 12; ++i)
+        if (d[i] == lo) { who += " cta" + std::to_string((i - 16) / LL_WARPS) + ".w" + std::to_string((i - 16) % LL_WARPS); ++shown; }
+    fail(CRANE_B200_CUDA_ERROR,
+         "persistent decode kernel: a dependency wait timed out (results discarded): %s wait in CTA %u warp %u at step %u phase %u wanted tag %u, "
+         "saw %u; earliest unfinished wait: step %u phase %u site %u in%s",
+         sites[d[1] < 5 ? d[1] : 0], d[2], d[3], d[4], d[5], d[6], d[7], lo >> 20, (lo >> 8) & 0xfff, lo & 0xff, who.c_str());
 }
 
 // =================================================================================================
@@ -1169,7 +1240,8 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     CUDA_OK(cudaMemcpyAsync(pos3_dev, p3.data(), p3.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     if (ids) {
         CUDA_OK(cudaMemcpyAsync(ids_dev, ids, S * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        LAUNCH_OK(embed_rows_launch(stream, ids_dev, S, embed, H, x));
+        if (q_embed) LAUNCH_OK(embed_rows_q_launch(stream, qt_embed, q_embed, H, ids_dev, nullptr, S, x, prefill_pdl()));
+        else LAUNCH_OK(embed_rows_launch(stream, ids_dev, S, embed, H, x));
         ++launches;
     } else {
         CUDA_OK(cudaMemcpyAsync(x, embeds, (size_t)S * H * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -1184,16 +1256,23 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     const int qd = q_dim();
     for (int li = 0; li < L; ++li) {
         LayerW& l = layers[li];
-        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln1, eps, xn, lo_xn));
+        const bool q_qkv = l.full && l.qt_q != 0;
+        if (!q_qkv) LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln1, eps, xn, lo_xn));
         if (l.full) {
-            const bf16* wqkv = l.wqkv;
-            if (l.qt_q) {   // dequantise q | k | v into consecutive rows of the scratch -> one merged GEMM
-                const size_t qs = (size_t)nh * q_stride(), kvd = (size_t)nkv * D;
-                dequant_for_gemm(l.q_wq, l.qt_q, qs, H, 0);
-                dequant_for_gemm(l.q_wk, l.qt_k, kvd, H, qs);
-                wqkv = dequant_for_gemm(l.q_wv, l.qt_v, kvd, H, qs + kvd);
+            if (q_qkv) {   // GGUF keeps q / k / v separate and quantised (qwen3/modeling.rs:252-255): integer-dot rows, 4 at a time
+                const int qs = nh * q_stride(), kvd = nkv * D;
+                for (int s0 = 0; s0 < S;) {
+                    const int B = (S - s0 >= 4) ? 4 : (S - s0 >= 2) ? 2 : 1;
+                    const float* xr = x + (size_t)s0 * H;
+                    float* yr = qkv + (size_t)s0 * qkv_dim();
+                    linear_decode(GEMV_STORE, true, nullptr, l.q_wq, l.qt_q, qs, H, xr, H, l.ln1, yr, qkv_dim(), nullptr, B);
+                    linear_decode(GEMV_STORE, true, nullptr, l.q_wk, l.qt_k, kvd, H, xr, H, l.ln1, yr + qs, qkv_dim(), nullptr, B, true);
+                    linear_decode(GEMV_STORE, true, nullptr, l.q_wv, l.qt_v, kvd, H, xr, H, l.ln1, yr + qs + kvd, qkv_dim(), nullptr, B, true);
+                    s0 += B;
+                }
+            } else {
+                gemm(xn, lo_xn, H, l.wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
             }
-            gemm(xn, lo_xn, H, wqkv, S, qkv_dim(), H, EPI_STORE_F32, qkv, qkv_dim(), nullptr);
             RopeAppendArgs ra = {};
             ra.qkv = qkv; ra.q_stride = q_stride(); ra.rot_half = rot_half;
             ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
@@ -1206,7 +1285,13 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             fa.q_lo_off = lo_q; fa.kv_lo_off = lo_kv; fa.out_lo_off = lo_attn;
             LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
             if (hybrid) { LAUNCH_OK(gate_mul_launch(stream, attn_bf, qkv, S, nh, D, q_stride(), qkv_dim(), lo_attn)); ++launches; }
-            gemm(attn_bf, lo_attn, qd, l.qt_o ? dequant_for_gemm(l.q_wo, l.qt_o, H, qd) : l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
+            if (l.qt_o) {
+                LAUNCH_OK(planes_to_f32_launch(stream, attn_bf, lo_attn, (size_t)S * qd, rows_f32));
+                ++launches;
+                qlinear_rows(GEMV_RESID, l.q_wo, l.qt_o, H, qd, rows_f32, qd, nullptr, x, H, S);
+            } else {
+                gemm(attn_bf, lo_attn, qd, l.wo, S, H, qd, EPI_RESID_F32, x, H, nullptr);
+            }
         } else {
             gemm(xn, lo_xn, H, l.w_in, S, gdn_in_pad, H, EPI_STORE_F32, g_proj, gdn_in_pad, nullptr);
             GdnArgs ga;
@@ -1216,9 +1301,17 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             gemm(attn_bf, lo_attn, value_dim(), l.w_out, S, H, value_dim(), EPI_RESID_F32, x, H, nullptr);
             launches += 3;
         }
-        LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln2, eps, xn, lo_xn));
-        gemm(xn, lo_xn, H, l.qt_gu ? dequant_for_gemm(l.q_wgu, l.qt_gu, (size_t)2 * I, H) : l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr, lo_act);
-        gemm(act_bf, lo_act, I, l.qt_down ? dequant_for_gemm(l.q_wdown, l.qt_down, H, I) : l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
+        // MLP: either linear may be quantised on its own (Q4_K_M keeps ffn_down in Q6_K, the others in Q4_K)
+        if (l.qt_gu) {
+            qlinear_rows(GEMV_SILU_MUL, l.q_wgu, l.qt_gu, 2 * I, H, x, H, l.ln2, rows_f32, I, S);
+            if (!l.qt_down) { LAUNCH_OK(cast_f32_bf16_launch(stream, rows_f32, act_bf, (size_t)S * I, lo_act)); ++launches; }
+        } else {
+            LAUNCH_OK(rmsnorm_rows_launch(stream, x, S, H, l.ln2, eps, xn, lo_xn));
+            gemm(xn, lo_xn, H, l.wgu, S, 2 * I, H, EPI_SILU_MUL_BF16, act_bf, I, nullptr, lo_act);
+            if (l.qt_down) { LAUNCH_OK(planes_to_f32_launch(stream, act_bf, lo_act, (size_t)S * I, rows_f32)); ++launches; }
+        }
+        if (l.qt_down) qlinear_rows(GEMV_RESID, l.q_wdown, l.qt_down, H, I, rows_f32, I, nullptr, x, H, S);
+        else gemm(act_bf, lo_act, I, l.wdown, S, H, I, EPI_RESID_F32, x, H, nullptr);
         launches += 4;
         if (n_vis > 0 && li < (int)v_deepstack.size()) {   // DeepStack (qwen3_vl/text.rs:262-268)
             LAUNCH_OK(set_rows_launch(stream, x, H, rows_dev, n_vis, ds_embeds + (size_t)li * n_vis * H, true));
@@ -1228,12 +1321,13 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     // state for the last-row lm_head / a following on-device decode loop
     const int last_p[3] = {p3[(size_t)0 * S + S - 1], p3[(size_t)1 * S + S - 1], p3[(size_t)2 * S + S - 1]};
     (void)last_p;
+    stage_state();
     h_state[0].kv_len = (int)(start_pos + S - 1);   // lm_head(advance) bumps it to start_pos + S
     h_state[0].pos[0] = h_state[0].pos[1] = h_state[0].pos[2] = (int)next_mrope_pos - 1;
     h_state[0].token = 0;
     h_state[0].step = 0;
     h_state[0].slot = cur;
-    CUDA_OK(cudaMemcpyAsync(state, h_state, sizeof(SeqState), cudaMemcpyHostToDevice, stream));
+    push_state(1);
     lm_head_last_row(x + (size_t)(S - 1) * H, advance);
     CUDA_OK(cudaEventRecord(pev1, stream));
     kv_len = start_pos + S;
@@ -1454,9 +1548,11 @@ void crane_b200_destroy(crane_b200_model* m) {
     if (m->cp) { crane_b200_destroy(m->cp); m->cp = nullptr; }
     for (auto& g : m->graph_step) if (g) cudaGraphExecDestroy(g);
     for (void* p : m->allocs) cudaFree(p);
-    if (m->h_state) cudaFreeHost(m->h_state);
+    if (m->h_state_ring) cudaFreeHost(m->h_state_ring);
+    for (cudaEvent_t e : m->h_state_ev) if (e) cudaEventDestroy(e);
     if (m->h_tokens) cudaFreeHost(m->h_tokens);
     if (m->h_ll_err) cudaFreeHost(m->h_ll_err);
+    m->sampler.release();
     for (cudaEvent_t e : {m->pev0, m->pev1, m->dev0, m->dev1}) if (e) cudaEventDestroy(e);
     if (m->stream && m->owns_stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -1495,8 +1591,7 @@ int crane_b200_forward_step(crane_b200_model* m, const uint32_t* ids, size_t n, 
     if (n == 1) {
         CUDA_OK(cudaEventRecord(m->dev0, m->stream));
         m->arm_state(ids[0], start_pos, (int)start_pos, (int)start_pos, (int)start_pos);
-        LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
-        ++m->launches;
+        m->embed_step_input(1);
         m->decode_steps(1, 0);
         CUDA_OK(cudaEventRecord(m->dev1, m->stream));
         m->last_decode_steps = 1;
@@ -1602,8 +1697,7 @@ int crane_b200_decode_greedy(crane_b200_model* m, uint32_t first_token, size_t s
     CUDA_OK(cudaEventRecord(m->dev0, m->stream));
     const int p = (int)m->next_mrope_pos;
     m->arm_state(first_token, start_pos, p, p, p);
-    LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
-    ++m->launches;
+    m->embed_step_input(1);
     m->decode_steps((int)n_steps, 1);
     CUDA_OK(cudaEventRecord(m->dev1, m->stream));
     CUDA_OK(cudaMemcpyAsync(m->h_tokens, m->out_tokens, n_steps * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
@@ -1707,8 +1801,7 @@ int crane_b200_vl_forward(crane_b200_model* m, const uint32_t* ids, size_t n, co
     m->next_mrope_pos = next_pos;
     if (n == 1 && vis_rows.empty()) {
         m->arm_state(ids[0], start_pos, (int)pos3[0], (int)pos3[1], (int)pos3[2]);
-        LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
-        ++m->launches;
+        m->embed_step_input(1);
         m->decode_steps(1, 0);
         m->kv_len = start_pos + 1;
     } else {
@@ -1726,8 +1819,7 @@ int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token, size_t start_
     const int p = (int)m->next_mrope_pos;
     if (p > m->max_seq) fail(CRANE_B200_OOM, "rotary position exceeds max_seq_len");
     m->arm_state(token, start_pos, p, p, p);
-    LAUNCH_OK(embed_decode_launch(m->stream, 1, m->embed, m->H, m->state, m->x_dec, false));
-    ++m->launches;
+    m->embed_step_input(1);
     m->decode_steps(1, 0);
     m->next_mrope_pos = (uint32_t)(p + 1);
     m->kv_len = start_pos + 1;
@@ -1753,6 +1845,7 @@ int crane_b200_seq_create(crane_b200_model* m, int* seq_out) {
 
 int crane_b200_seq_free(crane_b200_model* m, int seq) {
     API_BEGIN(m)
+    need_ready(m);
     if (seq < 0 || seq >= m->max_batch || !m->seq_used[seq]) fail(CRANE_B200_INVALID_ARG, "seq_free: bad sequence %d", seq);
     if (seq == 0) fail(CRANE_B200_INVALID_ARG, "sequence 0 is the handle's implicit sequence (use clear_kv_cache)");
     m->select_seq(0);
@@ -1792,6 +1885,7 @@ int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t
     size_t done = 0;
     while (done < n) {
         const int B = std::min(maxg, (n - done >= 4) ? 4 : (n - done >= 2) ? 2 : 1);
+        m->stage_state();
         for (int b = 0; b < B; ++b) {
             const int s = seqs[done + b];
             SeqState& st = m->h_state[b];
@@ -1801,16 +1895,15 @@ int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t
             st.step = 0;
             st.slot = s;
         }
-        CUDA_OK(cudaMemcpyAsync(m->state, m->h_state, B * sizeof(SeqState), cudaMemcpyHostToDevice, m->stream));
-        LAUNCH_OK(embed_decode_launch(m->stream, B, m->embed, m->H, m->state, m->x_dec, false));
-        ++m->launches;
+        m->push_state(B);
+        m->embed_step_input(B);
         for (size_t t = 0; t < n_steps; ++t) m->enqueue_decode_step(1, false, B);
         for (int b = 0; b < B; ++b)
             CUDA_OK(cudaMemcpyAsync(tokens_out + (done + b) * n_steps, m->out_tokens + (size_t)b * m->out_cap, n_steps * sizeof(uint32_t),
                                     cudaMemcpyDeviceToHost, m->stream));
         if (logits_host)
             CUDA_OK(cudaMemcpyAsync(logits_host + done * (size_t)m->V, m->logits, (size_t)B * m->V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-        CUDA_OK(cudaStreamSynchronize(m->stream));     // h_state is reused by the next group
+        CUDA_OK(cudaStreamSynchronize(m->stream));     // tokens_out / logits_host are the caller's memory: complete before returning
         for (int b = 0; b < B; ++b) {
             const int s = seqs[done + b];
             m->seq_kv[s] += n_steps;
@@ -1822,6 +1915,156 @@ int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t
     m->last_decode_steps = n_steps;
     m->kv_len = m->seq_kv[m->cur]; m->next_mrope_pos = m->seq_pos[m->cur];
     API_END(m)
+}
+
+// ---- device-side sampling (crane-serve/src/engine/sampling.rs:169-480) ----
+int crane_b200_sample(crane_b200_model* m, const crane_b200_sampling* p, uint32_t* token_out) {
+    API_BEGIN(m)
+    need_ready(m);
+    sampler_run(m->stream, m->sampler, m->logits, m->V, 1, p, token_out);
+    m->ll_err_fetch();
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->ll_err_verify();
+    API_END(m)
+}
+
+int crane_b200_forward_step_sample(crane_b200_model* m, const uint32_t* ids, size_t n, size_t start_pos, const crane_b200_sampling* p,
+                                   uint32_t* token_out) {
+    if (!p || !token_out) return CRANE_B200_INVALID_ARG;
+    const int r = crane_b200_forward_step(m, ids, n, start_pos, nullptr);
+    if (r != CRANE_B200_OK) return r;
+    return crane_b200_sample(m, p, token_out);
+}
+
+int crane_b200_topk(crane_b200_model* m, size_t k, uint32_t* idx_out, float* vals_out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!idx_out || k == 0 || k > (size_t)TOPK_MAX || k > (size_t)m->V) fail(CRANE_B200_INVALID_ARG, "topk: k must be in 1..min(%d, vocab)", TOPK_MAX);
+    m->sampler.reserve(1, 0, 0);
+    LAUNCH_OK(sampler_topk_launch(m->stream, m->logits, m->V, 1, (int)k, m->sampler.tk_idx, m->sampler.tk_val));
+    CUDA_OK(cudaMemcpyAsync(idx_out, m->sampler.tk_idx, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    if (vals_out) CUDA_OK(cudaMemcpyAsync(vals_out, m->sampler.tk_val, k * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    API_END(m)
+}
+
+int crane_b200_decode_batch_sample(crane_b200_model* m, const int* seqs, const uint32_t* tokens, size_t n, const crane_b200_sampling* params,
+                                   uint32_t* tokens_out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!seqs || !tokens || !tokens_out || !params || n == 0) fail(CRANE_B200_INVALID_ARG, "decode_batch_sample: bad arguments");
+    if (m->hybrid) fail(CRANE_B200_UNSUPPORTED, "decode_batch_sample on the hybrid model");
+    m->seq_kv[m->cur] = m->kv_len; m->seq_pos[m->cur] = m->next_mrope_pos;
+    for (size_t i = 0; i < n; ++i) {
+        const int s = seqs[i];
+        if (s < 0 || s >= m->max_batch || !m->seq_used[s]) fail(CRANE_B200_INVALID_ARG, "decode_batch_sample: bad sequence %d", s);
+        for (size_t j = 0; j < i; ++j) if (seqs[j] == s) fail(CRANE_B200_INVALID_ARG, "decode_batch_sample: sequence %d listed twice", s);
+        if (tokens[i] >= (uint32_t)m->V) fail(CRANE_B200_INVALID_ARG, "token id %u >= vocab %d", tokens[i], m->V);
+        if (m->seq_kv[s] + 1 > (size_t)m->max_seq) fail(CRANE_B200_OOM, "sequence %d would exceed max_seq_len %d", s, m->max_seq);
+    }
+    int maxg = 4;
+    if (!m->any_quant)
+        for (int K : {m->H, m->I, m->q_dim()}) maxg = std::min(maxg, gemv_max_group(K, m->V, m->num_sms));
+    size_t done = 0;
+    while (done < n) {
+        const int B = std::min(maxg, (n - done >= 4) ? 4 : (n - done >= 2) ? 2 : 1);
+        m->stage_state();
+        for (int b = 0; b < B; ++b) {
+            const int s = seqs[done + b];
+            SeqState& st = m->h_state[b];
+            st.kv_len = (int)m->seq_kv[s];
+            st.pos[0] = st.pos[1] = st.pos[2] = (int)m->seq_pos[s];
+            st.token = tokens[done + b];
+            st.step = 0;
+            st.slot = s;
+        }
+        m->push_state(B);
+        m->embed_step_input(B);
+        m->enqueue_decode_step(0, false, B);         // logits [B, V] stay on the device; the host picks the next inputs from the sampled ids
+        sampler_run(m->stream, m->sampler, m->logits, m->V, (size_t)B, params + done, tokens_out + done);
+        for (int b = 0; b < B; ++b) {
+            const int s = seqs[done + b];
+            m->seq_kv[s] += 1;
+            m->seq_pos[s] += 1;
+        }
+        done += B;
+    }
+    m->kv_len = m->seq_kv[m->cur]; m->next_mrope_pos = m->seq_pos[m->cur];
+    API_END(m)
+}
+
+int crane_b200_op_qlinear(int device, const float* x, size_t m, size_t k, const void* raw, size_t raw_bytes, int ggml_type, size_t n,
+                          const float* norm_w, float eps, float* y) {
+    if (!x || !raw || !y || m == 0 || n == 0 || k == 0 || (k % 256) != 0) return CRANE_B200_INVALID_ARG;
+    if (ggml_type != QT_Q4_K && ggml_type != QT_Q6_K && ggml_type != QT_Q8_0) return CRANE_B200_UNSUPPORTED;
+    if (raw_bytes != n * (k / q_src_block_elems(ggml_type)) * q_src_block_bytes(ggml_type)) return CRANE_B200_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return CRANE_B200_CUDA_ERROR;
+    int rc = CRANE_B200_OK;
+    float *dx = nullptr, *dy = nullptr, *dn = nullptr;
+    unsigned char *dw = nullptr, *dxq = nullptr;
+    try {
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        const size_t rb = (k / 256) * (size_t)q_sb_bytes(ggml_type);
+        std::vector<unsigned char> packed(n * rb);
+        q_repack_rows(ggml_type, (const unsigned char*)raw, packed.data(), n, (int)k);
+        CUDA_OK(cudaMalloc((void**)&dx, m * k * 4)); CUDA_OK(cudaMalloc((void**)&dy, m * n * 4)); CUDA_OK(cudaMalloc((void**)&dw, packed.size()));
+        CUDA_OK(cudaMalloc((void**)&dxq, xquant_bytes(4, (int)k)));
+        CUDA_OK(cudaMemcpy(dx, x, m * k * 4, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(dw, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemset(dy, 0, m * n * 4));
+        if (norm_w) { CUDA_OK(cudaMalloc((void**)&dn, k * 4)); CUDA_OK(cudaMemcpy(dn, norm_w, k * 4, cudaMemcpyHostToDevice)); }
+        for (size_t s0 = 0; s0 < m;) {
+            const int B = (m - s0 >= 4) ? 4 : (m - s0 >= 2) ? 2 : 1;
+            LAUNCH_OK(xquant_launch(nullptr, B, dx + s0 * k, (int)k, (int)k, dn, eps, xq_mode_for(ggml_type), dxq, false));
+            QGemvArgs qa = {};
+            qa.g.W = reinterpret_cast<const bf16*>(dw); qa.g.N = (int)n; qa.g.K = (int)k; qa.g.y = dy + s0 * n; qa.g.ldy = (int)n; qa.g.eps = eps;
+            qa.qtype = ggml_type; qa.epi = GEMV_STORE; qa.norm = dn ? 1 : 0; qa.xq = dxq;
+            LAUNCH_OK(qgemv_launch(nullptr, B, qa, prop.multiProcessorCount, false));
+            s0 += B;
+        }
+        CUDA_OK(cudaDeviceSynchronize());
+        CUDA_OK(cudaMemcpy(y, dy, m * n * 4, cudaMemcpyDeviceToHost));
+    } catch (const EngineError& e) {
+        g_create_error = e.msg;
+        rc = e.code;
+    }
+    for (void* p : {(void*)dx, (void*)dy, (void*)dn, (void*)dw, (void*)dxq}) if (p) cudaFree(p);
+    return rc;
+}
+
+static int op_sampler(int device, const float* logits, size_t vocab, size_t k, const crane_b200_sampling* p, uint32_t* out, float* logits_after) {
+    if (!logits || !out || vocab == 0 || vocab > (size_t)INT32_MAX) return CRANE_B200_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return CRANE_B200_CUDA_ERROR;
+    SamplerScratch sc;
+    float* dl = nullptr;
+    int rc = CRANE_B200_OK;
+    try {
+        CUDA_OK(cudaMalloc((void**)&dl, vocab * sizeof(float)));
+        CUDA_OK(cudaMemcpy(dl, logits, vocab * sizeof(float), cudaMemcpyHostToDevice));
+        if (p) {
+            sampler_run(nullptr, sc, dl, (int)vocab, 1, p, out);
+            if (logits_after) CUDA_OK(cudaMemcpy(logits_after, dl, vocab * sizeof(float), cudaMemcpyDeviceToHost));
+        } else {
+            if (k == 0 || k > (size_t)TOPK_MAX || k > vocab) fail(CRANE_B200_INVALID_ARG, "op_topk: k must be in 1..min(%d, vocab)", TOPK_MAX);
+            sc.reserve(1, 0, 0);
+            LAUNCH_OK(sampler_topk_launch(nullptr, dl, (int)vocab, 1, (int)k, sc.tk_idx, nullptr));
+            CUDA_OK(cudaMemcpy(out, sc.tk_idx, k * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        }
+    } catch (const EngineError& e) {
+        g_create_error = e.msg;
+        rc = e.code;
+    }
+    if (dl) cudaFree(dl);
+    sc.release();
+    return rc;
+}
+int crane_b200_op_topk(int device, const float* logits, size_t vocab, size_t k, uint32_t* idx_out) {
+    return op_sampler(device, logits, vocab, k, nullptr, idx_out, nullptr);
+}
+int crane_b200_op_sample(int device, const float* logits, size_t vocab, const crane_b200_sampling* p, uint32_t* token_out, float* logits_after) {
+    if (!p) return CRANE_B200_INVALID_ARG;
+    return op_sampler(device, logits, vocab, 0, p, token_out, logits_after);
 }
 
 int crane_b200_last_timing(const crane_b200_model* m, float* prefill_ms, float* decode_ms, size_t* decode_steps) {

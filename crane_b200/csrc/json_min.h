@@ -1,4 +1,6 @@
-// Minimal JSON reader for HF config.json (objects, arrays, numbers, strings, true/false/null).
+// Minimal JSON reader for HF config.json and safetensors headers (objects, arrays, numbers, strings, true/false/null).
+// The input is untrusted (file headers): every read is bounded by the terminating NUL, nesting is limited, \uXXXX escapes
+// (surrogate pairs included) are decoded to UTF-8.
 #pragma once
 
 #include <cstdlib>
@@ -42,11 +44,20 @@ public:
 
 private:
     const char* p_;
+    int depth_ = 0;
+    static constexpr int kMaxDepth = 64;
     [[noreturn]] void fail(const char* m) { throw std::runtime_error(std::string("config json: ") + m); }
     void ws() { while (*p_ == ' ' || *p_ == '\n' || *p_ == '\t' || *p_ == '\r') ++p_; }
+    struct Nest {
+        int& d;
+        explicit Nest(int& dd) : d(dd) { ++d; }
+        ~Nest() { --d; }
+    };
     Value value() {
         ws();
         Value v;
+        Nest nest(depth_);
+        if (depth_ > kMaxDepth) fail("nesting too deep");
         if (*p_ == '{') {
             v.type = Value::OBJ;
             ++p_; ws();
@@ -90,20 +101,54 @@ private:
         }
         return v;
     }
+    int hex4() {               // four hex digits at p_ (each checked: a NUL ends the buffer)
+        int v = 0;
+        for (int i = 0; i < 4; ++i) {
+            const char c = p_[i];
+            int d;
+            if (c >= '0' && c <= '9') d = c - '0';
+            else if (c >= 'a' && c <= 'f') d = c - 'a' + 10;
+            else if (c >= 'A' && c <= 'F') d = c - 'A' + 10;
+            else fail("bad \\u escape");
+            v = v * 16 + d;
+        }
+        p_ += 4;
+        return v;
+    }
+    static void utf8(std::string& out, unsigned cp) {
+        if (cp < 0x80) out += (char)cp;
+        else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+        else if (cp < 0x10000) { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+        else { out += (char)(0xF0 | (cp >> 18)); out += (char)(0x80 | ((cp >> 12) & 0x3F)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+    }
     std::string str() {
         std::string out;
         ++p_;
         while (*p_ && *p_ != '"') {
-            if (*p_ == '\\') {
-                ++p_;
-                switch (*p_) {
-                    case 'n': out += '\n'; break;
-                    case 't': out += '\t'; break;
-                    case 'u': p_ += 4; out += '?'; break;
-                    default: out += *p_;
+            if (*p_ != '\\') { out += *p_++; continue; }
+            ++p_;
+            const char c = *p_;
+            if (c == 0) fail("unterminated string");
+            ++p_;
+            switch (c) {
+                case 'n': out += '\n'; break;
+                case 't': out += '\t'; break;
+                case 'r': out += '\r'; break;
+                case 'b': out += '\b'; break;
+                case 'f': out += '\f'; break;
+                case 'u': {
+                    unsigned cp = (unsigned)hex4();
+                    if (cp >= 0xD800 && cp < 0xDC00 && p_[0] == '\\' && p_[1] == 'u') {      // surrogate pair
+                        p_ += 2;
+                        const unsigned lo = (unsigned)hex4();
+                        if (lo < 0xDC00 || lo > 0xDFFF) fail("bad surrogate pair");
+                        cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                    }
+                    utf8(out, cp);
+                    break;
                 }
-                ++p_;
-            } else out += *p_++;
+                default: out += c;          // \" \\ \/
+            }
         }
         if (*p_ != '"') fail("unterminated string");
         ++p_;

@@ -510,6 +510,28 @@ int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n,
     return launch_k(cast_f32_bf16_kernel, dim3(grid), dim3(256), 0, st, prefill_pdl(), src, dst, n4, lo_off);
 }
 
+// split-precision planes (hi [+ lo]) -> f32: the input of a quantised linear that follows a tensor-core kernel
+__global__ void __launch_bounds__(256)
+planes_to_f32_kernel(const bf16* __restrict__ src, long long lo_off, size_t n4, float* __restrict__ dst) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint2 h = reinterpret_cast<const uint2*>(src)[i];
+        float4 v = make_float4(bf16lo(h.x), bf16hi(h.x), bf16lo(h.y), bf16hi(h.y));
+        if (lo_off) {
+            const uint2 l = reinterpret_cast<const uint2*>(src + lo_off)[i];
+            v.x += bf16lo(l.x); v.y += bf16hi(l.x); v.z += bf16lo(l.y); v.w += bf16hi(l.y);
+        }
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
+}
+int planes_to_f32_launch(cudaStream_t st, const bf16* src, long long lo_off, size_t n, float* dst) {
+    if (n % 4 || (lo_off % 4)) return -1000;
+    const size_t n4 = n / 4;
+    const int grid = (int)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184);
+    return launch_k(planes_to_f32_kernel, dim3(grid), dim3(256), 0, st, prefill_pdl(), src, lo_off, n4, dst);
+}
+
 // x[p] += sum_c w4[c][p] * table[idx4[c][p]]      (bilinear pos-embed, qwen3_5/vision.rs:445-459)
 __global__ void __launch_bounds__(256)
 vit_pos_embed_add_kernel(float* __restrict__ x, int N, int Hv, const float* __restrict__ table,

@@ -3,14 +3,17 @@
 //
 // Replaces candle's `QMatMul::forward` behind `LinearLayer::Quantized` (crane-core/src/ops/linear.rs:23-48) /
 // `Gguf::linear` (crane-core/src/models/hunyuan_dense/modeling.rs:37-41).  Like candle's own paths (CPU: activations
-// quantised to Q8_K blocks; CUDA: mmvq with q8_1 activations) the activation vector is quantised to int8 per 32-element
-// block (d = amax/127) before the integer dot; block formats follow ggml exactly (oracle/ggml_quant.py is pinned to the
-// `gguf` package byte for byte).  Parity status: "unpinned" in SURVEY.md section 8c -- the oracle is f32 x . dequant(W).
+// quantised to Q8_K blocks) the activation vector is quantised to int8 blocks -- Q8_K (256 elements) in front of K-quant
+// weights, Q8_0 (32 elements) in front of Q8_0 weights, with candle's own rounding rules (xquant_kernel) -- before the
+// integer dot; block formats follow ggml exactly (oracle/ggml_quant.py is pinned to the `gguf` package byte for byte, and
+// its `qmatmul` restates the ggml integer dots this kernel reproduces).
 //
 // Kernel shape is the bf16 GEMV's (decode.cu): grid = #SMs, contiguous row block per CTA, one private cp.async ring per
 // warp, weights primed before griddepcontrol.wait, fused epilogues.  Two (Q4_K, Q6_K) or four (Q8_0) lanes share one
 // 256-element super-block.
 #include "quant.cuh"
+
+#include <cuda_fp16.h>
 
 #include <cstring>
 #include <vector>
@@ -190,14 +193,20 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane, int
 }
 
 // ------------------------------------------------------------------------------------------------ activation quantiser
-// One CTA per sequence: x (f32, optionally times the RMSNorm weight; 1/rms kept aside) -> int8 per 32-element block in
-// exactly the shared-memory image the GEMV consumes (see xq_swz), written once to global so the 148 GEMV CTAs fetch
-// 1.5 B/element with one bulk copy each instead of re-reading and re-quantising 4 B/element.
+// One CTA per sequence: the (optionally RMS-normalised) activation row -> int8 blocks in exactly the shared-memory image the
+// GEMV consumes (see xq_swz), written once to global so the 148 GEMV CTAs fetch 1.5 B/element with one bulk copy each instead
+// of re-reading and re-quantising 4 B/element.  The block rule is the one candle's CPU `QMatMul::forward` applies to the
+// activations before its integer dots (`LinearLayer::Quantized`, crane-core/src/ops/linear.rs:23-48):
+//   XQ_Q8_K (Q4_K / Q6_K weights): BlockQ8K::from_float -- 256 elements; max = first element of largest magnitude, sign kept;
+//                                  iscale = -128 / max; q = min(127, round(iscale * x)); d = 1 / iscale
+//   XQ_Q8_0 (Q8_0 weights)       : BlockQ8_0::from_float -- 32 elements; d = amax / 127; q = round(x * (1 / d)); the dot uses f16(d)
+// (round = half away from zero, Rust's f32::round).  RMSNorm is applied BEFORE quantising, as the reference does
+// (rms_norm -> linear), so the GEMV epilogue has nothing left to scale.
 constexpr int XQ_THREADS = 1024;
 __host__ __device__ inline size_t xq_seq_bytes(int K) { return (size_t)K + (size_t)(K / 32) * 8 + (size_t)(K / 16) * 4; }
 
 __global__ void __launch_bounds__(XQ_THREADS, 1)
-xquant_kernel(const float* __restrict__ x, int ldx, int K, const float* __restrict__ norm_w, float eps, int B, unsigned char* __restrict__ out) {
+xquant_kernel(const float* __restrict__ x, int ldx, int K, const float* __restrict__ norm_w, float eps, int B, int mode, unsigned char* __restrict__ out) {
     __shared__ float red[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char* xq = out + (size_t)b * xq_seq_bytes(K);
@@ -205,38 +214,79 @@ xquant_kernel(const float* __restrict__ x, int ldx, int K, const float* __restri
     int* isp = reinterpret_cast<int*>(xq + K + (K / 32) * 8);
     pdl_wait();
     pdl_launch_dependents();
-    float ssq = 0.f;
-    for (int g = warp; g < K / 128; g += XQ_THREADS / 32) {          // 4 blocks per warp pass, 4 elements per lane
-        const int e = g * 128 + lane * 4;
-        float4 w = *reinterpret_cast<const float4*>(x + (size_t)b * ldx + e);
-        if (norm_w) {
-            ssq += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
-            const float4 nw = *reinterpret_cast<const float4*>(norm_w + e);
-            w.x *= nw.x; w.y *= nw.y; w.z *= nw.z; w.w *= nw.w;
+    const float* xrow = x + (size_t)b * ldx;
+    float rstd = 1.f;
+    if (norm_w) {
+        float ssq = 0.f;
+        for (int i = tid * 4; i < K; i += XQ_THREADS * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xrow + i);
+            ssq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         }
-        float amax = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fmaxf(fabsf(w.z), fabsf(w.w)));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-        const float d = amax / 127.f;
-        int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-        if (d > 0.f) { q0 = __float2int_rn(w.x / d); q1 = __float2int_rn(w.y / d); q2 = __float2int_rn(w.z / d); q3 = __float2int_rn(w.w / d); }
-        *reinterpret_cast<uint32_t*>(xq + xq_swz(e)) =
-            (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
-        int s16 = q0 + q1 + q2 + q3;
-        s16 += __shfl_xor_sync(0xffffffffu, s16, 1); s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
-        const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 4);
-        if ((lane & 3) == 0) isp[e >> 4] = s16;
-        if ((lane & 7) == 0) dsp[e >> 5] = make_float2(d, d * (float)s32);
+        rstd = rsqrtf(block_sum(ssq, red) / (float)K + eps);
     }
-    const float tot = block_sum(ssq, red);
-    if (tid == 0) reinterpret_cast<float*>(out + (size_t)B * xq_seq_bytes(K))[b] = norm_w ? rsqrtf(tot / (float)K + eps) : 1.f;
+    for (int g = warp; g < K / 256; g += XQ_THREADS / 32) {           // one 256-element super-block per warp pass, 8 elements per lane
+        const int e = g * 256 + lane * 8;
+        float v[8];
+        {
+            const float4 a0 = *reinterpret_cast<const float4*>(xrow + e), a1 = *reinterpret_cast<const float4*>(xrow + e + 4);
+            v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        }
+        if (norm_w) {
+            const float4 w0 = *reinterpret_cast<const float4*>(norm_w + e), w1 = *reinterpret_cast<const float4*>(norm_w + e + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (v[j] * rstd) * wv[j];
+        }
+        float am = 0.f, mx = 0.f;
+        int ai = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (fabsf(v[j]) > am) { am = fabsf(v[j]); mx = v[j]; ai = j; }       // strict: the first occurrence wins
+        int q[8];
+        float d;
+        if (mode == XQ_Q8_K) {
+            int idx = lane * 8 + ai;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float oa = __shfl_xor_sync(0xffffffffu, am, o), om = __shfl_xor_sync(0xffffffffu, mx, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                if (oa > am || (oa == am && oi < idx)) { am = oa; mx = om; idx = oi; }
+            }
+            if (am > 0.f) {
+                const float iscale = -128.f / mx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q[j] = (int)fminf(roundf(iscale * v[j]), 127.f);
+                d = 1.f / iscale;
+            } else {
+                d = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q[j] = 0;
+            }
+        } else {
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+            const float df = am / 127.f;
+            const float id = df != 0.f ? 1.f / df : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = (int)roundf(v[j] * id);
+            d = __half2float(__float2half_rn(df));
+        }
+        const uint32_t p0 = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+        const uint32_t p1 = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+        *reinterpret_cast<uint2*>(xq + xq_swz(e)) = make_uint2(p0, p1);
+        const int s8 = q[0] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + q[7];
+        const int s16 = s8 + __shfl_xor_sync(0xffffffffu, s8, 1);
+        const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 2);
+        if ((lane & 1) == 0) isp[e >> 4] = s16;
+        if ((lane & 3) == 0) dsp[e >> 5] = make_float2(d, d * (float)s32);
+    }
+    if (tid == 0) reinterpret_cast<float*>(out + (size_t)B * xq_seq_bytes(K))[b] = 1.f;      // the rows are already normalised
 }
 
 size_t xquant_bytes(int B, int K) { return (size_t)B * xq_seq_bytes(K) + 16; }
 
-int xquant_launch(cudaStream_t st, int B, const float* x, int ldx, int K, const float* norm_w, float eps, unsigned char* out, bool pdl) {
-    if ((K % 256) != 0 || B < 1 || B > 4) return -1000;
+int xquant_launch(cudaStream_t st, int B, const float* x, int ldx, int K, const float* norm_w, float eps, int mode, unsigned char* out, bool pdl) {
+    if ((K % 256) != 0 || B < 1 || B > 4 || (ldx % 4) != 0) return -1000;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B);
     cfg.blockDim = dim3(XQ_THREADS);
@@ -246,7 +296,7 @@ int xquant_launch(cudaStream_t st, int B, const float* x, int ldx, int K, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, xquant_kernel, x, ldx, K, norm_w, eps, B, out);
+    return (int)cudaLaunchKernelEx(&cfg, xquant_kernel, x, ldx, K, norm_w, eps, B, mode, out);
 }
 
 #ifndef QG_R_DEF                    // tools/qgemv_bench.cu sweeps these
@@ -447,6 +497,7 @@ qgemv_kernel(QGemvArgs qa) {
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
+                if ((unsigned)bi >= (unsigned)a.N) bi = 0;       // an all-NaN row has no maximum: never gather from an out-of-range id
                 if (lane == 0) {
                     tok_s[b] = (uint32_t)bi;
                     SeqState* s = a.state + b;
@@ -515,19 +566,10 @@ int qgemv_launch(cudaStream_t st, int B, const QGemvArgs& qa, int num_sms, bool 
     }
 }
 
-// ------------------------------------------------------------------------------------------------ dequantise to bf16
-// One thread per (super-block, 8-element group) -- the prefill GEMMs consume the bf16 copy of one layer at a time.
+// ------------------------------------------------------------------------------------------------ dequantise
+// elements [8g, 8g + 8) of one 256-element super-block (device layout) -> f32, exactly d * sc * q - dmin * m / d * sc * (q - 32) / d * q
 template <int QT>
-__global__ void __launch_bounds__(256)
-q_dequant_kernel(const unsigned char* __restrict__ w, size_t nsb, bf16* __restrict__ out) {
-    pdl_wait();                 // `out` is a scratch an earlier GEMM of the chain may still be reading
-    pdl_launch_dependents();
-    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const size_t sbi = gid >> 5;
-    const int g = (int)(gid & 31);               // elements [8g, 8g+8)
-    if (sbi >= nsb) return;
-    const unsigned char* sb = w + sbi * QTraits<QT>::SB;
-    float v[8];
+__device__ __forceinline__ void dequant8(const unsigned char* sb, int g, float (&v)[8]) {
     if constexpr (QT == QT_Q4_K) {
         const float d = f16_bits_to_float(*reinterpret_cast<const unsigned short*>(sb));
         const float dmin = f16_bits_to_float(*reinterpret_cast<const unsigned short*>(sb + 2));
@@ -565,6 +607,20 @@ q_dequant_kernel(const unsigned char* __restrict__ w, size_t nsb, bf16* __restri
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = d * (float)q[i];
     }
+}
+
+// One thread per (super-block, 8-element group): a whole quantised matrix -> bf16
+template <int QT>
+__global__ void __launch_bounds__(256)
+q_dequant_kernel(const unsigned char* __restrict__ w, size_t nsb, bf16* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t sbi = gid >> 5;
+    const int g = (int)(gid & 31);               // elements [8g, 8g+8)
+    if (sbi >= nsb) return;
+    float v[8];
+    dequant8<QT>(w + sbi * QTraits<QT>::SB, g, v);
     uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     *reinterpret_cast<uint4*>(out + sbi * 256 + 8 * g) = o;
 }
@@ -579,7 +635,38 @@ int q_dequant_bf16_launch(cudaStream_t st, int qt, const unsigned char* w, size_
         case QT_Q8_0: return launch_k(q_dequant_kernel<QT_Q8_0>, dim3(grid), dim3(256), 0, st, prefill_pdl(), w, nsb, out);
         default: return -1000;
     }
-    return (int)cudaGetLastError();
+}
+
+// Quantised embedding: the table stays in its ggml blocks and only the gathered rows are dequantised, to f32
+// (`QuantizedEmbedding::forward`, crane-core/src/models/modules/embedding.rs:31-105: index_select of Q-blocks + dequantize).
+// Row ids come from `ids` (prefill) or, when ids == nullptr, from state[row].token (the decode step's input).
+template <int QT>
+__global__ void __launch_bounds__(256)
+embed_rows_q_kernel(const unsigned char* __restrict__ table, int H, const uint32_t* __restrict__ ids, const SeqState* __restrict__ state,
+                    float* __restrict__ x) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int r = blockIdx.x;
+    const uint32_t tok = ids ? ids[r] : state[r].token;
+    const unsigned char* row = table + (size_t)tok * (H / 256) * QTraits<QT>::SB;
+    for (int it = threadIdx.x; it < H / 8; it += 256) {
+        float v[8];
+        dequant8<QT>(row + (size_t)(it >> 5) * QTraits<QT>::SB, it & 31, v);
+        float4* o = reinterpret_cast<float4*>(x + (size_t)r * H + it * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+int embed_rows_q_launch(cudaStream_t st, int qt, const unsigned char* table, int H, const uint32_t* ids, const SeqState* state, int rows,
+                        float* x, bool pdl) {
+    if (rows <= 0 || (H % 256) != 0) return -1000;
+    switch (qt) {
+        case QT_Q4_K: return launch_k(embed_rows_q_kernel<QT_Q4_K>, dim3(rows), dim3(256), 0, st, pdl, table, H, ids, state, x);
+        case QT_Q6_K: return launch_k(embed_rows_q_kernel<QT_Q6_K>, dim3(rows), dim3(256), 0, st, pdl, table, H, ids, state, x);
+        case QT_Q8_0: return launch_k(embed_rows_q_kernel<QT_Q8_0>, dim3(rows), dim3(256), 0, st, pdl, table, H, ids, state, x);
+        default: return -1000;
+    }
 }
 
 }  // namespace cb

@@ -25,16 +25,22 @@ struct QGemvArgs {
     GemvArgs g;        // W is reinterpreted as the quantised bytes; epilogue fields as for the bf16 GEMV; g.x / g.norm_w unused
     int qtype;
     int epi;           // GemvEpi
-    int norm;          // the activations were RMS-normalised by xquant_launch: scale the outputs by its 1/rms
+    int norm;          // (kept for the epilogue contract) xquant_launch already normalised the rows: the stored scale is 1
     const unsigned char* xq;   // activations of the B sequences, quantised by xquant_launch (xquant_bytes(B, K) bytes)
 };
 
-// Quantise B activation rows (f32, row stride ldx; times norm_w when non-null) for qgemv_launch.
+// Quantise B activation rows (f32, row stride ldx; RMS-normalised with norm_w first when non-null) for qgemv_launch, with the
+// activation block rule candle pairs with the weight type: XQ_Q8_K for Q4_K / Q6_K, XQ_Q8_0 for Q8_0 (see xquant_kernel).
+enum XQMode : int { XQ_Q8_0 = 0, XQ_Q8_K = 1 };
+inline int xq_mode_for(int qt) { return qt == QT_Q8_0 ? XQ_Q8_0 : XQ_Q8_K; }
 size_t xquant_bytes(int B, int K);
-int xquant_launch(cudaStream_t st, int B, const float* x, int ldx, int K, const float* norm_w, float eps, unsigned char* out, bool pdl);
+int xquant_launch(cudaStream_t st, int B, const float* x, int ldx, int K, const float* norm_w, float eps, int mode, unsigned char* out, bool pdl);
 
 int qgemv_launch(cudaStream_t st, int B, const QGemvArgs& a, int num_sms, bool pdl);
-// rows x K quantised -> bf16 row-major (prefill GEMM operand)
+// rows x K quantised -> bf16 row-major
 int q_dequant_bf16_launch(cudaStream_t st, int qt, const unsigned char* w, size_t rows, int K, bf16* out);
+// gather + dequantise rows of a quantised embedding table to f32: ids[rows] (prefill) or, with ids == nullptr, state[r].token
+int embed_rows_q_launch(cudaStream_t st, int qt, const unsigned char* table, int H, const uint32_t* ids, const SeqState* state, int rows,
+                        float* x, bool pdl);
 
 }  // namespace cb

@@ -165,6 +165,36 @@ CRANE_B200_API int crane_b200_seq_select(crane_b200_model* m, int seq);
 CRANE_B200_API int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t* tokens, size_t n, size_t n_steps,
                                            uint32_t* tokens_out, float* logits_host);
 
+/* ---- device-side sampling (crane-serve/src/engine/sampling.rs:169-480) ------------------------------------------ */
+/* Per-sequence sampling request = the fields of `Sequence` that `sampling::sample` reads.  The draw needs uniforms in
+ * (1e-7, 0.999) (`rand_like(1e-7, 0.999)`, sampling.rs:387): the reference takes them from candle's device RNG, whose stream no
+ * test pins, so they are an input here -- `uniforms` (host, top_k values, or vocab values when neither top-k nor top-p applies), or
+ * NULL to have them derived on the device from `seed`. */
+typedef struct {
+    float temperature;          /* <= 0: greedy (argmax after penalties, lowest index among maxima) */
+    float top_p;                /* in (0, 1): nucleus over the top-k candidates; anything else: off */
+    int32_t top_k;              /* 0: unset -- 64 when top_p is active (CRANE_TOPP_FALLBACK_TOPK), else the whole vocabulary; capped at 64 */
+    float repetition_penalty;   /* 1 = off: logit >= 0 ? logit / p : logit * p, once per distinct context token */
+    float frequency_penalty;    /* 0 = off: minus count * frequency_penalty */
+    float presence_penalty;     /* 0 = off: minus presence_penalty for any token present */
+    const uint32_t* context;    /* host: the trailing `repeat_last_n` tokens of the sequence */
+    size_t n_context;
+    const float* uniforms;      /* host or NULL */
+    uint64_t seed;
+} crane_b200_sampling;
+/* `sampling::sample` on the logits of the LAST forward call of the current sequence (they stay on the device; 4 bytes return). */
+CRANE_B200_API int crane_b200_sample(crane_b200_model* m, const crane_b200_sampling* p, uint32_t* token_out);
+/* forward_step + sample in one call: the server's non-greedy decode step (crane-serve/src/engine/mod.rs:938-1062). */
+CRANE_B200_API int crane_b200_forward_step_sample(crane_b200_model* m, const uint32_t* input_ids, size_t n, size_t start_pos,
+                                                  const crane_b200_sampling* p, uint32_t* token_out);
+/* One decode round for `n` sequences with per-sequence sampling (params[n]): step_batch_decode + sample per row, logits never
+ * leave the device; tokens_out [n]. */
+CRANE_B200_API int crane_b200_decode_batch_sample(crane_b200_model* m, const int* seqs, const uint32_t* tokens, size_t n,
+                                                  const crane_b200_sampling* params, uint32_t* tokens_out);
+/* `crane_core::ops::topk_indices` (ops/fused_ops/portable.rs:28-66, kernels/cuda/topk.cu:213-259) on the logits of the last call:
+ * the k largest in the total order (value descending, index ascending), k <= 512.  vals_out is optional. */
+CRANE_B200_API int crane_b200_topk(crane_b200_model* m, size_t k, uint32_t* idx_out, float* vals_out);
+
 /* ---- vision-language surface (crane-core/src/models/qwen3_5/vlm.rs) ------------------------------ */
 
 /* `Qwen3_5VLModel::encode_images` -> `Qwen3_5VisionModel::forward` (vlm.rs:150-170, vision.rs:558-584).
@@ -214,6 +244,18 @@ CRANE_B200_API uint64_t crane_b200_kernel_launches(const crane_b200_model* m);
  * (NULL: plain bf16); mode = cb::GemmEpiMode; out dtype follows the mode. */
 CRANE_B200_API int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* a_lo, const uint16_t* w, int M, int N, int K, int mode,
                        const float* bias, void* out_inout, int use_simt);
+
+/* y[m, n] = quantised linear of x[m, k] (host f32) through the decode kernels (xquant + qgemv, rows in groups of <= 4): `raw` = n rows
+ * of ggml blocks (ggml_type 8 / 12 / 14), optional RMSNorm weight norm_w[k] applied first (eps).  = candle's CPU `QMatMul::forward`
+ * (crane-core/src/ops/linear.rs:23-48). */
+CRANE_B200_API int crane_b200_op_qlinear(int device, const float* x, size_t m, size_t k, const void* raw, size_t raw_bytes, int ggml_type, size_t n,
+                                         const float* norm_w, float eps, float* y);
+/* top-k order / sampler on caller-supplied logits [rows = 1, vocab] (host): the reference's own known-answer vectors run through these
+ * (crane-core/tests/rocm_kernels.rs:96-198, crane-serve/src/engine/sampling.rs:489-640).  logits_after (optional, host) receives the
+ * row after the penalties. */
+CRANE_B200_API int crane_b200_op_topk(int device, const float* logits, size_t vocab, size_t k, uint32_t* idx_out);
+CRANE_B200_API int crane_b200_op_sample(int device, const float* logits, size_t vocab, const crane_b200_sampling* p, uint32_t* token_out,
+                                        float* logits_after);
 
 #ifdef __cplusplus
 }

@@ -3,8 +3,17 @@
 The reference keeps GGUF weights in these blocks and multiplies through candle's `QMatMul`
 (crane-core/src/ops/linear.rs:23-48; hunyuan_dense/modeling.rs:37-41).  candle is not vendored, so the byte layouts are
 restated from the published ggml definitions and PINNED against the `gguf` Python package (gguf.quants.dequantize /
-quantize, installed here) in tests/test_oracle_golden.py.  The linear oracle is  y = x_f32 . dequant(W)^T  in f32
-(QMatMul's activation quantisation is not pinned by any reference test -- "parity unpinned").
+quantize, installed here) in tests/test_oracle_golden.py.
+
+The quantised LINEAR (`qmatmul` below) restates what candle's CPU `QMatMul::forward` computes behind
+`LinearLayer::Quantized` (crane-core/src/ops/linear.rs:23-48): activations are quantised row by row to the weight type's
+`VecDotType` -- Q8_K blocks (256 elements, iscale = -128 / max, q = min(127, round(iscale x)), d = 1 / iscale, per-16 sums) for
+the K-quants, Q8_0 blocks (32 elements, d = amax / 127 stored as f16, q = round(x / d)) for Q8_0 weights -- and every output is
+the published ggml integer dot `vec_dot_q4_K_q8_K` / `vec_dot_q6_K_q8_K` / `vec_dot_q8_0_q8_0`.  candle is a crates.io
+dependency that is not vendored (Cargo.toml:12-14, "0.11"), so this is a restatement of the published ggml / candle k_quants
+algorithms; it is pinned by identity checks (integer dot == dequant(W) . dequant(Q8(x)) in f64) and by the `gguf` package for
+the weight side, NOT by a candle binary: "parity unpinned" for the activation rounding rule (round-half-away, as Rust's
+f32::round) stays in force.
 
 Layouts (little endian):
   Q8_0 : 32 elems / 34 B  : f16 d | 32 x i8                      y = d * q
@@ -175,3 +184,100 @@ def quantize(x: np.ndarray, qtype: str) -> np.ndarray:
 
 def dequantize(raw: np.ndarray, qtype: str, k: int) -> np.ndarray:
     return DEQUANTIZE[qtype](np.ascontiguousarray(raw, np.uint8), k)
+
+
+# ---------------------------------------------------------------------------------------------- activation blocks + integer dots
+def _round_half_away(x: np.ndarray) -> np.ndarray:
+    """Rust `f32::round` / C `roundf`: halves away from zero (np.rint is half-to-even)."""
+    return np.sign(x) * np.floor(np.abs(x) + np.float32(0.5))
+
+
+def quantize_act_q8_k(x: np.ndarray):
+    """candle `BlockQ8K::from_float` / ggml `quantize_row_q8_K_ref`: x [m, k] f32 -> (q int8 [m, k/256, 256], d f32 [m, k/256],
+    bsums int32 [m, k/256, 16]).  `max` is the FIRST element of largest magnitude, sign kept; iscale = -128 / max."""
+    x = np.ascontiguousarray(x, np.float32)
+    m, k = x.shape
+    b = x.reshape(m, k // 256, 256)
+    idx = np.abs(b).argmax(-1)                                  # first occurrence of the maximum magnitude
+    mx = np.take_along_axis(b, idx[..., None], -1)[..., 0]
+    nz = mx != 0
+    iscale = np.where(nz, np.float32(-128.0) / np.where(nz, mx, 1).astype(np.float32), 0).astype(np.float32)
+    v = _round_half_away((iscale[..., None] * b).astype(np.float32))
+    q = np.minimum(v, 127).astype(np.int8)
+    d = np.where(nz, np.float32(1.0) / np.where(nz, iscale, 1), 0).astype(np.float32)
+    bsums = q.reshape(m, k // 256, 16, 16).astype(np.int32).sum(-1)
+    return q, d, bsums
+
+
+def quantize_act_q8_0(x: np.ndarray):
+    """candle `BlockQ8_0::from_float` / ggml `quantize_row_q8_0_ref`: d = amax / 127 (q uses the f32 value, the block stores
+    the f16 rounding of it), q = round(x * (1 / d)).  Returns (q int8 [m, k/32, 32], d_f16_as_f32 [m, k/32])."""
+    x = np.ascontiguousarray(x, np.float32)
+    m, k = x.shape
+    b = x.reshape(m, k // 32, 32)
+    d = (np.abs(b).max(-1) / np.float32(127.0)).astype(np.float32)
+    inv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), 0).astype(np.float32)
+    q = _round_half_away((b * inv[..., None]).astype(np.float32)).astype(np.int8)
+    return q, d.astype(np.float16).astype(np.float32)
+
+
+def dequantize_act(x: np.ndarray, qtype: str) -> np.ndarray:
+    """What the quantised activations stand for: d * q, shaped like x (f32)."""
+    if qtype == "Q8_0":
+        q, d = quantize_act_q8_0(x)
+    else:
+        q, d, _ = quantize_act_q8_k(x)
+    return (q.astype(np.float32) * d[..., None]).reshape(x.shape)
+
+
+def qmatmul(x: np.ndarray, raw: np.ndarray, qtype: str) -> np.ndarray:
+    """y[m, n] = ggml vec_dot(row n of the quantised weight, quantised row m of x): candle CPU `QMatMul::forward`.
+    raw: [n, row_bytes] uint8 ggml blocks.  Integer sums are exact (int64); the float combination follows ggml's order
+    (d = y.d * x.d, then d * isum, minus dmin * sum(mins * bsums))."""
+    x = np.ascontiguousarray(x, np.float32)
+    raw = np.ascontiguousarray(raw, np.uint8)
+    m, k = x.shape
+    n = raw.shape[0]
+    if qtype == "Q8_0":
+        qx, dx = quantize_act_q8_0(x)                                        # [m, nb, 32], [m, nb]
+        b = raw.reshape(n, k // 32, 34)
+        dw = b[..., :2].copy().view(np.float16).astype(np.float32)[..., 0]   # [n, nb]
+        qw = b[..., 2:].view(np.int8)
+        isum = np.einsum("mbk,nbk->mnb", qx.astype(np.int64), qw.astype(np.int64))
+        return (isum.astype(np.float32) * (dx[:, None, :] * dw[None, :, :])).sum(-1, dtype=np.float32)
+    qx, dx, bs = quantize_act_q8_k(x)                                        # [m, nb, 256], [m, nb], [m, nb, 16]
+    nb = k // 256
+    if qtype == "Q4_K":
+        b = raw.reshape(n, nb, 144)
+        dw = b[..., 0:2].copy().view(np.float16).astype(np.float32)[..., 0]
+        dmin = b[..., 2:4].copy().view(np.float16).astype(np.float32)[..., 0]
+        sc, mn = _unpack_scales_k4(b[..., 4:16])                             # [n, nb, 8] uint8
+        qs = b[..., 16:].reshape(n, nb, 4, 32)
+        q4 = np.empty((n, nb, 8, 32), np.int64)
+        q4[:, :, 0::2, :] = qs & 0xF
+        q4[:, :, 1::2, :] = qs >> 4
+        sub = np.einsum("mbjk,nbjk->mnbj", qx.reshape(m, nb, 8, 32).astype(np.int64), q4)       # per 32-element sub-block
+        isum = (sub * sc.astype(np.int64)[None]).sum(-1)                                        # [m, n, nb]
+        bs32 = bs.reshape(m, nb, 8, 2).sum(-1).astype(np.int64)                                 # bsums[2j] + bsums[2j+1]
+        summ = np.einsum("mbj,nbj->mnb", bs32, mn.astype(np.int64))
+        d = dx[:, None, :] * dw[None, :, :]
+        dm = dx[:, None, :] * dmin[None, :, :]
+        return (d * isum.astype(np.float32) - dm * summ.astype(np.float32)).sum(-1, dtype=np.float32)
+    if qtype == "Q6_K":
+        b = raw.reshape(n, nb, 210)
+        ql, qh = b[..., 0:128], b[..., 128:192]
+        sc = b[..., 192:208].view(np.int8).astype(np.int64)                  # [n, nb, 16]
+        dw = b[..., 208:210].copy().view(np.float16).astype(np.float32)[..., 0]
+        q6 = np.empty((n, nb, 256), np.int64)
+        l = np.arange(32)
+        for half in range(2):
+            qlh, qhh = ql[:, :, 64 * half:64 * half + 64], qh[:, :, 32 * half:32 * half + 32]
+            base = 128 * half
+            q6[:, :, base + l] = ((qlh[:, :, l] & 0xF) | (((qhh[:, :, l] >> 0) & 3) << 4)).astype(np.int64) - 32
+            q6[:, :, base + l + 32] = ((qlh[:, :, l + 32] & 0xF) | (((qhh[:, :, l] >> 2) & 3) << 4)).astype(np.int64) - 32
+            q6[:, :, base + l + 64] = ((qlh[:, :, l] >> 4) | (((qhh[:, :, l] >> 4) & 3) << 4)).astype(np.int64) - 32
+            q6[:, :, base + l + 96] = ((qlh[:, :, l + 32] >> 4) | (((qhh[:, :, l] >> 6) & 3) << 4)).astype(np.int64) - 32
+        sub = np.einsum("mbjk,nbjk->mnbj", qx.reshape(m, nb, 16, 16).astype(np.int64), q6.reshape(n, nb, 16, 16))
+        isum = (sub * sc[None]).sum(-1)
+        return ((dx[:, None, :] * dw[None, :, :]) * isum.astype(np.float32)).sum(-1, dtype=np.float32)
+    raise ValueError(qtype)

@@ -86,7 +86,10 @@ def silu(x):
 class Qwen3Oracle:
     """Stateful (KV-cached) single-sequence forward, mirroring `Qwen3Model`."""
 
-    def __init__(self, cfg: dict, weights: dict, prefix: str = "model.", max_pos: int | None = None):
+    def __init__(self, cfg: dict, weights: dict, prefix: str = "model.", max_pos: int | None = None, quantised: dict | None = None):
+        """`quantised`: full tensor name -> (raw ggml blocks [rows, row_bytes] uint8, "Q4_K" | "Q6_K" | "Q8_0").  Those linears run
+        through candle's CPU `QMatMul` semantics (ops/linear.rs:23-48): activations quantised to Q8_K / Q8_0 blocks, ggml integer
+        dots (oracle/ggml_quant.py `qmatmul`); their entry in `weights` is not used for the product."""
         tc = text_config(cfg)
         self.tc = tc
         self.H = tc["hidden_size"]
@@ -98,6 +101,7 @@ class Qwen3Oracle:
         self.eps = float(tc.get("rms_norm_eps", 1e-6))
         self.theta = float(tc.get("rope_theta", 1_000_000.0))
         self.prefix = prefix
+        self.q = dict(quantised or {})
         self.w = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).float() for k, v in weights.items()}
         tied = cfg.get("tie_word_embeddings", tc.get("tie_word_embeddings", True))
         self.lm_head = self.w[prefix + "embed_tokens.weight"] if tied or "lm_head.weight" not in self.w \
@@ -118,6 +122,18 @@ class Qwen3Oracle:
     def _p(self, i, name):
         return self.w[f"{self.prefix}layers.{i}.{name}"]
 
+    def _linear(self, full_name: str, x: torch.Tensor, w: torch.Tensor | None = None) -> torch.Tensor:
+        """x @ W^T, or LinearLayer::Quantized (ops/linear.rs:23-48: x -> f32, QMatMul::forward, cast back) when `full_name` is quantised."""
+        if full_name in self.q:
+            from . import ggml_quant as gq
+            raw, qt = self.q[full_name]
+            x2 = x.reshape(-1, x.shape[-1]).numpy()
+            return torch.from_numpy(gq.qmatmul(x2, raw, qt)).reshape(*x.shape[:-1], -1)
+        return x @ (self.w[full_name] if w is None else w).T
+
+    def _lin(self, i, name, x):
+        return self._linear(f"{self.prefix}layers.{i}.{name}", x)
+
     def embed(self, ids) -> torch.Tensor:
         ids = torch.as_tensor(np.asarray(ids, dtype=np.int64))
         return self.w[self.prefix + "embed_tokens.weight"][ids]
@@ -126,9 +142,9 @@ class Qwen3Oracle:
     def _layer(self, i, x, cos, sin, kv_offset):
         S = x.shape[0]
         h = rms_norm(x, self._p(i, "input_layernorm.weight"), self.eps)
-        q = (h @ self._p(i, "self_attn.q_proj.weight").T).view(S, self.nh, self.d)
-        k = (h @ self._p(i, "self_attn.k_proj.weight").T).view(S, self.nkv, self.d)
-        v = (h @ self._p(i, "self_attn.v_proj.weight").T).view(S, self.nkv, self.d)
+        q = self._lin(i, "self_attn.q_proj.weight", h).view(S, self.nh, self.d)
+        k = self._lin(i, "self_attn.k_proj.weight", h).view(S, self.nkv, self.d)
+        v = self._lin(i, "self_attn.v_proj.weight", h).view(S, self.nkv, self.d)
         q = rms_norm(q, self._p(i, "self_attn.q_norm.weight"), self.eps)   # QK-norm BEFORE RoPE
         k = rms_norm(k, self._p(i, "self_attn.k_norm.weight"), self.eps)
         q = rope_half(q, cos, sin)
@@ -139,11 +155,11 @@ class Qwen3Oracle:
             self.k_cache[i] = torch.cat([self.k_cache[i], k], 0)
             self.v_cache[i] = torch.cat([self.v_cache[i], v], 0)
         a = causal_attention(q, self.k_cache[i], self.v_cache[i], kv_offset, 1.0 / math.sqrt(self.d))
-        x = x + a @ self._p(i, "self_attn.o_proj.weight").T
+        x = x + self._lin(i, "self_attn.o_proj.weight", a)
         h = rms_norm(x, self._p(i, "post_attention_layernorm.weight"), self.eps)
-        g = h @ self._p(i, "mlp.gate_proj.weight").T
-        u = h @ self._p(i, "mlp.up_proj.weight").T
-        x = x + (silu(g) * u) @ self._p(i, "mlp.down_proj.weight").T
+        g = self._lin(i, "mlp.gate_proj.weight", h)
+        u = self._lin(i, "mlp.up_proj.weight", h)
+        x = x + self._lin(i, "mlp.down_proj.weight", silu(g) * u)
         return x
 
     def _cos_sin(self, start_pos, S):
@@ -161,7 +177,8 @@ class Qwen3Oracle:
                 x = after_layer(i, x)
         x = rms_norm(x, self.w[self.prefix + "norm.weight"], self.eps)
         self.last_hidden_states = x
-        return x[-1] @ self.lm_head.T
+        head = "lm_head.weight" if self.lm_head is self.w.get("lm_head.weight") else self.prefix + "embed_tokens.weight"
+        return self._linear(head, x[-1:], self.lm_head)[0]
 
     def forward(self, ids, start_pos: int) -> torch.Tensor:
         """Qwen3Model::forward (qwen3/modeling.rs:942-953)."""

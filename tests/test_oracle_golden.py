@@ -232,3 +232,37 @@ def test_tts_oracle_frame_loop_properties():
     # teacher forcing reproduces the same logits (KV / code-predictor cache handling is consistent)
     _, trace2 = o.generate_codes(ids, 4, repetition_penalty=1.05, forced_frames=frames)
     assert all(torch.allclose(a["group_logits"], b["group_logits"]) for a, b in zip(trace, trace2))
+
+
+# ---- sampler oracle against the reference's own literal cases (crane-serve/src/engine/sampling.rs:489-640) -----------------
+
+def test_sampling_penalties_known_answers():
+    from oracle import sampling as smp
+    assert smp.apply_penalties([1.0, 2.0, 3.0], 1.0, 0.0, 0.0, [0, 1, 2]).tolist() == [1.0, 2.0, 3.0]          # all off (:501-506)
+    assert smp.apply_penalties([1.0, 2.0, 3.0], 1.1, 0.5, 0.5, []).tolist() == [1.0, 2.0, 3.0]                  # empty context (:510-514)
+    np.testing.assert_allclose(smp.apply_penalties([10.0, -10.0, 3.0], 2.0, 0.0, 0.0, [0, 1]), [5.0, -20.0, 3.0], atol=1e-6)   # :520-536
+    np.testing.assert_allclose(smp.apply_penalties([10.0, 10.0], 2.0, 1.0, 0.0, [0, 0, 1]), [3.0, 4.0], atol=1e-6)              # :543-551
+    assert smp.apply_penalties([10.0] * 3, 1.0, 0.5, 0.0, [0, 0, 0, 1]).tolist() == [8.5, 9.5, 10.0]             # :557-564
+    assert smp.apply_penalties([10.0] * 3, 1.0, 0.0, 0.5, [0, 0, 0, 1]).tolist() == [9.5, 9.5, 10.0]             # :569-576
+    out = smp.apply_penalties([5.0, 4.9], 1.0, 0.1, 0.0, [0, 1, 0, 0, 0, 0])                                       # :585-593
+    np.testing.assert_allclose(out, [4.5, 4.8], atol=1e-6)
+    assert out[1] > out[0]
+    np.testing.assert_allclose(smp.apply_penalties([10.0] * 3, 1.0, 0.5, 0.2, [0, 0, 0, 1]), [10 - 1.7, 10 - 0.7, 10.0], atol=1e-6)   # :599-606
+    np.testing.assert_allclose(smp.apply_penalties([10.0, 10.0], 1.0, -0.5, 0.0, [0, 0, 1]), [11.0, 10.5], atol=1e-6)          # :612-622
+    np.testing.assert_allclose(smp.apply_penalties([10.0] * 3, 1.0, 0.0, -0.5, [0, 1]), [10.5, 10.5, 10.0], atol=1e-6)         # :628-640
+
+
+def test_sampling_topk_known_answers_and_nucleus_rule():
+    from oracle import sampling as smp
+    assert smp.topk_indices([0.5, -3.0, 7.25, 1.0, 7.5], 5).tolist() == [4, 2, 3, 0, 1]                           # rocm_kernels.rs:180-189
+    v = (np.arange(240_000) % 4).astype(np.float32) * 0.5                                                          # :156-172
+    for k in (1, 40, 64):
+        assert smp.topk_indices(v, k).tolist() == [j * 4 + 3 for j in range(k)]
+    # greedy = lowest index among the maxima; temperature -> Gumbel-max with the supplied uniforms
+    assert smp.sample([1.0, 3.0, 3.0, 2.0], 0.0)[0] == 1
+    # nucleus: probabilities 0.6439, 0.2369, 0.0871, 0.0321 at T = 1: top_p = 0.7 keeps the first token that crosses p too (sampling.rs:312-330)
+    lg = np.array([4.0, 3.0, 2.0, 1.0], np.float32)
+    u = np.array([0.5, 0.5, 0.999, 0.999], np.float32)               # huge Gumbel noise on tokens 2 and 3: they only win if they are unmasked
+    assert smp.sample(lg, 1.0, top_p=0.7, top_k=4, uniforms=u)[0] in (0, 1)
+    assert smp.sample(lg, 1.0, top_p=0.95, top_k=4, uniforms=u)[0] == 2
+    assert smp.sample(lg, 1.0, top_p=None, top_k=4, uniforms=u)[0] == 2

@@ -19,7 +19,7 @@ static int run(cudaStream_t st, int B, const Shape& s, const unsigned char* W, b
     q.g.W = reinterpret_cast<const bf16*>(W); q.g.N = s.N; q.g.K = s.K; q.g.x = s.K == 4096 ? x : act; q.g.ldx = s.K; q.g.norm_w = nw; q.g.eps = 1e-6f;
     q.g.y = s.epi == GEMV_SILU_MUL ? act : y; q.g.ldy = (s.epi == GEMV_SILU_MUL) ? s.N / 2 : s.N;
     q.qtype = s.qt; q.epi = s.epi; q.norm = s.norm; q.xq = xqb;
-    if (s.name[0] != 'k' && s.name[0] != 'v') { int r = xquant_launch(st, B, q.g.x, s.K, s.K, s.norm ? nw : nullptr, 1e-6f, xqb, pdl); if (r) return r; }
+    if (s.name[0] != 'k' && s.name[0] != 'v') { int r = xquant_launch(st, B, q.g.x, s.K, s.K, s.norm ? nw : nullptr, 1e-6f, xq_mode_for(q.qtype), xqb, pdl); if (r) return r; }
     return qgemv_launch(st, B, q, 148, pdl);
 }
 
