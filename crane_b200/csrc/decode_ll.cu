@@ -89,6 +89,24 @@ struct Waiter {
     }
 };
 
+// Shared row accumulators.  The eight warps of a CTA own different columns of the same rows and finish a tile at the same moment;
+// atomicAdd(float) -- and the 64-bit integer add -- on shared memory are CAS spin loops, only the 32-bit integer add is native.  So a
+// row sum is kept as two independent 32-bit fixed-point words, v = A * 2^-8 + B * 2^-32 with A = round(v * 2^8) and B the exact
+// remainder: each addend keeps its full f32 mantissa (down to 2^-32), no carry links the two words, integer addition is exact and
+// therefore independent of arrival order.  |sum| < 2^23 (A) and at most 2^8 addends (B): far beyond any activation.
+struct FixAcc { int a, b; };
+__device__ __forceinline__ void fix_add(FixAcc* p, float v) {
+    const int A = __float2int_rn(v * 256.0f);
+    const int B = __float2int_rn((v - (float)A * (1.0f / 256.0f)) * 4294967296.0f);
+    atomicAdd(&p->a, A);
+    atomicAdd(&p->b, B);
+}
+__device__ __forceinline__ float fix_take(FixAcc* p) {       // read and clear (one reader per row, after the CTA barrier)
+    const FixAcc v = *p;
+    *p = FixAcc{0, 0};
+    return (float)((double)v.a * (1.0 / 256.0) + (double)v.b * (1.0 / 4294967296.0));
+}
+
 // ---- phase geometry --------------------------------------------------------------------------------------------------
 // A weight matrix [N, K] as seen by one CTA (row block [r0, r0 + nrows)) and one warp (columns [col0, col0 + 64 * ncs)): the warp
 // walks its block in tiles of 16 rows x 64 columns = one 2 KB ring slot = four m16n8k16 tensor-core steps.  Only five distinct
@@ -236,10 +254,11 @@ __global__ void __launch_bounds__(LL_THREADS, 1)
 decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
     constexpr int D = 128;
     extern __shared__ __align__(1024) unsigned char lsm[];
-    // dynamic: [rings: LL_WARPS * DEPTH * 2 KB][acc: 2 x max_rows f32][xres: residual rows owned by this CTA]
-    float* acc_s = reinterpret_cast<float*>(lsm + (size_t)LL_WARPS * DEPTH * LL_SEG_BYTES);
-    float* xres_s = acc_s + 2 * max_rows;
-    __shared__ float ssq_s[4];
+    // dynamic: [rings: LL_WARPS * DEPTH * 2 KB][acc: 2 x max_rows fixed-point pairs][xres: residual rows owned by this CTA]
+    FixAcc* acc_s = reinterpret_cast<FixAcc*>(lsm + (size_t)LL_WARPS * DEPTH * LL_SEG_BYTES);
+    float* xres_s = reinterpret_cast<float*>(acc_s + 2 * max_rows);
+    __shared__ float ssq_s[4][LL_WARPS];                       // RMSNorm statistic: one slot per warp and phase parity (no float atomics:
+                                                               // atomicAdd(float) on shared memory is a CAS spin loop)
     __shared__ __align__(16) float q_s[LL_MAX_NREP][D];
     __shared__ __align__(16) float knew_s[D];
     __shared__ __align__(16) float vnew_s[D];
@@ -318,8 +337,8 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
     const int res_rpc = (a.H + grid - 1) / grid;
     const int res_r0 = cta * res_rpc;
     const int res_n = max(0, min(a.H, res_r0 + res_rpc) - res_r0);
-    for (int i = tid; i < 2 * max_rows; i += LL_THREADS) acc_s[i] = 0.f;
-    if (tid < 4) ssq_s[tid] = 0.f;
+    for (int i = tid; i < 2 * max_rows; i += LL_THREADS) acc_s[i] = FixAcc{0, 0};
+    if (tid < 4 * LL_WARPS) (&ssq_s[0][0])[tid] = 0.f;
     for (int i = tid; i < res_n; i += LL_THREADS) {
         const float v = a.x_io[res_r0 + i];
         xres_s[i] = v;
@@ -369,7 +388,9 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                             if (split_kv) { rkl = ldg_stream(ly.k_pool + a.kv_lo_off + off); rvl = ldg_stream(ly.v_pool + a.kv_lo_off + off); }
                         }
                     };
-                    if (npass > 0) load_pass(0, kh, kl, vh, vl);        // in flight while the query is still being produced
+                    uint4 nkh = make_uint4(0, 0, 0, 0), nkl = nkh, nvh = nkh, nvl = nkh;
+                    if (npass > 0) load_pass(0, kh, kl, vh, vl);        // two passes in flight while the query is still being produced
+                    if (npass > 1) load_pass(1, nkh, nkl, nvh, nvl);
                     // ---- q (NREP heads), and on the owning split the new k / v: poll, RMSNorm, rotate ----
                     for (int vec = warp; vec < NREP + 2; vec += LL_WARPS) {
                         if (vec >= NREP && !owner) continue;
@@ -433,11 +454,14 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) { o[h][j] = 0.f; qr[h][j] = (h < HG) ? q_s[hg0 + h][hl * 8 + j] * a.scale : 0.f; }
                         }
-                        if (hg0 != 0 && npass > 0) load_pass(0, kh, kl, vh, vl);
+                        if (hg0 != 0) {
+                            if (npass > 0) load_pass(0, kh, kl, vh, vl);
+                            if (npass > 1) load_pass(1, nkh, nkl, nvh, nvl);
+                        }
 #pragma unroll 1
                         for (int ps = 0; ps < npass; ++ps) {
-                            uint4 nkh = make_uint4(0, 0, 0, 0), nkl = nkh, nvh = nkh, nvl = nkh;
-                            if (ps + 1 < npass) load_pass(ps + 1, nkh, nkl, nvh, nvl);
+                            uint4 fkh = make_uint4(0, 0, 0, 0), fkl = fkh, fvh = fkh, fvl = fkh;      // pass ps + 2
+                            if (ps + 2 < npass) load_pass(ps + 2, fkh, fkl, fvh, fvl);
                             const bool valid = (t0 + ps * TPP + warp * 2 + half) < t_end;
                             float kf[8], vf[8];
                             kf[0] = bf16lo(kh.x); kf[1] = bf16hi(kh.x); kf[2] = bf16lo(kh.y); kf[3] = bf16hi(kh.y);
@@ -469,6 +493,7 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                                 }
                             }
                             kh = nkh; kl = nkl; vh = nvh; vl = nvl;
+                            nkh = fkh; nkl = fkl; nvh = fvh; nvl = fvl;
                         }
                         // the token being decoded: half 0 of warp 0 on the owning split
                         if (owner && warp == 0) {
@@ -605,8 +630,9 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
             const LLLayer& ly = a.layers[l];
             const float* nw = (kind == 0) ? ly.ln1 : (kind == 2) ? ly.ln2 : (kind == 4) ? a.final_norm : nullptr;
             const unsigned long long* xin = (kind == 0 || kind == 4) ? a.xa : (kind == 1) ? a.att : (kind == 2) ? a.xb : a.act;
-            float* acc = acc_s + (gphase & 1u) * max_rows;
-            float* ssq_p = &ssq_s[gphase & 3u];
+            FixAcc* acc = acc_s + (gphase & 1u) * max_rows;
+            float* ssq_p = ssq_s[gphase & 3u];
+            const unsigned int aw = (unsigned int)ll_active_warps(w.K);
 
             auto run = [&](auto ncs_tag, auto norm_tag) {
                 constexpr int NCS = decltype(ncs_tag)::value;
@@ -621,7 +647,7 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                 load_xb<NCS, NORM>(xin, tagl, w.col0, lane, nw, xb, ssq, wt);
                 if (NORM) {
                     ssq = warp_sum(ssq);
-                    if (lane == 0) atomicAdd(ssq_p, ssq);
+                    if (lane == 0) ssq_p[warp] = ssq;
                 }
                 prof(1);
                 trace(2);
@@ -651,11 +677,12 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                         issue_next();
                         cslot = (cslot + LL_SEG_BYTES == DEPTH * LL_SEG_BYTES) ? 0u : cslot + LL_SEG_BYTES;
                     }
-                    // D: lane l holds rows l / 4 and l / 4 + 8, columns 2 (l % 4) + {0, 1}; columns 0 and 1 are the hi and lo products
+                    // D: lane l holds rows l / 4 and l / 4 + 8, columns 2 (l % 4) + {0, 1}; columns 0 and 1 are the hi and lo products.
+                    // The warps own different columns of the same 16 rows: exact fixed-point accumulation in shared memory (fix_add).
                     if ((lane & 3) == 0) {
                         const int r = rt * 16 + (lane >> 2);
-                        if (r < w.nrows) atomicAdd(&acc[r], (d0[0] + d1[0]) + (d0[1] + d1[1]));
-                        if (r + 8 < w.nrows) atomicAdd(&acc[r + 8], (d0[2] + d1[2]) + (d0[3] + d1[3]));
+                        if (r < w.nrows) fix_add(&acc[r], (d0[0] + d1[0]) + (d0[1] + d1[1]));
+                        if (r + 8 < w.nrows) fix_add(&acc[r + 8], (d0[2] + d1[2]) + (d0[3] + d1[3]));
                     }
                 }
             };
@@ -676,35 +703,35 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
             trace(5);
 
             // ============================ epilogue: publish this CTA's rows ============================
-            const float rstd = (nw != nullptr) ? rsqrtf(*ssq_p / (float)w.K + a.eps) : 1.f;
-            if (tid == 0) ssq_s[(gphase + 2u) & 3u] = 0.f;          // last read two phases ago, next written two phases from now
+            float rstd = 1.f;
+            if (nw != nullptr) {
+                float tot = 0.f;
+                for (unsigned int ww = 0; ww < aw; ++ww) tot += ssq_p[ww];
+                rstd = rsqrtf(tot / (float)w.K + a.eps);
+            }
             if (kind == 0) {
                 for (int i = tid; i < w.nrows; i += LL_THREADS) {
-                    st_pair(a.qkv + w.r0 + i, acc[i] * rstd, tagl);
-                    acc[i] = 0.f;
+                    st_pair(a.qkv + w.r0 + i, fix_take(&acc[i]) * rstd, tagl);
                 }
             } else if (kind == 1 || kind == 3) {
                 unsigned long long* dst = (kind == 1) ? a.xb : a.xa;
                 const uint32_t tg = (kind == 1) ? tagl : tagl + 1u;   // down-proj output = input of the next layer (or of the lm_head)
                 for (int i = tid; i < w.nrows; i += LL_THREADS) {
-                    const float v = xres_s[i] + acc[i];
+                    const float v = xres_s[i] + fix_take(&acc[i]);
                     xres_s[i] = v;
                     st_pair(dst + w.r0 + i, v, tg);
-                    acc[i] = 0.f;
                 }
             } else if (kind == 2) {
                 for (int u = tid; u < w.nrows / 2; u += LL_THREADS) {
-                    const float g = acc[2 * u] * rstd, up = acc[2 * u + 1] * rstd;
+                    const float g = fix_take(&acc[2 * u]) * rstd, up = fix_take(&acc[2 * u + 1]) * rstd;
                     st_pair(a.act + w.r0 / 2 + u, silu_f(g) * up, tagl);
-                    acc[2 * u] = 0.f; acc[2 * u + 1] = 0.f;
                 }
             } else {
                 // logits + (value, lowest index) argmax: per thread rows ascend, so the first maximum wins
                 float bv = -INFINITY; int bi = 0x7fffffff;
                 for (int i = tid; i < w.nrows; i += LL_THREADS) {
-                    const float v = acc[i] * rstd;
+                    const float v = fix_take(&acc[i]) * rstd;
                     a.logits[w.r0 + i] = v;
-                    acc[i] = 0.f;
                     if (v > bv) { bv = v; bi = w.r0 + i; }
                 }
 #pragma unroll
@@ -799,7 +826,7 @@ static int ll_max_rows(const LLArgs& a, int grid) {
 }
 static size_t ll_smem(const LLArgs& a, int grid, int depth) {
     const int mr = ll_max_rows(a, grid);
-    return (size_t)LL_WARPS * depth * LL_SEG_BYTES + (size_t)2 * mr * 4 + (size_t)((a.H + grid - 1) / grid) * 4 + 16;
+    return (size_t)LL_WARPS * depth * LL_SEG_BYTES + (size_t)2 * mr * 8 + (size_t)((a.H + grid - 1) / grid) * 4 + 16;
 }
 
 bool decode_ll_supported(int D, int rot_half, int nh, int nkv, int H, int I, int q_dim, int qkv_dim, int V, int num_sms) {

@@ -2033,6 +2033,18 @@ int crane_b200_op_qlinear(int device, const float* x, size_t m, size_t k, const 
     return rc;
 }
 
+/* debugging aid (not in the public header): copy a prefill workspace to the host -- 0: residual stream x [S, H], 1: qkv [S, qkv_dim],
+ * 2: the f32 rows in front of / behind a quantised linear [S, max(I, q_dim)] */
+extern "C" CRANE_B200_API int crane_b200_debug_peek(crane_b200_model* m, int which, float* out, size_t n_floats) {
+    API_BEGIN(m)
+    need_ready(m);
+    const float* src = which == 0 ? m->x : which == 1 ? m->qkv : m->rows_f32;
+    if (!src || !out) fail(CRANE_B200_INVALID_ARG, "debug_peek: buffer %d does not exist", which);
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    CUDA_OK(cudaMemcpy(out, src, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    API_END(m)
+}
+
 static int op_sampler(int device, const float* logits, size_t vocab, size_t k, const crane_b200_sampling* p, uint32_t* out, float* logits_after) {
     if (!logits || !out || vocab == 0 || vocab > (size_t)INT32_MAX) return CRANE_B200_INVALID_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return CRANE_B200_CUDA_ERROR;
