@@ -104,7 +104,7 @@ __device__ __forceinline__ void fix_add(FixAcc* p, float v) {
 __device__ __forceinline__ float fix_take(FixAcc* p) {       // read and clear (one reader per row, after the CTA barrier)
     const FixAcc v = *p;
     *p = FixAcc{0, 0};
-    return (float)((double)v.a * (1.0 / 256.0) + (double)v.b * (1.0 / 4294967296.0));
+    return (float)v.a * (1.0f / 256.0f) + (float)v.b * (1.0f / 4294967296.0f);      // (float)a is exact below 2^24 (|v| < 65 536)
 }
 
 // ---- phase geometry --------------------------------------------------------------------------------------------------
@@ -183,6 +183,17 @@ __device__ __forceinline__ void cursor_enter(const LLArgs& a, Cursor& pf, const 
             return;
         }
         ++pf.p;
+    }
+}
+
+// HBM -> L2 prefetch of a contiguous range (one thread).  The shared-memory rings can only run ~4 us ahead; while the CTAs sit in a
+// dependency wait the rings are full and HBM would idle.  The weights of a phase a little further ahead are therefore pulled into
+// the 126 MB L2 in the meantime, so that the ring later refills at L2 speed.
+__device__ __forceinline__ void ll_prefetch_l2(const unsigned char* p, size_t bytes) {
+    while (bytes != 0) {
+        const uint32_t n = (uint32_t)(bytes < (size_t)(1u << 20) ? bytes : (size_t)(1u << 20));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n) : "memory");
+        p += n; bytes -= n;
     }
 }
 
@@ -570,7 +581,8 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
                                 ly.v_pool[a.kv_lo_off + off + i] = __float2bfloat16_rn(vnew_s[i] - __bfloat162float(vb));
                             }
                         }
-                        __threadfence();
+                        // no fence: the page row is first read a whole decode step later, through L2 (the loads bypass L1), and a fence
+                        // here would sit on the critical path of every layer (this CTA's O-projection rows wait behind it)
                         __syncthreads();  // knew_s / vnew_s are rewritten by the next layer's item
                     }
                 }
@@ -626,6 +638,14 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
             }
 
             // ============================ weight phase: y = W . x over this CTA's row block ============================
+            if (a.l2_ahead > 0 && tid == 0) {          // this CTA's slab of a phase `l2_ahead` phases from now -> L2 (never the lm_head: 4x the L2)
+                int pp = p + a.l2_ahead, ss = s;
+                if (pp >= n_phase) { pp -= n_phase; ++ss; }
+                if (ss < a.n_steps && pp < 4 * a.L) {
+                    const WGeo& wf = wgeo_s[0][phase_kind(pp, a.L)];
+                    if (wf.nrows > 0) ll_prefetch_l2(phase_weights(a, pp) + (size_t)wf.r0 * wf.K * 2, (size_t)wf.nrows * wf.K * 2);
+                }
+            }
             const WGeo w = wg[kind];
             const LLLayer& ly = a.layers[l];
             const float* nw = (kind == 0) ? ly.ln1 : (kind == 2) ? ly.ln2 : (kind == 4) ? a.final_norm : nullptr;
@@ -702,7 +722,7 @@ decode_ll_kernel(const __grid_constant__ LLArgs a, int max_rows) {
             prof(3);
             trace(5);
 
-            // ============================ epilogue: publish this CTA's rows ============================
+            // ============================ epilogue ============================
             float rstd = 1.f;
             if (nw != nullptr) {
                 float tot = 0.f;

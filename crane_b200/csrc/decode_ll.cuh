@@ -45,6 +45,7 @@ struct LLArgs {
     unsigned int tag_base;         // tags of this launch are tag_base + 1 .. tag_base + n_steps * (L + 2)
     int n_steps;
     int advance;                   // 1: feed each argmax back as the next input
+    int l2_ahead;                  // > 0: every phase pulls its CTA's weight slab of the phase l2_ahead later into L2
     unsigned int* err;             // [1] set when a wait timed out (the launch then drains without waiting)
     unsigned long long* prof;      // optional [16] cycle accumulators of CTA 0
     unsigned long long* trace;     // optional [6][LL_TRACE_CAP][2] (event | phase << 8, globaltimer ns) of CTAs 0 / 73 / 140, warps 0 / 9, during step trace_step

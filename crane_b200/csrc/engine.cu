@@ -1174,6 +1174,7 @@ void crane_b200_model::decode_steps(int n_steps, int advance) {
         p.tag_base = ll_tag;
         ll_tag += need;
         p.n_steps = n_steps; p.advance = advance; p.err = ll_err; p.prof = ll_prof;
+        { static const int la = [] { const char* e = getenv("CRANE_B200_LL_L2AHEAD"); return e ? atoi(e) : 0; }(); p.l2_ahead = la; }
         if (ll_trace && n_steps > 8) { CUDA_OK(cudaMemsetAsync(ll_trace, 0, (size_t)6 * LL_TRACE_CAP * 16, stream)); p.trace = ll_trace; p.trace_step = 6; }
         LAUNCH_OK(decode_ll_launch(stream, p, num_sms));
         ++launches;

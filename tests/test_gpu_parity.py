@@ -391,17 +391,22 @@ def test_quantised_linear_kernel_against_integer_dot_oracle(qt, shape):
 
 
 def _gpu_linear_oracle(cfg, wq, qd):
-    """The oracle with every quantised linear executed by the GPU kernels (xquant + qgemv through crane_b200.op_qlinear) on the
-    oracle's own activations: isolates the arithmetic of the kernels from everything around them."""
+    """The oracle with every quantised linear ALSO executed by the GPU kernels (xquant + qgemv through crane_b200.op_qlinear) on the
+    oracle's own activations; the oracle's result is what flows on, so every linear of the pass is compared on bit-identical inputs
+    (`.worst` = largest relative error over the calls, `.calls` = how many)."""
     from oracle import ggml_quant as gq
 
     class GpuLinearOracle(Qwen3Oracle):
+        worst, calls = 0.0, 0
+
         def _linear(self, full_name, x, w=None):
+            y = super()._linear(full_name, x, w)
             if full_name in self.q:
                 raw, qt = self.q[full_name]
-                y = crane_b200.op_qlinear(x.reshape(-1, x.shape[-1]).numpy(), raw, gq.GGML_TYPE_ID[qt], raw.shape[0])
-                return torch.from_numpy(y).reshape(*x.shape[:-1], -1)
-            return super()._linear(full_name, x, w)
+                g = crane_b200.op_qlinear(x.reshape(-1, x.shape[-1]).numpy(), raw, gq.GGML_TYPE_ID[qt], raw.shape[0])
+                self.worst = max(self.worst, rel_err(g, y.reshape(-1, y.shape[-1]).numpy()))
+                self.calls += 1
+            return y
 
     return GpuLinearOracle(cfg, wq, quantised=qd)
 
@@ -426,8 +431,10 @@ def test_quantised_linears_against_integer_dot_oracle(recipe_name):
     ids = synth.synth_token_ids(70, cfg["vocab_size"], "quant")
     ref = orc.forward(ids, 0).numpy()
     # 1. kernels on the oracle's activations
-    e_kernels = rel_err(_gpu_linear_oracle(cfg, wq, qd).forward(ids, 0).numpy(), ref)
-    assert e_kernels < 1e-5, e_kernels
+    chk = _gpu_linear_oracle(cfg, wq, qd)
+    chk.forward(ids, 0)
+    e_kernels = chk.worst
+    assert chk.calls >= 7 * cfg["num_hidden_layers"] and e_kernels < 1e-5, (chk.calls, e_kernels)
     # 3. engine, full depth
     gap = rel_err(plain.forward(ids, 0).numpy(), ref)
     e_pre = rel_err(m.forward_step(ids, 0), ref)
