@@ -103,9 +103,11 @@ _SIGNATURES = {
     "crane_b200_tts_codec_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "crane_b200_tts_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "crane_b200_tts_generate": (C.c_int, [C.c_void_p, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]),
+    "crane_b200_vl_decode_step_argmax": (C.c_int, [C.c_void_p, C.c_uint32, C.c_size_t, C.POINTER(C.c_uint32)]),
     "crane_b200_next_mrope_pos": (C.c_uint32, [C.c_void_p]),
     "crane_b200_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_size_t)]),
     "crane_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "crane_b200_decode_path": (C.c_int, [C.c_void_p]),
     "crane_b200_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int]),
 }
@@ -338,6 +340,11 @@ class Engine:
         self._ck(self.lib.crane_b200_vl_decode_step(self.h, token, start_pos, C.byref(lg)))
         return self.copy_logits()
 
+    def vl_decode_step_argmax(self, token: int, start_pos: int) -> int:
+        t = C.c_uint32()
+        self._ck(self.lib.crane_b200_vl_decode_step_argmax(self.h, token, start_pos, C.byref(t)))
+        return int(t.value)
+
     def next_mrope_pos(self) -> int:
         return int(self.lib.crane_b200_next_mrope_pos(self.h))
 
@@ -348,6 +355,9 @@ class Engine:
 
     def kernel_launches(self) -> int:
         return int(self.lib.crane_b200_kernel_launches(self.h))
+
+    def decode_path(self) -> str:
+        return "persistent" if self.lib.crane_b200_decode_path(self.h) else "chain"
 
 
 class Qwen3Model(Engine):
@@ -385,6 +395,9 @@ class Qwen3VLModel(Engine):
 
     def decode_step(self, token: int, start_pos: int):
         return self.vl_decode_step(token, start_pos)
+
+    def decode_step_argmax(self, token: int, start_pos: int) -> int:
+        return self.vl_decode_step_argmax(token, start_pos)
 
     def generate(self, input_ids, pixel_values, image_grid_thw, max_new_tokens: int, eos_token_id=()):
         """vlm.rs:355-414: prefill (argmax on device), then greedy decode on the device."""

@@ -1640,6 +1640,7 @@ uint64_t crane_b200_active_kv_cache_bytes(const crane_b200_model* m) {
            (m->hybrid ? (uint64_t)(m->L - full) * ((uint64_t)m->nv * m->dk * m->dv + (uint64_t)m->conv_dim() * m->ck) * 4 : 0);
 }
 uint64_t crane_b200_kernel_launches(const crane_b200_model* m) { return m ? m->launches : 0; }
+int crane_b200_decode_path(const crane_b200_model* m) { return m && m->finalized && m->use_persistent ? 1 : 0; }
 
 int crane_b200_warmup(crane_b200_model* m) {
     API_BEGIN(m)
@@ -1825,6 +1826,19 @@ int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token, size_t start_
     m->next_mrope_pos = (uint32_t)(p + 1);
     m->kv_len = start_pos + 1;
     fill_logits(m, out);
+    API_END(m)
+}
+
+int crane_b200_vl_decode_step_argmax(crane_b200_model* m, uint32_t token, size_t start_pos, uint32_t* token_out) {
+    if (!token_out) return CRANE_B200_INVALID_ARG;
+    int r = crane_b200_vl_decode_step(m, token, start_pos, nullptr);
+    if (r != CRANE_B200_OK) return r;
+    API_BEGIN(m)
+    CUDA_OK(cudaMemcpyAsync(m->h_tokens, m->out_tokens, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    m->ll_err_fetch();
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->ll_err_verify();
+    *token_out = m->h_tokens[0];
     API_END(m)
 }
 

@@ -209,6 +209,8 @@ CRANE_B200_API int crane_b200_vl_forward(crane_b200_model* m, const uint32_t* in
 /* `Qwen3_5VLModel::decode_step` (vlm.rs:294-301): one token at cache position start_pos with the scalar
  * MRoPE counter seeded by vl_forward. */
 CRANE_B200_API int crane_b200_vl_decode_step(crane_b200_model* m, uint32_t token, size_t start_pos, crane_b200_logits* out);
+/* The same step returning only the greedy token (4 bytes back instead of the logits row): the serving loop's call. */
+CRANE_B200_API int crane_b200_vl_decode_step_argmax(crane_b200_model* m, uint32_t token, size_t start_pos, uint32_t* token_out);
 /* The MRoPE counter (`next_mrope_pos`, vlm.rs:272-282). */
 CRANE_B200_API uint32_t crane_b200_next_mrope_pos(const crane_b200_model* m);
 
@@ -238,6 +240,9 @@ CRANE_B200_API int crane_b200_tts_generate(crane_b200_model* m, size_t max_frame
 CRANE_B200_API int crane_b200_last_timing(const crane_b200_model* m, float* prefill_ms, float* decode_ms, size_t* decode_steps);
 /* Kernels launched by this handle since creation (graph replays count their nodes). */
 CRANE_B200_API uint64_t crane_b200_kernel_launches(const crane_b200_model* m);
+/* Which decode path single-sequence greedy decode takes after finalize: 1 = the persistent kernel (one launch for n steps),
+ * 0 = the kernel chain (one graph replay per step: hybrid / quantised / TTS models, batched sequences, borrowed streams). */
+CRANE_B200_API int crane_b200_decode_path(const crane_b200_model* m);
 
 /* ---- kernel-level test hooks (used by tests/ only; host buffers in, host buffers out) ------------ */
 /* C[M,N] = epilogue((A + A_lo)[M,K] bf16 x W[N,K]^T bf16); a_lo = optional low-order plane of a split-precision A

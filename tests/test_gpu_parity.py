@@ -284,6 +284,12 @@ def test_vl_generate_matches_oracle():
     got = m.generate(ids, pv, [grid], 8)
     print("vl generate:", list(got), "oracle:", ref)
     assert [int(x) for x in got] == ref
+    # the serving loop's per-token call (4 bytes back per step) walks the same M-RoPE positions as the on-device loop
+    m.clear_kv_cache()
+    step = [int(np.argmax(m.forward(ids, pv, [grid], 0)))]
+    for i in range(7):
+        step.append(m.decode_step_argmax(step[-1], len(ids) + i))
+    assert step == ref
     m.close()
 
 
