@@ -108,6 +108,8 @@ _SIGNATURES = {
     "crane_b200_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_size_t)]),
     "crane_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "crane_b200_decode_path": (C.c_int, [C.c_void_p]),
+    "crane_b200_prof_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "crane_b200_prof_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "crane_b200_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int]),
 }
@@ -355,6 +357,18 @@ class Engine:
 
     def kernel_launches(self) -> int:
         return int(self.lib.crane_b200_kernel_launches(self.h))
+
+    def prof_enable(self, on: bool = True):
+        self._ck(self.lib.crane_b200_prof_enable(self.h, 1 if on else 0))
+
+    def prof_report(self) -> dict:
+        """Per-pass averages since prof_enable: {"decode" | "prefill": {passes, tokens, enqueue_ms, wall_ms, device_ms, spans}}."""
+        import json
+        n = C.c_size_t()
+        self._ck(self.lib.crane_b200_prof_report(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._ck(self.lib.crane_b200_prof_report(self.h, buf, n.value, C.byref(n)))
+        return json.loads(buf.value.decode())
 
     def decode_path(self) -> str:
         return "persistent" if self.lib.crane_b200_decode_path(self.h) else "chain"

@@ -12,6 +12,7 @@
 // (32 registers each), so a timestep needs two 2-step shuffle reductions and NO block barrier; q/k/v/gates of 16
 // timesteps are staged in shared memory per barrier pair.  State is read once and written once per call.
 #include "gdn.cuh"
+#include "prof.h"
 
 namespace cb {
 
@@ -309,16 +310,20 @@ int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     const bool pdl = prefill_pdl();
     if (a.S == 1 && a.nk == a.nv && a.dv == 128 && a.ck >= 2 && a.out_f32 != nullptr && a.out_bf16 == nullptr)
         return launch_k(gdn_decode_kernel, dim3(a.nv), dim3(512), 0, st, pdl, a);
+    span_mark(SP_GDN_CONV);
     int r = launch_k(gdn_conv_kernel, dim3((conv_dim + 127) / 128, a.S), dim3(128), 0, st, pdl, a);
     if (!r) r = launch_k(gdn_conv_state_kernel, dim3((conv_dim + 127) / 128), dim3(128), 0, st, pdl, a);
+    span_mark(SP_GDN_QKV);
     if (!r) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);
     // NOT a programmatic dependent: launched early, its 64 long-running CTAs land wherever the previous kernel leaves room and
     // pile up several to an SM; launched after it, they spread one per SM (measured: 4.4 vs 2.4 ms per layer at 4096 tokens)
+    span_mark(SP_GDN_RECUR);
     if (!r) {
         static SmemOptIn seen;
         r = ensure_dyn_smem(gdn_recur_kernel, GDN_RECUR_SMEM, seen);
         if (!r) r = launch_k(gdn_recur_kernel, dim3(a.nv * (a.dv / 32)), dim3(128), GDN_RECUR_SMEM, st, false, a);
     }
+    span_mark(SP_GDN_FINISH);
     if (!r) r = launch_k(gdn_gated_norm_kernel, dim3((a.S * a.nv + 3) / 4), dim3(128), 0, st, pdl, a);
     return r;
 }

@@ -2,16 +2,15 @@
 #include "gemm.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
 namespace cb {
 
-// CRANE_B200_GEMM_CLUSTERS=1 turns the 2x2 TMA-multicast clusters on.  Measured on B200 (tools/gemm_probe.py) they do not pay:
-// the L2 already de-duplicates concurrent requests for a line from a few CTAs, and what bounds the small-M GEMMs is per-CTA
-// latency, not L2 -> SM bytes.  CRANE_B200_GEMM_BN=64|128|256 pins the tile width (sweeps).
-static const bool g_gemm_clusters = [] { const char* e = getenv("CRANE_B200_GEMM_CLUSTERS"); return e && e[0] == '1'; }();
+// CRANE_B200_GEMM_BN=64|128|256 pins the tile width (sweeps).  (Round 1 also had 2x2 TMA-multicast clusters; measured on B200 they
+// did not pay -- the L2 already merges concurrent requests for a line from a few CTAs -- and they are gone.)
 static const int g_gemm_bn = [] { const char* e = getenv("CRANE_B200_GEMM_BN"); return e ? atoi(e) : 0; }();
 
 // =====================================================================================
@@ -22,15 +21,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-// Same, delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster whose rank bit is set in `mask`.
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -38,6 +28,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
@@ -53,10 +45,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // Arrives on `bar` when every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -181,21 +169,47 @@ __device__ __forceinline__ void epi_block(const GemmEpi& ep, uint8_t* stg, int m
 }
 
 // =====================================================================================
-// tcgen05 kernel: one 128 x BN tile per CTA, 256 threads
+// tcgen05 kernel: persistent, stream-K over (tile, k-step) iterations, 256 threads per CTA, one CTA per SM
 //   warp 0 : TMA producer (one elected lane)       warp 1 : MMA issuer (one elected lane)
 //   warp 2 : TMEM allocator / deallocator           warps 4-7 : epilogue (TMEM lane quadrant = warp % 4)
+//
+// Why stream-K.  At the prefill shapes of this engine (M = 454 text rows, 784 patches) a 128 x BN grid of output tiles is either too
+// few CTAs (BN = 256: 32-64 tiles for N = 2048-4096) or, with narrow tiles, bound by L2 -> SM operand traffic: measured (tools/
+// gemm_probe.py) a k-step costs ~325 ns whether BN is 64, 128 or 256, i.e. the ~12 TB/s the L2 can hand out, while the tensor pipe
+// needs 32 / 64 / 128 cycles per MMA.  Only BN = 256 tiles are MMA-bound, so the work is cut the other way: the iteration space
+// tiles x k-steps is dealt out evenly, in order, to min(#SMs, ...) CTAs; a CTA whose range starts or ends inside a tile owns a
+// PARTIAL sum of that tile.  Partials go to a workspace; the contributor that arrives last adds them IN CONTRIBUTOR ORDER (so the
+// result does not depend on who was last: bitwise reproducible) and runs the fused epilogue.  Nobody ever waits for another CTA.
+// The accumulator is double-buffered in TMEM (2 x BN columns): the MMAs of a CTA's next segment run under the epilogue of the last.
 // =====================================================================================
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_SMEM_BUDGET = 192 * 1024;
+constexpr int GEMM_STAGE_BUDGET = 192 * 1024;
+constexpr int GEMM_MAX_CTAS = 160;                 // workspace slots: two partial tiles per CTA
+
+struct GemmSched {
+    int tiles_m, tiles_n, KB;      // output tiles and k-steps per tile; tile t = n_tile * tiles_m + m_tile (the CTAs working at the
+                                   // same time share their weight rows: the L2 merges those requests)
+    int G, unit, base, rem;        // G CTAs; CTA c owns iterations [unit * (c * base + min(c, rem)), ...): base or base + 1 units of
+                                   // `unit` k-steps -- unit = KB deals out whole tiles (nothing is split), unit = 1 is stream-K
+    float* ws;                     // [2 * G][128 * BN] partial tiles
+    int* counters;                 // [tiles] arrivals per tile, zero between launches (the finisher resets its tile)
+};
+__host__ __device__ inline int sched_start(const GemmSched& s, int c) { return s.unit * (c * s.base + (c < s.rem ? c : s.rem)); }
+__host__ __device__ inline int sched_owner(const GemmSched& s, int it) {       // CTA whose range holds iteration `it`
+    const int u = it / s.unit, big = s.rem * (s.base + 1);
+    return u < big ? u / (s.base + 1) : s.rem + (u - big) / s.base;
+}
 
 template <int BN, bool SPLIT>
 struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES * (SPLIT ? 2 : 1) + B_BYTES;     // [A hi | A lo (SPLIT) | B]
-    static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STAGES = (GEMM_STAGE_BUDGET / STAGE_BYTES) < 8 ? (GEMM_STAGE_BUDGET / STAGE_BYTES) : 8;
+    static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;                        // transpose patches of the four epilogue warps
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;
 };
 
 // SPLIT: the activation operand comes as two bf16 planes A = hi + lo (lo = bf16(x - hi), ~16 mantissa bits together); the
@@ -203,90 +217,77 @@ struct GemmCfg {
 template <int BN, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmB,
-               GemmEpi ep, int M, int N, int K, int cx, int cy) {
-    // (cx, cy) = thread-block cluster shape (1 or 2 each).  The cx CTAs of a cluster row work on the same 128 activation rows:
-    // each fetches 128/cx of them and TMA-multicasts its part to the others; likewise the cy CTAs of a cluster column share the
-    // BN weight rows.  At M ~ 450 these GEMMs are bound by L2->SM traffic, which this divides by up to 2.
+               GemmEpi ep, int M, int N, int K, GemmSched sc) {
     using Cfg = GemmCfg<BN, SPLIT>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2] accumulator b complete
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] accumulator b drained by the four epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * BN;
-    const int KB = K / GEMM_BK;
+    const int cta = blockIdx.x;
+    const int KB = sc.KB;
+    const int it_begin = sched_start(sc, cta), it_end = sched_start(sc, cta + 1);
     // optional timeline of this CTA (tools/gemm_probe.py): 8 globaltimer stamps per CTA
-    unsigned long long* prof = ep.prof ? ep.prof + 8 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    unsigned long long* prof = ep.prof ? ep.prof + 8 * (size_t)cta : nullptr;
     auto stamp = [&](int i) {
         if (prof) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); prof[i] = t; }
     };
     if (threadIdx.x == 0) stamp(0);
-    const bool clustered = cx * cy > 1;
-    const int rx = blockIdx.x % cx, ry = blockIdx.y % cy;                 // position inside the cluster; rank = rx + ry * cx
-    const uint16_t mask_a = (uint16_t)(((1u << cx) - 1u) << (ry * cx));   // CTAs sharing my activation rows
-    const uint16_t mask_b = (uint16_t)((cy == 2 ? ((1u << cx) | 1u) : 1u) << rx);   // CTAs sharing my weight rows
-    const uint16_t mask_all = mask_a | mask_b;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         if (SPLIT) tma_prefetch_desc(&tmAlo);
         tma_prefetch_desc(&tmB);
-        // a stage is refilled by every CTA that multicasts into it: it is free once all of their consumers have drained it
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cx + cy - 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, BN);
+    if (warp == 2) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
-    if (clustered) cluster_sync_all();          // peers' barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) stamp(1);                 // setup done
 
     pdl_launch_dependents();                        // the next kernel may begin its own setup / weight prefetch now
+    auto tile_origin = [&](int it, int& m0, int& n0) {
+        const int t = it / KB;
+        m0 = (t % sc.tiles_m) * GEMM_BM;
+        n0 = (t / sc.tiles_m) * BN;
+    };
     if (warp == 0) {
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            int kb0 = 0;
-            if (!clustered && !ep.w_dynamic) {
-                // weights do not depend on the predecessor kernel: their first tiles go out before the dependency wait
-                const int npre = min(KB, STAGES);
-                for (int kb = 0; kb < npre; ++kb) {
-                    uint8_t* a_dst = smem + kb * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[kb], Cfg::STAGE_BYTES);
-                    tma_load_2d(a_dst + Cfg::A_BYTES * (SPLIT ? 2 : 1), &tmB, &full_bar[kb], kb * GEMM_BK, n0);
-                }
-                pdl_wait();
-                for (int kb = 0; kb < npre; ++kb) {
-                    uint8_t* a_dst = smem + kb * Cfg::STAGE_BYTES;
-                    tma_load_2d(a_dst, &tmA, &full_bar[kb], kb * GEMM_BK, m0);
-                    if (SPLIT) tma_load_2d(a_dst + Cfg::A_BYTES, &tmAlo, &full_bar[kb], kb * GEMM_BK, m0);
-                }
-                kb0 = npre;
-                if (npre == STAGES) ph = 1; else s = npre;
-            } else {
-                pdl_wait();
+            // weights do not depend on the predecessor kernel: their first tiles go out before the dependency wait
+            const int npre = ep.w_dynamic ? 0 : min(it_end - it_begin, STAGES);
+            for (int i = 0; i < npre; ++i) {
+                int m0, n0;
+                tile_origin(it_begin + i, m0, n0);
+                uint8_t* st = smem + i * Cfg::STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+                tma_load_2d(st + Cfg::A_BYTES * (SPLIT ? 2 : 1), &tmB, &full_bar[i], ((it_begin + i) % KB) * GEMM_BK, n0);
             }
-            for (int kb = kb0; kb < KB; ++kb) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
+            pdl_wait();
+            int s = 0; uint32_t ph = 0;
+            for (int it = it_begin; it < it_end; ++it) {
+                int m0, n0;
+                tile_origin(it, m0, n0);
+                const int kc = (it % KB) * GEMM_BK;
                 uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + Cfg::A_BYTES * (SPLIT ? 2 : 1);
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);     // own parts + the parts the peers multicast here
-                if (!clustered) {
-                    tma_load_2d(a_dst, &tmA, &full_bar[s], kb * GEMM_BK, m0);
-                    if (SPLIT) tma_load_2d(a_dst + Cfg::A_BYTES, &tmAlo, &full_bar[s], kb * GEMM_BK, m0);
-                    tma_load_2d(b_dst, &tmB, &full_bar[s], kb * GEMM_BK, n0);
-                } else {
-                    const int ar = rx * (GEMM_BM / cx), br = ry * (BN / cy);      // my slice of the shared tiles (rows)
-                    tma_load_2d_mc(a_dst + ar * 128, &tmA, &full_bar[s], kb * GEMM_BK, m0 + ar, mask_a);
-                    if (SPLIT) tma_load_2d_mc(a_dst + Cfg::A_BYTES + ar * 128, &tmAlo, &full_bar[s], kb * GEMM_BK, m0 + ar, mask_a);
-                    tma_load_2d_mc(b_dst + br * 128, &tmB, &full_bar[s], kb * GEMM_BK, n0 + br, mask_b);
+                const bool pre = it - it_begin < npre;
+                if (!pre) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    tma_load_2d(a_dst + Cfg::A_BYTES * (SPLIT ? 2 : 1), &tmB, &full_bar[s], kc, n0);
                 }
+                tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
+                if (SPLIT) tma_load_2d(a_dst + Cfg::A_BYTES, &tmAlo, &full_bar[s], kc, m0);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -294,53 +295,134 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
             int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(&full_bar[s], ph);
+            int seg = 0;
+            for (int it = it_begin; it < it_end; ++seg) {
+                const int seg_end = min(it_end, (it / KB + 1) * KB);
+                const int b = seg & 1;
+                mbar_wait(&tmem_empty_bar[b], ((seg >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator (first two: free)
                 tc_fence_after();
-                if (kb == 0) stamp(2);              // first operands landed
-                const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t adesc = make_smem_desc_sw128(a_addr);
-                const uint64_t aldesc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
-                const uint64_t bdesc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES * (SPLIT ? 2 : 1));
+                const uint32_t acc = tmem_base + (uint32_t)(b * BN);
+                for (int i = it; i < seg_end; ++i) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    if (i == it_begin) stamp(2);        // first operands landed
+                    const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc_sw128(a_addr);
+                    const uint64_t aldesc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES);
+                    const uint64_t bdesc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES * (SPLIT ? 2 : 1));
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k) {
-                    // +32 B per K=16 step inside the 128 B swizzle atom -> +2 in the >>4-encoded start address
-                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    if (SPLIT) umma_bf16(tmem_base, aldesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // +32 B per K=16 step inside the 128 B swizzle atom -> +2 in the >>4-encoded start address
+                        umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i != it) | (k != 0)));
+                        if (SPLIT) umma_bf16(acc, aldesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[s]);         // frees the smem stage once these MMAs retire
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                // frees the smem stage (here and in every CTA that refills it) once these MMAs retire
-                if (clustered) umma_commit_mc(&empty_bar[s], mask_all); else umma_commit(&empty_bar[s]);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
+                umma_commit(&tmem_full_bar[b]);         // this segment's accumulator is complete
+                it = seg_end;
             }
-            umma_commit(tmem_full_bar);                 // accumulator complete
             stamp(3);                                   // last MMA issued
         }
     } else if (warp >= 4) {
         pdl_wait();                                 // the epilogue reads / overwrites activations of the predecessor too
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        if (threadIdx.x == 128) stamp(4);               // accumulator ready
         const int q = warp & 3;
-        uint8_t* stg = smem + q * EPI_WARP_BYTES;       // the pipeline stages are dead once the accumulator is complete
+        uint8_t* stg = epi_smem + q * EPI_WARP_BYTES;
+        constexpr int CHUNKS = BN / 32;
+        constexpr size_t TILE_F = (size_t)GEMM_BM * BN;
+        int seg = 0;
+        for (int it = it_begin; it < it_end; ++seg) {
+            const int seg_end = min(it_end, (it / KB + 1) * KB);
+            const int t = it / KB, kb0 = it % KB, kb1 = kb0 + (seg_end - it);
+            const int m0 = (t % sc.tiles_m) * GEMM_BM, n0 = (t / sc.tiles_m) * BN;
+            const int b = seg & 1;
+            const uint32_t acc = tmem_base + (uint32_t)(b * BN) + ((uint32_t)(q * 32) << 16);
+            const bool sole = kb0 == 0 && kb1 == KB;
+            mbar_wait(&tmem_full_bar[b], (seg >> 1) & 1);
+            tc_fence_after();
+            if (threadIdx.x == 128 && seg == 0) stamp(4);   // first accumulator ready
+            if (sole) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            const int n = n0 + c * 32;
-            if (n < N) {                                // warp-uniform
-                float v[32];
+                for (int c = 0; c < CHUNKS; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(acc + (uint32_t)(c * 32), r);
+                    const int n = n0 + c * 32;
+                    if (n < N) {                            // warp-uniform
+                        float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                epi_block<MODE>(ep, stg, m0 + q * 32, M, n, v, lane);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        epi_block<MODE>(ep, stg, m0 + q * 32, M, n, v, lane);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[b]);
+            } else {
+                // partial sum of tile t: park it.  A 32 x 32 block of (row = lane, column j) is stored as 8 rows of 32 float4: the float4
+                // of lane l in row k holds columns 4k .. 4k+3 of row l, so every store / reload instruction moves 512 contiguous bytes
+                float* mine = sc.ws + (size_t)(2 * cta + (it == it_begin ? 0 : 1)) * TILE_F + (size_t)q * CHUNKS * 1024;
+#pragma unroll 1
+                for (int c = 0; c < CHUNKS; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(acc + (uint32_t)(c * 32), r);
+                    float4* dst = reinterpret_cast<float4*>(mine + c * 1024) + lane;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        dst[k * 32] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[b]);
+                // arrive at the tile; the last of its contributors finishes it
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int c_first = sched_owner(sc, t * KB), c_last = sched_owner(sc, t * KB + KB - 1);
+                if (threadIdx.x == 128) *last_flag = atomicAdd(&sc.counters[t], 1) == c_last - c_first;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*last_flag) {
+                    __threadfence();
+#pragma unroll 1
+                    for (int c = 0; c < CHUNKS; ++c) {
+                        const int n = n0 + c * 32;
+                        if (n >= N) break;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        auto part = [&](int cc) {
+                            return reinterpret_cast<const float4*>(sc.ws + (size_t)(2 * cc + (sched_start(sc, cc) < t * KB ? 1 : 0)) * TILE_F +
+                                                                   (size_t)(q * CHUNKS + c) * 1024) + lane;
+                        };
+                        // contributor order, whoever came last; two contributors' loads in flight together (the additions stay in order)
+                        for (int cc = c_first; cc <= c_last; cc += 2) {
+                            const bool two = cc + 1 <= c_last;
+                            const float4* p0 = part(cc);
+                            const float4* p1 = part(two ? cc + 1 : cc);
+                            float4 x0[8], x1[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) x0[k] = __ldcg(p0 + k * 32);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) x1[k] = two ? __ldcg(p1 + k * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { v[4 * k] += x0[k].x; v[4 * k + 1] += x0[k].y; v[4 * k + 2] += x0[k].z; v[4 * k + 3] += x0[k].w; }
+                            if (two) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) { v[4 * k] += x1[k].x; v[4 * k + 1] += x1[k].y; v[4 * k + 2] += x1[k].z; v[4 * k + 3] += x1[k].w; }
+                            }
+                        }
+                        epi_block<MODE>(ep, stg, m0 + q * 32, M, n, v, lane);
+                    }
+                    if (threadIdx.x == 128) sc.counters[t] = 0;       // clean for the next launch on this stream
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");           // last_flag is rewritten by the next segment
             }
+            it = seg_end;
         }
-        if (threadIdx.x == 128) stamp(5);               // this warp's rows stored
+        if (threadIdx.x == 128) stamp(5);               // this CTA's rows stored
     }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) stamp(6);                 // whole CTA done
-    if (clustered) cluster_sync_all();          // nobody leaves while a peer may still signal its barriers
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); if (lane == 0) stamp(7); }
 }
 
 // =====================================================================================
@@ -437,37 +519,117 @@ static bool make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, ui
     return true;
 }
 
+// Per-stream stream-K scratch: partial tiles + arrival counters.  GEMMs on one stream are ordered (and a programmatic dependent only
+// touches the scratch after its dependency wait), so one set per stream is enough; gemm_release_stream frees it with the stream.
+struct GemmScratch { float* ws = nullptr; int* counters = nullptr; size_t ws_floats = 0; int n_counters = 0; };
+static std::mutex g_scratch_mu;
+static std::unordered_map<uint64_t, GemmScratch> g_scratch;
+static uint64_t scratch_key(cudaStream_t st) { int dev = 0; cudaGetDevice(&dev); return ((uint64_t)(uintptr_t)st << 6) ^ (uint64_t)dev; }
+
+static int scratch_get(cudaStream_t st, size_t ws_floats, int n_counters, GemmScratch* out) {
+    std::lock_guard<std::mutex> g(g_scratch_mu);
+    GemmScratch& sc = g_scratch[scratch_key(st)];
+    if (sc.ws_floats < ws_floats || sc.n_counters < n_counters) {
+        // (growing: the old buffers may still be in use by kernels in flight on this stream)
+        if (sc.ws || sc.counters) { cudaStreamSynchronize(st); cudaFree(sc.ws); cudaFree(sc.counters); }
+        sc.ws_floats = std::max(ws_floats, sc.ws_floats);
+        sc.n_counters = std::max(n_counters, std::max(sc.n_counters, 4096));
+        if (cudaMalloc(&sc.ws, sc.ws_floats * sizeof(float)) != cudaSuccess) { sc = GemmScratch{}; return (int)cudaErrorMemoryAllocation; }
+        if (cudaMalloc(&sc.counters, (size_t)sc.n_counters * sizeof(int)) != cudaSuccess) { cudaFree(sc.ws); sc = GemmScratch{}; return (int)cudaErrorMemoryAllocation; }
+        if (cudaMemsetAsync(sc.counters, 0, (size_t)sc.n_counters * sizeof(int), st) != cudaSuccess) return (int)cudaGetLastError();
+    }
+    *out = sc;
+    return 0;
+}
+void gemm_release_stream(cudaStream_t st) {
+    std::lock_guard<std::mutex> g(g_scratch_mu);
+    auto it = g_scratch.find(scratch_key(st));
+    if (it == g_scratch.end()) return;
+    cudaFree(it->second.ws); cudaFree(it->second.counters);
+    g_scratch.erase(it);
+}
+static int device_sms() {
+    static int sms[CB_MAX_DEV] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= CB_MAX_DEV) return 148;
+    if (!sms[dev]) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); sms[dev] = v > 0 ? v : 148; }
+    return sms[dev];
+}
+// CRANE_B200_GEMM_MINIT: fewest k-steps worth giving a CTA (below that the fixed cost of a CTA -- setup, first operand latency,
+// parking and re-reading partial tiles -- outweighs the parallelism)
+static const int g_gemm_minit = [] { const char* e = getenv("CRANE_B200_GEMM_MINIT"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+
 template <int BN, int MODE, bool SPLIT>
 static int launch_tc(cudaStream_t stream, const bf16* A, const bf16* A_lo, int lda, const bf16* W, int M, int N, int K, const GemmEpi& epi,
-                     int cx, int cy) {
+                     bool stream_k) {
     using Cfg = GemmCfg<BN, SPLIT>;
     CUtensorMap tmA, tmAlo, tmB;
-    if (!make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM / cx)) return -1001;
-    if (!make_tmap_bf16(&tmAlo, SPLIT ? A_lo : A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM / cx)) return -1001;
-    if (!make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN / cy)) return -1001;
+    if (!make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1001;
+    if (!make_tmap_bf16(&tmAlo, SPLIT ? A_lo : A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1001;
+    if (!make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN)) return -1001;
     static SmemOptIn seen;
     if (const int e = ensure_dyn_smem(gemm_tc_kernel<BN, MODE, SPLIT>, (size_t)Cfg::SMEM_BYTES, seen)) return e;
-    dim3 grid((N + BN - 1) / BN, ((M + GEMM_BM - 1) / GEMM_BM + cy - 1) / cy * cy);   // whole clusters; surplus tiles are all-OOB
+    GemmSched sc = {};
+    sc.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    sc.tiles_n = (N + BN - 1) / BN;
+    sc.KB = K / GEMM_BK;
+    const long long tiles = (long long)sc.tiles_m * sc.tiles_n, iters = tiles * sc.KB;
+    if (iters > 0x7fffffffLL) return -1000;
+    const int cap = std::min(device_sms(), GEMM_MAX_CTAS);
+    sc.unit = stream_k ? 1 : sc.KB;
+    const long long units = iters / sc.unit;
+    sc.G = (int)std::max<long long>(1, std::min<long long>(cap, stream_k ? iters / g_gemm_minit : tiles));
+    sc.base = (int)(units / sc.G);
+    sc.rem = (int)(units % sc.G);
+    GemmScratch scratch;
+    if (const int e = scratch_get(stream, (size_t)2 * GEMM_MAX_CTAS * GEMM_BM * 256, (int)std::max<long long>(tiles, 1), &scratch)) return e;
+    sc.ws = scratch.ws;
+    sc.counters = scratch.counters;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
+    cfg.gridDim = dim3(sc.G);
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     int na = 0;
     if (prefill_pdl()) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
     }
-    if (cx * cy > 1) {
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = cx; attr[na].val.clusterDim.y = cy; attr[na].val.clusterDim.z = 1;
-        ++na;
-    }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, SPLIT>, tmA, tmAlo, tmB, epi, M, N, K, cx, cy);
+    return (int)cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, SPLIT>, tmA, tmAlo, tmB, epi, M, N, K, sc);
+}
+
+// Tile width and schedule from a cost model fitted to tools/gemm_probe.py on B200 (microseconds):
+//   a k-step costs t_k(BN): the L2 hands a CTA its operands at ~0.33 us per k-step whatever the tile width (0.46 with the second
+//   activation plane), only the 128 x 256 tile is slower than that because its MMAs are (0.34 / 0.60);
+//   whole tiles: each CTA runs ceil(tiles / CTAs) tiles, the epilogue of all but the last hidden under the next tile's MMAs;
+//   stream-K:    tiles x k-steps dealt evenly to all SMs, plus parking a partial tile and the last contributor re-reading c of them.
+struct GemmPlan { int bn; bool stream_k; double cost; };
+static GemmPlan gemm_plan(int M, int N, int K, bool split, int sms) {
+    static const int g_mode = [] { const char* e = getenv("CRANE_B200_GEMM_SCHED"); return e ? atoi(e) : 0; }();   // 1: whole tiles, 2: stream-K
+    const int tm = (M + GEMM_BM - 1) / GEMM_BM, KB = K / GEMM_BK;
+    GemmPlan best{64, false, 1e30};
+    for (int bn : {256, 128, 64}) {
+        if (g_gemm_bn && bn != g_gemm_bn) continue;
+        if (!g_gemm_bn && bn > 64 && N < bn) continue;
+        const long long tiles = (long long)tm * ((N + bn - 1) / bn);
+        const bool busy = tiles >= sms - 20;                                  // (nearly) every SM pulling operands: the L2 is the limit
+        const double tk = split ? (bn == 256 ? (busy ? 0.68 : 0.60) : 0.46) : (bn == 256 ? 0.34 : 0.33);
+        const double epi = 6.0 * bn / 256.0;
+        const long long per = (tiles + std::min<long long>(tiles, sms) - 1) / std::min<long long>(tiles, sms);
+        const double whole = 1.5 + (double)per * KB * tk + epi;
+        const double it = (double)tiles * KB / sms;
+        const double contrib = std::ceil((double)KB / std::max(it, 1.0)) + 1.0;
+        const double tks = split ? (bn == 256 ? 0.68 : 0.46) : (bn == 256 ? 0.36 : 0.33);
+        const double sk = it < g_gemm_minit ? 1e30 : 1.5 + it * tks + 1.6 * epi + contrib * 6.0 * bn / 256.0;
+        if (g_mode != 2 && whole < best.cost) best = GemmPlan{bn, false, whole};
+        // stream-K only below one wave of whole tiles: above it the extra partial-tile traffic costs more than the idle SMs
+        if (g_mode != 1 && (tiles < sms || g_mode == 2) && tiles * KB >= 2LL * sms && sk < best.cost) best = GemmPlan{bn, true, sk};
+    }
+    return best;
 }
 
 template <int MODE>
@@ -478,40 +640,18 @@ static int launch_mode(cudaStream_t stream, const bf16* A, const bf16* A_lo, int
         gemm_simt_kernel<MODE><<<grid, 128, 0, stream>>>(A, A_lo, lda, W, epi, M, N, K);
         return (int)cudaGetLastError();
     }
-    // Tile width and cluster shape from a two-term cost model (times in "A-tile loads"): the tensor pipe needs
-    // waves x k-steps x (BN / 64) x (split ? 2 : 1); the L2 -> SM fabric moves, per tile and k-step, the A planes / cx plus the
-    // B tile / cy.  At M ~ 450 the second term dominates, which is what the clusters attack.
-    const int mt = (M + GEMM_BM - 1) / GEMM_BM;
-    const bool split = A_lo != nullptr;
-    int best_bn = 64, best_cx = 1, best_cy = 1;
-    double best = 1e30;
-    const int cands[3] = {256, 128, 64};
-    for (int i = 0; i < 3; ++i) {
-        const int bn = cands[i];
-        if (g_gemm_bn && bn != g_gemm_bn) continue;
-        const int nt = (N + bn - 1) / bn;
-        for (int cy = 1; cy <= (mt > 1 && g_gemm_clusters ? 2 : 1); ++cy)
-            for (int cx = 1; cx <= ((nt % 2) == 0 && g_gemm_clusters ? 2 : 1); ++cx) {
-                const int mtp = (mt + cy - 1) / cy * cy;
-                const int tiles = mtp * nt;
-                const int waves = (tiles + 147) / 148;
-                const double mma = (double)waves * (bn / 64.0) * (split ? 2.0 : 1.0) * 0.55;     // 128x64x64 MMA vs one 16 KB tile over the fabric
-                const double bytes = (double)tiles * ((split ? 2.0 : 1.0) / cx + (bn / 128.0) / cy) / 148.0;
-                const double cost = std::max(mma, bytes) + 0.15 * std::min(mma, bytes) + (cx * cy > 1 ? 0.02 : 0.0);
-                if (cost < best) { best = cost; best_bn = bn; best_cx = cx; best_cy = cy; }
-            }
-    }
+    const GemmPlan p = gemm_plan(M, N, K, A_lo != nullptr, std::min(device_sms(), GEMM_MAX_CTAS));
     if (A_lo != nullptr) {
-        switch (best_bn) {
-            case 256: return launch_tc<256, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi, best_cx, best_cy);
-            case 128: return launch_tc<128, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi, best_cx, best_cy);
-            default:  return launch_tc<64, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi, best_cx, best_cy);
+        switch (p.bn) {
+            case 256: return launch_tc<256, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi, p.stream_k);
+            case 128: return launch_tc<128, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi, p.stream_k);
+            default:  return launch_tc<64, MODE, true>(stream, A, A_lo, lda, W, M, N, K, epi, p.stream_k);
         }
     }
-    switch (best_bn) {
-        case 256: return launch_tc<256, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi, best_cx, best_cy);
-        case 128: return launch_tc<128, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi, best_cx, best_cy);
-        default:  return launch_tc<64, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi, best_cx, best_cy);
+    switch (p.bn) {
+        case 256: return launch_tc<256, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi, p.stream_k);
+        case 128: return launch_tc<128, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi, p.stream_k);
+        default:  return launch_tc<64, MODE, false>(stream, A, nullptr, lda, W, M, N, K, epi, p.stream_k);
     }
 }
 

@@ -1,10 +1,10 @@
 // Prefill / ViT GEMM:  C[M,N] (+)= A[M,K] (bf16, row-major) x W[N,K]^T (bf16, row-major = K-major)
 //
-// B200 design: one 128 x BN output tile per CTA; A and W tiles stream HBM -> shared memory by TMA
-// (cp.async.bulk.tensor, SWIZZLE_128B, 64-element K slabs) through a multi-stage mbarrier ring;
-// one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, bf16 x bf16 -> f32) into a TMEM
-// accumulator; four epilogue warps pull the accumulator back with tcgen05.ld and apply the fused
-// epilogue (bias / residual add / SiLU*up / GELU / dtype cast) straight into global memory.
+// B200 design: a persistent kernel, one CTA per SM, stream-K over the (128 x BN output tile, 64-wide k-step) iteration space; A and W
+// tiles stream HBM/L2 -> shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a multi-stage mbarrier ring; one elected
+// thread issues tcgen05.mma (UMMA 128 x BN x 16, bf16 x bf16 -> f32) into a double-buffered TMEM accumulator; four epilogue warps
+// pull it back with tcgen05.ld and apply the fused epilogue (bias / residual add / SiLU*up / GELU / dtype cast) straight into
+// global memory, or park a partial tile for the tile's last contributor to sum in a fixed order (see gemm.cu).
 //
 // Replaces the cuBLAS GEMMs Candle launches for every `Linear` on the reference's GPU path and the
 // f32 gemm on its CPU path (crane-core/src/models/qwen3/modeling.rs:318-329,532,608-642;
@@ -42,5 +42,7 @@ struct TmaEncoder;  // host: resolves cuTensorMapEncodeTiled once
 // `A_lo` (nullable): low-order plane of a split-precision activation operand, same shape/stride as A (see gemm.cu).
 int gemm_bf16_launch(cudaStream_t stream, const bf16* A, const bf16* A_lo, int lda, const bf16* W, int M, int N, int K,
                      const GemmEpi& epi, bool use_simt);
+// Frees the stream-K scratch (partial tiles, arrival counters) kept for `stream`; call before destroying the stream.
+void gemm_release_stream(cudaStream_t stream);
 
 }  // namespace cb

@@ -240,6 +240,14 @@ CRANE_B200_API int crane_b200_tts_generate(crane_b200_model* m, size_t max_frame
 CRANE_B200_API int crane_b200_last_timing(const crane_b200_model* m, float* prefill_ms, float* decode_ms, size_t* decode_steps);
 /* Kernels launched by this handle since creation (graph replays count their nodes). */
 CRANE_B200_API uint64_t crane_b200_kernel_launches(const crane_b200_model* m);
+/* Forward-pass profiling, the counterpart of crane-core/src/ops/prof.rs:1-61,99-197: `CRANE_PROF=1` in the environment (summary
+ * line on stderr every `CRANE_PROF_EVERY` passes, default 64) or this switch.  Every pass is timed twice on the host (`enqueue`:
+ * last launch submitted, `wall`: after a stream sync) and split into the reference's stage names (embed norm attn gdn mlp resid
+ * head | proj conv qkv recur finish | prep launch post) with DEVICE time from cudaEvents beside the host submission time.
+ * prof_report writes the running totals as JSON ({"decode": {...}, "prefill": {...}}, per pass); *needed = bytes incl. the NUL.
+ * A profiled pass syncs and loses kernel overlap: never quote its times as benchmark numbers. */
+CRANE_B200_API int crane_b200_prof_enable(crane_b200_model* m, int on);
+CRANE_B200_API int crane_b200_prof_report(const crane_b200_model* m, char* buf, size_t cap, size_t* needed);
 /* Which decode path single-sequence greedy decode takes after finalize: 1 = the persistent kernel (one launch for n steps),
  * 0 = the kernel chain (one graph replay per step: hybrid / quantised / TTS models, batched sequences, borrowed streams). */
 CRANE_B200_API int crane_b200_decode_path(const crane_b200_model* m);

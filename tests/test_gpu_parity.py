@@ -86,6 +86,33 @@ def test_gemm_epilogues(simt):
         assert rel_err(out, torch.nn.functional.gelu(x, approximate=approx).numpy()) < 5e-3
 
 
+@pytest.mark.parametrize("shape", [(454, 2048, 6144), (784, 1024, 4096), (454, 12288, 2048), (300, 1184, 512), (1, 2048, 64), (2000, 4096, 1024)],
+                         ids=["down", "vit-fc2", "gate-up", "ragged-n", "one-row-one-kstep", "multi-wave"])
+def test_gemm_stream_k_full_width(shape):
+    """The persistent stream-K schedule at the widths of the BASELINE models: tiles shared by 2..5 CTAs (partials parked and summed
+    in contributor order), CTAs spanning several tiles (double-buffered accumulator), a ragged last column tile, every fused
+    epilogue -- against float64, and bitwise equal from run to run."""
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((M, K), dtype=np.float32)
+    hi_bits, hi = _bf16(a)
+    lo_bits, lo = _bf16(a - hi)
+    w_bits, w = _bf16(rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K))
+    ref = a.astype(np.float64) @ w.astype(np.float64).T
+    init = rng.standard_normal((M, N)).astype(np.float32)
+    o1 = crane_b200.op_gemm(hi_bits, w_bits, crane_b200.EPI_RESID_F32, out_init=init, a_lo_bits=lo_bits)
+    o2 = crane_b200.op_gemm(hi_bits, w_bits, crane_b200.EPI_RESID_F32, out_init=init, a_lo_bits=lo_bits)
+    e = rel_err(o1, init + ref)
+    print(f"stream-k {shape}: split resid rel {e:.2e}")
+    assert e < 3e-5 and np.array_equal(o1, o2)
+    plain = hi.astype(np.float64) @ w.astype(np.float64).T
+    assert rel_err(crane_b200.op_gemm(hi_bits, w_bits, crane_b200.EPI_STORE_F32), plain) < 1e-5
+    if N % 64 == 0:
+        g, u = ref[:, 0::2], ref[:, 1::2]
+        out = synth.bf16_bits_to_f32(crane_b200.op_gemm(hi_bits, w_bits, crane_b200.EPI_SILU_MUL_BF16, a_lo_bits=lo_bits))
+        assert out.shape == (M, N // 2) and rel_err(out, g / (1 + np.exp(-g)) * u) < 5e-3
+
+
 # (gemm kernel, precision mode): the default engine twice (debug SIMT GEMM / tcgen05 GEMM) + the plain-bf16 fast mode
 MODES = [("simt", "split"), ("tcgen05", "split"), ("tcgen05", "bf16")]
 MODE_IDS = ["simt-split", "tcgen05-split", "tcgen05-bf16"]
@@ -777,4 +804,31 @@ def test_sampling_through_the_model_handle():
         pr = params[i]
         assert int(got[i]) == smp.sample(raw, pr["temperature"], pr.get("top_p"), pr.get("top_k"), uniforms=pr.get("uniforms"))[0], f"seq {i}"
         m2.close()
+    m.close()
+
+
+def test_pass_profiler_spans_partition_the_pass():
+    """crane_b200_prof_enable / prof_report (ops/prof.rs:37-61): enqueue <= wall, the stage spans carry device time, their sum is
+    the pass's device time, and profiling does not change results."""
+    cfg = synth.TINY_QWEN3_VL
+    m, w = _model(cfg, cls=crane_b200.Qwen3VLModel)
+    image = synth.synth_image(96, 64, "prof")
+    pv, grid = synth.patchify(image)
+    ids = synth.build_vl_prompt(cfg, 30, grid, "prof")
+    ref = m.forward(ids, pv, [grid], 0).copy()
+    m.clear_kv_cache()
+    m.prof_enable(True)
+    got = m.forward(ids, pv, [grid], 0)
+    toks = m.decode_greedy(int(np.argmax(got)), len(ids), 5)
+    rep = m.prof_report()
+    m.prof_enable(False)
+    assert np.array_equal(got, ref) and len(toks) == 5
+    pre, dec = rep["prefill"], rep["decode"]
+    assert pre["passes"] == 1 and pre["tokens"] == len(ids) and dec["passes"] == 5
+    assert 0 < pre["enqueue_ms"] <= pre["wall_ms"] and pre["device_ms"] > 0
+    for name in ("embed", "norm", "attn.qkv", "attn.rope", "attn.flash", "attn.o", "mlp.gate_up", "mlp.down", "head", "vit.patch", "vit.qkv",
+                 "vit.flash", "vit.fc1", "vit.merger"):
+        assert pre["spans"][name]["device_ms"] > 0, name
+    assert abs(sum(v["device_ms"] for v in pre["spans"].values()) - pre["device_ms"]) < 1e-3 * pre["device_ms"] + 1e-3
+    assert dec["spans"]["decode"]["device_ms"] > 0
     m.close()
