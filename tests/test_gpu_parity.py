@@ -369,6 +369,85 @@ def test_qwen3_5_chunked_prefill_state_handoff_and_decode(equal_heads):
     m.close()
 
 
+# ---- full-width geometries of the BASELINE models (few layers, small vocabulary: seconds on the CPU oracle) -----------------------
+
+WIDE_QWEN3_8B = dict(synth.QWEN3_8B, num_hidden_layers=2, vocab_size=4096, max_position_embeddings=4096)
+WIDE_QWEN3_5 = dict(synth.QWEN3_5_0_8B, num_hidden_layers=4, vocab_size=4096, max_position_embeddings=4096)
+WIDE_QWEN3_VL = dict(synth.QWEN3_VL_2B, image_token_id=4001, vision_start_token_id=4002, vision_end_token_id=4003,
+                     text_config=dict(synth.QWEN3_VL_2B["text_config"], num_hidden_layers=2, vocab_size=4096, max_position_embeddings=4096),
+                     vision_config=dict(synth.QWEN3_VL_2B["vision_config"], depth=2, deepstack_visual_indexes=[0, 1]))
+
+
+@pytest.mark.parametrize("persistent", [True, False], ids=["persistent-mlp6144", "chain"])
+def test_full_width_qwen3_8b_geometry(persistent):
+    """Qwen3-8B's layer at full width (hidden 4096, 32 query heads over 8 KV heads = 4 per group, head_dim 128, MLP 12288), two
+    layers: prefill across several KV pages, then decode steps through the kernel chain (attention kernel instance NREP = 4,
+    D = 128; the persistent kernel has no 24-slice column split for K = 12288 and declines the shape).  The persistent kernel
+    runs the same attention geometry with the MLP at 6144."""
+    cfg = dict(WIDE_QWEN3_8B, intermediate_size=6144) if persistent else WIDE_QWEN3_8B
+    m, w = _model(cfg)
+    assert m.decode_path() == ("persistent" if persistent else "chain")
+    orc = Qwen3Oracle(cfg, w)
+    ids = synth.synth_token_ids(200, cfg["vocab_size"], "wide8b")
+    ref = orc.forward(ids, 0).numpy()
+    e0 = rel_err(m.forward_step(ids, 0), ref)
+    errs, tok, toks = [], int(np.argmax(ref)), []
+    for i in range(6):
+        ref = orc.forward([tok], len(ids) + i).numpy()
+        errs.append(rel_err(m.forward_step([tok], len(ids) + i), ref))
+        tok = int(np.argmax(ref))
+        toks.append(tok)
+    print(f"Qwen3-8B geometry x2 layers ({'persistent' if persistent else 'chain'}): prefill rel {e0:.2e}, decode rel max {max(errs):.2e}")
+    assert e0 < PREFILL_TOL and max(errs) < DECODE_TOL
+    m.clear_kv_cache()
+    assert [int(t) for t in m.generate(ids, max_new_tokens=7)][1:] == toks
+    m.close()
+
+
+def test_full_width_qwen3_5_geometry():
+    """Qwen3.5-0.8B's layers at full width: 16 + 16 linear-attention heads of 128 (nk == nv: the fused GDN decode kernel), gated
+    attention with head_dim 256 and 4 query heads per KV head (attention kernel instance NREP = 4, D = 256), partial rotary 0.25."""
+    from oracle.qwen3_5 import Qwen3_5Oracle
+    cfg = WIDE_QWEN3_5
+    m, w = _model(cfg, cls=crane_b200.Qwen3_5Model)
+    orc = Qwen3_5Oracle(cfg, w)
+    ids = synth.synth_token_ids(150, cfg["vocab_size"], "wide35")
+    ref = orc.forward(ids, 0).numpy()
+    e0 = rel_err(m.forward_step(ids, 0), ref)
+    errs, tok = [], int(np.argmax(ref))
+    for i in range(6):
+        ref = orc.forward([tok], len(ids) + i).numpy()
+        errs.append(rel_err(m.forward_step([tok], len(ids) + i), ref))
+        tok = int(np.argmax(ref))
+    print(f"Qwen3.5-0.8B geometry x4 layers: prefill rel {e0:.2e}, decode rel max {max(errs):.2e}")
+    assert e0 < PREFILL_TOL and max(errs) < DECODE_TOL
+    m.close()
+
+
+def test_full_width_vit_784_patches():
+    """The headline request's vision side at full width: one 448 x 448 image = 784 patches of 1536 values through a ViT of width 1024
+    (16 heads of 64, MLP 4096, two blocks, both feeding DeepStack mergers), 196 image tokens spliced into a text model of width 2048."""
+    cfg = WIDE_QWEN3_VL
+    m, w = _model(cfg, cls=crane_b200.Qwen3VLModel)
+    image = synth.synth_image(448, 448, "wide-vit")
+    pv, grid = synth.patchify(image)
+    assert pv.shape[0] == 784
+    ids = synth.build_vl_prompt(cfg, 40, grid, "wide-vit")
+    orc = Qwen3VLOracle(cfg, w)
+    with torch.no_grad():
+        ref_img, ref_ds = orc.vision.forward(torch.from_numpy(pv), [grid])
+    got_img, got_ds = m.encode_images(pv, [grid], want_deepstack=2)
+    e_img = rel_err(got_img, ref_img.numpy())
+    e_ds = max(rel_err(g, r.numpy()) for g, r in zip(got_ds, ref_ds))
+    ref = orc.prefill(ids, pv, [grid]).numpy()
+    e0 = rel_err(m.forward(ids, pv, [grid], 0), ref)
+    tok = int(np.argmax(ref))
+    e1 = rel_err(m.decode_step(tok, len(ids)), orc.decode_step(tok, len(ids)).numpy())
+    print(f"784-patch ViT: image embeddings rel {e_img:.2e}, deepstack rel {e_ds:.2e}; prefill logits rel {e0:.2e}, decode rel {e1:.2e}")
+    assert max(e_img, e_ds) < 1e-3 and e0 < PREFILL_TOL and e1 < DECODE_TOL
+    m.close()
+
+
 # ---- GGUF-quantised linears (config 4 path): Q4_K / Q6_K / Q8_0 bytes streamed by the decode GEMV, dequantised for prefill ----
 
 def _quantised_model(cfg, recipe, gemm="tcgen05", **opts):
