@@ -84,6 +84,7 @@ _SIGNATURES = {
     "crane_b200_generate_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
                                              C.c_void_p, C.POINTER(C.c_size_t)]),
     "crane_b200_seq_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "crane_b200_seq_fork": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "crane_b200_seq_free": (C.c_int, [C.c_void_p, C.c_int]),
     "crane_b200_seq_select": (C.c_int, [C.c_void_p, C.c_int]),
     "crane_b200_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
@@ -267,6 +268,12 @@ class Engine:
     def seq_create(self) -> int:
         s = C.c_int()
         self._ck(self.lib.crane_b200_seq_create(self.h, C.byref(s)))
+        return int(s.value)
+
+    def seq_fork(self, src: int) -> int:
+        """A new sequence that starts as a copy of `src` (KV pages, GDN state, length, rotary position)."""
+        s = C.c_int()
+        self._ck(self.lib.crane_b200_seq_fork(self.h, src, C.byref(s)))
         return int(s.value)
 
     def seq_free(self, seq: int):

@@ -404,7 +404,10 @@ attn_decode_kernel(AttnDecArgs a) {
 
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kvh = blockIdx.x / ATTN_NSPLIT, split = blockIdx.x % ATTN_NSPLIT;
+    // a KV head whose query group is wider than NREP is served by `groups` CTA clusters of NREP query heads each (6 = 2 x 3,
+    // 8 = 2 x 4, ...): kvv numbers those sub-groups, query head = kvv * NREP + h; only sub-group 0 appends the new K/V row
+    const int kvv = blockIdx.x / ATTN_NSPLIT, split = blockIdx.x % ATTN_NSPLIT;
+    const int kvh = kvv / a.groups, sub = kvv % a.groups;
     const int b = blockIdx.y;
     const int q_dim = a.nh * D, kv_dim = a.nkv * D;
     const int q_span = a.nh * a.q_stride;
@@ -468,7 +471,7 @@ attn_decode_kernel(AttnDecArgs a) {
     for (int vec = warp; vec < NREP + 1; vec += NW) {      // NW > NREP: one vector per warp, vec == warp
         const bool is_k = (vec == NREP);
         if (is_k && split != s_last) continue;
-        const float* src = is_k ? (qkv + q_span + kvh * D) : (qkv + (kvh * NREP + vec) * a.q_stride);
+        const float* src = is_k ? (qkv + q_span + kvh * D) : (qkv + (kvv * NREP + vec) * a.q_stride);
         float e[NE];
         float ssq = 0.f;
 #pragma unroll
@@ -497,7 +500,7 @@ attn_decode_kernel(AttnDecArgs a) {
         for (int i = lane; i < D; i += 32) vnew_s[i] = split_kv ? round_bf16_split(vsrc[i]) : round_bf16(vsrc[i]);
     }
     __syncthreads();
-    if (split == s_last) {   // append the new token to its page
+    if (split == s_last && sub == 0) {   // append the new token to its page
         const int t = T - 1;
         const int page = bt[t / KV_PAGE];
         const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
@@ -654,7 +657,7 @@ attn_decode_kernel(AttnDecArgs a) {
             L += rml[h * 2 + 1] * c;
             O += ro[h * D + i] * c;
         }
-        const int head = kvh * NREP + h;
+        const int head = kvv * NREP + h;
         float r = O / L;
         if (a.gated) r *= 1.0f / (1.0f + expf(-qkv[head * a.q_stride + D + i]));   // y * sigmoid(gate), modeling.rs:516-523
         a.out[(size_t)b * q_dim + head * D + i] = r;
@@ -668,7 +671,7 @@ static int attn_decode_launch_t(cudaStream_t st, int B, const AttnDecArgs& a, bo
     static SmemOptIn seen;
     if (const int e = ensure_dyn_smem(attn_decode_kernel<D, NREP>, (size_t)SMEM, seen)) return e;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(a.nkv * ATTN_NSPLIT, B);
+    cfg.gridDim = dim3(a.nkv * a.groups * ATTN_NSPLIT, B);
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
@@ -682,19 +685,26 @@ static int attn_decode_launch_t(cudaStream_t st, int B, const AttnDecArgs& a, bo
     return (int)cudaLaunchKernelEx(&cfg, attn_decode_kernel<D, NREP>, a);
 }
 
-int attn_decode_launch(cudaStream_t st, int B, int D, const AttnDecArgs& a, bool pdl) {
+int attn_decode_launch(cudaStream_t st, int B, int D, const AttnDecArgs& a_in, bool pdl) {
+    AttnDecArgs a = a_in;
+    if (a.nkv <= 0 || a.nh <= 0 || a.nh % a.nkv) return -1000;
     const int nrep = a.nh / a.nkv;
     if (a.rot_half < 32 || (a.rot_half % 32) != 0 || 2 * a.rot_half > D) return -1000;
+    // any group width: the widest instantiated sub-group (4, 3, 2, 1 query heads) that divides it
+    const int sub = nrep % 4 == 0 ? 4 : nrep % 3 == 0 ? 3 : nrep % 2 == 0 ? 2 : 1;
+    a.groups = nrep / sub;
     if (D == 128) {
-        switch (nrep) {
+        switch (sub) {
             case 1: return attn_decode_launch_t<128, 1>(st, B, a, pdl);
             case 2: return attn_decode_launch_t<128, 2>(st, B, a, pdl);
+            case 3: return attn_decode_launch_t<128, 3>(st, B, a, pdl);
             case 4: return attn_decode_launch_t<128, 4>(st, B, a, pdl);
         }
     } else if (D == 256) {
-        switch (nrep) {
+        switch (sub) {
             case 1: return attn_decode_launch_t<256, 1>(st, B, a, pdl);
             case 2: return attn_decode_launch_t<256, 2>(st, B, a, pdl);
+            case 3: return attn_decode_launch_t<256, 3>(st, B, a, pdl);
             case 4: return attn_decode_launch_t<256, 4>(st, B, a, pdl);
         }
     }

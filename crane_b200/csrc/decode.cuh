@@ -78,6 +78,7 @@ struct AttnDecArgs {
     float scale;
     float* out;              // [B, nh*D] f32
     long long kv_lo_off;     // split precision: element offset of the pools' low-order planes (0 = plain bf16 pages)
+    int groups = 1;          // set by attn_decode_launch: CTA clusters per KV head (query group width / kernel sub-group width)
 };
 
 int gemv_max_group(int K, int N, int num_sms);

@@ -115,7 +115,8 @@ struct LayerW {
     bool full = true;                       // softmax-attention layer (else GDN)
     bf16 *w_in = nullptr, *w_out = nullptr; // [in_pad, H] rows = q|k|v|z|b|a ; [H, value_dim]
     float *conv_w = nullptr, *neg_exp_a = nullptr, *dt_bias = nullptr, *gnorm = nullptr;
-    float *conv_state = nullptr, *rec_state = nullptr;
+    float *conv_state = nullptr, *rec_state = nullptr;   // working state of the CURRENT sequence slot
+    float *conv_slots = nullptr, *rec_slots = nullptr;   // [max_batch] parked states (max_batch > 1): swapped in by select_seq
 };
 struct VitBlockW {
     float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
@@ -281,12 +282,9 @@ struct crane_b200_model {
     std::vector<size_t> seq_kv;
     std::vector<uint32_t> seq_pos;
     std::vector<char> seq_used;
-    void select_seq(int s) {
-        if (s == cur) return;
-        seq_kv[cur] = kv_len; seq_pos[cur] = next_mrope_pos;
-        cur = s;
-        kv_len = seq_kv[s]; next_mrope_pos = seq_pos[s];
-    }
+    void select_seq(int s);               // parks the current slot's view (and GDN state) and brings slot s in
+    void park_gdn_state(int slot);         // working recurrent / conv state -> the slot's store (hybrid models)
+    void fork_seq(int src, int dst);
     const int* bt_cur() const { return block_table + (size_t)cur * max_pages; }
     cudaGraphExec_t graph_step[2] = {nullptr, nullptr};   // [advance]
     bool graph_failed = false;
@@ -483,7 +481,6 @@ void crane_b200_model::parse_config(const char* json) {
     if (max_batch < 1 || max_batch > 64) fail(CRANE_B200_INVALID_ARG, "max_batch %d (1..64 sequence slots)", max_batch);
     max_seq = (max_seq + KV_PAGE - 1) / KV_PAGE * KV_PAGE;
     max_pages = max_seq / KV_PAGE;
-    if (hybrid && max_batch != 1) fail(CRANE_B200_UNSUPPORTED, "the Qwen3.5 hybrid keeps one recurrent state: max_batch must be 1");
     if (is_vl) {
         const cbjson::Value& vc = root.at("vision_config");
         v_depth = (int)vc.integer("depth");
@@ -945,6 +942,12 @@ void crane_b200_model::finalize() {
         } else {   // GdnLayerCache (ops/gdn/cache.rs:15-45): conv window + [Hv, K, V] f32 state, zero-initialised
             l.conv_state = dalloc<float>((size_t)conv_dim() * ck);
             l.rec_state = dalloc<float>((size_t)nv * dk * dv);
+            if (max_batch > 1) {   // one parked copy per sequence slot (the reference keeps a GdnLayerCache per sequence, cache.rs:15-45)
+                l.conv_slots = dalloc<float>((size_t)max_batch * conv_dim() * ck);
+                l.rec_slots = dalloc<float>((size_t)max_batch * nv * dk * dv);
+                CUDA_OK(cudaMemset(l.conv_slots, 0, (size_t)max_batch * conv_dim() * ck * sizeof(float)));
+                CUDA_OK(cudaMemset(l.rec_slots, 0, (size_t)max_batch * nv * dk * dv * sizeof(float)));
+            }
         }
     }
     if (hybrid) {
@@ -1105,6 +1108,57 @@ void crane_b200_model::gdn_args(GdnArgs& g, const LayerW& l, int S, const float*
     g.proj = proj; g.ldp = gdn_in_pad; g.S = S; g.nk = nk; g.nv = nv; g.dk = dk; g.dv = dv; g.ck = ck;
     g.conv_w = l.conv_w; g.conv_state = l.conv_state; g.neg_exp_a = l.neg_exp_a; g.dt_bias = l.dt_bias; g.norm_w = l.gnorm; g.eps = eps;
     g.rec_state = l.rec_state; g.conv_out = conv; g.qn = qn; g.kn = kn; g.gb = gb; g.y = y;
+}
+
+void crane_b200_model::park_gdn_state(int slot) {
+    if (!hybrid || max_batch <= 1) return;
+    const size_t cs = (size_t)conv_dim() * ck, rs = (size_t)nv * dk * dv;
+    for (auto& l : layers)
+        if (!l.full) {
+            CUDA_OK(cudaMemcpyAsync(l.conv_slots + slot * cs, l.conv_state, cs * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+            CUDA_OK(cudaMemcpyAsync(l.rec_slots + slot * rs, l.rec_state, rs * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        }
+}
+
+void crane_b200_model::select_seq(int s) {
+    if (s == cur) return;
+    seq_kv[cur] = kv_len; seq_pos[cur] = next_mrope_pos;
+    park_gdn_state(cur);
+    cur = s;
+    kv_len = seq_kv[s]; next_mrope_pos = seq_pos[s];
+    if (hybrid && max_batch > 1) {
+        const size_t cs = (size_t)conv_dim() * ck, rs = (size_t)nv * dk * dv;
+        for (auto& l : layers)
+            if (!l.full) {
+                CUDA_OK(cudaMemcpyAsync(l.conv_state, l.conv_slots + s * cs, cs * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+                CUDA_OK(cudaMemcpyAsync(l.rec_state, l.rec_slots + s * rs, rs * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+            }
+    }
+}
+
+// dst becomes a copy of src: the used KV pages of every attention layer (both precision planes) and the parked GDN state.
+// Pages are statically owned by their slot, so a fork copies bytes; it is O(context), device to device, on the engine stream.
+void crane_b200_model::fork_seq(int src, int dst) {
+    seq_kv[cur] = kv_len; seq_pos[cur] = next_mrope_pos;
+    if (src == cur) park_gdn_state(cur);
+    const size_t len = seq_kv[src];
+    const size_t pages = (len + KV_PAGE - 1) / KV_PAGE;
+    const size_t page_elems = (size_t)nkv * KV_PAGE * D;
+    const size_t so = (size_t)src * max_pages * page_elems, dofs = (size_t)dst * max_pages * page_elems, n = pages * page_elems;
+    const size_t cs = hybrid ? (size_t)conv_dim() * ck : 0, rs = hybrid ? (size_t)nv * dk * dv : 0;
+    for (auto& l : layers) {
+        if (l.full) {
+            if (!n) continue;
+            for (bf16* pool : {l.k_pool, l.v_pool}) {
+                CUDA_OK(cudaMemcpyAsync(pool + dofs, pool + so, n * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
+                if (lo_kv) CUDA_OK(cudaMemcpyAsync(pool + lo_kv + dofs, pool + lo_kv + so, n * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
+            }
+        } else if (max_batch > 1) {
+            CUDA_OK(cudaMemcpyAsync(l.conv_slots + dst * cs, l.conv_slots + src * cs, cs * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+            CUDA_OK(cudaMemcpyAsync(l.rec_slots + dst * rs, l.rec_slots + src * rs, rs * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    seq_kv[dst] = len; seq_pos[dst] = seq_pos[src];
 }
 
 void crane_b200_model::reset_recurrent_state() {
@@ -1923,6 +1977,29 @@ int crane_b200_seq_create(crane_b200_model* m, int* seq_out) {
     m->seq_used[s] = 1;
     m->seq_kv[s] = 0; m->seq_pos[s] = 0;
     if (s == m->cur) { m->kv_len = 0; m->next_mrope_pos = 0; }
+    if (m->hybrid && m->max_batch > 1) {
+        const size_t cs = (size_t)m->conv_dim() * m->ck, rs = (size_t)m->nv * m->dk * m->dv;
+        for (auto& l : m->layers)
+            if (!l.full) {
+                CUDA_OK(cudaMemsetAsync(l.conv_slots + s * cs, 0, cs * sizeof(float), m->stream));
+                CUDA_OK(cudaMemsetAsync(l.rec_slots + s * rs, 0, rs * sizeof(float), m->stream));
+            }
+    }
+    *seq_out = s;
+    API_END(m)
+}
+
+int crane_b200_seq_fork(crane_b200_model* m, int src, int* seq_out) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (!seq_out) fail(CRANE_B200_INVALID_ARG, "seq_fork: null output");
+    if (src < 0 || src >= m->max_batch || !m->seq_used[src]) fail(CRANE_B200_INVALID_ARG, "seq_fork: bad sequence %d", src);
+    int s = -1;
+    for (int i = 0; i < m->max_batch; ++i)
+        if (!m->seq_used[i]) { s = i; break; }
+    if (s < 0) fail(CRANE_B200_OOM, "all %d sequence slots are in use (engine.max_batch)", m->max_batch);
+    m->seq_used[s] = 1;
+    m->fork_seq(src, s);
     *seq_out = s;
     API_END(m)
 }

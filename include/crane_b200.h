@@ -155,6 +155,10 @@ CRANE_B200_API int crane_b200_generate_greedy(crane_b200_model* m, const uint32_
  * above).  `seq_select` makes a slot current: forward_step / forward_embeds / clear_kv_cache / kv_len then act on it -- the
  * handle-level counterpart of the engine's per-Sequence swap-in (`set_kv_caches`, crane-serve/src/engine/mod.rs:1172). */
 CRANE_B200_API int crane_b200_seq_create(crane_b200_model* m, int* seq_out);
+/* A new sequence that starts as a copy of `src` (KV pages of every attention layer, the Gated-Delta-Net conv / recurrent state of
+ * a hybrid model, cached length and rotary position): prefix sharing for the server's scheduler, what the reference does by cloning
+ * its per-sequence caches (backend.rs:65-84 get_kv_caches / set_kv_caches).  Device-to-device, O(context), on the engine stream. */
+CRANE_B200_API int crane_b200_seq_fork(crane_b200_model* m, int src, int* seq_out);
 CRANE_B200_API int crane_b200_seq_free(crane_b200_model* m, int seq);
 CRANE_B200_API int crane_b200_seq_select(crane_b200_model* m, int seq);
 /* `n_steps` greedy decode rounds for `n` sequences at once: replaces setup_batch_decode + step_batch_decode x rounds +

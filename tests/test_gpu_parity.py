@@ -369,6 +369,26 @@ def test_qwen3_5_chunked_prefill_state_handoff_and_decode(equal_heads):
     m.close()
 
 
+@pytest.mark.parametrize("nh,nkv", [(6, 2), (12, 2), (16, 2), (10, 2), (24, 4)], ids=["nrep3", "nrep6", "nrep8", "nrep5", "nrep6-24over4"])
+def test_decode_attention_any_group_width(nh, nkv):
+    """Query groups wider than the attention kernel's sub-group (4 heads) are served by several CTA clusters per KV head: 6 = 2 x 3,
+    8 = 2 x 4, 5 = 5 x 1 -- the north star's "4 KV heads broadcast to 24 Q heads" is the last case."""
+    cfg = dict(synth.TINY_QWEN3, num_attention_heads=nh, num_key_value_heads=nkv, num_hidden_layers=2)
+    m, w = _model(cfg, persistent=False)
+    orc = Qwen3Oracle(cfg, w)
+    ids = synth.synth_token_ids(70, cfg["vocab_size"], f"nrep{nh}")
+    ref = orc.forward(ids, 0).numpy()
+    e0 = rel_err(m.forward_step(ids, 0), ref)
+    errs, tok = [], int(np.argmax(ref))
+    for i in range(5):
+        ref = orc.forward([tok], len(ids) + i).numpy()
+        errs.append(rel_err(m.forward_step([tok], len(ids) + i), ref))
+        tok = int(np.argmax(ref))
+    print(f"nh={nh} nkv={nkv}: prefill rel {e0:.2e}, decode rel max {max(errs):.2e}")
+    assert e0 < PREFILL_TOL and max(errs) < DECODE_TOL
+    m.close()
+
+
 # ---- full-width geometries of the BASELINE models (few layers, small vocabulary: seconds on the CPU oracle) -----------------------
 
 WIDE_QWEN3_8B = dict(synth.QWEN3_8B, num_hidden_layers=2, vocab_size=4096, max_position_embeddings=4096)
@@ -656,6 +676,47 @@ def test_batched_decode_matches_per_sequence_decode(quant):
 
 
 # ---- Qwen3-TTS codec-LM frame loop (config 5): talker + 16-pass code predictor on the device ----------------------------------
+
+@pytest.mark.parametrize("kind", ["dense", "hybrid"])
+def test_seq_fork_shares_a_prefix_and_then_diverges(kind):
+    """crane_b200_seq_fork: the fork continues exactly like its source (KV pages; for the hybrid model also the parked Gated-Delta-Net
+    conv / recurrent state of every slot), and afterwards the two sequences do not see each other."""
+    if kind == "dense":
+        cfg, cls = synth.TINY_QWEN3, crane_b200.Qwen3Model
+        orc_cls = Qwen3Oracle
+    else:
+        from oracle.qwen3_5 import Qwen3_5Oracle as orc_cls
+        cfg, cls = synth.TINY_QWEN3_5, crane_b200.Qwen3_5Model
+    m, w = _model(cfg, cls=cls, max_batch=3)
+    orc = orc_cls(cfg, w)
+    ids = synth.synth_token_ids(75, cfg["vocab_size"], "fork")       # the prefix ends inside its second KV page
+    orc.forward(ids, 0)
+    m.forward_step(ids, 0)
+    f = m.seq_fork(0)
+    assert f == 1
+    a_tok, b_tok = [5, 17, 200], [9, 300, 4]
+    m.seq_select(f)
+    assert m.kv_len() == len(ids)
+    got_b = [m.forward_step([t], len(ids) + i).copy() for i, t in enumerate(b_tok)]
+    m.seq_select(0)
+    got_a = [m.forward_step([t], len(ids) + i).copy() for i, t in enumerate(a_tok)]
+    g = m.seq_fork(f)                                                 # fork of a fork, taken while another slot is current
+    m.seq_select(g)
+    got_b2 = m.forward_step([77], len(ids) + 3).copy()
+    ref_a = [orc.forward([t], len(ids) + i).numpy() for i, t in enumerate(a_tok)]
+    orc2 = orc_cls(cfg, w)
+    orc2.forward(ids, 0)
+    ref_b = [orc2.forward([t], len(ids) + i).numpy() for i, t in enumerate(b_tok)]
+    ref_b2 = orc2.forward([77], len(ids) + 3).numpy()
+    ea = max(rel_err(x, r) for x, r in zip(got_a, ref_a))
+    eb = max(rel_err(x, r) for x, r in zip(got_b, ref_b))
+    print(f"seq_fork {kind}: source rel {ea:.2e}, fork rel {eb:.2e}, fork-of-fork rel {rel_err(got_b2, ref_b2):.2e}")
+    assert max(ea, eb, rel_err(got_b2, ref_b2)) < DECODE_TOL
+    m.seq_free(f); m.seq_free(g)
+    with pytest.raises(crane_b200.CraneB200Error):
+        m.seq_fork(2)                                                 # not a live sequence
+    m.close()
+
 
 def test_tts_frame_loop_against_oracle():
     from oracle.qwen3_tts import Qwen3TTSOracle
