@@ -98,3 +98,22 @@ def test_every_entry_point_survives_null_arguments():
             assert r <= 0, f"{name}(NULL...) returned {r}"
         elif res in (ctypes.c_uint64, ctypes.c_size_t, ctypes.c_uint32):
             assert r == 0, f"{name}(NULL...) returned {r}"
+
+
+def test_rust_sys_crate_declares_every_entry_point():
+    """rust/crane-b200-sys/src/lib.rs is generated from include/crane_b200.h (tools/gen_rust_sys.py): regenerating reproduces the
+    committed file, and every symbol the header declares has exactly one `pub fn` there (no Rust toolchain in this image, so the
+    crate is checked textually)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"]).returncode == 0
+    hdr = open(os.path.join(root, "include", "crane_b200.h")).read()
+    rs = open(os.path.join(root, "rust", "crane-b200-sys", "src", "lib.rs")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = re.findall(r"CRANE_B200_API[^;(]*?\b(crane_b200_\w+)\s*\(", hdr)
+    assert len(names) >= 49 and len(set(names)) == len(names)
+    for n in names:
+        assert len(re.findall(r"pub fn " + n + r"\(", rs)) == 1, n
