@@ -88,6 +88,11 @@ _SIGNATURES = {
     "crane_b200_seq_free": (C.c_int, [C.c_void_p, C.c_int]),
     "crane_b200_seq_select": (C.c_int, [C.c_void_p, C.c_int]),
     "crane_b200_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "crane_b200_comm_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "crane_b200_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    "crane_b200_comm_world": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "crane_b200_decode_batch_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(Logits)]),
+    "crane_b200_copy_gathered_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "crane_b200_sample": (C.c_int, [C.c_void_p, C.POINTER(Sampling), C.POINTER(C.c_uint32)]),
     "crane_b200_forward_step_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(Sampling), C.POINTER(C.c_uint32)]),
     "crane_b200_decode_batch_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Sampling), C.c_void_p]),
@@ -114,6 +119,25 @@ _SIGNATURES = {
     "crane_b200_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int]),
 }
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and ships the 128 bytes to the other ranks)."""
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.crane_b200_comm_unique_id(buf, 128)
+    if rc != OK:
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
+def shard_sequences(n_total: int, world: int, rank: int):
+    """Sequence indices rank `rank` of `world` decodes: contiguous blocks, equal sizes (the all-gather needs the same n on every
+    rank, so n_total must divide by world -- the caller pads its batch with idle sequences otherwise)."""
+    if n_total % world:
+        raise ValueError(f"{n_total} sequences do not divide over {world} ranks")
+    per = n_total // world
+    return list(range(rank * per, (rank + 1) * per))
 
 
 def load_library():
@@ -269,6 +293,27 @@ class Engine:
         s = C.c_int()
         self._ck(self.lib.crane_b200_seq_create(self.h, C.byref(s)))
         return int(s.value)
+
+    # ---- multi-GPU: sequences sharded over ranks, NCCL all-gather of each round's results ----
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * len(unique_id)).from_buffer_copy(unique_id)
+        self._ck(self.lib.crane_b200_comm_init(self.h, buf, len(unique_id), rank, world))
+        self._world = world
+
+    def decode_batch_gather(self, seqs, tokens, want_logits: bool = False):
+        """One decode round of this rank's sequences, then the all-gather: (tokens [world * n], logits [world * n, V] or None)."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.int32)
+        tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
+        world = getattr(self, "_world", 1)
+        out = np.empty(world * seqs.size, dtype=np.uint32)
+        lg = Logits()
+        self._ck(self.lib.crane_b200_decode_batch_gather(self.h, _ptr(seqs), _ptr(tokens), seqs.size, _ptr(out), C.byref(lg) if want_logits else None))
+        if not want_logits:
+            return out, None
+        rows, V = int(lg.rows), int(lg.vocab)
+        host = np.empty((rows, V), dtype=np.float32)
+        self._ck(self.lib.crane_b200_copy_gathered_logits(self.h, _ptr(host), host.size))
+        return out, host
 
     def seq_fork(self, src: int) -> int:
         """A new sequence that starts as a copy of `src` (KV pages, GDN state, length, rotary position)."""

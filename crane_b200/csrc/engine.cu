@@ -153,6 +153,7 @@ struct crane_b200_model {
     std::vector<int> layer_is_full;
     int max_seq = 4096, max_batch = 1, max_pages = 0;
     bool use_simt = false, use_graphs = true, use_pdl = true, use_persistent = true;
+    struct crane_b200_comm* comm = nullptr;   // multi-GPU: NCCL communicator + gather buffers (engine_comm.inc)
     PassProfiler spans;                     // CRANE_PROF=1 / crane_b200_prof_enable: enqueue vs wall per pass + stage spans (ops/prof.rs)
     // persistent decode kernel (decode_ll.cu): exchange buffers of (value, tag) pairs, the tag counter, the timeout flag
     unsigned long long *ll_xa = nullptr, *ll_xb = nullptr, *ll_qkv = nullptr, *ll_att = nullptr, *ll_act = nullptr, *ll_part = nullptr, *ll_amax = nullptr;
@@ -286,14 +287,14 @@ struct crane_b200_model {
     void park_gdn_state(int slot);         // working recurrent / conv state -> the slot's store (hybrid models)
     void fork_seq(int src, int dst);
     const int* bt_cur() const { return block_table + (size_t)cur * max_pages; }
-    cudaGraphExec_t graph_step[2] = {nullptr, nullptr};   // [advance]
+    cudaGraphExec_t graph_step[2][5] = {};   // [advance][sequences in the group: 1, 2, 4]
     bool graph_failed = false;
     cudaEvent_t pev0 = nullptr, pev1 = nullptr, dev0 = nullptr, dev1 = nullptr;
     bool pev0_armed = false;
     float last_prefill_ms = 0.f, last_decode_ms = 0.f;
     size_t last_decode_steps = 0;
     uint64_t launches = 0;
-    uint64_t graph_launches[3] = {0, 0, 0};
+    uint64_t graph_launches[2][5] = {};
     unsigned char* xq_buf = nullptr;   // activations quantised for the quantised GEMVs (xquant_launch)
     int xq_mode_last = -1;
     // Split precision (default): every bf16 activation operand / KV page has a low-order plane (x = hi + lo) so the prefill
@@ -366,7 +367,7 @@ struct crane_b200_model {
     // forward paths
     void arm_state(uint32_t token, size_t start_pos, int p0, int p1, int p2);
     void enqueue_decode_step(int advance, bool with_embed, int B = 1);
-    void decode_step_graphed(int advance);
+    void decode_step_graphed(int advance, int B = 1);
     void decode_steps(int n_steps, int advance);
     void prefill(const uint32_t* ids, const float* embeds, size_t S, const uint32_t* pos3_host, size_t start_pos,
                  const int* vis_rows, int n_vis, int advance);
@@ -1181,28 +1182,29 @@ void crane_b200_model::lm_head_last_row(const float* xrow, int advance, int B) {
 }
 
 // One decode step (layers + lm_head), replayed from a CUDA graph when capture is available.
-void crane_b200_model::decode_step_graphed(int advance) {
-    if (use_graphs && !graph_failed && graph_step[advance] == nullptr) {
+void crane_b200_model::decode_step_graphed(int advance, int B) {
+    cudaGraphExec_t& ge = graph_step[advance][B];
+    if (use_graphs && !graph_failed && ge == nullptr) {
         cudaGraph_t g = nullptr;
         const uint64_t before = launches;
         cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
         bool ok = (e == cudaSuccess);
         if (ok) {
-            try { enqueue_decode_step(advance, false); } catch (const EngineError&) { ok = false; }
+            try { enqueue_decode_step(advance, false, B); } catch (const EngineError&) { ok = false; }
             e = cudaStreamEndCapture(stream, &g);
             ok = ok && e == cudaSuccess && g != nullptr;
         }
-        if (ok) ok = cudaGraphInstantiate(&graph_step[advance], g, 0) == cudaSuccess;
+        if (ok) ok = cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
         if (g) cudaGraphDestroy(g);
-        graph_launches[advance] = launches - before;     // kernels one replay stands for
+        graph_launches[advance][B] = launches - before;     // kernels one replay stands for
         launches = before;
-        if (!ok) { graph_failed = true; graph_step[advance] = nullptr; cudaGetLastError(); }
+        if (!ok) { graph_failed = true; ge = nullptr; cudaGetLastError(); }
     }
-    if (graph_step[advance]) {
-        CUDA_OK(cudaGraphLaunch(graph_step[advance], stream));
-        launches += graph_launches[advance];
+    if (ge) {
+        CUDA_OK(cudaGraphLaunch(ge, stream));
+        launches += graph_launches[advance][B];
     } else {
-        enqueue_decode_step(advance, false);
+        enqueue_decode_step(advance, false, B);
     }
 }
 
@@ -1649,12 +1651,15 @@ int crane_b200_create(const char* config_json, int device_ordinal, crane_b200_mo
     return CRANE_B200_OK;
 }
 
+static void comm_release(crane_b200_model* m);
+
 void crane_b200_destroy(crane_b200_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
+    comm_release(m);
     if (m->cp) { crane_b200_destroy(m->cp); m->cp = nullptr; }
-    for (auto& g : m->graph_step) if (g) cudaGraphExecDestroy(g);
+    for (auto& ga : m->graph_step) for (auto& g : ga) if (g) cudaGraphExecDestroy(g);
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_state_ring) cudaFreeHost(m->h_state_ring);
     for (cudaEvent_t e : m->h_state_ev) if (e) cudaEventDestroy(e);
@@ -2058,7 +2063,7 @@ int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t
         }
         m->push_state(B);
         m->embed_step_input(B);
-        for (size_t t = 0; t < n_steps; ++t) m->enqueue_decode_step(1, false, B);
+        for (size_t t = 0; t < n_steps; ++t) m->decode_step_graphed(1, B);
         for (int b = 0; b < B; ++b)
             CUDA_OK(cudaMemcpyAsync(tokens_out + (done + b) * n_steps, m->out_tokens + (size_t)b * m->out_cap, n_steps * sizeof(uint32_t),
                                     cudaMemcpyDeviceToHost, m->stream));
@@ -2141,7 +2146,7 @@ int crane_b200_decode_batch_sample(crane_b200_model* m, const int* seqs, const u
         }
         m->push_state(B);
         m->embed_step_input(B);
-        m->enqueue_decode_step(0, false, B);         // logits [B, V] stay on the device; the host picks the next inputs from the sampled ids
+        m->decode_step_graphed(0, B);                // logits [B, V] stay on the device; the host picks the next inputs from the sampled ids
         sampler_run(m->stream, m->sampler, m->logits, m->V, (size_t)B, params + done, tokens_out + done);
         for (int b = 0; b < B; ++b) {
             const int s = seqs[done + b];
@@ -2351,4 +2356,5 @@ int crane_b200_op_gemm(int device, const uint16_t* a, const uint16_t* a_lo, cons
 }  // extern "C"
 
 #include "engine_tts.inc"
+#include "engine_comm.inc"
 #include "engine_loaders.inc"

@@ -169,6 +169,23 @@ CRANE_B200_API int crane_b200_seq_select(crane_b200_model* m, int seq);
 CRANE_B200_API int crane_b200_decode_batch(crane_b200_model* m, const int* seqs, const uint32_t* tokens, size_t n, size_t n_steps,
                                            uint32_t* tokens_out, float* logits_host);
 
+/* ---- multi-GPU batch decode (BASELINE.json config 4: 32 sequences over 8 x B200) ----------------------------------------------
+ * One process and one handle per GPU, every rank holding the full weights and its share of the sequences; the only data-path
+ * exchange is the all-gather of each round's results (NCCL over NVLink, enqueued on the engine stream behind the lm_head).
+ * NCCL (libnccl.so.2) is bound at run time by the first of these calls; a single-GPU deployment never loads it.
+ *   rank 0: crane_b200_comm_unique_id(id, 128) -> ship the 128 bytes to the other ranks (the launcher's job: file, TCP store, MPI)
+ *   every rank: crane_b200_comm_init(h, id, 128, rank, world)            (collective: returns when all ranks have joined)
+ *   every round: crane_b200_decode_batch_gather(h, seqs, tokens, n, tokens_all, &logits_all)   (collective, the same n everywhere)
+ * tokens_all [world * n]: greedy token of every sequence of every rank, rank-major; logits_all (nullable): [world * n, V] f32 in
+ * device memory on every rank -- what `step_batch_decode` (crane-serve/src/engine/backend.rs:86-150) returns for the whole batch. */
+CRANE_B200_API int crane_b200_comm_unique_id(uint8_t* id_out, size_t capacity);
+CRANE_B200_API int crane_b200_comm_init(crane_b200_model* m, const uint8_t* id, size_t id_bytes, int rank, int world);
+CRANE_B200_API int crane_b200_comm_world(const crane_b200_model* m, int* rank_out, int* world_out);
+CRANE_B200_API int crane_b200_decode_batch_gather(crane_b200_model* m, const int* seqs, const uint32_t* tokens, size_t n,
+                                                  uint32_t* tokens_all_out, crane_b200_logits* logits_all);
+/* Host copy of the rows gathered by the last decode_batch_gather that asked for logits ([world * n, V] f32; tests, host samplers). */
+CRANE_B200_API int crane_b200_copy_gathered_logits(crane_b200_model* m, float* host_out, size_t n_floats);
+
 /* ---- device-side sampling (crane-serve/src/engine/sampling.rs:169-480) ------------------------------------------ */
 /* Per-sequence sampling request = the fields of `Sequence` that `sampling::sample` reads.  The draw needs uniforms in
  * (1e-7, 0.999) (`rand_like(1e-7, 0.999)`, sampling.rs:387): the reference takes them from candle's device RNG, whose stream no

@@ -73,6 +73,11 @@ extern "C" {
     pub fn crane_b200_seq_free(m: *mut crane_b200_model, seq: c_int) -> c_int;
     pub fn crane_b200_seq_select(m: *mut crane_b200_model, seq: c_int) -> c_int;
     pub fn crane_b200_decode_batch(m: *mut crane_b200_model, seqs: *const c_int, tokens: *const u32, n: usize, n_steps: usize, tokens_out: *mut u32, logits_host: *mut f32) -> c_int;
+    pub fn crane_b200_comm_unique_id(id_out: *mut u8, capacity: usize) -> c_int;
+    pub fn crane_b200_comm_init(m: *mut crane_b200_model, id: *const u8, id_bytes: usize, rank: c_int, world: c_int) -> c_int;
+    pub fn crane_b200_comm_world(m: *const crane_b200_model, rank_out: *mut c_int, world_out: *mut c_int) -> c_int;
+    pub fn crane_b200_decode_batch_gather(m: *mut crane_b200_model, seqs: *const c_int, tokens: *const u32, n: usize, tokens_all_out: *mut u32, logits_all: *mut crane_b200_logits) -> c_int;
+    pub fn crane_b200_copy_gathered_logits(m: *mut crane_b200_model, host_out: *mut f32, n_floats: usize) -> c_int;
     pub fn crane_b200_sample(m: *mut crane_b200_model, p: *const crane_b200_sampling, token_out: *mut u32) -> c_int;
     pub fn crane_b200_forward_step_sample(m: *mut crane_b200_model, input_ids: *const u32, n: usize, start_pos: usize, p: *const crane_b200_sampling, token_out: *mut u32) -> c_int;
     pub fn crane_b200_decode_batch_sample(m: *mut crane_b200_model, seqs: *const c_int, tokens: *const u32, n: usize, params: *const crane_b200_sampling, tokens_out: *mut u32) -> c_int;
