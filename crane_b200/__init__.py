@@ -84,6 +84,9 @@ _SIGNATURES = {
     "crane_b200_generate_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
                                              C.c_void_p, C.POINTER(C.c_size_t)]),
     "crane_b200_seq_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "crane_b200_kv_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "crane_b200_kv_import": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "crane_b200_kv_set_len": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32]),
     "crane_b200_seq_fork": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "crane_b200_seq_free": (C.c_int, [C.c_void_p, C.c_int]),
     "crane_b200_seq_select": (C.c_int, [C.c_void_p, C.c_int]),
@@ -314,6 +317,37 @@ class Engine:
         host = np.empty((rows, V), dtype=np.float32)
         self._ck(self.lib.crane_b200_copy_gathered_logits(self.h, _ptr(host), host.size))
         return out, host
+
+    # ---- KV swap: ModelBackend::get_kv_caches / set_kv_caches ----
+    def get_kv_caches(self):
+        """[(K, V)] per layer for the current sequence: attention layers [n_kv, T, D] f32; GDN layers (conv window, recurrent state)."""
+        from . import synth
+        tc = synth.text_config(self.config)
+        out = []
+        for layer in range(self.num_layers()):
+            n = C.c_size_t()
+            self._ck(self.lib.crane_b200_kv_export(self.h, layer, None, None, 0, C.byref(n)))
+            if "linear_num_value_heads" in tc and not synth.is_full_attention_layer(tc, layer):
+                conv_dim = 2 * tc["linear_num_key_heads"] * tc["linear_key_head_dim"] + tc["linear_num_value_heads"] * tc["linear_value_head_dim"]
+                k = np.empty((conv_dim, tc.get("linear_conv_kernel_dim", 4)), np.float32)
+                v = np.empty((tc["linear_num_value_heads"], tc["linear_key_head_dim"], tc["linear_value_head_dim"]), np.float32)
+                cap = max(k.size, v.size)
+            else:
+                nkv, D = tc["num_key_value_heads"], synth.head_dim(tc)
+                k = np.empty((nkv, n.value, D), np.float32)
+                v = np.empty_like(k)
+                cap = k.size
+            if cap:
+                self._ck(self.lib.crane_b200_kv_export(self.h, layer, _ptr(k), _ptr(v), cap, C.byref(n)))
+            out.append((k, v))
+        return out
+
+    def set_kv_caches(self, caches, n_tokens: int, next_rotary_pos: int = None):
+        for layer, (k, v) in enumerate(caches):
+            k = np.ascontiguousarray(k, dtype=np.float32)
+            v = np.ascontiguousarray(v, dtype=np.float32)
+            self._ck(self.lib.crane_b200_kv_import(self.h, layer, _ptr(k), _ptr(v), n_tokens))
+        self._ck(self.lib.crane_b200_kv_set_len(self.h, n_tokens, n_tokens if next_rotary_pos is None else next_rotary_pos))
 
     def seq_fork(self, src: int) -> int:
         """A new sequence that starts as a copy of `src` (KV pages, GDN state, length, rotary position)."""

@@ -1994,6 +1994,80 @@ int crane_b200_seq_create(crane_b200_model* m, int* seq_out) {
     API_END(m)
 }
 
+// ---- KV swap: get_kv_caches / set_kv_caches (backend.rs:65-84) of the CURRENT sequence, one layer at a time ----
+int crane_b200_kv_export(crane_b200_model* m, int layer, float* k_out, float* v_out, size_t capacity_floats, size_t* n_tokens) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (layer < 0 || layer >= m->L || !n_tokens) fail(CRANE_B200_INVALID_ARG, "kv_export: bad layer %d", layer);
+    LayerW& l = m->layers[layer];
+    const size_t T = m->kv_len;
+    if (!l.full) {   // Gated-Delta-Net layer: k_out = conv window [conv_dim, ck], v_out = recurrent state [nv, dk, dv]; *n_tokens = 0
+        const size_t cs = (size_t)m->conv_dim() * m->ck, rs = (size_t)m->nv * m->dk * m->dv;
+        *n_tokens = 0;
+        if (k_out || v_out) {
+            if (capacity_floats < std::max(cs, rs)) fail(CRANE_B200_INVALID_ARG, "kv_export: GDN layer needs %zu floats", std::max(cs, rs));
+            if (k_out) CUDA_OK(cudaMemcpyAsync(k_out, l.conv_state, cs * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+            if (v_out) CUDA_OK(cudaMemcpyAsync(v_out, l.rec_state, rs * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+        }
+    } else {
+        *n_tokens = T;
+        const size_t n = (size_t)m->nkv * T * m->D;
+        if ((k_out || v_out) && T) {
+            if (capacity_floats < n) fail(CRANE_B200_INVALID_ARG, "kv_export: layer holds %zu floats per tensor, capacity %zu", n, capacity_floats);
+            float* tmp = nullptr;
+            CUDA_OK(cudaMalloc((void**)&tmp, n * sizeof(float)));
+            for (int which = 0; which < 2; ++which) {
+                float* dst = which ? v_out : k_out;
+                if (!dst) continue;
+                const int r = kv_pages_to_rows_launch(m->stream, which ? l.v_pool : l.k_pool, m->lo_kv, m->bt_cur(), m->nkv, m->D, (int)T, tmp);
+                if (r) { cudaFree(tmp); fail(CRANE_B200_CUDA_ERROR, "kv_export kernel: %d", r); }
+                cudaMemcpyAsync(dst, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream);
+                cudaStreamSynchronize(m->stream);
+            }
+            cudaFree(tmp);
+        }
+    }
+    API_END(m)
+}
+
+int crane_b200_kv_import(crane_b200_model* m, int layer, const float* k, const float* v, size_t n_tokens) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (layer < 0 || layer >= m->L || !k || !v) fail(CRANE_B200_INVALID_ARG, "kv_import: bad arguments (layer %d)", layer);
+    LayerW& l = m->layers[layer];
+    if (!l.full) {
+        const size_t cs = (size_t)m->conv_dim() * m->ck, rs = (size_t)m->nv * m->dk * m->dv;
+        CUDA_OK(cudaMemcpyAsync(l.conv_state, k, cs * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        CUDA_OK(cudaMemcpyAsync(l.rec_state, v, rs * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    } else if (n_tokens) {
+        if (n_tokens > (size_t)m->max_seq) fail(CRANE_B200_OOM, "kv_import: %zu tokens exceed max_seq_len %d", n_tokens, m->max_seq);
+        const size_t n = (size_t)m->nkv * n_tokens * m->D;
+        float* tmp = nullptr;
+        CUDA_OK(cudaMalloc((void**)&tmp, n * sizeof(float)));
+        for (int which = 0; which < 2; ++which) {
+            cudaMemcpyAsync(tmp, which ? v : k, n * sizeof(float), cudaMemcpyHostToDevice, m->stream);
+            const int r = kv_rows_to_pages_launch(m->stream, which ? l.v_pool : l.k_pool, m->lo_kv, m->bt_cur(), m->nkv, m->D, (int)n_tokens, tmp);
+            cudaStreamSynchronize(m->stream);
+            if (r) { cudaFree(tmp); fail(CRANE_B200_CUDA_ERROR, "kv_import kernel: %d", r); }
+        }
+        cudaFree(tmp);
+    }
+    API_END(m)
+}
+
+// After importing every layer: the cached length and next rotary position of the current sequence (set_kv_caches leaves them to
+// the caller in the reference too -- `forward_step(.., start_pos)` carries them).
+int crane_b200_kv_set_len(crane_b200_model* m, size_t n_tokens, uint32_t next_rotary_pos) {
+    API_BEGIN(m)
+    need_ready(m);
+    if (n_tokens > (size_t)m->max_seq) fail(CRANE_B200_OOM, "kv_set_len: %zu exceeds max_seq_len %d", n_tokens, m->max_seq);
+    m->kv_len = n_tokens;
+    m->next_mrope_pos = next_rotary_pos;
+    API_END(m)
+}
+
 int crane_b200_seq_fork(crane_b200_model* m, int src, int* seq_out) {
     API_BEGIN(m)
     need_ready(m);

@@ -510,6 +510,40 @@ int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n,
     return launch_k(cast_f32_bf16_kernel, dim3(grid), dim3(256), 0, st, prefill_pdl(), src, dst, n4, lo_off);
 }
 
+// KV swap (ModelBackend::get_kv_caches / set_kv_caches, crane-serve/src/engine/backend.rs:65-84): one layer's pages of one sequence
+// <-> the reference's contiguous cache tensors [n_kv, T, D] (f32 here: the two bf16 planes of the split mode summed / re-split).
+__global__ void __launch_bounds__(128)
+kv_pages_to_rows_kernel(const bf16* __restrict__ pool, long long lo_off, const int* __restrict__ bt, int nkv, int D, int T, float* __restrict__ out) {
+    const int t = blockIdx.x, h = blockIdx.y;
+    const size_t off = (((size_t)bt[t / KV_PAGE] * nkv + h) * KV_PAGE + (t % KV_PAGE)) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        float v = __bfloat162float(pool[off + i]);
+        if (lo_off) v += __bfloat162float(pool[lo_off + off + i]);
+        out[((size_t)h * T + t) * D + i] = v;
+    }
+}
+__global__ void __launch_bounds__(128)
+kv_rows_to_pages_kernel(bf16* __restrict__ pool, long long lo_off, const int* __restrict__ bt, int nkv, int D, int T, const float* __restrict__ in) {
+    const int t = blockIdx.x, h = blockIdx.y;
+    const size_t off = (((size_t)bt[t / KV_PAGE] * nkv + h) * KV_PAGE + (t % KV_PAGE)) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float v = in[((size_t)h * T + t) * D + i];
+        const bf16 hi = __float2bfloat16_rn(v);
+        pool[off + i] = hi;
+        if (lo_off) pool[lo_off + off + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+int kv_pages_to_rows_launch(cudaStream_t st, const bf16* pool, long long lo_off, const int* bt, int nkv, int D, int T, float* out) {
+    if (T <= 0) return 0;
+    kv_pages_to_rows_kernel<<<dim3(T, nkv), 128, 0, st>>>(pool, lo_off, bt, nkv, D, T, out);
+    return (int)cudaGetLastError();
+}
+int kv_rows_to_pages_launch(cudaStream_t st, bf16* pool, long long lo_off, const int* bt, int nkv, int D, int T, const float* in) {
+    if (T <= 0) return 0;
+    kv_rows_to_pages_kernel<<<dim3(T, nkv), 128, 0, st>>>(pool, lo_off, bt, nkv, D, T, in);
+    return (int)cudaGetLastError();
+}
+
 // split-precision planes (hi [+ lo]) -> f32: the input of a quantised linear that follows a tensor-core kernel
 __global__ void __launch_bounds__(256)
 planes_to_f32_kernel(const bf16* __restrict__ src, long long lo_off, size_t n4, float* __restrict__ dst) {

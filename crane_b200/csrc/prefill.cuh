@@ -57,6 +57,8 @@ int gate_mul_launch(cudaStream_t st, bf16* attn, const float* qkv, int S, int nh
 int set_rows_launch(cudaStream_t st, float* x, int H, const int* rows, int n, const float* src, bool add);
 int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n, long long lo_off = 0);
 int planes_to_f32_launch(cudaStream_t st, const bf16* src, long long lo_off, size_t n, float* dst);
+int kv_pages_to_rows_launch(cudaStream_t st, const bf16* pool, long long lo_off, const int* bt, int nkv, int D, int T, float* out);
+int kv_rows_to_pages_launch(cudaStream_t st, bf16* pool, long long lo_off, const int* bt, int nkv, int D, int T, const float* in);
 int vit_pos_embed_add_launch(cudaStream_t st, float* x, int N, int Hv, const float* table, const int* idx4, const float* w4);
 int vit_rope_launch(cudaStream_t st, const float* qkv, int N, int nh, int hd, const float* cos, const float* sin, bf16* out, long long lo_off = 0);
 

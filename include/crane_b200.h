@@ -155,6 +155,14 @@ CRANE_B200_API int crane_b200_generate_greedy(crane_b200_model* m, const uint32_
  * above).  `seq_select` makes a slot current: forward_step / forward_embeds / clear_kv_cache / kv_len then act on it -- the
  * handle-level counterpart of the engine's per-Sequence swap-in (`set_kv_caches`, crane-serve/src/engine/mod.rs:1172). */
 CRANE_B200_API int crane_b200_seq_create(crane_b200_model* m, int* seq_out);
+/* KV swap, the legacy surface (ModelBackend::get_kv_caches / set_kv_caches, crane-serve/src/engine/backend.rs:65-84; per-layer
+ * `(Tensor, Tensor)` of shape [1, n_kv, T, d]): the CURRENT sequence's cache of one layer as contiguous host tensors [n_kv, T, D]
+ * f32.  export with k_out == v_out == NULL only reports *n_tokens.  For a Gated-Delta-Net layer of the hybrid model the pair is
+ * (conv window [conv_dim, 4], recurrent state [n_v, d_k, d_v]) (ops/gdn/cache.rs:15-55) and *n_tokens is 0.  After importing every
+ * layer, kv_set_len states the cached length and the next rotary position.  Synchronous; O(context) per call. */
+CRANE_B200_API int crane_b200_kv_export(crane_b200_model* m, int layer, float* k_out, float* v_out, size_t capacity_floats, size_t* n_tokens);
+CRANE_B200_API int crane_b200_kv_import(crane_b200_model* m, int layer, const float* k, const float* v, size_t n_tokens);
+CRANE_B200_API int crane_b200_kv_set_len(crane_b200_model* m, size_t n_tokens, uint32_t next_rotary_pos);
 /* A new sequence that starts as a copy of `src` (KV pages of every attention layer, the Gated-Delta-Net conv / recurrent state of
  * a hybrid model, cached length and rotary position): prefix sharing for the server's scheduler, what the reference does by cloning
  * its per-sequence caches (backend.rs:65-84 get_kv_caches / set_kv_caches).  Device-to-device, O(context), on the engine stream. */

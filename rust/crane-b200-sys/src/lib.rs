@@ -69,6 +69,9 @@ extern "C" {
     pub fn crane_b200_decode_greedy(m: *mut crane_b200_model, first_token: u32, start_pos: usize, n_steps: usize, eos_ids: *const u32, n_eos: usize, tokens_out: *mut u32, n_out: *mut usize) -> c_int;
     pub fn crane_b200_generate_greedy(m: *mut crane_b200_model, prompt: *const u32, n_prompt: usize, max_new_tokens: usize, eos_ids: *const u32, n_eos: usize, tokens_out: *mut u32, n_out: *mut usize) -> c_int;
     pub fn crane_b200_seq_create(m: *mut crane_b200_model, seq_out: *mut c_int) -> c_int;
+    pub fn crane_b200_kv_export(m: *mut crane_b200_model, layer: c_int, k_out: *mut f32, v_out: *mut f32, capacity_floats: usize, n_tokens: *mut usize) -> c_int;
+    pub fn crane_b200_kv_import(m: *mut crane_b200_model, layer: c_int, k: *const f32, v: *const f32, n_tokens: usize) -> c_int;
+    pub fn crane_b200_kv_set_len(m: *mut crane_b200_model, n_tokens: usize, next_rotary_pos: u32) -> c_int;
     pub fn crane_b200_seq_fork(m: *mut crane_b200_model, src: c_int, seq_out: *mut c_int) -> c_int;
     pub fn crane_b200_seq_free(m: *mut crane_b200_model, seq: c_int) -> c_int;
     pub fn crane_b200_seq_select(m: *mut crane_b200_model, seq: c_int) -> c_int;

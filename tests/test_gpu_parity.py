@@ -718,6 +718,34 @@ def test_seq_fork_shares_a_prefix_and_then_diverges(kind):
     m.close()
 
 
+@pytest.mark.parametrize("kind", ["dense", "hybrid"])
+def test_kv_swap_export_import_round_trip(kind):
+    """get_kv_caches / set_kv_caches (backend.rs:65-84): per-layer [n_kv, T, D] tensors (GDN layers: conv window + recurrent state);
+    a fresh handle that imports them continues the sequence exactly like the one that computed them."""
+    if kind == "dense":
+        cfg, cls, orc_cls = synth.TINY_QWEN3, crane_b200.Qwen3Model, Qwen3Oracle
+    else:
+        from oracle.qwen3_5 import Qwen3_5Oracle as orc_cls
+        cfg, cls = synth.TINY_QWEN3_5, crane_b200.Qwen3_5Model
+    m, w = _model(cfg, cls=cls)
+    ids = synth.synth_token_ids(70, cfg["vocab_size"], "swap")
+    m.forward_step(ids, 0)
+    caches = m.get_kv_caches()
+    assert len(caches) == cfg["num_hidden_layers"]
+    full = [i for i in range(len(caches)) if synth.is_full_attention_layer(cfg, i)] if kind == "hybrid" else list(range(len(caches)))
+    for i in full:
+        assert caches[i][0].shape == (cfg["num_key_value_heads"], 70, cfg["head_dim"])
+    ref = [m.forward_step([t], 70 + i).copy() for i, t in enumerate([3, 99, 512])]
+    m2, _ = _model(cfg, cls=cls)
+    m2.set_kv_caches(caches, 70)
+    assert m2.kv_len() == 70
+    got = [m2.forward_step([t], 70 + i).copy() for i, t in enumerate([3, 99, 512])]
+    e = max(rel_err(g, r) for g, r in zip(got, ref))
+    print(f"kv swap {kind}: continuation after import rel {e:.2e}")
+    assert e < 1e-6                                       # f32 export of hi + lo re-splits into the same two planes
+    m.close(); m2.close()
+
+
 def test_tts_frame_loop_against_oracle():
     from oracle.qwen3_tts import Qwen3TTSOracle
     cfg = synth.TINY_QWEN3_TTS
