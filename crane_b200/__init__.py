@@ -441,6 +441,9 @@ class Engine:
         self._ck(self.lib.crane_b200_last_timing(self.h, C.byref(p), C.byref(d), C.byref(n)))
         return {"prefill_ms": p.value, "decode_ms": d.value, "decode_steps": int(n.value)}
 
+    def active_kv_cache_bytes(self) -> int:
+        return int(self.lib.crane_b200_active_kv_cache_bytes(self.h))
+
     def kernel_launches(self) -> int:
         return int(self.lib.crane_b200_kernel_launches(self.h))
 

@@ -394,7 +394,7 @@ attn_decode_kernel(AttnDecArgs a) {
     bf16* v_t = k_t + TILE * D;
     bf16* kl_t = v_t + TILE * D;          // split precision only: low-order planes of the same tile
     bf16* vl_t = kl_t + TILE * D;
-    const bool split_kv = a.kv_lo_off != 0;
+    const bool split_kv = a.kv_bits ? (a.kv_split != 0) : (a.kv_lo_off != 0);
     float* mo_s = reinterpret_cast<float*>(asm_);          // [NW][NREP][D], aliases the tiles after the token loop
     __shared__ float q_s[NREP][D];
     __shared__ float knew_s[D], vnew_s[D];
@@ -424,6 +424,40 @@ attn_decode_kernel(AttnDecArgs a) {
     const int* bt = a.block_table + (size_t)st.slot * a.max_pages;
     auto load_tile = [&](int tb) {
         const int n = min(TILE, t_end - tb);
+        if (a.kv_bits) {
+            // codes -> (code - offset) * scale -> bf16 hi (+ lo) rows of the tile: 16 elements per thread and pass
+            const int off = a.kv_bits == 8 ? 128 : 8;
+            for (int c = tid; c < n * (D / 16) * 2; c += 256) {
+                const int which = c & 1, cc = c >> 1;
+                const int r = cc / (D / 16), ch = cc % (D / 16);
+                const int t = tb + r;
+                const size_t prow = ((size_t)bt[t / KV_PAGE] * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE);
+                const unsigned char* codes = which ? a.v_codes : a.k_codes;
+                const float scale = (which ? a.v_scale : a.k_scale)[prow];
+                int q[16];
+                if (a.kv_bits == 8) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(codes + prow * D + ch * 16);
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) q[e] = (int)((w[e >> 2] >> (8 * (e & 3))) & 255u);
+                } else {
+                    const uint2 u = *reinterpret_cast<const uint2*>(codes + prow * (D / 2) + ch * 8);
+                    const uint32_t w[2] = {u.x, u.y};
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) q[e] = (int)((w[e >> 3] >> (4 * (e & 7))) & 15u);
+                }
+                bf16* hi_t = (which ? v_t : k_t) + r * D + ch * 16;
+                bf16* lo_t = (which ? vl_t : kl_t) + r * D + ch * 16;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float y = (float)(q[e] - off) * scale;
+                    const bf16 hb = __float2bfloat16_rn(y);
+                    hi_t[e] = hb;
+                    if (split_kv) lo_t[e] = __float2bfloat16_rn(y - __bfloat162float(hb));
+                }
+            }
+            return;
+        }
         for (int c = tid; c < n * CPR; c += 256) {
             const int r = c / CPR, ch = c % CPR;
             const int t = tb + r;
@@ -492,15 +526,38 @@ attn_decode_kernel(AttnDecArgs a) {
                 for (int jj = 0; jj < NE; ++jj) if (jj == (lo ? j + RJ : j - RJ)) other = e[jj];
                 r = lo ? (e[j] * c - other * s) : (other * s + e[j] * c);
             }
-            dst[lane + 32 * j] = is_k ? (split_kv ? round_bf16_split(r) : round_bf16(r)) : r;
+            dst[lane + 32 * j] = (is_k && !a.kv_bits) ? (split_kv ? round_bf16_split(r) : round_bf16(r)) : r;
         }
     }
     if (split == s_last && warp == NW - 1) {
         const float* vsrc = qkv + q_span + kv_dim + kvh * D;
-        for (int i = lane; i < D; i += 32) vnew_s[i] = split_kv ? round_bf16_split(vsrc[i]) : round_bf16(vsrc[i]);
+        for (int i = lane; i < D; i += 32) vnew_s[i] = a.kv_bits ? vsrc[i] : (split_kv ? round_bf16_split(vsrc[i]) : round_bf16(vsrc[i]));
     }
     __syncthreads();
-    if (split == s_last && sub == 0) {   // append the new token to its page
+    if (a.kv_bits && split == s_last && warp < 2) {
+        // quantise the new K (warp 0) / V (warp 1) row per token and head; attention -- here and in every later step -- sees code * scale
+        float* row = warp ? vnew_s : knew_s;
+        const int t = T - 1;
+        const size_t prow = ((size_t)bt[t / KV_PAGE] * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE);
+        float am = 0.f;
+        for (int i = lane; i < D; i += 32) am = fmaxf(am, fabsf(row[i]));
+        am = warp_max(am);
+        const float inv = a.kv_bits == 8 ? (float)(1.0 / 127.0) : (float)(1.0 / 7.0);
+        const float scale = __fadd_rn(__fmul_rn(am, inv), 1e-8f);
+        const int off = a.kv_bits == 8 ? 128 : 8;
+        unsigned char* codes = warp ? a.v_codes : a.k_codes;
+        for (int i = 2 * lane; i < D; i += 64) {          // an (even, odd) pair per lane and pass
+            const int q0 = (int)roundf(__fdiv_rn(row[i], scale)), q1 = (int)roundf(__fdiv_rn(row[i + 1], scale));
+            row[i] = (float)q0 * scale; row[i + 1] = (float)q1 * scale;
+            if (sub == 0) {
+                if (a.kv_bits == 8) { codes[prow * D + i] = (unsigned char)(q0 + off); codes[prow * D + i + 1] = (unsigned char)(q1 + off); }
+                else codes[prow * (D / 2) + (i >> 1)] = (unsigned char)((q0 + off) + 16 * (q1 + off));
+            }
+        }
+        if (sub == 0 && lane == 0) (warp ? a.v_scale : a.k_scale)[prow] = scale;
+    }
+    if (a.kv_bits) __syncthreads();
+    if (!a.kv_bits && split == s_last && sub == 0) {   // append the new token to its page
         const int t = T - 1;
         const int page = bt[t / KV_PAGE];
         const size_t off = (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
@@ -667,7 +724,7 @@ attn_decode_kernel(AttnDecArgs a) {
 
 template <int D, int NREP>
 static int attn_decode_launch_t(cudaStream_t st, int B, const AttnDecArgs& a, bool pdl) {
-    const int SMEM = a.kv_lo_off ? 131072 : 65536;
+    const int SMEM = (a.kv_bits ? a.kv_split : (a.kv_lo_off != 0)) ? 131072 : 65536;
     static SmemOptIn seen;
     if (const int e = ensure_dyn_smem(attn_decode_kernel<D, NREP>, (size_t)SMEM, seen)) return e;
     cudaLaunchConfig_t cfg = {};

@@ -78,6 +78,12 @@ struct AttnDecArgs {
     float scale;
     float* out;              // [B, nh*D] f32
     long long kv_lo_off;     // split precision: element offset of the pools' low-order planes (0 = plain bf16 pages)
+    // quantised KV pages (QuantKvCache, qwen3_5/kv_cache.rs:209-342): kv_bits 8 / 4 -> k_pool / v_pool are unused, the pages are
+    // u8 codes [n_pages, nkv, KV_PAGE, D * bits / 8] + f32 scales [n_pages, nkv, KV_PAGE]; dequantised while the tile is staged
+    int kv_bits = 0;
+    int kv_split = 0;        // kv_bits != 0: stage the dequantised value as hi + lo bf16 planes (the parity mode) or hi only
+    unsigned char *k_codes = nullptr, *v_codes = nullptr;
+    float *k_scale = nullptr, *v_scale = nullptr;
     int groups = 1;          // set by attn_decode_launch: CTA clusters per KV head (query group width / kernel sub-group width)
 };
 

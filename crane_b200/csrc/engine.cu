@@ -107,6 +107,8 @@ struct LayerW {
     bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr;
     float *ln1 = nullptr, *ln2 = nullptr, *qn = nullptr, *kn = nullptr;
     bf16 *k_pool = nullptr, *v_pool = nullptr;
+    unsigned char *k_codes = nullptr, *v_codes = nullptr;   // engine.kv_cache = int8 / int4: quantised pages (codes + per-token scales)
+    float *k_scale = nullptr, *v_scale = nullptr;
     int loaded = 0;   // bit per tensor
     // GGUF-quantised linears (ggml bytes repacked by q_repack_rows): qt_* == 0 means the bf16 buffer above is used
     unsigned char *q_wq = nullptr, *q_wk = nullptr, *q_wv = nullptr, *q_wo = nullptr, *q_wgu = nullptr, *q_wdown = nullptr;
@@ -301,6 +303,15 @@ struct crane_b200_model {
     // tensor-core path carries ~16 mantissa bits; lo_* = element offset of that plane from the buffer base, 0 when off.
     bool split = true;
     long long lo_xn = 0, lo_q = 0, lo_attn = 0, lo_act = 0, lo_kv = 0;
+    int kv_bits = 0;                        // 0: bf16 (+lo) pages; 8 / 4: QuantKvCache pages (qwen3_5/kv_cache.rs:209-342)
+    bf16 *kq_sk = nullptr, *kq_sv = nullptr; // quantised mode: one layer's K / V of one sequence, dequantised, page layout (prefill scratch)
+    int* bt_identity = nullptr;             // block table of that scratch: page p at p
+    KvQuantArgs kvq_args(LayerW& l) {
+        KvQuantArgs a = {};
+        a.k_codes = l.k_codes; a.v_codes = l.v_codes; a.k_scale = l.k_scale; a.v_scale = l.v_scale; a.bt = bt_cur();
+        a.nkv = nkv; a.D = D; a.bits = kv_bits; a.sk = kq_sk; a.sv = kq_sv; a.s_lo = lo_kv;
+        return a;
+    }
     long long lo_vpvb = 0, lo_vxn = 0, lo_vqkvb = 0, lo_vattn = 0, lo_vact = 0, lo_vm1 = 0;
     bf16* dalloc_act(size_t n, long long& lo_off) {     // bf16 activation buffer (+ its lo plane)
         lo_off = split ? (long long)n : 0;
@@ -468,6 +479,10 @@ void crane_b200_model::parse_config(const char* json) {
         const std::string prec = e.string("precision", "split");
         if (prec == "bf16") split = false;
         else if (prec != "split") fail(CRANE_B200_INVALID_ARG, "engine.precision must be \"split\" or \"bf16\"");
+        const std::string kvc = e.string("kv_cache", "fp");
+        if (kvc == "int8") kv_bits = 8;
+        else if (kvc == "int4") kv_bits = 4;
+        else if (kvc != "fp") fail(CRANE_B200_INVALID_ARG, "engine.kv_cache must be \"fp\", \"int8\" or \"int4\"");
         if (e.string("vit_act", "erf") == "tanh") vit_gelu_mode = EPI_GELU_TANH_BF16;
         if (e.string("merger_act", "tanh") == "erf") merger_gelu_mode = EPI_GELU_ERF_BF16;
     }
@@ -937,7 +952,11 @@ void crane_b200_model::finalize() {
 
     const size_t page_elems = (size_t)nkv * KV_PAGE * D;
     for (auto& l : layers) {
-        if (l.full) {
+        if (l.full && kv_bits) {
+            const size_t rows = (size_t)max_batch * max_pages * nkv * KV_PAGE;
+            l.k_codes = dalloc<unsigned char>(rows * D * kv_bits / 8); l.v_codes = dalloc<unsigned char>(rows * D * kv_bits / 8);
+            l.k_scale = dalloc<float>(rows); l.v_scale = dalloc<float>(rows);
+        } else if (l.full) {
             l.k_pool = dalloc_act((size_t)max_batch * max_pages * page_elems, lo_kv);
             l.v_pool = dalloc_act((size_t)max_batch * max_pages * page_elems, lo_kv);
         } else {   // GdnLayerCache (ops/gdn/cache.rs:15-45): conv window + [Hv, K, V] f32 state, zero-initialised
@@ -956,6 +975,15 @@ void crane_b200_model::finalize() {
         gd_qn = dalloc<float>((size_t)nk * dk); gd_kn = dalloc<float>((size_t)nk * dk);
         gd_gb = dalloc<float>((size_t)nv * 2); gd_y = dalloc<float>(value_dim()); gd_out = dalloc<float>(value_dim());
         reset_recurrent_state();
+    }
+    if (kv_bits) {
+        if (is_tts) fail(CRANE_B200_UNSUPPORTED, "engine.kv_cache = int8 / int4 is not wired into the TTS handle");
+        kq_sk = dalloc_act((size_t)max_pages * page_elems, lo_kv);       // (lo_kv now names the scratch's low-order plane)
+        kq_sv = dalloc_act((size_t)max_pages * page_elems, lo_kv);
+        std::vector<int> idn(max_pages);
+        for (int i = 0; i < max_pages; ++i) idn[i] = i;
+        bt_identity = dalloc<int>(max_pages);
+        CUDA_OK(cudaMemcpy(bt_identity, idn.data(), idn.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     // page tables: slot s owns pages [s * max_pages, (s+1) * max_pages) -- static assignment, 64-token pages
     std::vector<int> bt((size_t)max_batch * max_pages);
@@ -984,7 +1012,7 @@ void crane_b200_model::finalize() {
     CUDA_OK(cudaMemset(ticket, 0, sizeof(unsigned int)));
     CUDA_OK(cudaMemset(state, 0, B * sizeof(SeqState)));
     // single-sequence bf16 decode runs as ONE persistent launch per call (decode_ll.cu) when the geometry allows it
-    use_persistent = use_persistent && !hybrid && !any_quant && !is_tts && owns_stream && L <= LL_MAX_LAYERS &&
+    use_persistent = use_persistent && !hybrid && !any_quant && !is_tts && !kv_bits && owns_stream && L <= LL_MAX_LAYERS &&
                      decode_ll_supported(D, rot_half, nh, nkv, H, I, q_dim(), qkv_dim(), V, num_sms);
     if (use_persistent) {
         int coop = 0;
@@ -1080,7 +1108,8 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) 
             a.q_norm_w = l.qn; a.k_norm_w = l.kn; a.eps = eps; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.axis_of = axis_of;
             a.state = state; a.block_table = block_table; a.max_pages = max_pages; a.k_pool = l.k_pool; a.v_pool = l.v_pool;
             a.nh = nh; a.nkv = nkv; a.scale = 1.0f / std::sqrt((float)D);
-            a.out = attn_dec; a.kv_lo_off = lo_kv;
+            a.out = attn_dec; a.kv_lo_off = kv_bits ? 0 : lo_kv;
+            a.kv_bits = kv_bits; a.kv_split = split ? 1 : 0; a.k_codes = l.k_codes; a.v_codes = l.v_codes; a.k_scale = l.k_scale; a.v_scale = l.v_scale;
             LAUNCH_OK(attn_decode_launch(stream, B, D, a, pdl));
             ++launches;   // attention
             linear_decode(GEMV_RESID, false, l.wo, l.q_wo, l.qt_o, H, q_dim(), attn_dec, q_dim(), nullptr, x_dec, H, nullptr, B);
@@ -1148,7 +1177,15 @@ void crane_b200_model::fork_seq(int src, int dst) {
     const size_t so = (size_t)src * max_pages * page_elems, dofs = (size_t)dst * max_pages * page_elems, n = pages * page_elems;
     const size_t cs = hybrid ? (size_t)conv_dim() * ck : 0, rs = hybrid ? (size_t)nv * dk * dv : 0;
     for (auto& l : layers) {
-        if (l.full) {
+        if (l.full && kv_bits) {
+            if (!pages) continue;
+            const size_t rows = pages * nkv * KV_PAGE, rs0 = (size_t)src * max_pages * nkv * KV_PAGE, rd0 = (size_t)dst * max_pages * nkv * KV_PAGE;
+            const size_t cb = (size_t)D * kv_bits / 8;
+            for (unsigned char* c : {l.k_codes, l.v_codes})
+                CUDA_OK(cudaMemcpyAsync(c + rd0 * cb, c + rs0 * cb, rows * cb, cudaMemcpyDeviceToDevice, stream));
+            for (float* sc : {l.k_scale, l.v_scale})
+                CUDA_OK(cudaMemcpyAsync(sc + rd0, sc + rs0, rows * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        } else if (l.full) {
             if (!n) continue;
             for (bf16* pool : {l.k_pool, l.v_pool}) {
                 CUDA_OK(cudaMemcpyAsync(pool + dofs, pool + so, n * sizeof(bf16), cudaMemcpyDeviceToDevice, stream));
@@ -1349,12 +1386,17 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             RopeAppendArgs ra = {};
             ra.qkv = qkv; ra.q_stride = q_stride(); ra.rot_half = rot_half;
             ra.q_norm_w = l.qn; ra.k_norm_w = l.kn; ra.eps = eps; ra.cos_tab = cos_tab; ra.sin_tab = sin_tab; ra.axis_of = axis_of;
-            ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = bt_cur(); ra.k_pool = l.k_pool; ra.v_pool = l.v_pool;
+            // quantised pages: the prefix is dequantised into the scratch, the new rows go through it (prefill.cu, KvQuantArgs)
+            bf16 *kp = kv_bits ? kq_sk : l.k_pool, *vp = kv_bits ? kq_sv : l.v_pool;
+            const int* btp = kv_bits ? bt_identity : bt_cur();
+            if (kv_bits && start_pos > 0) { LAUNCH_OK(kv_dequant_pages_launch(stream, kvq_args(l), (int)start_pos)); ++launches; }
+            ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = btp; ra.k_pool = kp; ra.v_pool = vp;
             ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf; ra.q_lo_off = lo_q; ra.kv_lo_off = lo_kv;
             LAUNCH_OK(rope_append_launch(stream, D, ra));
+            if (kv_bits) { LAUNCH_OK(kv_quant_rows_launch(stream, kvq_args(l), (int)start_pos, S)); ++launches; }
             spans.mark(SP_ATTN_FLASH);
             FlashArgs fa = {};
-            fa.q = q_bf; fa.q_stride = qd; fa.k_pool = l.k_pool; fa.v_pool = l.v_pool; fa.block_table = bt_cur(); fa.nh = nh; fa.nkv = nkv;
+            fa.q = q_bf; fa.q_stride = qd; fa.k_pool = kp; fa.v_pool = vp; fa.block_table = btp; fa.nh = nh; fa.nkv = nkv;
             fa.out = attn_bf; fa.o_stride = qd; fa.S = S; fa.kv_offset = (int)start_pos; fa.scale = 1.0f / std::sqrt((float)D); fa.nseq = 1;
             fa.q_lo_off = lo_q; fa.kv_lo_off = lo_kv; fa.out_lo_off = lo_attn;
             LAUNCH_OK(flash_prefill_launch(stream, D, true, true, fa));
@@ -1750,7 +1792,8 @@ uint64_t crane_b200_active_kv_cache_bytes(const crane_b200_model* m) {
     if (!m) return 0;
     uint64_t full = 0;
     for (int f : m->layer_is_full) full += f;
-    return (uint64_t)m->kv_len * m->nkv * m->D * 2 /*K,V*/ * (m->split ? 4 : 2) /*bf16 (+ lo plane)*/ * full +
+    const uint64_t per_row = m->kv_bits ? (uint64_t)m->D * m->kv_bits / 8 + 4 /*codes + f32 scale*/ : (uint64_t)m->D * (m->split ? 4 : 2) /*bf16 (+ lo plane)*/;
+    return (uint64_t)m->kv_len * m->nkv * 2 /*K,V*/ * per_row * full +
            (m->hybrid ? (uint64_t)(m->L - full) * ((uint64_t)m->nv * m->dk * m->dv + (uint64_t)m->conv_dim() * m->ck) * 4 : 0);
 }
 uint64_t crane_b200_kernel_launches(const crane_b200_model* m) { return m ? m->launches : 0; }
@@ -2020,7 +2063,9 @@ int crane_b200_kv_export(crane_b200_model* m, int layer, float* k_out, float* v_
             for (int which = 0; which < 2; ++which) {
                 float* dst = which ? v_out : k_out;
                 if (!dst) continue;
-                const int r = kv_pages_to_rows_launch(m->stream, which ? l.v_pool : l.k_pool, m->lo_kv, m->bt_cur(), m->nkv, m->D, (int)T, tmp);
+                if (m->kv_bits && which == 0) { const int rq = kv_dequant_pages_launch(m->stream, m->kvq_args(l), (int)T); if (rq) { cudaFree(tmp); fail(CRANE_B200_CUDA_ERROR, "kv_export dequant: %d", rq); } }
+                const int r = m->kv_bits ? kv_pages_to_rows_launch(m->stream, which ? m->kq_sv : m->kq_sk, m->lo_kv, m->bt_identity, m->nkv, m->D, (int)T, tmp)
+                                         : kv_pages_to_rows_launch(m->stream, which ? l.v_pool : l.k_pool, m->lo_kv, m->bt_cur(), m->nkv, m->D, (int)T, tmp);
                 if (r) { cudaFree(tmp); fail(CRANE_B200_CUDA_ERROR, "kv_export kernel: %d", r); }
                 cudaMemcpyAsync(dst, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream);
                 cudaStreamSynchronize(m->stream);
@@ -2048,11 +2093,16 @@ int crane_b200_kv_import(crane_b200_model* m, int layer, const float* k, const f
         CUDA_OK(cudaMalloc((void**)&tmp, n * sizeof(float)));
         for (int which = 0; which < 2; ++which) {
             cudaMemcpyAsync(tmp, which ? v : k, n * sizeof(float), cudaMemcpyHostToDevice, m->stream);
-            const int r = kv_rows_to_pages_launch(m->stream, which ? l.v_pool : l.k_pool, m->lo_kv, m->bt_cur(), m->nkv, m->D, (int)n_tokens, tmp);
+            const int r = m->kv_bits ? kv_rows_to_pages_launch(m->stream, which ? m->kq_sv : m->kq_sk, m->lo_kv, m->bt_identity, m->nkv, m->D, (int)n_tokens, tmp)
+                                     : kv_rows_to_pages_launch(m->stream, which ? l.v_pool : l.k_pool, m->lo_kv, m->bt_cur(), m->nkv, m->D, (int)n_tokens, tmp);
             cudaStreamSynchronize(m->stream);
             if (r) { cudaFree(tmp); fail(CRANE_B200_CUDA_ERROR, "kv_import kernel: %d", r); }
         }
         cudaFree(tmp);
+        if (m->kv_bits) {   // the imported rows are re-quantised: codes of code * scale values reproduce themselves
+            LAUNCH_OK(kv_quant_rows_launch(m->stream, m->kvq_args(l), 0, (int)n_tokens));
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+        }
     }
     API_END(m)
 }

@@ -510,6 +510,98 @@ int cast_f32_bf16_launch(cudaStream_t st, const float* src, bf16* dst, size_t n,
     return launch_k(cast_f32_bf16_kernel, dim3(grid), dim3(256), 0, st, prefill_pdl(), src, dst, n4, lo_off);
 }
 
+// Quantised KV pages (QuantKvCache, crane-core/src/models/qwen3_5/kv_cache.rs:209-342): per (token, KV head) symmetric int8 / int4
+// codes + one f32 scale.  scale = amax * f32(1 / qmax) + 1e-8, code = round_half_away(x / scale) + offset (128 / 8); int4 packs
+// (even, odd) elements as lo + 16 * hi.  What attention sees is (code - offset) * scale.
+// The prefill side works through a bf16 (hi + lo) scratch in page layout (one sequence, one layer at a time, identity block table):
+//   kv_dequant_pages: the cached prefix [0, T) of the sequence -> scratch       (the reference dequantises the whole cache per step)
+//   rope_append writes the new rows into the scratch as for a lossless cache
+//   kv_quant_rows: new rows [t0, t0 + S) scratch -> codes + scales in the int pages, and the scratch rows are replaced by their
+//                  dequantised values, so the flash kernel reads exactly what the reference's attention reads.
+__device__ __forceinline__ float kvq_scale(float amax, int bits) {
+    const float inv = bits == 8 ? (float)(1.0 / 127.0) : (float)(1.0 / 7.0);
+    return __fadd_rn(__fmul_rn(amax, inv), 1e-8f);
+}
+__global__ void __launch_bounds__(128)
+kv_quant_rows_kernel(KvQuantArgs a, int t0) {
+    __shared__ float red[4];
+    const int t = t0 + blockIdx.x, h = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
+    bf16* sp = which ? a.sv : a.sk;
+    const size_t srow = (((size_t)(t / KV_PAGE) * a.nkv + h) * KV_PAGE + (t % KV_PAGE)) * a.D;
+    const size_t prow = ((size_t)a.bt[t / KV_PAGE] * a.nkv + h) * KV_PAGE + (t % KV_PAGE);
+    float x[2];
+    float am = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = tid * 2 + j;                   // (even, odd) pair per thread: D <= 256
+        x[j] = 0.f;
+        if (i < a.D) {
+            x[j] = __bfloat162float(sp[srow + i]);
+            if (a.s_lo) x[j] += __bfloat162float(sp[a.s_lo + srow + i]);
+        }
+        am = fmaxf(am, fabsf(x[j]));
+    }
+    am = warp_max(am);
+    if ((tid & 31) == 0) red[tid >> 5] = am;
+    __syncthreads();
+    am = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    const float scale = kvq_scale(am, a.bits);
+    const int off = a.bits == 8 ? 128 : 8;
+    int q[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) q[j] = (int)roundf(__fdiv_rn(x[j], scale));
+    if (tid * 2 < a.D) {
+        unsigned char* codes = which ? a.v_codes : a.k_codes;
+        if (a.bits == 8) {
+            codes[prow * a.D + tid * 2] = (unsigned char)(q[0] + off);
+            codes[prow * a.D + tid * 2 + 1] = (unsigned char)(q[1] + off);
+        } else {
+            codes[prow * (a.D / 2) + tid] = (unsigned char)((q[0] + off) + 16 * (q[1] + off));
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float y = (float)q[j] * scale;
+            const bf16 hi = __float2bfloat16_rn(y);
+            sp[srow + tid * 2 + j] = hi;
+            if (a.s_lo) sp[a.s_lo + srow + tid * 2 + j] = __float2bfloat16_rn(y - __bfloat162float(hi));
+        }
+    }
+    if (tid == 0) (which ? a.v_scale : a.k_scale)[prow] = scale;
+}
+__global__ void __launch_bounds__(128)
+kv_dequant_pages_kernel(KvQuantArgs a) {
+    const int t = blockIdx.x, h = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
+    bf16* sp = which ? a.sv : a.sk;
+    const size_t srow = (((size_t)(t / KV_PAGE) * a.nkv + h) * KV_PAGE + (t % KV_PAGE)) * a.D;
+    const size_t prow = ((size_t)a.bt[t / KV_PAGE] * a.nkv + h) * KV_PAGE + (t % KV_PAGE);
+    const unsigned char* codes = which ? a.v_codes : a.k_codes;
+    const float scale = (which ? a.v_scale : a.k_scale)[prow];
+    const int off = a.bits == 8 ? 128 : 8;
+    if (tid * 2 >= a.D) return;
+    int q[2];
+    if (a.bits == 8) { q[0] = codes[prow * a.D + tid * 2]; q[1] = codes[prow * a.D + tid * 2 + 1]; }
+    else { const int b = codes[prow * (a.D / 2) + tid]; q[0] = b & 15; q[1] = b >> 4; }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float y = (float)(q[j] - off) * scale;
+        const bf16 hi = __float2bfloat16_rn(y);
+        sp[srow + tid * 2 + j] = hi;
+        if (a.s_lo) sp[a.s_lo + srow + tid * 2 + j] = __float2bfloat16_rn(y - __bfloat162float(hi));
+    }
+}
+int kv_quant_rows_launch(cudaStream_t st, const KvQuantArgs& a, int t0, int S) {
+    if (S <= 0) return 0;
+    if (a.D > 256 || (a.D & 1) || (a.bits != 8 && a.bits != 4)) return -1000;
+    kv_quant_rows_kernel<<<dim3(S, a.nkv, 2), 128, 0, st>>>(a, t0);
+    return (int)cudaGetLastError();
+}
+int kv_dequant_pages_launch(cudaStream_t st, const KvQuantArgs& a, int T) {
+    if (T <= 0) return 0;
+    if (a.D > 256 || (a.D & 1) || (a.bits != 8 && a.bits != 4)) return -1000;
+    kv_dequant_pages_kernel<<<dim3(T, a.nkv, 2), 128, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
 // KV swap (ModelBackend::get_kv_caches / set_kv_caches, crane-serve/src/engine/backend.rs:65-84): one layer's pages of one sequence
 // <-> the reference's contiguous cache tensors [n_kv, T, D] (f32 here: the two bf16 planes of the split mode summed / re-split).
 __global__ void __launch_bounds__(128)

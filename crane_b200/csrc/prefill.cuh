@@ -47,6 +47,18 @@ struct FlashArgs {
     long long q_lo_off, kv_lo_off, out_lo_off;
 };
 
+// quantised KV pages <-> the bf16 (hi + lo) scratch the prefill kernels read and write (see prefill.cu)
+struct KvQuantArgs {
+    unsigned char *k_codes, *v_codes;   // [n_pages, nkv, KV_PAGE, D * bits / 8]
+    float *k_scale, *v_scale;           // [n_pages, nkv, KV_PAGE]
+    const int* bt;                      // the sequence's block table into the int pages
+    int nkv, D, bits;
+    bf16 *sk, *sv;                      // scratch K / V in page layout, page p of the sequence at scratch page p
+    long long s_lo;                     // element offset of the scratch's low-order planes (0: plain bf16)
+};
+int kv_quant_rows_launch(cudaStream_t st, const KvQuantArgs& a, int t0, int S);
+int kv_dequant_pages_launch(cudaStream_t st, const KvQuantArgs& a, int T);
+
 int embed_rows_launch(cudaStream_t st, const uint32_t* ids, int S, const bf16* embed, int H, float* x);
 // bf16 outputs take `lo_off`: element offset (from `out`) of a second plane receiving bf16(v - bf16(v)); 0 = none
 int rmsnorm_rows_launch(cudaStream_t st, const float* x, int S, int H, const float* w, float eps, bf16* out, long long lo_off = 0);

@@ -65,7 +65,10 @@ typedef struct {
  * (qwen3: crane-core/src/models/qwen3/modeling.rs:94-130 `Config`; qwen3_vl: text_config + vision_config
  * as crane-core/src/models/qwen3_5/config.rs:112-137) optionally extended with an "engine" object:
  *   {"max_seq_len": 4096, "max_batch": 1, "gemm": "tcgen05"|"simt", "graphs": true, "pdl": true,
- *    "precision": "split"|"bf16", "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf"}
+ *    "precision": "split"|"bf16", "kv_cache": "fp"|"int8"|"int4", "persistent": true, "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf"}
+ * "kv_cache": "int8" / "int4" = the reference's QuantKvCache (crane-core/src/models/qwen3_5/kv_cache.rs:209-342): per (token, KV
+ * head) symmetric codes + an f32 scale, 8.25 / 4.25 bits per cached element instead of 32 (split) or 16; attention reads
+ * code * scale, dequantised while the decode kernel stages its tile.
  * "precision": "split" (default) carries every bf16 tensor-core operand and KV page as a hi + lo pair (~16 mantissa bits:
  * logits within ~3e-5 of the f32 CPU path); "bf16" is the plain-bf16 fast mode (~1e-2, what the reference's GPU path does).
  * Replaces `model_factory::create_backend` / `Qwen3Backend::new`

@@ -83,10 +83,23 @@ def silu(x):
     return x * torch.sigmoid(x)
 
 
+def quant_kv_per_token(x: torch.Tensor, bits: int) -> torch.Tensor:
+    """`quantize_per_token` then `dequantize_per_token` (qwen3_5/kv_cache.rs:238-272): per (position, head) symmetric codes,
+    scale = amax / qmax + 1e-8 (qmax 127 or 7), code = round(x / scale) (f32 `round`: half away from zero), stored with an offset
+    of 128 / 8 (and two nibbles per byte for 4 bits -- storage only); what attention sees is code * scale.  x [..., D] f32."""
+    qmax = float((1 << (bits - 1)) - 1)
+    x = x.float()
+    scale = x.abs().amax(dim=-1, keepdim=True) * (1.0 / qmax) + 1e-8
+    q = x / scale
+    q = torch.sign(q) * torch.floor(q.abs() + 0.5)
+    return q * scale
+
+
 class Qwen3Oracle:
     """Stateful (KV-cached) single-sequence forward, mirroring `Qwen3Model`."""
 
-    def __init__(self, cfg: dict, weights: dict, prefix: str = "model.", max_pos: int | None = None, quantised: dict | None = None):
+    def __init__(self, cfg: dict, weights: dict, prefix: str = "model.", max_pos: int | None = None, quantised: dict | None = None,
+                 kv_bits: int = 0):
         """`quantised`: full tensor name -> (raw ggml blocks [rows, row_bytes] uint8, "Q4_K" | "Q6_K" | "Q8_0").  Those linears run
         through candle's CPU `QMatMul` semantics (ops/linear.rs:23-48): activations quantised to Q8_K / Q8_0 blocks, ggml integer
         dots (oracle/ggml_quant.py `qmatmul`); their entry in `weights` is not used for the product."""
@@ -102,6 +115,7 @@ class Qwen3Oracle:
         self.theta = float(tc.get("rope_theta", 1_000_000.0))
         self.prefix = prefix
         self.q = dict(quantised or {})
+        self.kv_bits = kv_bits         # 0: lossless cache; 8 / 4: QuantKvCache (qwen3_5/kv_cache.rs:209-342), see quant_kv_per_token
         self.w = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).float() for k, v in weights.items()}
         tied = cfg.get("tie_word_embeddings", tc.get("tie_word_embeddings", True))
         self.lm_head = self.w[prefix + "embed_tokens.weight"] if tied or "lm_head.weight" not in self.w \
@@ -149,6 +163,8 @@ class Qwen3Oracle:
         k = rms_norm(k, self._p(i, "self_attn.k_norm.weight"), self.eps)
         q = rope_half(q, cos, sin)
         k = rope_half(k, cos, sin)
+        if self.kv_bits:
+            k, v = quant_kv_per_token(k, self.kv_bits), quant_kv_per_token(v, self.kv_bits)
         if self.k_cache[i] is None:
             self.k_cache[i], self.v_cache[i] = k, v
         else:

@@ -79,7 +79,8 @@ def gated_delta_rule(q, k, v, g, beta, state):
 
 
 class Qwen3_5Oracle:
-    def __init__(self, cfg: dict, weights: dict, prefix="model.", max_pos=8192):
+    def __init__(self, cfg: dict, weights: dict, prefix="model.", max_pos=8192, kv_bits: int = 0):
+        self.kv_bits = kv_bits          # 8 / 4: QuantKvCache on the full-attention layers (qwen3_5/kv_cache.rs:209-342)
         tc = cfg.get("text_config", cfg)
         self.tc = tc
         self.H, self.L, self.V = tc["hidden_size"], tc["num_hidden_layers"], tc["vocab_size"]
@@ -125,6 +126,9 @@ class Qwen3_5Oracle:
         k = rms_norm_1p(k, self.W(i, "self_attn.k_norm.weight"), self.eps)
         q = apply_partial_rope(q, cos, sin, self.rot_dim)
         k = apply_partial_rope(k, cos, sin, self.rot_dim)
+        if self.kv_bits:
+            from .qwen3 import quant_kv_per_token
+            k, v = quant_kv_per_token(k, self.kv_bits), quant_kv_per_token(v, self.kv_bits)
         if self.k_cache[i] is None:
             self.k_cache[i], self.v_cache[i] = k, v
         else:

@@ -677,6 +677,56 @@ def test_batched_decode_matches_per_sequence_decode(quant):
 
 # ---- Qwen3-TTS codec-LM frame loop (config 5): talker + 16-pass code predictor on the device ----------------------------------
 
+@pytest.mark.parametrize("bits", [8, 4], ids=["int8", "int4"])
+@pytest.mark.parametrize("kind", ["dense", "hybrid"])
+def test_quantised_kv_pages_against_oracle(kind, bits):
+    """engine.kv_cache = int8 / int4 = QuantKvCache (qwen3_5/kv_cache.rs:209-342): per (token, head) codes + f32 scale, attention
+    reads code * scale.  Single-pass prefill, chunked prefill (the prefix is dequantised from its pages), decode steps (codes are
+    dequantised while the attention kernel stages its tile; the new row is quantised in the kernel), fork and export / import.
+    A code is a step function of its input: a K/V value within ~1e-6 of a rounding boundary may take the neighbouring code (one
+    int8 step is 0.8 % of the row's largest element, one int4 step 14 %), so the bar is the size of that effect, not 1e-3 blindly:
+    int8 1e-3, int4 2e-2 -- with the distance to the lossless cache printed beside it."""
+    if kind == "dense":
+        cfg, cls, orc_cls = synth.TINY_QWEN3, crane_b200.Qwen3Model, Qwen3Oracle
+    else:
+        from oracle.qwen3_5 import Qwen3_5Oracle as orc_cls
+        cfg, cls = synth.TINY_QWEN3_5, crane_b200.Qwen3_5Model
+    m, w = _model(cfg, cls=cls, kv_cache=f"int{bits}", max_batch=2)
+    assert m.decode_path() == "chain"
+    orc = orc_cls(cfg, w, kv_bits=bits)
+    lossless = orc_cls(cfg, w)
+    ids = synth.synth_token_ids(150, cfg["vocab_size"], "kvq")
+    ref = orc.forward(ids, 0).numpy()
+    gap = rel_err(lossless.forward(ids, 0).numpy(), ref)
+    tol = 1e-3 if bits == 8 else 2e-2
+    e_full = rel_err(m.forward_step(ids, 0), ref)
+    m.clear_kv_cache()
+    m.forward_step(ids[:70], 0)
+    m.forward_step(ids[70:71], 70)
+    e_chunk = rel_err(m.forward_step(ids[71:], 71), ref)
+    errs, tok = [], int(np.argmax(ref))
+    f = m.seq_fork(0)
+    for i in range(5):
+        ref = orc.forward([tok], len(ids) + i).numpy()
+        errs.append(rel_err(m.forward_step([tok], len(ids) + i), ref))
+        if i == 1:                                       # the fork must see the same quantised prefix
+            m.seq_select(f)
+            o2 = orc_cls(cfg, w, kv_bits=bits)
+            o2.forward(ids, 0)
+            errs.append(rel_err(m.forward_step([7], len(ids)), o2.forward([7], len(ids)).numpy()))
+            m.seq_select(0)
+        tok = int(np.argmax(ref))
+    caches = m.get_kv_caches()
+    m2, _ = _model(cfg, cls=cls, kv_cache=f"int{bits}")
+    m2.set_kv_caches(caches, m.kv_len())
+    nxt = orc.forward([tok], m.kv_len()).numpy()
+    e_imp = rel_err(m2.forward_step([tok], m.kv_len()), nxt)
+    print(f"kv int{bits} {kind}: prefill rel {e_full:.2e}, chunked {e_chunk:.2e}, decode / fork max {max(errs):.2e}, after export+import {e_imp:.2e} "
+          f"(the quantisation itself moves the logits by {gap:.1e}); cache bytes {m.active_kv_cache_bytes()}")
+    assert max(e_full, e_chunk, max(errs), e_imp) < tol
+    m.close(); m2.close()
+
+
 @pytest.mark.parametrize("kind", ["dense", "hybrid"])
 def test_seq_fork_shares_a_prefix_and_then_diverges(kind):
     """crane_b200_seq_fork: the fork continues exactly like its source (KV pages; for the hybrid model also the parked Gated-Delta-Net
