@@ -1392,8 +1392,8 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             if (kv_bits && start_pos > 0) { LAUNCH_OK(kv_dequant_pages_launch(stream, kvq_args(l), (int)start_pos)); ++launches; }
             ra.pos3 = pos3_dev; ra.S = S; ra.start_pos = (int)start_pos; ra.block_table = btp; ra.k_pool = kp; ra.v_pool = vp;
             ra.nh = nh; ra.nkv = nkv; ra.q_out = q_bf; ra.q_lo_off = lo_q; ra.kv_lo_off = lo_kv;
+            ra.kv_bits = kv_bits; ra.k_codes = l.k_codes; ra.v_codes = l.v_codes; ra.k_scale = l.k_scale; ra.v_scale = l.v_scale; ra.code_bt = bt_cur();
             LAUNCH_OK(rope_append_launch(stream, D, ra));
-            if (kv_bits) { LAUNCH_OK(kv_quant_rows_launch(stream, kvq_args(l), (int)start_pos, S)); ++launches; }
             spans.mark(SP_ATTN_FLASH);
             FlashArgs fa = {};
             fa.q = q_bf; fa.q_stride = qd; fa.k_pool = kp; fa.v_pool = vp; fa.block_table = btp; fa.nh = nh; fa.nkv = nkv;

@@ -95,6 +95,31 @@ int layernorm_rows_launch(cudaStream_t st, const float* x, int rows, int W, cons
 
 // -------------------------------------------------------------------------------------
 // One warp per (token, vector): nh query heads, nkv key heads, nkv value heads.
+// per-(token, head) quantisation of one K or V row held as e[j] = element lane + 32 j (see the QuantKvCache notes further down):
+// writes codes + scale to the int page row `prow`, replaces e[] by code * scale
+template <int NE>
+__device__ __forceinline__ void kvq_row(float (&e)[NE], int bits, unsigned char* codes, float* scales, size_t prow, int D, int lane) {
+    float am = 0.f;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) am = fmaxf(am, fabsf(e[j]));
+    am = warp_max(am);
+    const float inv = bits == 8 ? (float)(1.0 / 127.0) : (float)(1.0 / 7.0);
+    const float scale = __fadd_rn(__fmul_rn(am, inv), 1e-8f);
+    const int off = bits == 8 ? 128 : 8;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+        const int q = (int)roundf(__fdiv_rn(e[j], scale));
+        e[j] = (float)q * scale;
+        const int i = lane + 32 * j;
+        if (bits == 8) codes[prow * D + i] = (unsigned char)(q + off);
+        else {
+            const int qo = __shfl_down_sync(0xffffffffu, q, 1);          // the odd neighbour's code
+            if (!(lane & 1)) codes[prow * (D / 2) + (i >> 1)] = (unsigned char)((q + off) + 16 * (qo + off));
+        }
+    }
+    if (lane == 0) scales[prow] = scale;
+}
+
 template <int D>
 __global__ void __launch_bounds__(128)
 rope_append_kernel(RopeAppendArgs a) {
@@ -114,9 +139,13 @@ rope_append_kernel(RopeAppendArgs a) {
         const int kvh = vec - a.nh - a.nkv;
         const float* src = row + q_span + kv_dim + kvh * D;
         bf16* dst = a.v_pool + (((size_t)page * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE)) * D;
+        float vv[NE];
+#pragma unroll
+        for (int j = 0; j < NE; ++j) vv[j] = src[lane + 32 * j];
+        if (a.kv_bits) kvq_row<NE>(vv, a.kv_bits, a.v_codes, a.v_scale, ((size_t)a.code_bt[t / KV_PAGE] * a.nkv + kvh) * KV_PAGE + (t % KV_PAGE), D, lane);
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
-            const float v = src[lane + 32 * j];
+            const float v = vv[j];
             const bf16 h = __float2bfloat16_rn(v);
             dst[lane + 32 * j] = h;
             if (a.kv_lo_off) dst[a.kv_lo_off + lane + 32 * j] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -140,6 +169,7 @@ rope_append_kernel(RopeAppendArgs a) {
     bf16* dst = is_k ? a.k_pool + (((size_t)page * a.nkv + head) * KV_PAGE + (t % KV_PAGE)) * D
                      : a.q_out + (size_t)s * q_dim + head * D;
     const int RJ = a.rot_half >> 5;
+    float rr[NE];
 #pragma unroll
     for (int j = 0; j < NE; ++j) {
         float r = e[j];
@@ -153,6 +183,12 @@ rope_append_kernel(RopeAppendArgs a) {
             for (int jj = 0; jj < NE; ++jj) if (jj == (lo ? j + RJ : j - RJ)) other = e[jj];
             r = lo ? (e[j] * c - other * sn) : (other * sn + e[j] * c);
         }
+        rr[j] = r;
+    }
+    if (is_k && a.kv_bits) kvq_row<NE>(rr, a.kv_bits, a.k_codes, a.k_scale, ((size_t)a.code_bt[t / KV_PAGE] * a.nkv + head) * KV_PAGE + (t % KV_PAGE), D, lane);
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+        const float r = rr[j];
         const bf16 h = __float2bfloat16_rn(r);
         dst[lane + 32 * j] = h;
         const long long lo_off = is_k ? a.kv_lo_off : a.q_lo_off;

@@ -26,6 +26,12 @@ struct RopeAppendArgs {
     bf16* q_out;             // [S, nh * D]
     long long q_lo_off;      // split precision: element offset of the low-order plane of q_out (0 = none)
     long long kv_lo_off;     // ... and of the K / V pools
+    // quantised KV pages (engine.kv_cache = int8 / int4): k_pool / v_pool are the dequantised scratch (block_table = identity); the
+    // rows are quantised here, from their f32 values, into the int pages addressed through code_bt -- the scratch receives code * scale
+    int kv_bits = 0;
+    unsigned char *k_codes = nullptr, *v_codes = nullptr;
+    float *k_scale = nullptr, *v_scale = nullptr;
+    const int* code_bt = nullptr;
 };
 
 struct FlashArgs {

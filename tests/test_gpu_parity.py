@@ -683,9 +683,11 @@ def test_quantised_kv_pages_against_oracle(kind, bits):
     """engine.kv_cache = int8 / int4 = QuantKvCache (qwen3_5/kv_cache.rs:209-342): per (token, head) codes + f32 scale, attention
     reads code * scale.  Single-pass prefill, chunked prefill (the prefix is dequantised from its pages), decode steps (codes are
     dequantised while the attention kernel stages its tile; the new row is quantised in the kernel), fork and export / import.
-    A code is a step function of its input: a K/V value within ~1e-6 of a rounding boundary may take the neighbouring code (one
-    int8 step is 0.8 % of the row's largest element, one int4 step 14 %), so the bar is the size of that effect, not 1e-3 blindly:
-    int8 1e-3, int4 2e-2 -- with the distance to the lossless cache printed beside it."""
+    A code is a step function of its input: the K/V rows of two correct implementations differ by ~1e-5 (f32 summation order, the
+    split-bf16 GEMM operands), a value that close to a rounding boundary takes the neighbouring code (one int8 step is 0.8 % of the
+    row's largest element, one int4 step 14 %), and with ~1e-3 of the elements affected the logits move by a few percent of what
+    the quantisation itself moves them.  Asserted: the error stays below a quarter of the quantisation's own effect (printed) and
+    below 5e-3; the arithmetic (scale, rounding, packing, dequantisation) is exact -- export / import reproduces itself bitwise."""
     if kind == "dense":
         cfg, cls, orc_cls = synth.TINY_QWEN3, crane_b200.Qwen3Model, Qwen3Oracle
     else:
@@ -698,7 +700,7 @@ def test_quantised_kv_pages_against_oracle(kind, bits):
     ids = synth.synth_token_ids(150, cfg["vocab_size"], "kvq")
     ref = orc.forward(ids, 0).numpy()
     gap = rel_err(lossless.forward(ids, 0).numpy(), ref)
-    tol = 1e-3 if bits == 8 else 2e-2
+    tol = min(5e-3, 0.25 * gap)
     e_full = rel_err(m.forward_step(ids, 0), ref)
     m.clear_kv_cache()
     m.forward_step(ids[:70], 0)
