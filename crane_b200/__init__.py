@@ -583,7 +583,7 @@ class Qwen3TTSModel(Engine):
 def gguf_config(path: str) -> dict:
     """config.json of a GGUF checkpoint, derived by the library from the file's metadata (pure host code, no GPU needed)."""
     lib = load_library()
-    buf = C.create_string_buffer(2048)
+    buf = C.create_string_buffer(16384)
     need = C.c_size_t(0)
     rc = lib.crane_b200_gguf_config(os.fsencode(path), buf, len(buf), C.byref(need))
     if rc != OK:

@@ -103,6 +103,49 @@ void to_f32(const void* src, int dt, size_t n, std::vector<float>& out) {
     else { const uint16_t* s = (const uint16_t*)src; for (size_t i = 0; i < n; ++i) out[i] = f16_bits_to_f32(s[i]); }
 }
 
+// ggml block formats -> f32 on the host (dequantize_row_q8_0 / q4_K / q6_K of ggml-quants.c; restated in oracle/ggml_quant.py, which
+// is byte-exact against the `gguf` package).  Used where quantised weights are not run as such: the Qwen3.5 hybrid's GGUF tensors.
+void ggml_dequant_rows(int qt, const unsigned char* src, size_t rows, size_t K, std::vector<float>& out) {
+    out.resize(rows * K);
+    auto f16 = [](const unsigned char* p) { uint16_t h; std::memcpy(&h, p, 2); return f16_bits_to_f32(h); };
+    float* y = out.data();
+    if (qt == 8) {
+        for (size_t b = 0; b < rows * K / 32; ++b, src += 34, y += 32) {
+            const float d = f16(src);
+            for (int i = 0; i < 32; ++i) y[i] = d * (float)(int8_t)src[2 + i];
+        }
+    } else if (qt == 12) {
+        for (size_t b = 0; b < rows * K / 256; ++b, src += 144, y += 256) {
+            const float d = f16(src), dmin = f16(src + 2);
+            const unsigned char *sc = src + 4, *q = src + 16;
+            auto scale_min = [&](int j, int& s_, int& m_) {
+                if (j < 4) { s_ = sc[j] & 63; m_ = sc[j + 4] & 63; }
+                else { s_ = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4); m_ = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4); }
+            };
+            for (int j = 0; j < 4; ++j) {
+                int s1, m1, s2, m2;
+                scale_min(2 * j, s1, m1); scale_min(2 * j + 1, s2, m2);
+                const float d1 = d * s1, n1 = dmin * m1, d2 = d * s2, n2 = dmin * m2;
+                for (int l = 0; l < 32; ++l) { y[64 * j + l] = d1 * (q[32 * j + l] & 0xF) - n1; y[64 * j + 32 + l] = d2 * (q[32 * j + l] >> 4) - n2; }
+            }
+        }
+    } else {
+        for (size_t b = 0; b < rows * K / 256; ++b, src += 210, y += 256) {
+            const unsigned char *ql = src, *qh = src + 128;
+            const int8_t* sc = (const int8_t*)(src + 192);
+            const float d = f16(src + 208);
+            for (int n = 0; n < 2; ++n, ql += 64, qh += 32, sc += 8)
+                for (int l = 0; l < 32; ++l) {
+                    const int is = l / 16;
+                    const int q1 = (int)((ql[l] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32, q2 = (int)((ql[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
+                    const int q3 = (int)((ql[l] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32, q4 = (int)((ql[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
+                    float* yy = y + 128 * n;
+                    yy[l] = d * sc[is] * q1; yy[l + 32] = d * sc[is + 2] * q2; yy[l + 64] = d * sc[is + 4] * q3; yy[l + 96] = d * sc[is + 6] * q4;
+                }
+        }
+    }
+}
+
 struct LayerW {
     bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr;
     float *ln1 = nullptr, *ln2 = nullptr, *qn = nullptr, *kn = nullptr;
@@ -155,6 +198,7 @@ struct crane_b200_model {
     std::vector<int> layer_is_full;
     int max_seq = 4096, max_batch = 1, max_pages = 0;
     bool use_simt = false, use_graphs = true, use_pdl = true, use_persistent = true;
+    bool tensor_gguf_named = false;         // the tensor being loaded came under its llama.cpp name (Qwen3.5: folded norms, Chunked v-heads)
     struct crane_b200_comm* comm = nullptr;   // multi-GPU: NCCL communicator + gather buffers (engine_comm.inc)
     PassProfiler spans;                     // CRANE_PROF=1 / crane_b200_prof_enable: enqueue vs wall per pass + stage spans (ops/prof.rs)
     // persistent decode kernel (decode_ll.cu): exchange buffers of (value, tag) pairs, the tag counter, the timeout flag
@@ -371,7 +415,7 @@ struct crane_b200_model {
     void up_norm(float* dst, const void* data, int dt, size_t n) {
         std::vector<float> tmp;
         to_f32(data, dt, n, tmp);
-        if (hybrid) for (auto& v : tmp) v += 1.0f;
+        if (hybrid && !tensor_gguf_named) for (auto& v : tmp) v += 1.0f;   // (llama.cpp's converter stores the +1 folded in already)
         CUDA_OK(cudaMemcpy(dst, tmp.data(), n * 4, cudaMemcpyHostToDevice));
     }
 
@@ -637,22 +681,63 @@ bool crane_b200_model::load_text_tensor(const std::string& n, int dt, const int6
     else if (t == "self_attn.q_norm.weight") { want_shape(n, shape, ndim, {D}); up_norm(l.qn, data, dt, D); l.loaded |= 512; }
     else if (t == "self_attn.k_norm.weight") { want_shape(n, shape, ndim, {D}); up_norm(l.kn, data, dt, D); l.loaded |= 1024; }
     // ---- Gated-Delta-Net (names: ops/gdn/layer.rs:55-67, projection.rs:75-83); in_proj rows merged as q|k|v, z, b, a ----
-    else if (t == "linear_attn.in_proj_qkv.weight") { want_shape(n, shape, ndim, {conv_dim(), H}); rows_bf16(l.w_in, conv_dim(), H); l.loaded |= 1; }
-    else if (t == "linear_attn.in_proj_z.weight") { want_shape(n, shape, ndim, {value_dim(), H}); rows_bf16(l.w_in + (size_t)conv_dim() * H, value_dim(), H); l.loaded |= 2; }
-    else if (t == "linear_attn.in_proj_b.weight") { want_shape(n, shape, ndim, {nv, H}); rows_bf16(l.w_in + (size_t)(conv_dim() + value_dim()) * H, nv, H); l.loaded |= 4; }
-    else if (t == "linear_attn.in_proj_a.weight") { want_shape(n, shape, ndim, {nv, H}); rows_bf16(l.w_in + (size_t)(conv_dim() + value_dim() + nv) * H, nv, H); l.loaded |= 8; }
-    else if (t == "linear_attn.conv1d.weight") { want_shape(n, shape, ndim, {conv_dim(), 1, ck}); up_f32(l.conv_w, data, dt, (size_t)conv_dim() * ck); l.loaded |= 512; }
-    else if (t == "linear_attn.dt_bias") { want_shape(n, shape, ndim, {nv}); up_f32(l.dt_bias, data, dt, nv); l.loaded |= 1024; }
-    else if (t == "linear_attn.A_log") {
-        want_shape(n, shape, ndim, {nv});
-        std::vector<float> tmp;
-        to_f32(data, dt, nv, tmp);
-        for (auto& v : tmp) v = -expf(v);        // GdnGateConsts::new (ops/gdn/backend.rs:176-190)
-        CUDA_OK(cudaMemcpy(l.neg_exp_a, tmp.data(), nv * 4, cudaMemcpyHostToDevice));
-        l.loaded |= 2048;
+    // A llama.cpp-named tensor orders the value heads `Chunked` (index = replica * nk + key_head) where HF -- and every kernel here
+    // -- has them `Interleaved` (key_head * (nv / nk) + replica) (ops/gdn/config.rs:13-22).  The reference adapts its Q/K expansion;
+    // the tensors are dequantised here anyway, so the value-head blocks are simply put back into HF order: vhead() returns the f32
+    // tensor with the nv blocks of `blk` elements that start at element `first` of every `period`-element group permuted.
+    else if (t.rfind("linear_attn.", 0) == 0) {
+        size_t numel = 1;
+        for (int i = 0; i < ndim; ++i) numel *= (size_t)shape[i];
+        const bool chunked = tensor_gguf_named && nv != nk;
+        std::vector<float> f;
+        auto vhead = [&](size_t period, size_t first, size_t blk) -> const void* {
+            if (!chunked) return data;
+            to_f32(data, dt, numel, f);
+            std::vector<float> o(f);
+            const int vpg = nv / nk;
+            for (size_t g0 = 0; g0 + period <= numel; g0 += period)
+                for (int kh = 0; kh < nk; ++kh)
+                    for (int r = 0; r < vpg; ++r)
+                        std::memcpy(&o[g0 + first + (size_t)(kh * vpg + r) * blk], &f[g0 + first + (size_t)(r * nk + kh) * blk], blk * sizeof(float));
+            f.swap(o);
+            return f.data();
+        };
+        const int dtp = chunked ? (int)CRANE_B200_F32 : dt;
+        const size_t key2 = (size_t)2 * nk * dk;
+        if (t == "linear_attn.in_proj_qkv.weight") {
+            want_shape(n, shape, ndim, {conv_dim(), H});
+            up_bf16(l.w_in, vhead(numel, key2 * H, (size_t)dv * H), dtp, (size_t)conv_dim() * H); l.loaded |= 1;
+        } else if (t == "linear_attn.in_proj_z.weight") {
+            want_shape(n, shape, ndim, {value_dim(), H});
+            up_bf16(l.w_in + (size_t)conv_dim() * H, vhead(numel, 0, (size_t)dv * H), dtp, (size_t)value_dim() * H); l.loaded |= 2;
+        } else if (t == "linear_attn.in_proj_b.weight") {
+            want_shape(n, shape, ndim, {nv, H});
+            up_bf16(l.w_in + (size_t)(conv_dim() + value_dim()) * H, vhead(numel, 0, H), dtp, (size_t)nv * H); l.loaded |= 4;
+        } else if (t == "linear_attn.in_proj_a.weight") {
+            want_shape(n, shape, ndim, {nv, H});
+            up_bf16(l.w_in + (size_t)(conv_dim() + value_dim() + nv) * H, vhead(numel, 0, H), dtp, (size_t)nv * H); l.loaded |= 8;
+        } else if (t == "linear_attn.conv1d.weight") {      // HF [conv_dim, 1, ck]; GGUF stores it 2-D [conv_dim, ck]
+            want_shape(n, shape, ndim, {conv_dim(), 1, ck});
+            up_f32(l.conv_w, vhead(numel, key2 * ck, (size_t)dv * ck), dtp, (size_t)conv_dim() * ck); l.loaded |= 512;
+        } else if (t == "linear_attn.dt_bias") {
+            want_shape(n, shape, ndim, {nv});
+            up_f32(l.dt_bias, vhead(numel, 0, 1), dtp, nv); l.loaded |= 1024;
+        } else if (t == "linear_attn.A_log" || t == "linear_attn.neg_exp_a") {
+            want_shape(n, shape, ndim, {nv});
+            std::vector<float> tmp;
+            to_f32(vhead(numel, 0, 1), dtp, nv, tmp);
+            // HF stores A_log, the kernels want -exp(A_log) (GdnGateConsts::new, ops/gdn/backend.rs:176-190); llama.cpp's `ssm_a` already
+            // is -exp(A_log) (the reference takes (-ssm_a).ln() to get A_log back, qwen3_5/modeling.rs:747-750)
+            if (t == "linear_attn.A_log") for (auto& v : tmp) v = -expf(v);
+            CUDA_OK(cudaMemcpy(l.neg_exp_a, tmp.data(), nv * 4, cudaMemcpyHostToDevice));
+            l.loaded |= 2048;
+        } else if (t == "linear_attn.norm.weight") {
+            want_shape(n, shape, ndim, {dv}); up_f32(l.gnorm, data, dt, dv); l.loaded |= 4096;
+        } else if (t == "linear_attn.out_proj.weight") {     // value heads are COLUMN blocks here
+            want_shape(n, shape, ndim, {H, value_dim()});
+            up_bf16(l.w_out, vhead((size_t)value_dim(), 0, dv), dtp, (size_t)H * value_dim()); l.loaded |= 8192;
+        } else return false;
     }
-    else if (t == "linear_attn.norm.weight") { want_shape(n, shape, ndim, {dv}); up_f32(l.gnorm, data, dt, dv); l.loaded |= 4096; }
-    else if (t == "linear_attn.out_proj.weight") { want_shape(n, shape, ndim, {H, value_dim()}); rows_bf16(l.w_out, H, value_dim()); l.loaded |= 8192; }
     else return false;
     return true;
 }
@@ -709,6 +794,8 @@ bool crane_b200_model::load_vision_tensor(const std::string& n, int dt, const in
 void crane_b200_model::load_tensor(const std::string& name_in, int dt, const int64_t* shape, int ndim, const void* data) {
     if (is_tts && name_in.rfind("talker.", 0) == 0) { tts_load(name_in, dt, shape, ndim, data); return; }
     const std::string name = gguf_to_hf(name_in);
+    struct Flag { bool& f; ~Flag() { f = false; } } flag_reset{tensor_gguf_named};
+    tensor_gguf_named = name != name_in;
     if (finalized) fail(CRANE_B200_INVALID_ARG, "load_tensor after finalize");
     if (dt < 0 || dt > 2) fail(CRANE_B200_INVALID_ARG, "tensor %s: unknown dtype %d", name.c_str(), dt);
     CUDA_OK(cudaSetDevice(device));
@@ -772,7 +859,13 @@ static std::string gguf_to_hf(const std::string& n) {
         {"attn_q.weight", "self_attn.q_proj.weight"}, {"attn_k.weight", "self_attn.k_proj.weight"}, {"attn_v.weight", "self_attn.v_proj.weight"},
         {"attn_output.weight", "self_attn.o_proj.weight"}, {"attn_q_norm.weight", "self_attn.q_norm.weight"},
         {"attn_k_norm.weight", "self_attn.k_norm.weight"}, {"ffn_gate.weight", "mlp.gate_proj.weight"}, {"ffn_up.weight", "mlp.up_proj.weight"},
-        {"ffn_down.weight", "mlp.down_proj.weight"}};
+        {"ffn_down.weight", "mlp.down_proj.weight"},
+        // llama.cpp `qwen35` (qwen3_5/modeling.rs:688-775): the split Gated-Delta-Net projections and their side tensors
+        {"post_attention_norm.weight", "post_attention_layernorm.weight"}, {"attn_qkv.weight", "linear_attn.in_proj_qkv.weight"},
+        {"attn_gate.weight", "linear_attn.in_proj_z.weight"}, {"ssm_beta.weight", "linear_attn.in_proj_b.weight"},
+        {"ssm_alpha.weight", "linear_attn.in_proj_a.weight"}, {"ssm_conv1d.weight", "linear_attn.conv1d.weight"},
+        {"ssm_dt.bias", "linear_attn.dt_bias"}, {"ssm_a", "linear_attn.neg_exp_a"}, {"ssm_norm.weight", "linear_attn.norm.weight"},
+        {"ssm_out.weight", "linear_attn.out_proj.weight"}};
     for (auto& m : map)
         if (t == m[0]) return "model.layers." + idx + "." + m[1];
     return n;
@@ -791,8 +884,20 @@ unsigned char* crane_b200_model::up_quant(int qt, const void* data, size_t rows,
 void crane_b200_model::load_tensor_ggml(const std::string& name_in, int qt, const int64_t* shape, int ndim, const void* data, size_t nbytes) {
     if (finalized) fail(CRANE_B200_INVALID_ARG, "load_tensor after finalize");
     if (qt != QT_Q4_K && qt != QT_Q6_K && qt != QT_Q8_0) fail(CRANE_B200_UNSUPPORTED, "ggml type %d (supported: Q8_0=8, Q4_K=12, Q6_K=14)", qt);
-    if (hybrid || is_vl) fail(CRANE_B200_UNSUPPORTED, "quantised tensors are supported for the dense Qwen3 decoder only");
+    if (is_vl) fail(CRANE_B200_UNSUPPORTED, "quantised tensors are not supported for the VL model");
     if (ndim != 2) fail(CRANE_B200_INVALID_ARG, "tensor %s: quantised tensors are 2-D [rows, cols]", name_in.c_str());
+    if (hybrid) {
+        // The hybrid's kernels stream bf16: its GGUF tensors are dequantised at load (the reference keeps QTensor blocks for the
+        // linears -- qwen3_5/modeling.rs:379-411,704-775 -- so logits follow `x . dequant(W)^T`, not candle's int8-activation QMatMul)
+        const int64_t r_ = shape[0], k_ = shape[1];
+        const int be = q_src_block_elems(qt);
+        if (r_ <= 0 || k_ <= 0 || k_ % be) fail(CRANE_B200_INVALID_ARG, "tensor %s: bad quantised shape", name_in.c_str());
+        if (nbytes != (size_t)r_ * (k_ / be) * q_src_block_bytes(qt)) fail(CRANE_B200_INVALID_ARG, "tensor %s: byte count", name_in.c_str());
+        std::vector<float> f;
+        ggml_dequant_rows(qt, (const unsigned char*)data, (size_t)r_, (size_t)k_, f);
+        load_tensor(name_in, CRANE_B200_F32, shape, ndim, f.data());
+        return;
+    }
     CUDA_OK(cudaSetDevice(device));
     std::string name = gguf_to_hf(name_in);
     const int64_t rows = shape[0], K = shape[1];

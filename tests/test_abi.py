@@ -117,3 +117,32 @@ def test_rust_sys_crate_declares_every_entry_point():
     assert len(names) >= 49 and len(set(names)) == len(names)
     for n in names:
         assert len(re.findall(r"pub fn " + n + r"\(", rs)) == 1, n
+
+
+def test_gguf_config_for_the_qwen35_architecture(tmp_path):
+    """crane_b200_gguf_config on llama.cpp `qwen35` metadata (Qwen3_5Model::from_gguf, qwen3_5/model.rs:155-325) -- pure host code:
+    layer layout from `blk.{i}.ssm_a` presence, value-head size from ssm.inner_size / ssm.time_step_rank, partial rotary factor
+    from rope.dimension_count, mrope sections from an ARRAY value, tie_word_embeddings from the absence of output.weight."""
+    import gguf
+    import numpy as np
+    import crane_b200
+    path = str(tmp_path / "meta.gguf")
+    wr = gguf.GGUFWriter(path, "qwen35")
+    for k, v in (("block_count", 4), ("embedding_length", 256), ("feed_forward_length", 512), ("attention.head_count", 4),
+                 ("attention.head_count_kv", 2), ("attention.key_length", 256), ("rope.dimension_count", 64), ("ssm.conv_kernel", 4),
+                 ("ssm.state_size", 128), ("ssm.group_count", 2), ("ssm.time_step_rank", 4), ("ssm.inner_size", 512)):
+        wr.add_uint32("qwen35." + k, v)
+    wr.add_float32("qwen35.rope.freq_base", 1e7)
+    wr.add_array("qwen35.rope.dimension_sections", [11, 11, 10, 0])
+    wr.add_array("tokenizer.ggml.tokens", ["a", "b", "c"])
+    wr.add_tensor("token_embd.weight", np.zeros((1024, 256), np.float32))
+    for i in (0, 1, 2):
+        wr.add_tensor(f"blk.{i}.ssm_a", np.zeros(4, np.float32))
+    wr.add_tensor("blk.3.attn_q.weight", np.zeros((2 * 4 * 256, 256), np.float32))
+    wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+    c = crane_b200.gguf_config(path)
+    assert c["model_type"] == "qwen3_5_text" and c["vocab_size"] == 1024 and c["tie_word_embeddings"] is True
+    assert c["layer_types"] == ["linear_attention"] * 3 + ["full_attention"]
+    assert (c["linear_num_key_heads"], c["linear_num_value_heads"], c["linear_key_head_dim"], c["linear_value_head_dim"]) == (2, 4, 128, 128)
+    assert c["head_dim"] == 256 and abs(c["partial_rotary_factor"] - 0.25) < 1e-9
+    assert c["rope_parameters"]["mrope_section"] == [11, 11, 10, 0] and c["rope_parameters"]["rope_theta"] == 1e7

@@ -925,6 +925,135 @@ def test_gguf_file_reader(tmp_path):
     m2.close()
 
 
+def test_qwen3_5_gguf_file(tmp_path):
+    """A llama.cpp `qwen35` GGUF (Qwen3_5Model::from_gguf, qwen3_5/model.rs:155-325, modeling.rs:379-411,688-775): config from the
+    metadata alone (layer layout from `ssm_a` presence, mrope sections from an array value), llama.cpp tensor names, norms with the
+    +1 already folded in, `ssm_a = -exp(A_log)`, a 2-D conv kernel, and the value heads in `Chunked` order (nk = 2 < nv = 4 here,
+    so the order matters) -- must reproduce the safetensors-named model; a Q8_0 / Q4_K / Q6_K variant of the linears
+    is dequantised (and rounded to bf16) at load and must match the oracle run on those weights."""
+    import gguf
+    from oracle import ggml_quant as gq
+    from oracle.qwen3_5 import Qwen3_5Oracle
+    cfg = synth.TINY_QWEN3_5
+    w = dict(synth.synth_checkpoint(cfg))
+    ids = synth.synth_token_ids(40, cfg["vocab_size"], "gg35")
+    ref_m, _ = _model(cfg, cls=crane_b200.Qwen3_5Model)
+    ref = ref_m.forward_step(ids, 0).copy()
+    ref_m.close()
+    nk, nv, dk, dv = cfg["linear_num_key_heads"], cfg["linear_num_value_heads"], cfg["linear_key_head_dim"], cfg["linear_value_head_dim"]
+    vpg, key2 = nv // nk, 2 * nk * dk
+    order = [kh * vpg + r for r in range(vpg) for kh in range(nk)]        # chunked slot (r * nk + kh) holds HF head kh * vpg + r
+
+    def chunk_rows(a, first, blk):                                        # HF (interleaved) -> llama.cpp (chunked) over row blocks
+        a = a.copy()
+        v = a[first:first + nv * blk].reshape(nv, blk, *a.shape[1:])
+        a[first:first + nv * blk] = v[order].reshape(nv * blk, *a.shape[1:])
+        return a
+
+    ren = {"self_attn.q_proj": "attn_q", "self_attn.k_proj": "attn_k", "self_attn.v_proj": "attn_v", "self_attn.o_proj": "attn_output",
+           "self_attn.q_norm": "attn_q_norm", "self_attn.k_norm": "attn_k_norm", "mlp.gate_proj": "ffn_gate", "mlp.up_proj": "ffn_up",
+           "mlp.down_proj": "ffn_down", "input_layernorm": "attn_norm", "post_attention_layernorm": "post_attention_norm",
+           "linear_attn.in_proj_qkv": "attn_qkv", "linear_attn.in_proj_z": "attn_gate", "linear_attn.in_proj_b": "ssm_beta",
+           "linear_attn.in_proj_a": "ssm_alpha", "linear_attn.norm": "ssm_norm", "linear_attn.out_proj": "ssm_out"}
+
+    def convert(name, a):
+        a = np.asarray(a, dtype=np.float32)
+        if name == "model.embed_tokens.weight":
+            return "token_embd.weight", a
+        if name == "model.norm.weight":
+            return "output_norm.weight", a + 1.0
+        i, t = name.split(".")[2], ".".join(name.split(".")[3:])
+        if t == "linear_attn.conv1d.weight":
+            return f"blk.{i}.ssm_conv1d.weight", chunk_rows(a.reshape(a.shape[0], -1), key2, dv)
+        if t == "linear_attn.dt_bias":
+            return f"blk.{i}.ssm_dt.bias", chunk_rows(a, 0, 1)
+        if t == "linear_attn.A_log":
+            return f"blk.{i}.ssm_a", chunk_rows(-np.exp(a), 0, 1)
+        stem, suffix = t.rsplit(".", 1)
+        if stem in ("input_layernorm", "post_attention_layernorm", "self_attn.q_norm", "self_attn.k_norm"):
+            a = a + 1.0                                                   # folded
+        elif stem == "linear_attn.in_proj_qkv":
+            a = chunk_rows(a, key2, dv)
+        elif stem == "linear_attn.in_proj_z":
+            a = chunk_rows(a, 0, dv)
+        elif stem in ("linear_attn.in_proj_b", "linear_attn.in_proj_a"):
+            a = chunk_rows(a, 0, 1)
+        elif stem == "linear_attn.out_proj":
+            a = np.ascontiguousarray(chunk_rows(np.ascontiguousarray(a.T), 0, dv).T)
+        return f"blk.{i}.{ren[stem]}.{suffix}", a
+
+    def write(path, quant):
+        wr = gguf.GGUFWriter(path, "qwen35")
+        rp = cfg["rope_parameters"]
+        for k, v in (("block_count", cfg["num_hidden_layers"]), ("embedding_length", cfg["hidden_size"]), ("feed_forward_length", cfg["intermediate_size"]),
+                     ("attention.head_count", cfg["num_attention_heads"]), ("attention.head_count_kv", cfg["num_key_value_heads"]),
+                     ("attention.key_length", cfg["head_dim"]), ("rope.dimension_count", int(cfg["head_dim"] * rp["partial_rotary_factor"])),
+                     ("ssm.conv_kernel", cfg["linear_conv_kernel_dim"]), ("ssm.state_size", dk), ("ssm.group_count", nk), ("ssm.time_step_rank", nv),
+                     ("ssm.inner_size", nv * dv), ("full_attention_interval", cfg["full_attention_interval"]), ("context_length", 4096)):
+            wr.add_uint32("qwen35." + k, v)
+        wr.add_float32("qwen35.rope.freq_base", float(rp["rope_theta"]))
+        wr.add_float32("qwen35.attention.layer_norm_rms_epsilon", float(cfg["rms_norm_eps"]))
+        wr.add_array("qwen35.rope.dimension_sections", [int(x) for x in rp["mrope_section"]] + [0])
+        wr.add_array("tokenizer.ggml.tokens", ["a", "b"])
+        deq = {}
+        qtypes = {"Q4_K": gguf.GGMLQuantizationType.Q4_K, "Q6_K": gguf.GGMLQuantizationType.Q6_K, "Q8_0": gguf.GGMLQuantizationType.Q8_0}
+        for name, arr in w.items():
+            gname, a = convert(name, arr)
+            qt = None
+            if quant and a.ndim == 2 and a.shape[1] % 256 == 0 and not gname.endswith(("ssm_beta.weight", "ssm_alpha.weight", "ssm_conv1d.weight")):
+                qt = "Q6_K" if "attn_v" in gname or "ffn_down" in gname else "Q8_0" if "ssm_out" in gname else "Q4_K"
+            if qt:
+                raw = np.ascontiguousarray(gq.quantize(a, qt)).reshape(a.shape[0], -1)
+                wr.add_tensor(gname, raw, raw_dtype=qtypes[qt])
+                deq[name] = qt
+            else:
+                wr.add_tensor(gname, np.ascontiguousarray(a))
+        wr.write_header_to_file(); wr.write_kv_data_to_file(); wr.write_tensors_to_file(); wr.close()
+        return deq
+
+    p32 = str(tmp_path / "q35_f32.gguf")
+    write(p32, False)
+    got_cfg = crane_b200.gguf_config(p32)
+    assert got_cfg["model_type"] == "qwen3_5_text" and got_cfg["layer_types"] == ["linear_attention"] * 3 + ["full_attention"]
+    assert got_cfg["linear_num_value_heads"] == nv and got_cfg["linear_value_head_dim"] == dv and got_cfg["rope_parameters"]["mrope_section"][:3] == [11, 11, 10]
+    m = crane_b200.Qwen3_5Model.from_gguf(p32, device=0, max_seq_len=512)
+    got = m.forward_step(ids, 0)
+    e = rel_err(got, ref)
+    print(f"qwen35 gguf (f32 tensors, chunked v-heads, folded norms): rel {e:.1e} against the HF-named model")
+    assert e < 1e-4                                       # (numpy's exp / +1 and the loader's differ in the last bit)
+    m.close()
+    # quantised linears: dequantised at load
+    pq = str(tmp_path / "q35_q.gguf")
+    deq = write(pq, True)
+    assert len(deq) >= 20
+    wq = dict(w)
+    for name, qt in deq.items():
+        gname, a = convert(name, w[name])
+        # (quantise in the converted -- chunked -- layout, as the file does, then undo the layout for the oracle)
+        d = gq.dequantize(gq.quantize(a, qt), qt, a.shape[1]).astype(np.float32)
+        back = {v: k for k, v in enumerate(order)}
+        inv = [back[i] for i in range(nv)]
+
+        def unchunk(x, first, blk):
+            x = x.copy()
+            v = x[first:first + nv * blk].reshape(nv, blk, *x.shape[1:])
+            x[first:first + nv * blk] = v[inv].reshape(nv * blk, *x.shape[1:])
+            return x
+        stem = ".".join(name.split(".")[3:]).rsplit(".", 1)[0] if name.startswith("model.layers.") else ""
+        if stem == "linear_attn.in_proj_qkv":
+            d = unchunk(d, key2, dv)
+        elif stem == "linear_attn.in_proj_z":
+            d = unchunk(d, 0, dv)
+        elif stem == "linear_attn.out_proj":
+            d = np.ascontiguousarray(unchunk(np.ascontiguousarray(d.T), 0, dv).T)
+        wq[name] = synth.bf16_round(d)                    # the hybrid's kernels stream bf16: dequantised values are rounded once, at load
+    mq = crane_b200.Qwen3_5Model.from_gguf(pq, device=0, max_seq_len=512)
+    eq = rel_err(mq.forward_step(ids, 0), Qwen3_5Oracle(cfg, wq).forward(ids, 0).numpy())
+    print(f"qwen35 gguf (Q4_K / Q6_K / Q8_0 linears dequantised at load): rel {eq:.1e} against the oracle on the dequantised weights")
+    assert eq < 1e-3
+    mq.close()
+
+
 # ---- device-side sampler (SURVEY 8f N2 / A20): top-k total order, penalties, top-p, Gumbel-max ----------------------------------------
 
 def test_topk_kernel_known_answers_and_host_order():
