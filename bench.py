@@ -397,35 +397,42 @@ def main():
     wall = time.perf_counter() - t0
     launches = model.kernel_launches() - l0
 
-    # ---- e2e leg: host buffers in, token ids out, one C-ABI call per token (the server's greedy path) ----
-    def request_e2e():
+    # ---- e2e leg: the request through the public API with HOST buffers: image + prompt ids in (H2D inside), 256 token ids out.
+    # (a) the call a user makes to generate: vl_forward + ONE decode_greedy call (`Model::generate`, qwen3/model.rs:275-349), tokens
+    #     read back at the end; (b) the server's streaming path: one vl_decode_step_argmax call (4-byte D2H + host sync) per token.
+    def request_e2e(per_token):
         model.clear_kv_cache()
         t_a = time.perf_counter()
         lg = model.forward(ids, pv_pinned, [grid], 0)
         tok = int(np.argmax(lg))
         t_b = time.perf_counter()
-        toks_e = [tok]
-        for i in range(N_DECODE):
-            tok = model.decode_step_argmax(tok, S + i)
-            toks_e.append(tok)
-        gpu_out["tokens_e2e"] = toks_e
+        if per_token:
+            toks_e = [tok]
+            for i in range(N_DECODE):
+                tok = model.decode_step_argmax(tok, S + i)
+                toks_e.append(tok)
+        else:
+            toks_e = [tok] + [int(x) for x in model.decode_greedy(tok, S, N_DECODE)]
+        gpu_out["tokens_e2e_stream" if per_token else "tokens_e2e"] = toks_e
         return t_b - t_a, time.perf_counter() - t_b
 
-    request_e2e()
+    request_e2e(False)
+    request_e2e(True)
     barrier()
-    e_pre, e_dec = [], []
+    e_pre, e_dec, s_dec = [], [], []
     for _ in range(max(1, min(args.steps, 3))):
-        a, b = request_e2e()
+        a, b = request_e2e(False)
         e_pre.append(a)
         e_dec.append(b)
+        s_dec.append(request_e2e(True)[1])
     barrier()
     clocks = sampler.summary()
 
     dec_total_s = sum(dec_ms) / 1e3
-    stats = torch.tensor([wall, dec_total_s, sum(pre_ms) / 1e3, sum(e_dec), sum(e_pre)], dtype=torch.float64, device=f"cuda:{dev}")
+    stats = torch.tensor([wall, dec_total_s, sum(pre_ms) / 1e3, sum(e_dec), sum(e_pre), sum(s_dec)], dtype=torch.float64, device=f"cuda:{dev}")
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    wall_m, dec_m, pre_m, edec_m, epre_m = [float(x) for x in stats.tolist()]
+    wall_m, dec_m, pre_m, edec_m, epre_m, sdec_m = [float(x) for x in stats.tolist()]
     tokens_all = world * args.steps * N_DECODE
     value = tokens_all / dec_m
     fl = prefill_flops(cfg, S, n_patches, n_img_tok)
@@ -457,12 +464,14 @@ def main():
         "value": value, "ms_per_step": 1e3 * wall_m / args.steps,
         "prefill_tflops": prefill_tflops, "prefill_ms": 1e3 * pre_m / args.steps, "prefill_tflop_per_request": fl / 1e12,
         "prefill_frac_of_bf16_peak": prefill_tflops / world / (peaks["bf16_tflops"]),
-        "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": int(pv.nbytes + ids.nbytes + 4 * N_DECODE + 32 * (N_DECODE + 1)),
+        "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": int(pv.nbytes + ids.nbytes + 3 * 4 * S + 2 * 32),
                 "d2h_bytes_per_step": int(4 * N_DECODE + 4 * cfg["text_config"]["vocab_size"]),
                 "definition": "decode tokens / (ViT + prefill + decode) wall time of the request, host buffers in and out",
                 "decode_only_tok_s": e2e_decode_only, "prefill_s": epre_m / len(e_pre),
-                "api": "crane_b200_vl_forward + crane_b200_vl_decode_step_argmax per token",
-                "tokens_equal_device_loop": gpu_out["tokens_e2e"] == gpu_out["tokens"]},
+                "api": "crane_b200_vl_forward + one crane_b200_decode_greedy call (Model::generate); tokens read back at the end",
+                "streaming_tok_s": world * len(s_dec) * N_DECODE / (sdec_m + epre_m),
+                "streaming_api": "crane_b200_vl_forward + crane_b200_vl_decode_step_argmax per token (host sync + 4-byte D2H each)",
+                "tokens_equal_device_loop": gpu_out["tokens_e2e"] == gpu_out["tokens"] and gpu_out["tokens_e2e_stream"] == gpu_out["tokens"]},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],

@@ -106,6 +106,28 @@ class B200Backend : public ModelBackend {
         return out;
     }
 
+    // ---- prefix sharing and the legacy tensor swap (backend.rs:65-84 get_kv_caches / set_kv_caches) ----
+    int seq_fork(int src) { int s = -1; ck(crane_b200_seq_fork(h_, src, &s)); return s; }
+    struct LayerCache { std::vector<float> k, v; size_t n_tokens = 0; };      // attention layer: [n_kv, T, D] each
+    LayerCache kv_export(int layer, size_t floats_per_tensor) {
+        LayerCache c;
+        c.k.resize(floats_per_tensor); c.v.resize(floats_per_tensor);
+        ck(crane_b200_kv_export(h_, layer, c.k.data(), c.v.data(), floats_per_tensor, &c.n_tokens));
+        return c;
+    }
+    void kv_import(int layer, const LayerCache& c) { ck(crane_b200_kv_import(h_, layer, c.k.data(), c.v.data(), c.n_tokens)); }
+    void kv_set_len(size_t n_tokens, uint32_t next_rotary_pos) { ck(crane_b200_kv_set_len(h_, n_tokens, next_rotary_pos)); }
+
+    // ---- the server's sampler on the device (crane-serve/src/engine/sampling.rs:169-480) ----
+    static crane_b200_sampling greedy() { crane_b200_sampling p{}; p.repetition_penalty = 1.f; return p; }
+    uint32_t sample(const crane_b200_sampling& p) { uint32_t t = 0; ck(crane_b200_sample(h_, &p, &t)); return t; }
+    uint32_t forward_step_sample(const std::vector<uint32_t>& input_ids, size_t start_pos, const crane_b200_sampling& p) {
+        uint32_t t = 0;
+        ck(crane_b200_forward_step_sample(h_, input_ids.data(), input_ids.size(), start_pos, &p, &t));
+        return t;
+    }
+    std::vector<uint32_t> topk(size_t k) { std::vector<uint32_t> idx(k); ck(crane_b200_topk(h_, k, idx.data(), nullptr)); return idx; }
+
     int vocab_size() const { return crane_b200_vocab_size(h_); }
     int hidden_size() const { return crane_b200_hidden_size(h_); }
     uint64_t kernel_launches() const { return crane_b200_kernel_launches(h_); }

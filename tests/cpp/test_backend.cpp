@@ -96,6 +96,33 @@ static int run_gpu() {
         CHECK(first[i] == solo[i][0]);
         for (int j = 0; j < 4; ++j) CHECK(toks[i][j] == solo[i][j + 1]);
     }
+    // sampler: temperature 0 == argmax; top-k order starts at the argmax; a fork continues like its source
+    m.seq_select(0);
+    m.clear_kv_cache();
+    auto lg = m.forward_step(prompt, 0);
+    CHECK(m.sample(B200Backend::greedy()) == (uint32_t)am);
+    auto tk = m.topk(8);
+    CHECK(tk[0] == (uint32_t)am);
+    for (int j = 0; j + 1 < 8; ++j) CHECK(lg[tk[j]] > lg[tk[j + 1]] || (lg[tk[j]] == lg[tk[j + 1]] && tk[j] < tk[j + 1]));
+    crane_b200_sampling sp = B200Backend::greedy();
+    sp.temperature = 0.8f; sp.top_k = 8; sp.top_p = 0.9f; sp.seed = 42;
+    const uint32_t drawn = m.sample(sp);
+    bool in_topk = false;
+    for (uint32_t t : tk) in_topk = in_topk || t == drawn;
+    CHECK(in_topk);
+    const int f = m.seq_fork(0);
+    const uint32_t a1 = m.forward_step_argmax({(uint32_t)am}, prompt.size());
+    m.seq_select(f);
+    CHECK(m.kv_len() == prompt.size());
+    CHECK(m.forward_step_argmax({(uint32_t)am}, prompt.size()) == a1);
+    // KV swap: export layer 0 of the fork, import it back, nothing changes
+    const size_t per = (size_t)2 /*n_kv*/ * m.kv_len() * 128;
+    auto c0 = m.kv_export(0, per);
+    CHECK(c0.n_tokens == m.kv_len());
+    m.kv_import(0, c0);
+    m.kv_set_len(m.kv_len(), (uint32_t)m.kv_len());
+    auto again = m.kv_export(0, per);
+    CHECK(again.k == c0.k && again.v == c0.v);
     std::printf("C++ mirror: ok (%llu kernel launches, %llu KV bytes)\n", (unsigned long long)m.kernel_launches(), (unsigned long long)m.active_kv_cache_bytes());
     return 0;
 }

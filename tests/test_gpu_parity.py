@@ -811,7 +811,7 @@ def test_tts_frame_loop_against_oracle():
     pre, trail, pad = m.build_prefill_embeds(list(ids))
     e_glue = max(rel_err(pre, pre_o.numpy()), rel_err(trail, trail_o.numpy()), rel_err(pad, pad_o.numpy()))
     # greedy oracle frames, then teacher-force the same codes through the engine and compare every head's logits
-    n = 6
+    n = 12
     frames_o, trace = orc.generate_codes(ids, n, repetition_penalty=1.05)
     assert len(frames_o) == n
     frames, fl, gl = m.generate_codes(ids, n, repetition_penalty=1.05, forced_frames=frames_o, want_logits=True)
@@ -821,15 +821,28 @@ def test_tts_frame_loop_against_oracle():
     e_group = max(rel_err(gl[i], trace[i]["group_logits"].numpy()) for i in range(n))
     print(f"tts: glue {e_glue:.3e}, first-code logits {e_first:.3e}, code-predictor logits {e_group:.3e}")
     assert e_glue < PREFILL_TOL and e_first < PREFILL_TOL and e_group < PREFILL_TOL
-    # free-running greedy on the device: equal to the oracle's greedy frames up to the first near-tie
+    # free-running greedy on the device: equal to the oracle's greedy frames at least up to the first NEAR-TIE -- the first frame in
+    # which some head's top-2 gap (first code: after suppress mask / EOS rule / repetition penalty; the 15 predictor heads: raw) is
+    # not clearly above the logit error just measured.  Past such a frame both continuations are legitimate greedy decodes.
+    def gap(lg):
+        lg = np.asarray(lg, np.float64).reshape(-1)
+        fin = lg[np.isfinite(lg)]
+        top2 = np.partition(fin, -2)[-2:]
+        return float(top2[1] - top2[0]) / float(np.abs(fin).max())
+    err = max(e_first, e_group)
+    safe = 0
+    for t in trace:
+        if min([gap(t["first_logits"].numpy())] + [gap(row) for row in t["group_logits"].numpy()]) < 20 * err:
+            break
+        safe += 1
     g = m.generate_codes(ids, n, repetition_penalty=1.05)
     same = 0
     for a, b in zip(g.tolist(), frames_o):
         if a != b:
             break
         same += 1
-    print(f"tts greedy: {same}/{n} frames identical to the oracle")
-    assert same >= 1 and g.shape[1] == cfg["talker_config"]["num_code_groups"]
+    print(f"tts greedy: {same}/{n} frames identical to the oracle; the oracle's first near-tie (top-2 gap < 20 x {err:.1e}) is in frame {safe}")
+    assert same >= safe and same >= 1 and g.shape[1] == cfg["talker_config"]["num_code_groups"]
     m.close()
 
 
