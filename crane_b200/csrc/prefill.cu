@@ -230,22 +230,25 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //   S = qh.kh + qh.kl + ql.kh          O += ph.vh + ph.vl + pl.vh
 // so the result carries ~16 mantissa bits instead of 8 (the f32-oracle parity mode; 3x the tensor work of 4 % of the flops).
 template <int D, bool CAUSAL, bool PAGED, bool SPLIT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, D == 64 ? 2 : 1)
 flash_prefill_kernel(FlashArgs a) {
     pdl_wait();
     pdl_launch_dependents();
     constexpr int BM = 64;
-    constexpr int BN = (SPLIT && D > 128) ? 32 : 64;     // D = 256 with hi+lo planes: half-page key tiles keep the double buffer in 227 KB
+    constexpr int BN = (SPLIT || D > 128) ? 32 : 64;     // half-page key tiles wherever a 64-key tile x 2 groups x 2 stages would not fit
+    constexpr int STG = (SPLIT && D > 128) ? 1 : 2;      // stages per group (D = 256 with hi + lo planes: one)
     constexpr int LDS = D + 8;                 // padded row (elements): conflict-free ldmatrix
     constexpr int TILE = BN * LDS;             // elements per K or V tile plane
     constexpr int CPR = D / 8;                 // 16-byte chunks per row
     constexpr int P = SPLIT ? 2 : 1;           // planes per operand
-    constexpr int STG = 2;
     extern __shared__ __align__(16) unsigned char fsm[];
     bf16* q_s = reinterpret_cast<bf16*>(fsm);  // [P][BM x LDS]
-    bf16* kv_s = q_s + P * BM * LDS;           // [STG][K hi | K lo | V hi | V lo]
+    bf16* kv_s = q_s + P * BM * LDS;           // [2 groups][STG][K hi | K lo | V hi | V lo]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Two groups of four warps work on the SAME 64 query rows: group 0 takes the even key tiles, group 1 the odd ones, each through
+    // its own double-buffered tile ring, and the two online-softmax states are merged at the end.
+    // A causal CTA's critical path -- q tile i needs i + 1 key tiles, the last one 8 at 454 rows -- is halved that way.
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 7, gtid = tid & 127, warp = (tid >> 5) & 3;
     const int g = lane >> 2, tq = lane & 3;
     const int head = blockIdx.y, z = blockIdx.z;
     const int row0 = a.seq_start ? a.seq_start[z] : 0;
@@ -258,7 +261,7 @@ flash_prefill_kernel(FlashArgs a) {
     const int n_tiles = CAUSAL ? min((T + BN - 1) / BN, (kv_off + q0 + BM - 1) / BN + 1) : (T + BN - 1) / BN;
 
     // ---- Q tile -> smem (zero-fill rows past S) ----
-    for (int c = tid; c < BM * CPR; c += 128) {
+    for (int c = tid; c < BM * CPR; c += 256) {
         const int r = c / CPR, ch = c % CPR;
         const int qr = q0 + r;
         const bf16* src = a.q + (size_t)(row0 + min(qr, S - 1)) * a.q_stride + head * D + ch * 8;
@@ -266,10 +269,10 @@ flash_prefill_kernel(FlashArgs a) {
         if (SPLIT) cp_async16(smem_u32(q_s + BM * LDS + r * LDS + ch * 8), src + a.q_lo_off, qr < S ? 16 : 0);
     }
     auto load_kv = [&](int tile, int stage) {
-        bf16* ks = kv_s + stage * 2 * P * TILE;
+        bf16* ks = kv_s + (grp * STG + stage) * 2 * P * TILE;
         bf16* vs = ks + P * TILE;
         const int kv0 = tile * BN;
-        for (int c = tid; c < BN * CPR; c += 128) {
+        for (int c = gtid; c < BN * CPR; c += 128) {
             const int r = c / CPR, ch = c % CPR;
             const int t = kv0 + r;
             const bool ok = t < T;
@@ -290,8 +293,10 @@ flash_prefill_kernel(FlashArgs a) {
             }
         }
     };
-    load_kv(0, 0);
     cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();                           // the Q tile is complete for both groups
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
 
     float o_acc[D / 8][4];
 #pragma unroll
@@ -300,17 +305,21 @@ flash_prefill_kernel(FlashArgs a) {
     const float sl2 = a.scale * 1.4426950408889634f;
     uint32_t qf[SPLIT ? 1 : D / 16][4];        // plain mode keeps the Q fragments in registers; SPLIT re-reads them from smem
 
-    for (int tile = 0; tile < n_tiles; ++tile) {
-        const int stage = (STG == 2) ? (tile & 1) : 0;
+    bool first = true;
+    if (grp < n_tiles) load_kv(grp, 0);
+    cp_async_commit();
+    int it = 0;
+    for (int tile = grp; tile < n_tiles; tile += 2, ++it) {
+        const int stage = STG == 2 ? (it & 1) : 0;
         if (STG == 2) {
-            if (tile + 1 < n_tiles) load_kv(tile + 1, stage ^ 1);
+            if (tile + 2 < n_tiles) load_kv(tile + 2, stage ^ 1);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();
-        if (!SPLIT && tile == 0) {
+        group_sync();
+        if (!SPLIT && first) {
 #pragma unroll
             for (int kk = 0; kk < D / 16; ++kk) {
                 const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -318,7 +327,7 @@ flash_prefill_kernel(FlashArgs a) {
                 ldmatrix_x4(qf[SPLIT ? 0 : kk][0], qf[SPLIT ? 0 : kk][1], qf[SPLIT ? 0 : kk][2], qf[SPLIT ? 0 : kk][3], smem_u32(q_s + r * LDS + c));
             }
         }
-        const bf16* ks = kv_s + stage * 2 * P * TILE;
+        const bf16* ks = kv_s + (grp * STG + stage) * 2 * P * TILE;
         const bf16* vs = ks + P * TILE;
         // ---- S = Q K^T ----
         float s_acc[BN / 8][4];
@@ -434,10 +443,38 @@ flash_prefill_kernel(FlashArgs a) {
                 mma_bf16_16816(o_acc[dj + 1], pa, b2, b3);
             }
         }
-        __syncthreads();   // everyone done with this stage before it is refilled
-        if (STG == 1 && tile + 1 < n_tiles) { load_kv(tile + 1, 0); cp_async_commit(); }
+        first = false;
+        group_sync();      // the group is done with this stage before it is refilled
+        if (STG == 1 && tile + 2 < n_tiles) { load_kv(tile + 2, 0); cp_async_commit(); }
     }
     cp_async_wait<0>();
+    // ---- merge the two groups' states (group 1 -> group 0 through its own, now idle, tile buffer) ----
+    {
+        float* mg = reinterpret_cast<float*>(kv_s + STG * 2 * P * TILE);        // group 1's ring: [128 threads][D / 2 + 4] floats
+        constexpr int MW = D / 2 + 4;
+        __syncthreads();
+        if (grp == 1) {
+            float* d = mg + (size_t)gtid * MW;
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) { d[4 * i] = o_acc[i][0]; d[4 * i + 1] = o_acc[i][1]; d[4 * i + 2] = o_acc[i][2]; d[4 * i + 3] = o_acc[i][3]; }
+            d[D / 2] = m_row[0]; d[D / 2 + 1] = m_row[1]; d[D / 2 + 2] = l_row[0]; d[D / 2 + 3] = l_row[1];
+        }
+        __syncthreads();
+        if (grp == 1) return;
+        const float* d = mg + (size_t)gtid * MW;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float mo = d[D / 2 + r], lo = d[D / 2 + 2 + r];
+            const float mn = fmaxf(m_row[r], mo);
+            const float c0 = (m_row[r] == -INFINITY) ? 0.f : exp2f(m_row[r] - mn), c1 = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+            l_row[r] = l_row[r] * c0 + lo * c1;
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) {
+                o_acc[i][2 * r] = o_acc[i][2 * r] * c0 + d[4 * i + 2 * r] * c1;
+                o_acc[i][2 * r + 1] = o_acc[i][2 * r + 1] * c0 + d[4 * i + 2 * r + 1] * c1;
+            }
+        }
+    }
     // ---- normalise and store ----
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -463,14 +500,15 @@ flash_prefill_kernel(FlashArgs a) {
 
 template <int D, bool CAUSAL, bool PAGED, bool SPLIT>
 static int flash_launch_t(cudaStream_t st, const FlashArgs& a) {
-    constexpr int P = SPLIT ? 2 : 1, STG = 2, BN = (SPLIT && D > 128) ? 32 : 64;
-    constexpr int SMEM = (P * 64 * (D + 8) + STG * 2 * P * BN * (D + 8)) * 2;
+    constexpr int P = SPLIT ? 2 : 1, GROUPS = 2, BN = (SPLIT || D > 128) ? 32 : 64, STG = (SPLIT && D > 128) ? 1 : 2;
+    constexpr int SMEM = (P * 64 * (D + 8) + GROUPS * STG * 2 * P * BN * (D + 8)) * 2;
+    static_assert(STG * 2 * P * BN * (D + 8) * 2 >= 128 * (D / 2 + 4) * 4, "the merge buffer lives in group 1's ring");
     static_assert(SMEM <= 227 * 1024, "flash tile does not fit");
     static SmemOptIn seen;
     if (const int e = ensure_dyn_smem(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, (size_t)SMEM, seen)) return e;
     const int max_len = a.seq_len ? a.max_len : a.S;
     dim3 grid((max_len + 63) / 64, a.nh, a.seq_len ? a.nseq : 1);
-    return launch_k(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, grid, dim3(128), SMEM, st, prefill_pdl(), a);
+    return launch_k(flash_prefill_kernel<D, CAUSAL, PAGED, SPLIT>, grid, dim3(256), SMEM, st, prefill_pdl(), a);
 }
 
 int flash_prefill_launch(cudaStream_t st, int D, bool causal, bool paged, const FlashArgs& a) {
