@@ -308,6 +308,10 @@ struct crane_b200_model {
     float *g_proj = nullptr, *g_conv = nullptr, *g_qn = nullptr, *g_kn = nullptr, *g_gb = nullptr, *g_y = nullptr;   // GDN prefill workspaces
     float *gd_proj = nullptr, *gd_conv = nullptr, *gd_qn = nullptr, *gd_kn = nullptr, *gd_gb = nullptr, *gd_y = nullptr, *gd_out = nullptr;  // decode
     uint32_t* ids_dev = nullptr;
+    int* h_stage = nullptr;                 // pinned staging of a prefill's positions / ids / splice rows (5 x capacity ints)
+    cudaEvent_t stage_ev = nullptr;         // ... free again once this event has passed
+    cudaEvent_t pix_ev = nullptr;           // the caller's pixel buffer has been read (vl_forward returns no earlier)
+    bool stage_busy = false;
     int* pos3_dev = nullptr;
     int* rows_dev = nullptr;
     float* embeds_in = nullptr;
@@ -1166,6 +1170,10 @@ void crane_b200_model::ensure_prefill_ws(int S) {
         g_gb = dalloc<float>((size_t)cap * nv * 2); g_y = dalloc<float>((size_t)cap * value_dim());
     }
     act_bf = dalloc_act((size_t)cap * I, lo_act);
+    if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; }
+    CUDA_OK(cudaMallocHost((void**)&h_stage, (size_t)5 * cap * sizeof(int)));
+    if (!stage_ev) CUDA_OK(cudaEventCreateWithFlags(&stage_ev, cudaEventDisableTiming));
+    stage_busy = false;
     ids_dev = dalloc<uint32_t>(cap);
     pos3_dev = dalloc<int>((size_t)3 * cap);
     rows_dev = dalloc<int>(cap);
@@ -1442,15 +1450,19 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     spans.mark(SP_EMBED);
     if (!pev0_armed) CUDA_OK(cudaEventRecord(pev0, stream));
     pev0_armed = false;
-    // positions [3, S]
-    std::vector<int> p3((size_t)3 * S);
+    // positions [3, S], ids and splice rows go through pinned staging: nothing here makes the host wait for the GPU (a VL request is
+    // still running its vision tower at this point, and the text layers are enqueued underneath it)
+    if (stage_busy) { CUDA_OK(cudaEventSynchronize(stage_ev)); stage_busy = false; }
+    int* p3 = h_stage;                               // [3 S] | ids [S] | rows [n_vis]
     for (int a = 0; a < 3; ++a)
         for (int s = 0; s < S; ++s) p3[(size_t)a * S + s] = pos3_host ? (int)pos3_host[(size_t)a * S + s] : (int)(start_pos + s);
-    for (int v : p3)
-        if (v < 0 || v > max_seq) fail(CRANE_B200_INVALID_ARG, "rotary position %d outside the table (max_seq_len %d)", v, max_seq);
-    CUDA_OK(cudaMemcpyAsync(pos3_dev, p3.data(), p3.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    for (size_t i = 0; i < (size_t)3 * S; ++i)
+        if (p3[i] < 0 || p3[i] > max_seq) fail(CRANE_B200_INVALID_ARG, "rotary position %d outside the table (max_seq_len %d)", p3[i], max_seq);
+    CUDA_OK(cudaMemcpyAsync(pos3_dev, p3, (size_t)3 * S * sizeof(int), cudaMemcpyHostToDevice, stream));
     if (ids) {
-        CUDA_OK(cudaMemcpyAsync(ids_dev, ids, S * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        uint32_t* hid = reinterpret_cast<uint32_t*>(h_stage + (size_t)3 * S);
+        std::memcpy(hid, ids, S * sizeof(uint32_t));
+        CUDA_OK(cudaMemcpyAsync(ids_dev, hid, S * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         if (q_embed) LAUNCH_OK(embed_rows_q_launch(stream, qt_embed, q_embed, H, ids_dev, nullptr, S, x, prefill_pdl()));
         else LAUNCH_OK(embed_rows_launch(stream, ids_dev, S, embed, H, x));
         ++launches;
@@ -1459,11 +1471,16 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     }
     if (n_vis > 0) {   // splice the image features over the placeholder rows (qwen3_5/vlm.rs:433-468)
         spans.mark(SP_SPLICE);
-        CUDA_OK(cudaMemcpyAsync(rows_dev, vis_rows, n_vis * sizeof(int), cudaMemcpyHostToDevice, stream));
+        if (n_vis > S) fail(CRANE_B200_INVALID_ARG, "more image rows (%d) than positions (%d)", n_vis, S);
+        int* hr = h_stage + (size_t)4 * S;
+        std::memcpy(hr, vis_rows, n_vis * sizeof(int));
+        CUDA_OK(cudaMemcpyAsync(rows_dev, hr, n_vis * sizeof(int), cudaMemcpyHostToDevice, stream));
         LAUNCH_OK(set_rows_launch(stream, x, H, rows_dev, n_vis, img_embeds, false));
         ++launches;
     }
-    CUDA_OK(cudaStreamSynchronize(stream));   // p3 / ids staging buffers are host stack/heap memory
+    CUDA_OK(cudaEventRecord(stage_ev, stream));
+    stage_busy = true;
+    if (!ids) CUDA_OK(cudaStreamSynchronize(stream));   // caller-owned embeddings were copied from pageable memory
 
     const int qd = q_dim();
     for (int li = 0; li < L; ++li) {
@@ -1547,8 +1564,6 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
     }
     // state for the last-row lm_head / a following on-device decode loop
     spans.mark(SP_HEAD);
-    const int last_p[3] = {p3[(size_t)0 * S + S - 1], p3[(size_t)1 * S + S - 1], p3[(size_t)2 * S + S - 1]};
-    (void)last_p;
     stage_state();
     h_state[0].kv_len = (int)(start_pos + S - 1);   // lm_head(advance) bumps it to start_pos + S
     h_state[0].pos[0] = h_state[0].pos[1] = h_state[0].pos[2] = (int)next_mrope_pos - 1;
@@ -1671,12 +1686,14 @@ void crane_b200_model::encode_images(const float* pv, const uint32_t* grid, size
         CUDA_OK(cudaMemcpyAsync(v_seq_start, sstart.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaMemcpyAsync(v_seq_len, slen.data(), nseq * sizeof(int), cudaMemcpyHostToDevice, stream));
     }
+    if (!pix_ev) CUDA_OK(cudaEventCreateWithFlags(&pix_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(pix_ev, stream));
     LAUNCH_OK(cast_f32_bf16_launch(stream, v_pv, v_pvb, (size_t)N * pk, lo_vpvb));
     if (!tables_cached) {
         CUDA_OK(cudaStreamSynchronize(stream));   // host staging vectors go out of scope below
         v_tab_key = grid_key;                     // (only now: a failed upload must not leave a key behind)
     }
-    // (cached tables: the caller's pixel buffer is still being read -- every public entry point syncs the stream before it returns)
+    // (cached tables: the caller's pixel buffer may still be being read -- vl_forward waits for pix_ev before it returns)
 
     // patch embed: Conv3d(kernel == stride) == GEMM [N, C*T*P*P] x [Hv, C*T*P*P]^T + bias (vision.rs:46-58)
     spans.mark(SP_VIT_PATCH);
@@ -1812,6 +1829,9 @@ void crane_b200_destroy(crane_b200_model* m) {
     for (cudaEvent_t e : m->h_state_ev) if (e) cudaEventDestroy(e);
     if (m->h_tokens) cudaFreeHost(m->h_tokens);
     if (m->h_ll_err) cudaFreeHost(m->h_ll_err);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->stage_ev) cudaEventDestroy(m->stage_ev);
+    if (m->pix_ev) cudaEventDestroy(m->pix_ev);
     m->sampler.release();
     m->spans.release();
     for (cudaEvent_t e : {m->pev0, m->pev1, m->dev0, m->dev1}) if (e) cudaEventDestroy(e);
@@ -2085,6 +2105,7 @@ int crane_b200_vl_forward(crane_b200_model* m, const uint32_t* ids, size_t n, co
     } else {
         m->prefill(ids, nullptr, n, pos3.data(), start_pos, vis_rows.data(), (int)vis_rows.size(), 0);
     }
+    if (pixel_values && m->pix_ev) CUDA_OK(cudaEventSynchronize(m->pix_ev));   // the caller may reuse its pixel buffer on return
     fill_logits(m, out);
     API_END(m)
 }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 ncu evidence (one GPU, run ON the GPU box).  Usage: tools/profile_r02.sh [part ...]   parts: launches ll others
+# Round-2 ncu evidence (one GPU, run ON the GPU box).  Usage: tools/profile_r02.sh [part ...]   parts: launches ll others prefill
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 PARTS=${@:-launches ll others}
@@ -23,5 +23,10 @@ others)
     timeout 600 $NCU --set full --import-source on -k "regex:gdn_" -s 2 -c 6 -o gpurun_out/prof_gdn_r02 -f python tools/bench_configs.py c2 > gpurun_out/ncu_gdn_r02.log 2>&1
     timeout 600 $NCU --set full --import-source on -k "regex:attn_decode_kernel<256" -s 2 -c 2 -o gpurun_out/prof_attn256_r02 -f python tools/bench_configs.py c2 > gpurun_out/ncu_attn256_r02.log 2>&1
     CRANE_B200_GRAPHS=0 timeout 600 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file gpurun_out/launches_tts_r02.csv python tools/bench_configs.py c4 > gpurun_out/ncu_tts_r02.log 2>&1 ;;
+prefill)
+    # the prefill kernels after this round's rewrites: persistent stream-K GEMM (text layer: qkv, o, gate/up, down) and the
+    # two-group flash attention (ViT + text)
+    timeout 600 $NCU --set full --import-source on -k regex:gemm_tc_kernel -s 230 -c 6 -o gpurun_out/prof_gemm_r02 -f $BENCH > gpurun_out/ncu_gemm_r02.log 2>&1
+    timeout 600 $NCU --set full --import-source on -k regex:flash_prefill_kernel -s 30 -c 2 -o gpurun_out/prof_flash_r02 -f $BENCH > gpurun_out/ncu_flash_r02.log 2>&1 ;;
 esac; done
 ls -la gpurun_out | tail -24
