@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcrane_b200.so")
-SOURCES = ["gemm.cu", "decode.cu", "decode_ll.cu", "prefill.cu", "gdn.cu", "quant.cu", "sampler.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "decode.cu", "decode_ll.cu", "prefill.cu", "gdn.cu", "gdn_chunk.cu", "quant.cu", "sampler.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--threads", "2"]
 
@@ -29,7 +29,7 @@ def _stale(target: str, deps) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "crane_b200.h"))
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)

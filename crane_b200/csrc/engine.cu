@@ -306,6 +306,9 @@ struct crane_b200_model {
     bf16 *xn = nullptr, *q_bf = nullptr, *attn_bf = nullptr, *act_bf = nullptr;
     float* rows_f32 = nullptr;         // [S, max(I, q_dim)] f32 rows in front of / behind a quantised linear in prefill
     float *g_proj = nullptr, *g_conv = nullptr, *g_qn = nullptr, *g_kn = nullptr, *g_gb = nullptr, *g_y = nullptr;   // GDN prefill workspaces
+    float* g_gl = nullptr;                 // [S, nv] log decays for the chunkwise recurrence
+    unsigned char* g_chunk = nullptr;      // its scratch (gdn_chunk_ws_bytes)
+    int gdn_mode = 0;                      // engine.gdn: 0 = auto (chunkwise from 64 rows per call), 1 = sequential, 2 = chunked
     float *gd_proj = nullptr, *gd_conv = nullptr, *gd_qn = nullptr, *gd_kn = nullptr, *gd_gb = nullptr, *gd_y = nullptr, *gd_out = nullptr;  // decode
     uint32_t* ids_dev = nullptr;
     int* h_stage = nullptr;                 // pinned staging of a prefill's positions / ids / splice rows (5 x capacity ints)
@@ -501,7 +504,9 @@ void crane_b200_model::parse_config(const char* json) {
         rot_half = (int)(D * prf) / 2;
         gdn_in = conv_dim() + value_dim() + 2 * nv;
         gdn_in_pad = (gdn_in + 31) / 32 * 32;
-        if (dk != 128 || dv % 32 || nv % nk || ck < 1 || ck > 8) fail(CRANE_B200_UNSUPPORTED, "GDN geometry dk=%d dv=%d nk=%d nv=%d conv=%d", dk, dv, nk, nv, ck);
+        // key widths: the reference's kernel takes K <= 256 (kernels/cuda/gdn.cu:45-153); 64 / 128 / 256 are instantiated here
+        if ((dk != 64 && dk != 128 && dk != 256) || dv % 32 || dv <= 0 || nk <= 0 || nv % nk || nv > 256 || ck < 1 || ck > 8)
+            fail(CRANE_B200_UNSUPPORTED, "Gated-Delta-Net geometry key_head_dim=%d (64, 128 or 256) value_head_dim=%d (multiple of 32) key_heads=%d value_heads=%d (multiple of key_heads, <= 256) conv_kernel=%d (1..8)", dk, dv, nk, nv, ck);
         if (rot_half < 32 || rot_half % 32) fail(CRANE_B200_UNSUPPORTED, "rotary width %d", 2 * rot_half);
     }
     layer_is_full.assign(L, 1);
@@ -532,11 +537,16 @@ void crane_b200_model::parse_config(const char* json) {
         else if (kvc == "int4") kv_bits = 4;
         else if (kvc != "fp") fail(CRANE_B200_INVALID_ARG, "engine.kv_cache must be \"fp\", \"int8\" or \"int4\"");
         if (e.string("vit_act", "erf") == "tanh") vit_gelu_mode = EPI_GELU_TANH_BF16;
+        const std::string gm = e.string("gdn", "auto");
+        if (gm == "sequential") gdn_mode = 1;
+        else if (gm == "chunked") gdn_mode = 2;
+        else if (gm != "auto") fail(CRANE_B200_INVALID_ARG, "engine.gdn must be \"auto\", \"chunked\" or \"sequential\"");
         if (e.string("merger_act", "tanh") == "erf") merger_gelu_mode = EPI_GELU_ERF_BF16;
     }
     if (const char* g = getenv("CRANE_B200_GEMM")) use_simt = std::string(g) == "simt";
     if (const char* g = getenv("CRANE_B200_GRAPHS")) use_graphs = std::string(g) != "0";
     if (const char* g = getenv("CRANE_B200_PDL")) use_pdl = std::string(g) != "0";
+    if (const char* g = getenv("CRANE_B200_GDN")) gdn_mode = std::string(g) == "sequential" ? 1 : std::string(g) == "chunked" ? 2 : 0;
     cb::prefill_pdl() = use_pdl;          // process-wide: the prefill-side launchers read it
     if (const char* g = getenv("CRANE_B200_PRECISION")) split = std::string(g) != "bf16";
     if (root.has("engine")) use_persistent = root.at("engine").boolean("persistent", true);
@@ -1156,7 +1166,7 @@ void crane_b200_model::ensure_prefill_ws(int S) {
     if (S <= ws_S) return;
     CUDA_OK(cudaStreamSynchronize(stream));
     for (void* p : {(void*)x, (void*)qkv, (void*)xn, (void*)q_bf, (void*)attn_bf, (void*)act_bf, (void*)ids_dev, (void*)pos3_dev,
-                    (void*)rows_dev, (void*)embeds_in, (void*)rows_f32, (void*)g_proj, (void*)g_conv, (void*)g_qn, (void*)g_kn, (void*)g_gb, (void*)g_y})
+                    (void*)rows_dev, (void*)embeds_in, (void*)rows_f32, (void*)g_proj, (void*)g_conv, (void*)g_qn, (void*)g_kn, (void*)g_gb, (void*)g_y, (void*)g_gl, (void*)g_chunk})
         dfree(p);
     const int cap = (S + 127) / 128 * 128;
     x = dalloc<float>((size_t)cap * H);
@@ -1168,6 +1178,11 @@ void crane_b200_model::ensure_prefill_ws(int S) {
         g_proj = dalloc<float>((size_t)cap * gdn_in_pad); g_conv = dalloc<float>((size_t)cap * conv_dim());
         g_qn = dalloc<float>((size_t)cap * nk * dk); g_kn = dalloc<float>((size_t)cap * nk * dk);
         g_gb = dalloc<float>((size_t)cap * nv * 2); g_y = dalloc<float>((size_t)cap * value_dim());
+        g_gl = nullptr; g_chunk = nullptr;
+        if (gdn_mode != 1 && cap >= cb::GDN_CHUNK && dv % 64 == 0) {     // chunkwise recurrence: 0.9 KB of scratch per (token, value head) at dk = dv = 128
+            g_gl = dalloc<float>((size_t)cap * nv);
+            g_chunk = dalloc<unsigned char>(cb::gdn_chunk_ws_bytes(cap, nv, dk, dv));
+        }
     }
     act_bf = dalloc_act((size_t)cap * I, lo_act);
     if (h_stage) { cudaFreeHost(h_stage); h_stage = nullptr; }
@@ -1237,7 +1252,7 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) 
             GemvArgs o = {};
             o.W = l.w_out; o.N = H; o.K = value_dim(); o.x = gd_out; o.ldx = value_dim(); o.y = x_dec; o.ldy = H;
             LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
-            launches += (nk == nv && dv == 128 && B == 1) ? 3 : 7;     // gdn_forward_launch: one fused kernel or five
+            launches += (nk == nv && dk == 128 && dv == 128 && B == 1) ? 3 : 7;     // gdn_forward_launch: one fused kernel or five
         }
         linear_decode(GEMV_SILU_MUL, true, l.wgu, l.q_wgu, l.qt_gu, 2 * I, H, x_dec, H, l.ln2, act_dec, I, nullptr, B);
         linear_decode(GEMV_RESID, false, l.wdown, l.q_wdown, l.qt_down, H, I, act_dec, I, nullptr, x_dec, H, nullptr, B);
@@ -1537,9 +1552,10 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             GdnArgs ga;
             gdn_args(ga, l, S, g_proj, g_conv, g_qn, g_kn, g_gb, g_y);
             ga.out_bf16 = attn_bf; ga.out_lo_off = lo_attn;
+            if (g_chunk && S >= cb::GDN_CHUNK) { ga.glog = g_gl; ga.chunk_ws = g_chunk; }     // else: token-by-token recurrence
             LAUNCH_OK(gdn_forward_launch(stream, ga));      // marks conv / qkv / recur / finish itself
             gemm(attn_bf, lo_attn, value_dim(), l.w_out, S, H, value_dim(), EPI_RESID_F32, x, H, nullptr);
-            launches += 3;
+            launches += ga.chunk_ws ? 7 : 5;     // conv, conv state, prep, recurrence (1 kernel, or 3 chunkwise), gated norm
         }
         // MLP: either linear may be quantised on its own (Q4_K_M keeps ffn_down in Q6_K, the others in Q4_K)
         spans.mark(l.qt_gu ? SP_MLP_GATE_UP : SP_NORM);

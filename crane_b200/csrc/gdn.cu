@@ -80,6 +80,7 @@ gdn_prep_kernel(GdnArgs a) {
         const float g = a.neg_exp_a[h] * logf(1.0f + expf(av + a.dt_bias[h]));
         a.gb[((size_t)t * a.nv + h) * 2 + 0] = expf(g);
         a.gb[((size_t)t * a.nv + h) * 2 + 1] = beta;
+        if (a.glog) a.glog[(size_t)t * a.nv + h] = g;      // the chunkwise path sums g inside a chunk instead of multiplying decays
     }
 }
 
@@ -180,6 +181,100 @@ gdn_recur_kernel(GdnArgs a) {
     for (int i = 0; i < 32; ++i) sp[(size_t)i * a.dv] = s[i];
     pdl_launch_dependents();
 }
+
+// The same recurrence for the other key widths the reference accepts (K <= 256, kernels/cuda/gdn.cu:45-153): DK = 64 or 256.
+// Identical mapping -- 4 lanes per state column, DK / 4 state entries per lane, operands through the double-buffered ring --
+// with the row padding computed per 16-byte piece (a lane's slice crosses the 32-float padding groups when DK = 256).
+template <int DK>
+__global__ void __launch_bounds__(128)
+gdn_recur_any_kernel(GdnArgs a) {
+    pdl_wait();
+    constexpr int KP = DK + DK / 8, KPL = DK / 4;   // padded row, state entries per lane
+    extern __shared__ __align__(16) float gsm[];
+    float* q_s = gsm;                               // [2][TC][KP]
+    float* k_s = q_s + 2 * GDN_TC * KP;             // [2][TC][KP]
+    float* v_s = k_s + 2 * GDN_TC * KP;             // [2][TC][32]
+    float* gb_s = v_s + 2 * GDN_TC * 32;            // [2][TC][2]
+    const int tiles = a.dv / 32;
+    const int h = blockIdx.x / tiles, vt = blockIdx.x % tiles;
+    const int kh = h / (a.nv / a.nk);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c4 = lane & 3;
+    const int col_local = warp * 8 + (lane >> 2);
+    const int col = vt * 32 + col_local;
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    float s[KPL];
+    float* sp = a.rec_state + ((size_t)h * DK + KPL * c4) * a.dv + col;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) s[i] = sp[(size_t)i * a.dv];
+
+    auto prefetch = [&](int t0, int buf) {
+        const int nt = min(GDN_TC, a.S - t0);
+        if (nt > 0) {
+            for (int i = tid; i < nt * (DK / 4); i += 128) {   // DK / 4 16-byte pieces of q and of k per step
+                const int tt = i / (DK / 4), c = i % (DK / 4);
+                const size_t src = ((size_t)(t0 + tt) * a.nk + kh) * DK + c * 4;
+                const int dst = (buf * GDN_TC + tt) * KP + gdn_pad(c * 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(q_s + dst)), "l"(a.qn + src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(k_s + dst)), "l"(a.kn + src) : "memory");
+            }
+            for (int i = tid; i < nt * 8; i += 128) {
+                const int tt = i >> 3, c = i & 7;
+                const float* src = a.conv_out + (size_t)(t0 + tt) * conv_dim + 2 * a.nk * a.dk + h * a.dv + vt * 32 + c * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(v_s + (buf * GDN_TC + tt) * 32 + c * 4)), "l"(src) : "memory");
+            }
+            if (tid < nt) {
+                const float* src = a.gb + ((size_t)(t0 + tid) * a.nv + h) * 2;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(gb_s + (buf * GDN_TC + tid) * 2)), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < a.S; t0 += GDN_TC, buf ^= 1) {
+        const int nt = min(GDN_TC, a.S - t0);
+        prefetch(t0 + GDN_TC, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        for (int tt = 0; tt < nt; ++tt) {
+            const float decay = gb_s[(buf * GDN_TC + tt) * 2], beta = gb_s[(buf * GDN_TC + tt) * 2 + 1];
+            const float* krow = k_s + (buf * GDN_TC + tt) * KP;
+            const float* qrow = q_s + (buf * GDN_TC + tt) * KP;
+            float kx = 0.f, ky = 0.f, kz = 0.f, kw = 0.f;
+#pragma unroll
+            for (int i = 0; i < KPL / 4; ++i) {
+                const float4 k4 = *reinterpret_cast<const float4*>(krow + gdn_pad(KPL * c4 + 4 * i));
+                s[4 * i + 0] *= decay; s[4 * i + 1] *= decay; s[4 * i + 2] *= decay; s[4 * i + 3] *= decay;
+                kx = fmaf(s[4 * i + 0], k4.x, kx); ky = fmaf(s[4 * i + 1], k4.y, ky);
+                kz = fmaf(s[4 * i + 2], k4.z, kz); kw = fmaf(s[4 * i + 3], k4.w, kw);
+            }
+            float kv = (kx + ky) + (kz + kw);
+            kv += __shfl_xor_sync(0xffffffffu, kv, 1);
+            kv += __shfl_xor_sync(0xffffffffu, kv, 2);
+            const float delta = (v_s[(buf * GDN_TC + tt) * 32 + col_local] - kv) * beta;
+            float yx = 0.f, yy = 0.f, yz = 0.f, yw = 0.f;
+#pragma unroll
+            for (int i = 0; i < KPL / 4; ++i) {
+                const float4 k4 = *reinterpret_cast<const float4*>(krow + gdn_pad(KPL * c4 + 4 * i));
+                const float4 q4 = *reinterpret_cast<const float4*>(qrow + gdn_pad(KPL * c4 + 4 * i));
+                s[4 * i + 0] = fmaf(k4.x, delta, s[4 * i + 0]); yx = fmaf(s[4 * i + 0], q4.x, yx);
+                s[4 * i + 1] = fmaf(k4.y, delta, s[4 * i + 1]); yy = fmaf(s[4 * i + 1], q4.y, yy);
+                s[4 * i + 2] = fmaf(k4.z, delta, s[4 * i + 2]); yz = fmaf(s[4 * i + 2], q4.z, yz);
+                s[4 * i + 3] = fmaf(k4.w, delta, s[4 * i + 3]); yw = fmaf(s[4 * i + 3], q4.w, yw);
+            }
+            float y = (yx + yy) + (yz + yw);
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            if (c4 == 0) a.y[((size_t)(t0 + tt) * a.nv + h) * a.dv + col] = y;
+        }
+        __syncthreads();                               // this buffer is refilled by the prefetch of the next iteration
+    }
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) sp[(size_t)i * a.dv] = s[i];
+    pdl_launch_dependents();
+}
+template <int DK> constexpr size_t gdn_recur_any_smem() { return (size_t)2 * GDN_TC * (2 * (DK + DK / 8) + 32 + 2) * sizeof(float); }
 
 // One warp per (t, value head): y * rsqrt(mean(y^2) + eps) * w * silu(z)
 __global__ void __launch_bounds__(128)
@@ -304,24 +399,42 @@ gdn_decode_kernel(GdnArgs a) {
     }
 }
 
+template <int DK>
+static int recur_any_launch(cudaStream_t st, const GdnArgs& a) {
+    static SmemOptIn seen;
+    int r = ensure_dyn_smem(gdn_recur_any_kernel<DK>, gdn_recur_any_smem<DK>(), seen);
+    if (!r) r = launch_k(gdn_recur_any_kernel<DK>, dim3(a.nv * (a.dv / 32)), dim3(128), gdn_recur_any_smem<DK>(), st, false, a);
+    return r;
+}
+
+bool gdn_shape_supported(const GdnArgs& a) {
+    return (a.dk == 64 || a.dk == 128 || a.dk == 256) && a.dv > 0 && (a.dv % 32) == 0 && a.ck >= 1 && a.ck <= GDN_MAX_CK && a.nv <= 256 &&
+           a.nk > 0 && (a.nv % a.nk) == 0;
+}
+
 int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
-    if (a.dk != 128 || (a.dv % 32) != 0 || a.ck > GDN_MAX_CK || a.nv > 256 || (a.nv % a.nk) != 0) return -1000;
+    if (!gdn_shape_supported(a)) return -1000;
     const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
     const bool pdl = prefill_pdl();
-    if (a.S == 1 && a.nk == a.nv && a.dv == 128 && a.ck >= 2 && a.out_f32 != nullptr && a.out_bf16 == nullptr)
+    if (a.S == 1 && a.nk == a.nv && a.dk == 128 && a.dv == 128 && a.ck >= 2 && a.out_f32 != nullptr && a.out_bf16 == nullptr)
         return launch_k(gdn_decode_kernel, dim3(a.nv), dim3(512), 0, st, pdl, a);
     span_mark(SP_GDN_CONV);
     int r = launch_k(gdn_conv_kernel, dim3((conv_dim + 127) / 128, a.S), dim3(128), 0, st, pdl, a);
     if (!r) r = launch_k(gdn_conv_state_kernel, dim3((conv_dim + 127) / 128), dim3(128), 0, st, pdl, a);
     span_mark(SP_GDN_QKV);
     if (!r) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);
-    // NOT a programmatic dependent: launched early, its 64 long-running CTAs land wherever the previous kernel leaves room and
-    // pile up several to an SM; launched after it, they spread one per SM (measured: 4.4 vs 2.4 ms per layer at 4096 tokens)
     span_mark(SP_GDN_RECUR);
-    if (!r) {
+    if (!r && gdn_chunk_supported(a)) {
+        // prefill: 64 tokens per serial step on the tensor cores (gdn_chunk.cu)
+        r = gdn_chunk_recur_launch(st, a);
+    } else if (!r && a.dk == 128) {
+        // NOT a programmatic dependent: launched early, its 64 long-running CTAs land wherever the previous kernel leaves room and
+        // pile up several to an SM; launched after it, they spread one per SM (measured: 4.4 vs 2.4 ms per layer at 4096 tokens)
         static SmemOptIn seen;
         r = ensure_dyn_smem(gdn_recur_kernel, GDN_RECUR_SMEM, seen);
         if (!r) r = launch_k(gdn_recur_kernel, dim3(a.nv * (a.dv / 32)), dim3(128), GDN_RECUR_SMEM, st, false, a);
+    } else if (!r) {
+        r = a.dk == 64 ? recur_any_launch<64>(st, a) : recur_any_launch<256>(st, a);
     }
     span_mark(SP_GDN_FINISH);
     if (!r) r = launch_k(gdn_gated_norm_kernel, dim3((a.S * a.nv + 3) / 4), dim3(128), 0, st, pdl, a);

@@ -1,0 +1,56 @@
+// TEST INFRASTRUCTURE.  Runs the three chunkwise Gated-Delta-Net kernels of crane_b200/csrc/gdn_chunk_kernels.inc on CPU threads
+// (cuda_emu.h) so tests/test_gdn_chunk_emu.py can compare every intermediate with the numpy oracle.  Not part of the product.
+#include "cuda_emu.h"
+
+#include "../../crane_b200/csrc/gdn_args.h"
+
+namespace cb {
+#include "../../crane_b200/csrc/gdn_chunk_kernels.inc"
+}  // namespace cb
+
+using namespace cb;
+
+template <int DK>
+static int run(const GdnArgs& a, const GdnChunkWs& w) {
+    using Cfg = GdnChunkCfg<DK>;
+    const int n_chunks = gdn_n_chunks(a.S);
+    cuda_emu::Dim3 g1{n_chunks, a.nv, 1}, b1{256, 1, 1};
+    cuda_emu::launch(g1, b1, Cfg::PREP_SMEM, [&] { gdn_chunk_prep_kernel<DK>(a, w); });
+    cuda_emu::Dim3 g2{a.nv * (a.dv / 16), 1, 1}, b2{128, 1, 1};
+    cuda_emu::launch(g2, b2, Cfg::STATE_SMEM, [&] { gdn_chunk_state_kernel<DK>(a, w, n_chunks); });
+    cuda_emu::Dim3 g3{n_chunks, a.nv, a.dv / 64}, b3{256, 1, 1};
+    cuda_emu::launch(g3, b3, Cfg::OUT_SMEM, [&] { gdn_chunk_out_kernel<DK>(a, w); });
+    return 0;
+}
+
+extern "C" {
+
+size_t gdn_chunk_emu_ws_bytes(int S, int nv, int dk, int dv) { return gdn_chunk_ws_bytes(S, nv, dk, dv); }
+
+// Byte offsets of the scratch sub-buffers, in GdnChunkWs order (w, kt, qt, p, ut, gc, st, dt).
+void gdn_chunk_emu_ws_offsets(int S, int nv, int dk, int dv, size_t* out) {
+    unsigned char* base = reinterpret_cast<unsigned char*>(uintptr_t(4096));
+    const GdnChunkWs w = gdn_chunk_ws_carve(base, S, nv, dk, dv);
+    const void* p[8] = {w.w, w.kt, w.qt, w.p, w.ut, w.gc, w.st, w.dt};
+    for (int i = 0; i < 8; ++i) out[i] = (size_t)(static_cast<const unsigned char*>(p[i]) - base);
+}
+
+// qn, kn [S, nk, dk]; conv_out [S, conv_dim] (only the v part is read); gb [S, nv, 2]; glog [S, nv]; rec_state [nv, dk, dv] in/out;
+// y [S, nv, dv] out; ws = gdn_chunk_emu_ws_bytes bytes, 256-byte aligned.
+int gdn_chunk_emu_run(const float* qn, const float* kn, const float* conv_out, const float* gb, const float* glog, float* rec_state,
+                      float* y, void* ws, int S, int nk, int nv, int dk, int dv) {
+    GdnArgs a = {};
+    a.S = S; a.nk = nk; a.nv = nv; a.dk = dk; a.dv = dv; a.ck = 4;
+    a.qn = const_cast<float*>(qn); a.kn = const_cast<float*>(kn); a.conv_out = const_cast<float*>(conv_out);
+    a.gb = const_cast<float*>(gb); a.glog = const_cast<float*>(glog); a.rec_state = rec_state; a.y = y; a.chunk_ws = ws;
+    if (dv % 64 != 0 || nv % nk != 0) return -1;
+    const GdnChunkWs w = gdn_chunk_ws_carve(ws, S, nv, dk, dv);
+    switch (dk) {
+        case 64: return run<64>(a, w);
+        case 128: return run<128>(a, w);
+        case 256: return run<256>(a, w);
+        default: return -1;
+    }
+}
+
+}  // extern "C"

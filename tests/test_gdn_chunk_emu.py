@@ -1,0 +1,135 @@
+"""CPU check of the chunkwise Gated-Delta-Net kernels' index arithmetic.
+
+`crane_b200/csrc/gdn_chunk_kernels.inc` is compiled twice: by nvcc into libcrane_b200.so (the product, GPU only) and by g++
+against `tests/emu/cuda_emu.h` (OS threads for CUDA threads, ldmatrix / mma.sync emulated from the PTX fragment tables).  This test
+runs the second build and compares every buffer the three kernels exchange, the outputs and the final state with the numpy
+restatement `oracle/gdn_chunked.py`, which itself is checked against the token-by-token rule (`oracle.qwen3_5.gated_delta_rule`).
+The GPU tests (`tests/test_gpu_parity.py`) check the nvcc build against the same oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.gdn_chunked import CHUNK, chunk_apply, chunk_prepare, gated_delta_rule_chunked
+from oracle.qwen3_5 import gated_delta_rule, l2_norm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+LIB = os.path.join(EMU_DIR, "libgdn_chunk_emu.so")
+CSRC = os.path.join(os.path.dirname(HERE), "crane_b200", "csrc")
+
+
+def _build():
+    srcs = [os.path.join(EMU_DIR, "gdn_chunk_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
+            os.path.join(CSRC, "gdn_chunk_kernels.inc"), os.path.join(CSRC, "gdn_args.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
+        return
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I" + cuda_inc, srcs[0], "-o", LIB], check=True)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    _build()
+    lib = ctypes.CDLL(LIB)
+    lib.gdn_chunk_emu_ws_bytes.restype = ctypes.c_size_t
+    lib.gdn_chunk_emu_ws_bytes.argtypes = [ctypes.c_int] * 4
+    lib.gdn_chunk_emu_ws_offsets.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
+    lib.gdn_chunk_emu_run.restype = ctypes.c_int
+    lib.gdn_chunk_emu_run.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int] * 5
+    return lib
+
+
+def test_chunked_algebra_matches_the_token_by_token_rule():
+    torch.manual_seed(0)
+    S, Hv, K, V = 150, 3, 32, 16
+    q, k = l2_norm(torch.randn(S, Hv, K)), l2_norm(torch.randn(S, Hv, K))
+    v, g, beta = torch.randn(S, Hv, V), -torch.rand(S, Hv) * 3, torch.sigmoid(torch.randn(S, Hv))
+    st = torch.randn(Hv, K, V) * 0.3
+    y0, s0 = gated_delta_rule(*(x.double() for x in (q, k, v, g, beta, st)))
+    y1, s1 = gated_delta_rule_chunked(*(x.numpy() for x in (q, k, v, g, beta, st)))
+    assert np.abs(y0.numpy() - y1).max() < 1e-12 and np.abs(s0.numpy() - s1).max() < 1e-12
+    y2, s2 = gated_delta_rule_chunked(*(x.numpy() for x in (q, k, v, g, beta, st)), dtype=np.float32)
+    assert np.abs(y0.numpy() - y2).max() < 2e-6 and np.abs(s0.numpy() - s2).max() < 2e-6
+
+
+def _planes(buf, off, shape):
+    """(hi, lo) bf16 planes at byte offset `off`, shape [..., 2, rows, cols] -> hi + lo as float64."""
+    n = int(np.prod(shape))
+    raw = np.frombuffer(buf, dtype=np.uint16, count=n, offset=off).reshape(shape)
+    f = (raw.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    return f[..., 0, :, :] + f[..., 1, :, :]
+
+
+@pytest.mark.parametrize("S,nk,nv,dk,dv", [(150, 1, 2, 128, 64), (64, 2, 2, 64, 64), (70, 1, 1, 256, 128)])
+def test_chunk_kernels_on_the_host_emulator(emu, S, nk, nv, dk, dv):
+    rng = np.random.default_rng(S + dk)
+    rep = nv // nk
+    conv_dim = 2 * nk * dk + nv * dv
+    qn = l2_norm(torch.from_numpy(rng.standard_normal((S, nk, dk)).astype(np.float32))).numpy() / np.float32(np.sqrt(dk))
+    kn = l2_norm(torch.from_numpy(rng.standard_normal((S, nk, dk)).astype(np.float32))).numpy()
+    conv_out = np.full((S, conv_dim), np.nan, np.float32)                 # only the v part may be read
+    v = rng.standard_normal((S, nv, dv)).astype(np.float32)
+    conv_out[:, 2 * nk * dk:] = v.reshape(S, nv * dv)
+    glog = (-rng.random((S, nv)) * 2.0).astype(np.float32)
+    glog[S // 2] = -30.0                                                   # one near-total forget gate
+    beta = (1.0 / (1.0 + np.exp(-rng.standard_normal((S, nv))))).astype(np.float32)
+    gb = np.stack([np.exp(glog), beta], -1).astype(np.float32)
+    state0 = (rng.standard_normal((nv, dk, dv)) * 0.3).astype(np.float32)
+    state = state0.copy()
+    y = np.full((S, nv, dv), np.nan, np.float32)
+    nbytes = emu.gdn_chunk_emu_ws_bytes(S, nv, dk, dv)
+    ws = np.zeros(nbytes + 256, np.uint8)
+    base = (ws.ctypes.data + 255) // 256 * 256
+    ws_view = (ctypes.c_ubyte * nbytes).from_address(base)
+    offs = (ctypes.c_size_t * 8)()
+    emu.gdn_chunk_emu_ws_offsets(S, nv, dk, dv, offs)
+    arrs = [np.ascontiguousarray(x) for x in (qn, kn, conv_out, gb, glog)]
+    rc = emu.gdn_chunk_emu_run(*(x.ctypes.data for x in arrs), state.ctypes.data, y.ctypes.data, base, S, nk, nv, dk, dv)
+    assert rc == 0
+
+    # ---- every intermediate against the f64 statement, per (chunk, head) ----
+    n_chunks = (S + CHUNK - 1) // CHUNK
+    W = _planes(ws_view, offs[0], (n_chunks, nv, 2, CHUNK, dk))
+    Kt = _planes(ws_view, offs[1], (n_chunks, nv, 2, CHUNK, dk))
+    Qt = _planes(ws_view, offs[2], (n_chunks, nv, 2, CHUNK, dk))
+    P = _planes(ws_view, offs[3], (n_chunks, nv, 2, CHUNK, CHUNK))
+    Ut = np.frombuffer(ws_view, np.float32, n_chunks * nv * dv * CHUNK, offs[4]).reshape(n_chunks, nv, dv, CHUNK)
+    gC = np.frombuffer(ws_view, np.float32, n_chunks * nv, offs[5]).reshape(n_chunks, nv)
+    St = _planes(ws_view, offs[6], (n_chunks, nv, 2, dv, dk))
+    Dt = _planes(ws_view, offs[7], (n_chunks, nv, 2, dv, CHUNK))
+    pad = n_chunks * CHUNK - S
+    z = lambda x: np.concatenate([x.astype(np.float64), np.zeros((pad,) + x.shape[1:])], 0)
+    qe, ke = z(np.repeat(qn, rep, 1)), z(np.repeat(kn, rep, 1))            # value head h uses key head h // rep
+    ve, ge, be = z(v), z(glog), z(beta)
+    tol = dict(rtol=0, atol=2e-5)
+    for h in range(nv):
+        s = state0[h].astype(np.float64)
+        for c in range(n_chunks):
+            sl = slice(c * CHUNK, (c + 1) * CHUNK)
+            prep = chunk_prepare(qe[sl, h], ke[sl, h], ve[sl, h], ge[sl, h], be[sl, h])
+            np.testing.assert_allclose(W[c, h], prep["W"], err_msg=f"W c={c} h={h}", **tol)
+            np.testing.assert_allclose(Ut[c, h].T, prep["U"], err_msg=f"U c={c} h={h}", **tol)
+            np.testing.assert_allclose(Kt[c, h], prep["Kt"], err_msg=f"Kt c={c} h={h}", **tol)
+            np.testing.assert_allclose(Qt[c, h], prep["Qt"], err_msg=f"Qt c={c} h={h}", **tol)
+            np.testing.assert_allclose(P[c, h], prep["P"], err_msg=f"P c={c} h={h}", **tol)
+            np.testing.assert_allclose(gC[c, h], prep["gC"], err_msg=f"gC c={c} h={h}", **tol)
+            np.testing.assert_allclose(St[c, h].T, s, err_msg=f"chunk-start state c={c} h={h}", **tol)
+            yc, s, D = chunk_apply(prep, s)
+            np.testing.assert_allclose(Dt[c, h].T, D, err_msg=f"D c={c} h={h}", **tol)
+            n_valid = min(CHUNK, S - c * CHUNK)
+            np.testing.assert_allclose(y[sl, h][:n_valid], yc[:n_valid], err_msg=f"y c={c} h={h}", **tol)
+        np.testing.assert_allclose(state[h], s, err_msg=f"final state h={h}", **tol)
+    assert not np.isnan(y).any()
+
+    # ---- and the whole thing against the token-by-token rule (the reference's bar for chunked vs sequential is 1e-4) ----
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).double()
+    y_seq, s_seq = gated_delta_rule(t(np.repeat(qn, rep, 1)) * np.sqrt(dk), t(np.repeat(kn, rep, 1)), t(v), t(glog), t(beta), t(state0))
+    assert np.abs(y - y_seq.numpy()).max() < 2e-5
+    assert np.abs(state - s_seq.numpy()).max() < 2e-5

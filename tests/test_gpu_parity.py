@@ -369,6 +369,49 @@ def test_qwen3_5_chunked_prefill_state_handoff_and_decode(equal_heads):
     m.close()
 
 
+@pytest.mark.parametrize("dk", [128, 64, 256])
+def test_gdn_chunkwise_recurrence_against_sequential_and_oracle(dk):
+    """Prefill of >= 64 rows takes the chunkwise Gated-Delta-Net kernels (gdn_chunk.cu: 64 tokens per serial step on the tensor
+    cores); `engine.gdn = "sequential"` keeps the token-by-token kernel.  Both against the oracle, and against each other at the
+    reference's own bar for chunked vs sequential (1e-4, crane-core/tests/rocm_kernels.rs:39-84): a 50-row call (sequential in
+    either mode) leaves a non-zero state, then 280 rows = 4 chunks + a ragged 24-row tail, then decode steps from the state the
+    chunkwise pass left.  Key widths 64 and 256 run the generic-width sequential kernel (the reference accepts K <= 256)."""
+    from oracle.qwen3_5 import Qwen3_5Oracle
+    cfg = dict(synth.TINY_QWEN3_5, linear_key_head_dim=dk)
+    ids = synth.synth_token_ids(330, cfg["vocab_size"], f"gdn-chunk-{dk}")
+    outs = {}
+    for mode in ("chunked", "sequential"):
+        m, w = _model(cfg, cls=crane_b200.Qwen3_5Model, gdn=mode)
+        a = m.forward_step(ids[:50], 0)
+        b = m.forward_step(ids[50:], 50)
+        dec, tok = [], int(np.argmax(b))
+        toks = [tok]
+        for i in range(4):
+            lg = m.forward_step([tok], len(ids) + i)
+            dec.append(lg)
+            tok = int(np.argmax(lg))
+            toks.append(tok)
+        outs[mode] = (a, b, dec, toks)
+        m.close()
+    orc = Qwen3_5Oracle(cfg, w)
+    orc.forward(ids[:50], 0)
+    ref = orc.forward(ids[50:], 50).numpy()
+    e_chunk, e_seq = rel_err(outs["chunked"][1], ref), rel_err(outs["sequential"][1], ref)
+    e_cross = rel_err(outs["chunked"][1], outs["sequential"][1])
+    e_dec = max(rel_err(x, y) for x, y in zip(outs["chunked"][2], outs["sequential"][2]))
+    tok = outs["chunked"][3][0]
+    e_dec_orc = []
+    for i in range(4):
+        r = orc.forward([tok], len(ids) + i).numpy()
+        e_dec_orc.append(rel_err(outs["chunked"][2][i], r))
+        tok = outs["chunked"][3][i + 1]
+    print(f"GDN dk={dk}: chunkwise vs oracle {e_chunk:.2e}, sequential vs oracle {e_seq:.2e}, chunkwise vs sequential {e_cross:.2e}; "
+          f"decode after chunkwise prefill vs sequential {e_dec:.2e}, vs oracle {max(e_dec_orc):.2e}")
+    assert np.array_equal(outs["chunked"][0], outs["sequential"][0])          # the 50-row call is the same kernel in both modes
+    assert e_chunk < PREFILL_TOL and e_seq < PREFILL_TOL and max(e_dec_orc) < DECODE_TOL
+    assert e_cross < 1e-4 and e_dec < 1e-4
+
+
 @pytest.mark.parametrize("nh,nkv", [(6, 2), (12, 2), (16, 2), (10, 2), (24, 4)], ids=["nrep3", "nrep6", "nrep8", "nrep5", "nrep6-24over4"])
 def test_decode_attention_any_group_width(nh, nkv):
     """Query groups wider than the attention kernel's sub-group (4 heads) are served by several CTA clusters per KV head: 6 = 2 x 3,
