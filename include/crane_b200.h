@@ -65,7 +65,13 @@ typedef struct {
  * (qwen3: crane-core/src/models/qwen3/modeling.rs:94-130 `Config`; qwen3_vl: text_config + vision_config
  * as crane-core/src/models/qwen3_5/config.rs:112-137) optionally extended with an "engine" object:
  *   {"max_seq_len": 4096, "max_batch": 1, "gemm": "tcgen05"|"simt", "graphs": true, "pdl": true,
- *    "precision": "split"|"bf16", "kv_cache": "fp"|"int8"|"int4", "persistent": true, "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf"}
+ *    "precision": "split"|"bf16", "kv_cache": "fp"|"int8"|"int4", "persistent": true, "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf",
+ *    "gdn": "auto"|"chunked"|"sequential"}
+ * "gdn" (Qwen3.5 linear-attention layers): how a prefill call evaluates the gated delta rule (crane-core/src/ops/gdn/backend.rs:90-156).
+ * "sequential" = token by token, as the reference does; "auto" (default) and "chunked" = calls of 64 rows or more run the
+ * chunkwise form (64 tokens per serial step, tensor cores; same recurrence, results within 1e-4 of the sequential kernel --
+ * the reference's own bar for that pair, crane-core/tests/rocm_kernels.rs:39-84); shorter calls and decode stay sequential.
+ * linear_key_head_dim may be 64, 128 or 256 (the reference's kernel accepts K <= 256, kernels/cuda/gdn.cu:45-153).
  * "kv_cache": "int8" / "int4" = the reference's QuantKvCache (crane-core/src/models/qwen3_5/kv_cache.rs:209-342): per (token, KV
  * head) symmetric codes + an f32 scale, 8.25 / 4.25 bits per cached element instead of 32 (split) or 16; attention reads
  * code * scale, dequantised while the decode kernel stages its tile.
