@@ -297,13 +297,104 @@ def bench_config4(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def bench_config2(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: Qwen3.5-0.8B (3 Gated-Delta-Net layers per gated full-attention layer) bf16, one request =
+    4096-token prefill + 512 greedy decode tokens on one GPU; N > 1 = N independent replicas ("scaling": "weak").  A step = one request.
+    `value` = decode tok/s (CUDA events around the on-device loop), `prefill_*` from the events around the prefill pass, `e2e` =
+    decode tokens / wall time of the whole request through the generate call (host token ids in, host token ids out).
+    Weights are cheap tiled random bf16 blocks (timing only: parity of every kernel on this path is tests/test_gpu_parity.py, incl. the
+    full-width geometry and chunkwise-vs-sequential recurrence tests); the CPU arm of this config is not timed."""
+    import torch
+    import crane_b200
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as bc
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "config 2's CPU arm is not timed (a 4096-token f32 oracle prefill with a python-loop recurrence does not fit the bench budget); the headline config has the reference arm"}))
+        return
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    S, n_dec = 4096, 512
+    cfg = synth.QWEN3_5_0_8B
+    m = crane_b200.Qwen3_5Model(cfg, device=dev, max_seq_len=S + n_dec + 128)
+    bc.load_cheap(m, cfg)
+    ids = synth.synth_token_ids(S, cfg["vocab_size"], f"c2-{rank}")
+    sampler = ClockSampler(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def request():
+        m.clear_kv_cache()
+        t0 = time.perf_counter()
+        out = m.generate_greedy(ids, n_dec + 1)          # first token from the prefill's argmax, then n_dec decode steps on the device
+        wall = time.perf_counter() - t0
+        t = m.last_timing()
+        return wall, t["prefill_ms"], t["decode_ms"], len(out) - 1
+
+    for _ in range(max(args.warmup, 3)):
+        request()
+    barrier()
+    sampler.start()
+    l0 = m.kernel_launches()
+    walls, pres, decs, ntok = [], [], [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        w_, p_, d_, n_ = request()
+        walls.append(w_); pres.append(p_); decs.append(d_); ntok += n_
+    barrier()
+    wall_all = time.perf_counter() - t0
+    launches = m.kernel_launches() - l0
+    clocks = sampler.summary()
+    stats = torch.tensor([wall_all, sum(decs) / 1e3, sum(pres) / 1e3, sum(walls)], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    wall_m, dec_m, pre_m, req_m = [float(x) for x in stats.tolist()]
+    if rank == 0:
+        H, I, L, V = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"], cfg["vocab_size"]
+        full, gdn = L // 4, L - L // 4
+        w_full = (8 * 256 * 2 + 2 * 2 * 256) * H + H * 8 * 256
+        w_gdn = (6144 + 2048 + 32) * H + H * 2048
+        ctx = S + n_dec / 2
+        by = ((w_full * full + w_gdn * gdn + 3 * I * H * L) + V * H) * 2 + gdn * 2 * 16 * 128 * 128 * 4 + ctx * 2 * 2 * 256 * 2 * 2 * full
+        fl = 2 * (w_full * full + w_gdn * gdn + 3 * I * H * L) * S + 4 * S * (S / 2) * 8 * 256 * full + 2 * V * H
+        peaks = load_peaks()
+        n_steps_total = world * ntok
+        step_s = dec_m / ntok                               # seconds per decode step on the slowest rank
+        out = {"metric": "decode_tok_per_s", "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": f"Qwen3.5-0.8B hybrid (18 Gated-Delta-Net + 6 gated full-attention layers) bf16, {S}-token prefill + {n_dec} greedy decode tokens per request",
+                          "weights": "random bf16 blocks (timing only)", "l2": "per-token weight stream 1.5 GB >> 126 MB L2",
+                          "parallelism": f"dp{world} (replicas)", "gdn": os.environ.get("CRANE_B200_GDN", "auto (chunkwise recurrence for the prefill)")},
+               "value": n_steps_total / dec_m, "ms_per_step": 1e3 * wall_m / args.steps,
+               "prefill_ms": 1e3 * pre_m / args.steps, "prefill_tflops": world * fl * args.steps / pre_m / 1e12,
+               "prefill_frac_of_bf16_peak": fl * args.steps / pre_m / 1e12 / peaks["bf16_tflops"], "prefill_tok_per_s": world * S * args.steps / pre_m,
+               "e2e": {"value": n_steps_total / req_m, "unit": "tok/s", "h2d_bytes_per_step": int(S * 4), "d2h_bytes_per_step": int((n_dec + 1) * 4),
+                       "api": "crane_b200_generate_greedy (host prompt ids in, host token ids out; prefill inside the timed region)"},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "roofline": {"bound": "hbm", "achieved": by / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / step_s / 1e9 / peaks["hbm_gbs"],
+                            "traffic": None, "peak_source": peaks["source"], "kernel": "decode step of the hybrid model (gemv_kernel chain + gdn_decode_kernel + attn_decode_kernel<256,4>)",
+                            "algorithmic_bytes_per_launch": by, "launch": "one decode step: every weight once + 18 recurrent states read and written + KV of 6 layers"}}
+        print(json.dumps(out))
+    m.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="crane_b200", choices=["crane_b200", "reference"])
-    ap.add_argument("--config", default="qwen3_vl_2b", choices=["qwen3_vl_2b", "tiny", "qwen3_8b_q4km"])
+    ap.add_argument("--config", default="qwen3_vl_2b", choices=["qwen3_vl_2b", "tiny", "qwen3_8b_q4km", "qwen3_5_0_8b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -312,6 +403,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.config == "qwen3_8b_q4km":
         return bench_config4(args, rank, world, local_rank)
+    if args.config == "qwen3_5_0_8b":
+        return bench_config2(args, rank, world, local_rank)
     cfg = synth.QWEN3_VL_2B if args.config == "qwen3_vl_2b" else synth.TINY_QWEN3_VL
     name = "Qwen3-VL-2B" if args.config == "qwen3_vl_2b" else "tiny-Qwen3-VL"
     workload = f"{name} bf16, 1x(448x448) image + {N_TEXT}-tok prompt, prefill + {N_DECODE} greedy decode tokens per request"

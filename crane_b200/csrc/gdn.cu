@@ -35,6 +35,35 @@ gdn_conv_kernel(GdnArgs a) {
     a.conv_out[(size_t)t * conv_dim + c] = silu_f(acc);
 }
 
+// The same convolution for the usual 4-tap kernel over many rows: one thread per channel walks GDN_CONV_TT consecutive timesteps with
+// the tap window in registers, so every input element is loaded once (the per-element kernel above loads it ck times and, at
+// 4 096 rows, spends its time on 200 K tiny CTAs: 205 us per layer measured, profiles/r02_launches_gdn_chunk.csv).
+constexpr int GDN_CONV_TT = 32;
+__global__ void __launch_bounds__(128)
+gdn_conv4_rows_kernel(GdnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int t0 = blockIdx.y * GDN_CONV_TT;
+    if (c >= conv_dim) return;
+    const int t1 = min(t0 + GDN_CONV_TT, a.S);
+    const float w0 = a.conv_w[(size_t)c * 4 + 0], w1 = a.conv_w[(size_t)c * 4 + 1], w2 = a.conv_w[(size_t)c * 4 + 2], w3 = a.conv_w[(size_t)c * 4 + 3];
+    // history index m into [state(4) | x(S)]: the window of timestep t is m = t + 1 .. t + 4
+    auto hist = [&](int m) { return (m < 4) ? a.conv_state[(size_t)c * 4 + m] : a.proj[(size_t)(m - 4) * a.ldp + c]; };
+    float h0 = hist(t0 + 1), h1 = hist(t0 + 2), h2 = hist(t0 + 3);
+#pragma unroll 8
+    for (int t = t0; t < t1; ++t) {
+        const float h3 = a.proj[(size_t)t * a.ldp + c];          // m = t + 4 -> x[t]
+        float acc = w0 * h0;
+        acc = fmaf(w1, h1, acc);
+        acc = fmaf(w2, h2, acc);
+        acc = fmaf(w3, h3, acc);
+        a.conv_out[(size_t)t * conv_dim + c] = silu_f(acc);
+        h0 = h1; h1 = h2; h2 = h3;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 gdn_conv_state_kernel(GdnArgs a) {
     pdl_wait();
@@ -419,7 +448,9 @@ int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     if (a.S == 1 && a.nk == a.nv && a.dk == 128 && a.dv == 128 && a.ck >= 2 && a.out_f32 != nullptr && a.out_bf16 == nullptr)
         return launch_k(gdn_decode_kernel, dim3(a.nv), dim3(512), 0, st, pdl, a);
     span_mark(SP_GDN_CONV);
-    int r = launch_k(gdn_conv_kernel, dim3((conv_dim + 127) / 128, a.S), dim3(128), 0, st, pdl, a);
+    int r = (a.ck == 4 && a.S >= GDN_CONV_TT)
+                ? launch_k(gdn_conv4_rows_kernel, dim3((conv_dim + 127) / 128, (a.S + GDN_CONV_TT - 1) / GDN_CONV_TT), dim3(128), 0, st, pdl, a)
+                : launch_k(gdn_conv_kernel, dim3((conv_dim + 127) / 128, a.S), dim3(128), 0, st, pdl, a);
     if (!r) r = launch_k(gdn_conv_state_kernel, dim3((conv_dim + 127) / 128), dim3(128), 0, st, pdl, a);
     span_mark(SP_GDN_QKV);
     if (!r) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);

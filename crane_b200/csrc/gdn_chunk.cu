@@ -8,8 +8,6 @@
 #include "gdn.cuh"
 #include "prof.h"
 
-#include <cstdlib>
-
 namespace cb {
 
 namespace {
@@ -39,14 +37,13 @@ int launch_all(cudaStream_t st, const GdnArgs& a) {
     using Cfg = GdnChunkCfg<DK>;
     const int n_chunks = gdn_n_chunks(a.S);
     const GdnChunkWs w = gdn_chunk_ws_carve(a.chunk_ws, a.S, a.nv, a.dk, a.dv);
-    static SmemOptIn s1, s1b, s2, s3;
-    static const bool two_per_sm = [] { const char* e = getenv("CRANE_B200_GDN_PREP"); return e && e[0] == '2'; }();
-    int r = two_per_sm ? ensure_dyn_smem(gdn_chunk_prep_kernel<DK, 2>, Cfg::PREP_SMEM, s1b) : ensure_dyn_smem(gdn_chunk_prep_kernel<DK, 1>, Cfg::PREP_SMEM, s1);
+    const size_t prep_smem = gdn_chunk_prep_smem(DK, a.dv);
+    static SmemOptIn s1, s2, s3;
+    int r = ensure_dyn_smem(gdn_chunk_prep_kernel<DK>, prep_smem, s1);
     if (!r) r = ensure_dyn_smem(gdn_chunk_state_kernel<DK>, Cfg::STATE_SMEM, s2);
     if (!r) r = ensure_dyn_smem(gdn_chunk_out_kernel<DK>, Cfg::OUT_SMEM, s3);
     // plain stream order (no programmatic early start): each kernel reads what the one before it wrote in full
-    if (!r) r = two_per_sm ? launch_k(gdn_chunk_prep_kernel<DK, 2>, dim3(n_chunks, a.nv), dim3(256), Cfg::PREP_SMEM, st, false, a, w)
-                           : launch_k(gdn_chunk_prep_kernel<DK, 1>, dim3(n_chunks, a.nv), dim3(256), Cfg::PREP_SMEM, st, false, a, w);
+    if (!r) r = launch_k(gdn_chunk_prep_kernel<DK>, dim3(n_chunks, a.nv), dim3(256), prep_smem, st, false, a, w);
     if (!r) r = launch_k(gdn_chunk_state_kernel<DK>, dim3(a.nv * (a.dv / 16)), dim3(128), Cfg::STATE_SMEM, st, false, a, w, n_chunks);
     if (!r) r = launch_k(gdn_chunk_out_kernel<DK>, dim3(n_chunks, a.nv, a.dv / 64), dim3(256), Cfg::OUT_SMEM, st, false, a, w);
     return r;

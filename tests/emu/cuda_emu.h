@@ -27,11 +27,13 @@
 #undef __forceinline__
 #undef __launch_bounds__
 #undef __restrict__
+#undef __host__
 #define __global__
 #define __device__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#define __host__
 
 namespace cuda_emu {
 
