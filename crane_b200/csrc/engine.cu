@@ -1252,7 +1252,7 @@ void crane_b200_model::enqueue_decode_step(int advance, bool with_embed, int B) 
             GemvArgs o = {};
             o.W = l.w_out; o.N = H; o.K = value_dim(); o.x = gd_out; o.ldx = value_dim(); o.y = x_dec; o.ldy = H;
             LAUNCH_OK(gemv_launch(stream, B, GEMV_RESID, false, o, num_sms, pdl));
-            launches += (nk == nv && dk == 128 && dv == 128 && B == 1) ? 3 : 7;     // gdn_forward_launch: one fused kernel or five
+            launches += 2 + gdn_forward_launch_count(ga);     // the two GEMVs around it + one fused kernel or five
         }
         linear_decode(GEMV_SILU_MUL, true, l.wgu, l.q_wgu, l.qt_gu, 2 * I, H, x_dec, H, l.ln2, act_dec, I, nullptr, B);
         linear_decode(GEMV_RESID, false, l.wdown, l.q_wdown, l.qt_down, H, I, act_dec, I, nullptr, x_dec, H, nullptr, B);
@@ -1555,7 +1555,7 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             if (g_chunk && S >= cb::GDN_CHUNK) { ga.glog = g_gl; ga.chunk_ws = g_chunk; }     // else: token-by-token recurrence
             LAUNCH_OK(gdn_forward_launch(stream, ga));      // marks conv / qkv / recur / finish itself
             gemm(attn_bf, lo_attn, value_dim(), l.w_out, S, H, value_dim(), EPI_RESID_F32, x, H, nullptr);
-            launches += ga.chunk_ws ? 7 : 5;     // conv, conv state, prep, recurrence (1 kernel, or 3 chunkwise), gated norm
+            launches += gdn_forward_launch_count(ga);     // conv (+ norms + gates), conv state, recurrence (1 kernel, or 3 chunkwise), gated norm
         }
         // MLP: either linear may be quantised on its own (Q4_K_M keeps ffn_down in Q6_K, the others in Q4_K)
         spans.mark(l.qt_gu ? SP_MLP_GATE_UP : SP_NORM);

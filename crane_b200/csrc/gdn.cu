@@ -64,6 +64,66 @@ gdn_conv4_rows_kernel(GdnArgs a) {
     }
 }
 
+// Conv + SiLU + the per-head L2 norms + the gates in one pass, for 128-wide key heads: a thread owns 4 adjacent channels (16-byte
+// loads), a warp therefore owns exactly one q head, one k head or 128 value channels, and walks GDN_CONV_TT timesteps with the tap
+// window in registers.  q / k leave as l2norm(q) / sqrt(dk) and l2norm(k) (backend.rs:26-56) straight into qn / kn -- the q / k part
+// of conv_out is never materialised -- v goes to conv_out; the CTAs of the first channel block also write beta and g
+// (backend.rs:197-211).  Replaces gdn_conv4_rows_kernel + gdn_prep_kernel (75 + 30 us per layer at 4 096 rows).
+__global__ void __launch_bounds__(128)
+gdn_conv4_qkv_kernel(GdnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t0 = blockIdx.y * GDN_CONV_TT;
+    const int t1 = min(t0 + GDN_CONV_TT, a.S);
+    const int cb = (blockIdx.x * 4 + warp) * 128;          // this warp's 128 channels
+    if (cb < conv_dim) {
+        const int c = cb + lane * 4;
+        const int grp = cb / 128;                          // < nk: q head; < 2 nk: k head; else value channels
+        const float4* wp = reinterpret_cast<const float4*>(a.conv_w + (size_t)c * 4);
+        const float4 wa = wp[0], wb = wp[1], wc = wp[2], wd = wp[3];      // taps of channels c, c+1, c+2, c+3
+        auto hist = [&](int m) {                           // history index m into [state(4) | x(S)], 4 channels at once
+            if (m < 4) return make_float4(a.conv_state[(size_t)c * 4 + m], a.conv_state[(size_t)(c + 1) * 4 + m],
+                                          a.conv_state[(size_t)(c + 2) * 4 + m], a.conv_state[(size_t)(c + 3) * 4 + m]);
+            return *reinterpret_cast<const float4*>(a.proj + (size_t)(m - 4) * a.ldp + c);
+        };
+        float4 h0 = hist(t0 + 1), h1 = hist(t0 + 2), h2 = hist(t0 + 3);
+        const float qscale = 1.0f / sqrtf((float)a.dk);
+#pragma unroll 4
+        for (int t = t0; t < t1; ++t) {
+            const float4 h3 = *reinterpret_cast<const float4*>(a.proj + (size_t)t * a.ldp + c);
+            float4 y;
+            y.x = silu_f(fmaf(wa.w, h3.x, fmaf(wa.z, h2.x, fmaf(wa.y, h1.x, wa.x * h0.x))));
+            y.y = silu_f(fmaf(wb.w, h3.y, fmaf(wb.z, h2.y, fmaf(wb.y, h1.y, wb.x * h0.y))));
+            y.z = silu_f(fmaf(wc.w, h3.z, fmaf(wc.z, h2.z, fmaf(wc.y, h1.z, wc.x * h0.z))));
+            y.w = silu_f(fmaf(wd.w, h3.w, fmaf(wd.z, h2.w, fmaf(wd.y, h1.w, wd.x * h0.w))));
+            if (grp < 2 * a.nk) {
+                const float ssq = warp_sum((y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w));
+                float sc = 1.0f / sqrtf(ssq + 1e-6f);
+                const bool is_k = grp >= a.nk;
+                if (!is_k) sc *= qscale;
+                float* dst = (is_k ? a.kn : a.qn) + ((size_t)t * a.nk + (is_k ? grp - a.nk : grp)) * 128 + lane * 4;
+                *reinterpret_cast<float4*>(dst) = make_float4(y.x * sc, y.y * sc, y.z * sc, y.w * sc);
+            } else {
+                *reinterpret_cast<float4*>(a.conv_out + (size_t)t * conv_dim + c) = y;
+            }
+            h0 = h1; h1 = h2; h2 = h3;
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < (t1 - t0) * a.nv; i += 128) {
+            const int t = t0 + i / a.nv, h = i % a.nv;
+            const float* pr = a.proj + (size_t)t * a.ldp + conv_dim + a.nv * a.dv;
+            const float b = pr[h], av = pr[a.nv + h];
+            const float g = a.neg_exp_a[h] * logf(1.0f + expf(av + a.dt_bias[h]));
+            a.gb[((size_t)t * a.nv + h) * 2 + 0] = expf(g);
+            a.gb[((size_t)t * a.nv + h) * 2 + 1] = 1.0f / (1.0f + expf(-b));
+            if (a.glog) a.glog[(size_t)t * a.nv + h] = g;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 gdn_conv_state_kernel(GdnArgs a) {
     pdl_wait();
@@ -441,6 +501,14 @@ bool gdn_shape_supported(const GdnArgs& a) {
            a.nk > 0 && (a.nv % a.nk) == 0;
 }
 
+// kernels gdn_forward_launch enqueues for these arguments (the engine's launch counter)
+int gdn_forward_launch_count(const GdnArgs& a) {
+    const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
+    if (a.S == 1 && a.nk == a.nv && a.dk == 128 && a.dv == 128 && a.ck >= 2 && a.out_f32 != nullptr && a.out_bf16 == nullptr) return 1;
+    const bool fused_qkv = a.ck == 4 && a.dk == 128 && a.S >= GDN_CONV_TT && conv_dim % 128 == 0 && a.ldp % 4 == 0;
+    return 2 + (fused_qkv ? 0 : 1) + (gdn_chunk_supported(a) ? 3 : 1) + 1;
+}
+
 int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     if (!gdn_shape_supported(a)) return -1000;
     const int conv_dim = 2 * a.nk * a.dk + a.nv * a.dv;
@@ -448,12 +516,15 @@ int gdn_forward_launch(cudaStream_t st, const GdnArgs& a) {
     if (a.S == 1 && a.nk == a.nv && a.dk == 128 && a.dv == 128 && a.ck >= 2 && a.out_f32 != nullptr && a.out_bf16 == nullptr)
         return launch_k(gdn_decode_kernel, dim3(a.nv), dim3(512), 0, st, pdl, a);
     span_mark(SP_GDN_CONV);
-    int r = (a.ck == 4 && a.S >= GDN_CONV_TT)
+    const bool fused_qkv = a.ck == 4 && a.dk == 128 && a.S >= GDN_CONV_TT && conv_dim % 128 == 0 && a.ldp % 4 == 0;
+    int r = fused_qkv
+                ? launch_k(gdn_conv4_qkv_kernel, dim3((conv_dim + 511) / 512, (a.S + GDN_CONV_TT - 1) / GDN_CONV_TT), dim3(128), 0, st, pdl, a)
+            : (a.ck == 4 && a.S >= GDN_CONV_TT)
                 ? launch_k(gdn_conv4_rows_kernel, dim3((conv_dim + 127) / 128, (a.S + GDN_CONV_TT - 1) / GDN_CONV_TT), dim3(128), 0, st, pdl, a)
                 : launch_k(gdn_conv_kernel, dim3((conv_dim + 127) / 128, a.S), dim3(128), 0, st, pdl, a);
     if (!r) r = launch_k(gdn_conv_state_kernel, dim3((conv_dim + 127) / 128), dim3(128), 0, st, pdl, a);
     span_mark(SP_GDN_QKV);
-    if (!r) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);
+    if (!r && !fused_qkv) r = launch_k(gdn_prep_kernel, dim3(a.S), dim3(256), 0, st, pdl, a);
     span_mark(SP_GDN_RECUR);
     if (!r && gdn_chunk_supported(a)) {
         // prefill: 64 tokens per serial step on the tensor cores (gdn_chunk.cu)

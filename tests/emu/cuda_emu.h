@@ -121,6 +121,17 @@ inline void cp_async16(uint32_t dst, const void* src, int src_bytes) {
     memset(d, 0, 16);
     memcpy(d, src, src_bytes);
 }
+// mbarrier + bulk (TMA 1-D) copy: the copy is performed at issue, so the barrier has nothing left to wait for.  (A missing wait
+// or a stage overwritten too early is therefore NOT caught here -- only addressing is.)
+inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+inline void fence_barrier_init() {}
+inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+inline void mbar_wait(uint64_t*, uint32_t) {}
+inline void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t*) {
+    assert(bytes % 16 == 0 && reinterpret_cast<uintptr_t>(gsrc) % 16 == 0 && smem_u32(smem_dst) % 16 == 0 && "cp.async.bulk alignment");
+    assert((size_t)smem_u32(smem_dst) + bytes <= cuda_emu::t_block->smem_bytes);
+    memcpy(smem_dst, gsrc, bytes);
+}
 inline void cp_async_commit() {}
 template <int N> inline void cp_async_wait() {}
 

@@ -96,8 +96,11 @@ def test_chunk_kernels_on_the_host_emulator(emu, S, nk, nv, dk, dv):
 
     # ---- every intermediate against the f64 statement, per (chunk, head) ----
     n_chunks = (S + CHUNK - 1) // CHUNK
-    W = _planes(ws_view, offs[0], (n_chunks, nv, 2, CHUNK, dk))
-    Kt = _planes(ws_view, offs[1], (n_chunks, nv, 2, CHUNK, dk))
+    # W and K~ rows are stored with their 16-byte pieces permuted (gdn_swz: piece q of row i sits at q ^ (i & 7)); undo it
+    rows, cols = np.arange(CHUNK)[:, None], np.arange(dk)[None, :]
+    swz = (((cols >> 3) ^ (rows & 7)) << 3) | (cols & 7)
+    W = np.take_along_axis(_planes(ws_view, offs[0], (n_chunks, nv, 2, CHUNK, dk)), np.broadcast_to(swz, (n_chunks, nv, CHUNK, dk)), -1)
+    Kt = np.take_along_axis(_planes(ws_view, offs[1], (n_chunks, nv, 2, CHUNK, dk)), np.broadcast_to(swz, (n_chunks, nv, CHUNK, dk)), -1)
     Qt = _planes(ws_view, offs[2], (n_chunks, nv, 2, CHUNK, dk))
     P = _planes(ws_view, offs[3], (n_chunks, nv, 2, CHUNK, CHUNK))
     Ut = np.frombuffer(ws_view, np.float32, n_chunks * nv * dv * CHUNK, offs[4]).reshape(n_chunks, nv, dv, CHUNK)
