@@ -1552,7 +1552,8 @@ void crane_b200_model::prefill(const uint32_t* ids, const float* embeds, size_t 
             GdnArgs ga;
             gdn_args(ga, l, S, g_proj, g_conv, g_qn, g_kn, g_gb, g_y);
             ga.out_bf16 = attn_bf; ga.out_lo_off = lo_attn;
-            if (g_chunk && S >= cb::GDN_CHUNK) { ga.glog = g_gl; ga.chunk_ws = g_chunk; }     // else: token-by-token recurrence
+            // "auto": chunkwise from two chunks on (at one chunk its three launches cost what 64 sequential steps do); "chunked": from one
+            if (g_chunk && S >= (gdn_mode == 2 ? cb::GDN_CHUNK : 2 * cb::GDN_CHUNK)) { ga.glog = g_gl; ga.chunk_ws = g_chunk; }
             LAUNCH_OK(gdn_forward_launch(stream, ga));      // marks conv / qkv / recur / finish itself
             gemm(attn_bf, lo_attn, value_dim(), l.w_out, S, H, value_dim(), EPI_RESID_F32, x, H, nullptr);
             launches += gdn_forward_launch_count(ga);     // conv (+ norms + gates), conv state, recurrence (1 kernel, or 3 chunkwise), gated norm

@@ -68,7 +68,7 @@ typedef struct {
  *    "precision": "split"|"bf16", "kv_cache": "fp"|"int8"|"int4", "persistent": true, "vit_act": "erf"|"tanh", "merger_act": "tanh"|"erf",
  *    "gdn": "auto"|"chunked"|"sequential"}
  * "gdn" (Qwen3.5 linear-attention layers): how a prefill call evaluates the gated delta rule (crane-core/src/ops/gdn/backend.rs:90-156).
- * "sequential" = token by token, as the reference does; "auto" (default) and "chunked" = calls of 64 rows or more run the
+ * "sequential" = token by token, as the reference does; "auto" (default: calls of 128 rows or more) and "chunked" (64 or more) run the
  * chunkwise form (64 tokens per serial step, tensor cores; same recurrence, results within 1e-4 of the sequential kernel --
  * the reference's own bar for that pair, crane-core/tests/rocm_kernels.rs:39-84); shorter calls and decode stay sequential.
  * linear_key_head_dim may be 64, 128 or 256 (the reference's kernel accepts K <= 256, kernels/cuda/gdn.cu:45-153).
