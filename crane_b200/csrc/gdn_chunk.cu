@@ -40,11 +40,12 @@ int launch_all(cudaStream_t st, const GdnArgs& a) {
     const size_t prep_smem = gdn_chunk_prep_smem(DK, a.dv);
     static SmemOptIn s1, s2, s3;
     int r = ensure_dyn_smem(gdn_chunk_prep_kernel<DK>, prep_smem, s1);
-    if (!r) r = ensure_dyn_smem(gdn_chunk_state_kernel<DK>, Cfg::STATE_SMEM, s2);
+    constexpr int NW = DK >= 128 ? 8 : 4;          // warps of the serial kernel
+    if (!r) r = ensure_dyn_smem(gdn_chunk_state_kernel<DK, NW>, Cfg::STATE_SMEM, s2);
     if (!r) r = ensure_dyn_smem(gdn_chunk_out_kernel<DK>, Cfg::OUT_SMEM, s3);
     // plain stream order (no programmatic early start): each kernel reads what the one before it wrote in full
     if (!r) r = launch_k(gdn_chunk_prep_kernel<DK>, dim3(n_chunks, a.nv), dim3(256), prep_smem, st, false, a, w);
-    if (!r) r = launch_k(gdn_chunk_state_kernel<DK>, dim3(a.nv * (a.dv / 16)), dim3(128), Cfg::STATE_SMEM, st, false, a, w, n_chunks);
+    if (!r) r = launch_k(gdn_chunk_state_kernel<DK, NW>, dim3(a.nv * (a.dv / 16)), dim3(32 * NW), Cfg::STATE_SMEM, st, false, a, w, n_chunks);
     if (!r) r = launch_k(gdn_chunk_out_kernel<DK>, dim3(n_chunks, a.nv, a.dv / 64), dim3(256), Cfg::OUT_SMEM, st, false, a, w);
     return r;
 }

@@ -16,8 +16,9 @@ static int run(const GdnArgs& a, const GdnChunkWs& w) {
     const int n_chunks = gdn_n_chunks(a.S);
     cuda_emu::Dim3 g1{n_chunks, a.nv, 1}, b1{256, 1, 1};
     cuda_emu::launch(g1, b1, gdn_chunk_prep_smem(DK, a.dv), [&] { gdn_chunk_prep_kernel<DK>(a, w); });
-    cuda_emu::Dim3 g2{a.nv * (a.dv / 16), 1, 1}, b2{128, 1, 1};
-    cuda_emu::launch(g2, b2, Cfg::STATE_SMEM, [&] { gdn_chunk_state_kernel<DK>(a, w, n_chunks); });
+    constexpr int NW = DK >= 128 ? 8 : 4;
+    cuda_emu::Dim3 g2{a.nv * (a.dv / 16), 1, 1}, b2{32 * NW, 1, 1};
+    cuda_emu::launch(g2, b2, Cfg::STATE_SMEM, [&] { gdn_chunk_state_kernel<DK, NW>(a, w, n_chunks); });
     cuda_emu::Dim3 g3{n_chunks, a.nv, a.dv / 64}, b3{256, 1, 1};
     cuda_emu::launch(g3, b3, Cfg::OUT_SMEM, [&] { gdn_chunk_out_kernel<DK>(a, w); });
     return 0;
