@@ -40,7 +40,9 @@ int launch_all(cudaStream_t st, const GdnArgs& a) {
     const size_t prep_smem = gdn_chunk_prep_smem(DK, a.dv);
     static SmemOptIn s1, s2, s3;
     int r = ensure_dyn_smem(gdn_chunk_prep_kernel<DK>, prep_smem, s1);
-    constexpr int NW = DK >= 128 ? 8 : 4;          // warps of the serial kernel
+    // warps of the serial kernel: 4 = one per scheduler.  8 (two per scheduler, each with half the columns) was measured slower at
+    // DK = 128 -- 118 vs 112 us per layer: the A fragments of S^T are loaded by every warp and the hand-over barriers get wider
+    constexpr int NW = 4;
     if (!r) r = ensure_dyn_smem(gdn_chunk_state_kernel<DK, NW>, Cfg::STATE_SMEM, s2);
     if (!r) r = ensure_dyn_smem(gdn_chunk_out_kernel<DK>, Cfg::OUT_SMEM, s3);
     // plain stream order (no programmatic early start): each kernel reads what the one before it wrote in full

@@ -10,13 +10,12 @@ namespace cb {
 
 using namespace cb;
 
-template <int DK>
+template <int DK, int NW = 4>
 static int run(const GdnArgs& a, const GdnChunkWs& w) {
     using Cfg = GdnChunkCfg<DK>;
     const int n_chunks = gdn_n_chunks(a.S);
     cuda_emu::Dim3 g1{n_chunks, a.nv, 1}, b1{256, 1, 1};
     cuda_emu::launch(g1, b1, gdn_chunk_prep_smem(DK, a.dv), [&] { gdn_chunk_prep_kernel<DK>(a, w); });
-    constexpr int NW = DK >= 128 ? 8 : 4;
     cuda_emu::Dim3 g2{a.nv * (a.dv / 16), 1, 1}, b2{32 * NW, 1, 1};
     cuda_emu::launch(g2, b2, Cfg::STATE_SMEM, [&] { gdn_chunk_state_kernel<DK, NW>(a, w, n_chunks); });
     cuda_emu::Dim3 g3{n_chunks, a.nv, a.dv / 64}, b3{256, 1, 1};
@@ -39,7 +38,7 @@ void gdn_chunk_emu_ws_offsets(int S, int nv, int dk, int dv, size_t* out) {
 // qn, kn [S, nk, dk]; conv_out [S, conv_dim] (only the v part is read); gb [S, nv, 2]; glog [S, nv]; rec_state [nv, dk, dv] in/out;
 // y [S, nv, dv] out; ws = gdn_chunk_emu_ws_bytes bytes, 256-byte aligned.
 int gdn_chunk_emu_run(const float* qn, const float* kn, const float* conv_out, const float* gb, const float* glog, float* rec_state,
-                      float* y, void* ws, int S, int nk, int nv, int dk, int dv) {
+                      float* y, void* ws, int S, int nk, int nv, int dk, int dv, int state_warps) {
     GdnArgs a = {};
     a.S = S; a.nk = nk; a.nv = nv; a.dk = dk; a.dv = dv; a.ck = 4;
     a.qn = const_cast<float*>(qn); a.kn = const_cast<float*>(kn); a.conv_out = const_cast<float*>(conv_out);
@@ -48,7 +47,7 @@ int gdn_chunk_emu_run(const float* qn, const float* kn, const float* conv_out, c
     const GdnChunkWs w = gdn_chunk_ws_carve(ws, S, nv, dk, dv);
     switch (dk) {
         case 64: return run<64>(a, w);
-        case 128: return run<128>(a, w);
+        case 128: return state_warps == 8 ? run<128, 8>(a, w) : run<128>(a, w);
         case 256: return run<256>(a, w);
         default: return -1;
     }

@@ -42,7 +42,7 @@ def emu():
     lib.gdn_chunk_emu_ws_bytes.argtypes = [ctypes.c_int] * 4
     lib.gdn_chunk_emu_ws_offsets.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_size_t)]
     lib.gdn_chunk_emu_run.restype = ctypes.c_int
-    lib.gdn_chunk_emu_run.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int] * 5
+    lib.gdn_chunk_emu_run.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int] * 6
     return lib
 
 
@@ -67,8 +67,8 @@ def _planes(buf, off, shape):
     return f[..., 0, :, :] + f[..., 1, :, :]
 
 
-@pytest.mark.parametrize("S,nk,nv,dk,dv", [(150, 1, 2, 128, 64), (64, 2, 2, 64, 64), (70, 1, 1, 256, 128)])
-def test_chunk_kernels_on_the_host_emulator(emu, S, nk, nv, dk, dv):
+@pytest.mark.parametrize("S,nk,nv,dk,dv,state_warps", [(150, 1, 2, 128, 64, 4), (64, 2, 2, 64, 64, 4), (70, 1, 1, 256, 128, 4), (130, 1, 1, 128, 64, 8)])
+def test_chunk_kernels_on_the_host_emulator(emu, S, nk, nv, dk, dv, state_warps):
     rng = np.random.default_rng(S + dk)
     rep = nv // nk
     conv_dim = 2 * nk * dk + nv * dv
@@ -91,7 +91,7 @@ def test_chunk_kernels_on_the_host_emulator(emu, S, nk, nv, dk, dv):
     offs = (ctypes.c_size_t * 8)()
     emu.gdn_chunk_emu_ws_offsets(S, nv, dk, dv, offs)
     arrs = [np.ascontiguousarray(x) for x in (qn, kn, conv_out, gb, glog)]
-    rc = emu.gdn_chunk_emu_run(*(x.ctypes.data for x in arrs), state.ctypes.data, y.ctypes.data, base, S, nk, nv, dk, dv)
+    rc = emu.gdn_chunk_emu_run(*(x.ctypes.data for x in arrs), state.ctypes.data, y.ctypes.data, base, S, nk, nv, dk, dv, state_warps)
     assert rc == 0
 
     # ---- every intermediate against the f64 statement, per (chunk, head) ----
