@@ -130,7 +130,7 @@ def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     rc = lib.crane_b200_comm_unique_id(buf, 128)
     if rc != OK:
-        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode("utf-8", "replace"))
     return bytes(buf)
 
 
@@ -175,14 +175,14 @@ class Engine:
         h = C.c_void_p()
         rc = self.lib.crane_b200_create(json.dumps(cfg).encode(), device, C.byref(h))
         if rc != OK:
-            raise CraneB200Error(rc, (self.lib.crane_b200_last_error(None) or b"").decode())
+            raise CraneB200Error(rc, (self.lib.crane_b200_last_error(None) or b"").decode("utf-8", "replace"))
         self.h = h
         self.vocab = self.lib.crane_b200_vocab_size(h)
         self.hidden = self.lib.crane_b200_hidden_size(h)
 
     def _ck(self, rc: int):
         if rc != OK:
-            raise CraneB200Error(rc, (self.lib.crane_b200_last_error(self.h) or b"").decode())
+            raise CraneB200Error(rc, (self.lib.crane_b200_last_error(self.h) or b"").decode("utf-8", "replace"))
 
     def close(self):
         if getattr(self, "h", None):
@@ -586,8 +586,11 @@ def gguf_config(path: str) -> dict:
     buf = C.create_string_buffer(16384)
     need = C.c_size_t(0)
     rc = lib.crane_b200_gguf_config(os.fsencode(path), buf, len(buf), C.byref(need))
+    if rc != OK and need.value > len(buf):            # a model with very many layers: the text's size comes back in `needed`
+        buf = C.create_string_buffer(need.value)
+        rc = lib.crane_b200_gguf_config(os.fsencode(path), buf, len(buf), C.byref(need))
     if rc != OK:
-        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode("utf-8", "replace"))
     return json.loads(buf.value.decode())
 
 
@@ -605,7 +608,7 @@ def op_gemm(a_bits: np.ndarray, w_bits: np.ndarray, mode: int, bias=None, out_in
                                 _ptr(np.ascontiguousarray(w_bits)), M, N, K, mode,
                                 None if b is None else _ptr(b), _ptr(out), 1 if use_simt else 0)
     if rc != OK:
-        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode("utf-8", "replace"))
     return out
 
 
@@ -616,7 +619,7 @@ def op_topk(logits: np.ndarray, k: int, device=0) -> np.ndarray:
     out = np.empty(k, dtype=np.uint32)
     rc = lib.crane_b200_op_topk(device, _ptr(x), x.size, k, _ptr(out))
     if rc != OK:
-        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode("utf-8", "replace"))
     return out
 
 
@@ -629,7 +632,7 @@ def op_sample(logits: np.ndarray, device=0, **kw):
     after = np.empty_like(x)
     rc = lib.crane_b200_op_sample(device, _ptr(x), x.size, C.byref(sp), C.byref(tok), _ptr(after))
     if rc != OK:
-        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode("utf-8", "replace"))
     return int(tok.value), after
 
 
@@ -643,5 +646,5 @@ def op_qlinear(x: np.ndarray, raw: np.ndarray, ggml_type: int, n: int, norm_w=No
     nw = None if norm_w is None else np.ascontiguousarray(norm_w, dtype=np.float32)
     rc = lib.crane_b200_op_qlinear(device, _ptr(x), m, k, _ptr(raw), raw.size, ggml_type, n, None if nw is None else _ptr(nw), eps, _ptr(y))
     if rc != OK:
-        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode())
+        raise CraneB200Error(rc, (lib.crane_b200_last_error(None) or b"").decode("utf-8", "replace"))
     return y

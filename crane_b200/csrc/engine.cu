@@ -9,6 +9,7 @@
 #include "../../include/crane_b200.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
