@@ -1,5 +1,6 @@
 #!/bin/bash
-# Follow-up GPU session: parity of the reworked chunk-prep / state / conv kernels, probe timings, per-kernel launch list.
+# Follow-up GPU session (one per optimisation step of the chunkwise Gated-Delta-Net work, tag = $1): Qwen3.5 / hybrid parity tests,
+# probe timings with stage spans, per-kernel launch list, config-2 timing.  Full captures: tools/profile_gdn_chunk.sh.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out
