@@ -10,8 +10,10 @@
 #include <vector_types.h>
 #include <vector_functions.h>
 #include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
@@ -121,16 +123,27 @@ inline void cp_async16(uint32_t dst, const void* src, int src_bytes) {
     memset(d, 0, 16);
     memcpy(d, src, src_bytes);
 }
-// mbarrier + bulk (TMA 1-D) copy: the copy is performed at issue, so the barrier has nothing left to wait for.  (A missing wait
-// or a stage overwritten too early is therefore NOT caught here -- only addressing is.)
-inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+// mbarrier + bulk (TMA 1-D) copy.  The copy itself is performed by the issuing thread at issue, but its completion is published
+// through the barrier word exactly as the hardware does it (expect_tx arms a byte count, each copy retires its bytes, the phase
+// completes when the count reaches zero) and mbar_wait really waits, with acquire / release ordering -- so a consumer that skips
+// the wait, or a stage that is overwritten while it is still being read, is a data race ThreadSanitizer reports (the TSan build of
+// this harness is the CPU stand-in for compute-sanitizer's racecheck).  Word layout: low 32 bits = completed phases, high 32 = pending bytes.
+inline std::atomic<uint64_t>& mbar_word(uint64_t* bar) { return *reinterpret_cast<std::atomic<uint64_t>*>(bar); }
+inline void mbar_init(uint64_t* bar, uint32_t) { mbar_word(bar).store(0, std::memory_order_release); }
 inline void fence_barrier_init() {}
-inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
-inline void mbar_wait(uint64_t*, uint32_t) {}
-inline void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t*) {
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { mbar_word(bar).fetch_add((uint64_t)bytes << 32, std::memory_order_acq_rel); }
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (((uint32_t)mbar_word(bar).load(std::memory_order_acquire) & 1u) == parity) sched_yield();
+}
+inline void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     assert(bytes % 16 == 0 && reinterpret_cast<uintptr_t>(gsrc) % 16 == 0 && smem_u32(smem_dst) % 16 == 0 && "cp.async.bulk alignment");
     assert((size_t)smem_u32(smem_dst) + bytes <= cuda_emu::t_block->smem_bytes);
     memcpy(smem_dst, gsrc, bytes);
+    uint64_t old = mbar_word(bar).load(std::memory_order_relaxed), next;
+    do {                                               // retire the bytes; the copy that brings the count to zero completes the phase
+        const uint64_t pending = (old >> 32) - bytes;
+        next = (pending << 32) | (uint32_t)((uint32_t)old + (pending == 0 ? 1u : 0u));
+    } while (!mbar_word(bar).compare_exchange_weak(old, next, std::memory_order_acq_rel));
 }
 inline void cp_async_commit() {}
 template <int N> inline void cp_async_wait() {}

@@ -54,3 +54,33 @@ int gdn_chunk_emu_run(const float* qn, const float* kn, const float* conv_out, c
 }
 
 }  // extern "C"
+
+#ifdef GDN_EMU_MAIN
+// Stand-alone run on random inputs (no numeric check: tests/test_gdn_chunk_emu.py does that through the shared library).  Built with
+// -fsanitize=thread this is the race check of the three kernels: CUDA threads are OS threads, __syncthreads / warp collectives are
+// pthread barriers, mbarriers are acquire / release atomics -- every shared- or global-memory hazard between the threads of a CTA that
+// is not ordered by one of those is a data race TSan reports.
+#include <random>
+int main(int argc, char** argv) {
+    const int S = argc > 1 ? atoi(argv[1]) : 130, dk = argc > 2 ? atoi(argv[2]) : 128, dv = 64, nk = 1, nv = 1;
+    const int state_warps = argc > 3 ? atoi(argv[3]) : 4;
+    const int conv_dim = 2 * nk * dk + nv * dv;
+    std::mt19937 rng(1);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<float> qn((size_t)S * nk * dk), kn(qn.size()), conv((size_t)S * conv_dim), gb((size_t)S * nv * 2), gl((size_t)S * nv),
+        st((size_t)nv * dk * dv), y((size_t)S * nv * dv);
+    for (auto& x : qn) x = nd(rng) * 0.05f;
+    for (auto& x : kn) x = nd(rng) * 0.09f;
+    for (auto& x : conv) x = nd(rng);
+    for (auto& x : st) x = nd(rng) * 0.3f;
+    for (int i = 0; i < S * nv; ++i) { gl[i] = -0.5f; gb[2 * i] = expf(-0.5f); gb[2 * i + 1] = 0.5f; }
+    void* ws = nullptr;
+    if (posix_memalign(&ws, 256, gdn_chunk_emu_ws_bytes(S, nv, dk, dv))) return 2;
+    memset(ws, 0, gdn_chunk_emu_ws_bytes(S, nv, dk, dv));
+    const int rc = gdn_chunk_emu_run(qn.data(), kn.data(), conv.data(), gb.data(), gl.data(), st.data(), y.data(), ws, S, nk, nv, dk, dv, state_warps);
+    double acc = 0;
+    for (float v : y) acc += v;
+    printf("gdn chunk emu: rc %d, sum(y) %.6f\n", rc, acc);
+    return rc;
+}
+#endif
