@@ -151,4 +151,6 @@ def test_chunk_kernels_are_race_free_under_thread_sanitizer(tmp_path, S, dk, sta
     r = subprocess.run([exe, str(S), str(dk), str(state_warps)], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66"))
     print(r.stdout[-200:], r.stderr[-3000:])
+    if "FATAL: ThreadSanitizer" in r.stderr:          # the sanitizer runtime could not start in this sandbox (address-space layout): not a finding
+        pytest.skip("ThreadSanitizer cannot run here: " + r.stderr.strip().splitlines()[0][:200])
     assert r.returncode == 0 and "rc 0" in r.stdout and "ThreadSanitizer" not in r.stderr
