@@ -1180,7 +1180,7 @@ void crane_b200_model::ensure_prefill_ws(int S) {
         g_qn = dalloc<float>((size_t)cap * nk * dk); g_kn = dalloc<float>((size_t)cap * nk * dk);
         g_gb = dalloc<float>((size_t)cap * nv * 2); g_y = dalloc<float>((size_t)cap * value_dim());
         g_gl = nullptr; g_chunk = nullptr;
-        if (gdn_mode != 1 && cap >= cb::GDN_CHUNK && dv % 64 == 0) {     // chunkwise recurrence: 0.9 KB of scratch per (token, value head) at dk = dv = 128
+        if (gdn_mode != 1 && cap >= cb::GDN_CHUNK && dv % 64 == 0) {     // chunkwise recurrence: 3.8 KB of scratch per (token, value head) at dk = dv = 128
             g_gl = dalloc<float>((size_t)cap * nv);
             g_chunk = dalloc<unsigned char>(cb::gdn_chunk_ws_bytes(cap, nv, dk, dv));
         }
