@@ -138,15 +138,16 @@ def test_chunk_kernels_on_the_host_emulator(emu, S, nk, nv, dk, dv, state_warps)
     assert np.abs(state - s_seq.numpy()).max() < 2e-5
 
 
-@pytest.mark.parametrize("S,dk,state_warps", [(300, 128, 4), (130, 64, 4), (130, 256, 4), (130, 128, 8)])
-def test_chunk_kernels_are_race_free_under_thread_sanitizer(tmp_path, S, dk, state_warps):
+@pytest.mark.parametrize("S,dk,state_warps,gcs", [(300, 128, 4, 1024), (130, 64, 4, 1024), (130, 256, 4, 1024), (130, 128, 8, 1024), (300, 128, 4, 2)])
+def test_chunk_kernels_are_race_free_under_thread_sanitizer(tmp_path, S, dk, state_warps, gcs):
     """The race check of the three kernels without a GPU: the emulator built with -fsanitize=thread.  CUDA threads are OS threads,
     __syncthreads and the warp collectives are pthread barriers, mbarriers are acquire / release atomics, so a shared- or
     global-memory hazard inside a CTA that none of them orders is a data race TSan reports (removing the barrier after the S^T
     hand-over of the state kernel is reported, checked by hand).  S = 300: five chunks, so both operand stages are reused."""
     exe = str(tmp_path / "gdn_chunk_tsan")
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-DGDN_EMU_MAIN", "-I" + cuda_inc,
+    # gcs = 2: the decay table of the serial kernel holds two chunks, so its refill (every 1024 chunks = 65 536 rows in the product) runs
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-DGDN_EMU_MAIN", f"-DGDN_CHUNK_GCS={gcs}", "-I" + cuda_inc,
                     os.path.join(EMU_DIR, "gdn_chunk_emu.cpp"), "-o", exe], check=True)
     r = subprocess.run([exe, str(S), str(dk), str(state_warps)], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66"))
