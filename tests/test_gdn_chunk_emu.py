@@ -189,3 +189,22 @@ def test_chunk_kernels_on_the_reference_tests_own_distribution(emu, kdim):
     cy, cs = cos(y, y_ref.numpy()), cos(state, s_ref.numpy())
     print(f"K={kdim}: cos(y) {cy:.9f}, cos(state) {cs:.9f}, max|y| {np.abs(y_ref.numpy()).max():.3g}")
     assert cy >= 0.9999 and cs >= 0.9999
+
+
+def test_chunk_scratch_layout_is_aligned_and_fits(emu):
+    """gdn_args.h: the eight sub-buffers of the chunk scratch are carved in order, 256-byte aligned (bulk copies and 16-byte vector
+    accesses rely on it), and end inside gdn_chunk_ws_bytes -- for every geometry the launcher accepts and ragged row counts."""
+    for S in (64, 65, 127, 128, 4096, 5000):
+        for nv in (1, 4, 16, 48):
+            for dk in (64, 128, 256):
+                for dv in (64, 128, 256):
+                    total = emu.gdn_chunk_emu_ws_bytes(S, nv, dk, dv)
+                    offs = (ctypes.c_size_t * 8)()
+                    emu.gdn_chunk_emu_ws_offsets(S, nv, dk, dv, offs)
+                    n = ((S + CHUNK - 1) // CHUNK) * nv
+                    sizes = [n * 2 * CHUNK * dk * 2] * 3 + [n * 2 * CHUNK * CHUNK * 2, n * dv * CHUNK * 4, n * 4, n * 2 * dv * dk * 2, n * 2 * dv * CHUNK * 2]
+                    o = list(offs)
+                    assert o[0] == 0 and all(x % 256 == 0 for x in o)
+                    for i in range(8):
+                        end = o[i] + sizes[i]
+                        assert end <= (o[i + 1] if i < 7 else total), (S, nv, dk, dv, i)
