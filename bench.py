@@ -388,6 +388,28 @@ def bench_config2(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def other_config_summary(config, steps=2, timeout_s=120):
+    """One more BASELINE config measured by THIS script in a child process (`bench.py --config <config>`), condensed for the headline
+    line's `other_configs` field.  A child, so that nothing it does -- a failure, a hang (killed at the timeout) -- can keep the
+    headline line from being printed; whatever goes wrong comes back as {"error": ...}."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", config, "--steps", str(steps), "--warmup", "3", "--gpus", "1"],
+                           capture_output=True, text=True, timeout=timeout_s, env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"error": f"rc {r.returncode}: {(r.stderr or r.stdout).strip()[-200:]}"}
+        d = json.loads(line[-1])
+        keep = ("value", "unit", "steps", "ms_per_step", "prefill_ms", "prefill_tflops", "prefill_frac_of_bf16_peak", "prefill_tok_per_s", "gpu_launches", "clocks")
+        out = {k: d[k] for k in keep if k in d}
+        out["workload"] = d.get("config", {}).get("workload")
+        out["e2e_tok_s"] = d.get("e2e", {}).get("value")
+        out["decode_roofline_frac"] = d.get("roofline", {}).get("frac")
+        out["how"] = f"child process: bench.py --config {config} --steps {steps} --warmup 3 (same GPU, after the headline measurement)"
+        return out
+    except Exception as e:                                 # incl. subprocess.TimeoutExpired
+        return {"error": repr(e)[:200]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,6 +418,7 @@ def main():
     ap.add_argument("--impl", default="crane_b200", choices=["crane_b200", "reference"])
     ap.add_argument("--config", default="qwen3_vl_2b", choices=["qwen3_vl_2b", "tiny", "qwen3_8b_q4km", "qwen3_5_0_8b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config-2 (Qwen3.5-0.8B) child measurement appended to the headline line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -607,6 +630,9 @@ def main():
                          "teacher_forced_steps": n_par, "step_logits_rel_max": max(rels), "last_step_logits_rel": rels[-1],
                          "min_top2_margin_rel": min(margins), "min_top2_margin_at_step": int(np.argmin(margins)),
                          "against": "oracle (torch f32) on the same full-size request; rel = max|d| / max|ref|"}
+    if world == 1 and args.config == "qwen3_vl_2b" and not args.no_cpu_baseline and not args.no_other_configs and os.environ.get("CRANE_B200_BENCH_EXTRA", "1") != "0":
+        # BASELINE configs[2] beside the headline: Qwen3.5-0.8B, 4096-token prefill (chunkwise Gated-Delta-Net) + 512 decode tokens
+        out["other_configs"] = {"qwen3_5_0_8b": other_config_summary("qwen3_5_0_8b")}
     print(json.dumps(out))
     model.close()
     if dist is not None:
